@@ -1,0 +1,166 @@
+/* b2t.h -- C ABI of the B200-native batched SQP / Schur-complement / GBD-PCG trajectory-optimisation path.
+ *
+ * One shared library is built per robot (topology baked in at code-generation time): libb2t_<robot>.so.
+ * Every library exports exactly the symbols below.  All functions return 0 on success, a negative b2t_status
+ * otherwise; none throws, aborts or prints.  The caller owns every input/output buffer; the library owns only
+ * the opaque solver handle (its device workspace).  Thread-safe per handle.
+ *
+ * The reference (VCA-EPFL/TrajoptMPCReference) has no FFI: its boundary is the Python API.  Each entry point
+ * names the reference interface it replaces (file:line under /root/reference):
+ *
+ *   b2t_solver_create        TrajoptMPCReference.__init__ (TrajoptMPCReference.py:31-43) + URDFPlant.__init__
+ *                            (TrajoptPlant.py:274-281) + QuadraticCost/UrdfCost.__init__ (TrajoptCost.py:24-37,
+ *                            373-396) + TrajoptConstraint.set_*_limits (TrajoptConstraint.py:191-208)
+ *   b2t_set_trajectory / b2t_set_goals / b2t_set_multipliers
+ *                            arguments x, u of SQP() (:510), cost.xg, BoxConstraint mu/lambda/phi (:23-25)
+ *   b2t_sqp_solve            TrajoptMPCReference.SQP (:510-760), batched over independent instances
+ *   b2t_get_trajectory / b2t_get_status / b2t_get_trace / b2t_get_multipliers
+ *                            the 6-tuple SQP returns (:760), self.trace (:555-569), mu/lambda/phi state
+ *   b2t_sqp_solve_host       one call from host buffers to host buffers (what examples/exampleHelpers.py:80 does)
+ *   b2t_stage_dynamics       TrajoptPlant.integrator(.., return_gradient) (TrajoptPlant.py:83-138)
+ *   b2t_stage_kkt            formKKTSystemBlocks (:200-271) + Schur complement and preconditioner blocks
+ *                            (solveKKTSystem_Schur :419-424, PCG.compute_preconditioner PCG.py:166-212)
+ *   b2t_stage_pcg            PCG.solve (PCG.py:66-111, 214)
+ *   b2t_stage_recover        dxu = invG (g - C^T l) (:449-452)
+ *   b2t_stage_merit          totalCost (:296-310), totalHardConstraintViolation (:273-294), D (:635-648)
+ *   b2t_fetch                the reference's saved_* lists (exampleHelpers.py:136-154), one array at a time
+ *
+ * Array layouts at the ABI are the reference's:  x is [batch][nx][N] (C order, i.e. numpy (nx, N) per
+ * instance), u is [batch][nu][N-1], goals xg [batch][nx].  double precision at the boundary.
+ */
+#ifndef B2T_H
+#define B2T_H
+#include <stddef.h>
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define B2T_ABI_VERSION 1
+
+typedef enum {
+  B2T_OK = 0,
+  B2T_ERR_INVALID = -1,      /* bad argument (the reference print()s and exit()s) */
+  B2T_ERR_CUDA = -2,         /* CUDA runtime error; see b2t_last_error */
+  B2T_ERR_UNSUPPORTED = -3,  /* e.g. UrdfCost on a robot with n != 2 (reference limitation, RBDReference.py:263) */
+  B2T_ERR_NOMEM = -4
+} b2t_status;
+
+typedef enum { B2T_COST_QUADRATIC = 0, B2T_COST_URDF_EE = 1 } b2t_cost_kind;
+typedef enum { B2T_LIMIT_NONE = 0, B2T_LIMIT_QUADRATIC_PENALTY = 1, B2T_LIMIT_AUGMENTED_LAGRANGIAN = 2 } b2t_limit_mode;
+/* SQPSolverMethods (TrajoptMPCReference.py:13-18); N and S are exact solves of the same system */
+typedef enum { B2T_METHOD_PCG_J = 2, B2T_METHOD_PCG_BJ = 3, B2T_METHOD_PCG_SS = 4 } b2t_method;
+typedef enum { B2T_F64 = 0, B2T_F32 = 1 } b2t_dtype;
+/* limit types, index into the per-type arrays below */
+enum { B2T_LIM_JOINT = 0, B2T_LIM_VELOCITY = 1, B2T_LIM_TORQUE = 2 };
+
+typedef struct {
+  int batch;              /* independent MPC instances */
+  int knots;              /* N */
+  int integrator_type;    /* 0 euler, 1 semi-implicit euler (TrajoptPlant.py:92-138) */
+  int dtype;              /* b2t_dtype: arithmetic type of the whole path */
+  double dt;
+  double gravity;         /* options['gravity'], default -9.81 (TrajoptPlant.py:31) */
+  int cost_kind;          /* b2t_cost_kind */
+  int qf_start;           /* QF_start, -1 = None (TrajoptCost.py:40-47) */
+  const double* Q;        /* [nx*nx] row-major, host */
+  const double* QF;       /* [nx*nx] */
+  const double* R;        /* [nu*nu] */
+  int limit_mode[3];      /* b2t_limit_mode per limit type */
+  const double* lower;    /* [nx+nu] lower bounds of z = [q; qd; u] (read where the type's mode != NONE) */
+  const double* upper;    /* [nx+nu] */
+  double mu_init[3], mu_factor[3], mu_max[3], phi_init[3], phi_factor[3];   /* TrajoptConstraint.py:40-44 */
+} b2t_problem_desc;
+
+typedef struct {           /* TrajoptMPCReference.set_default_options (:91-115) */
+  double exit_tolerance_linSys;
+  int max_iter_linSys;
+  double exit_tolerance_SQP;
+  int max_iter_SQP;
+  double alpha_factor, alpha_min;
+  double rho_factor, rho_min, rho_max, rho_init;
+  double expected_reduction_min, expected_reduction_max;
+  double exit_tolerance_soft;
+  int max_iter_soft;
+  double merit_mu;        /* the reference hard-codes mu = 10 (:546) */
+} b2t_options;
+
+/* per-instance result record written by b2t_get_status: [batch][B2T_STATUS_FIELDS] ints */
+enum { B2T_ST_EXIT_SQP = 0, B2T_ST_EXIT_SOFT, B2T_ST_OUTER_ITER, B2T_ST_SQP_ITER, B2T_ST_TOTAL_QP, B2T_ST_TOTAL_PCG,
+       B2T_ST_TOTAL_TRIALS, B2T_ST_TRACE_ROWS, B2T_STATUS_FIELDS };
+/* per-instance scalar results written by b2t_get_scalars: [batch][B2T_SCALAR_FIELDS] doubles */
+enum { B2T_SC_J = 0, B2T_SC_C, B2T_SC_MERIT, B2T_SC_RHO, B2T_SCALAR_FIELDS };
+/* one trace row (b2t_get_trace): [batch][trace_cap][B2T_TRACE_FIELDS] doubles, same keys as self.trace (:555-569) */
+enum { B2T_TR_OUTER = 0, B2T_TR_ITER, B2T_TR_LS_ITER, B2T_TR_ALPHA, B2T_TR_RHO, B2T_TR_J, B2T_TR_C, B2T_TR_MERIT, B2T_TR_D,
+       B2T_TR_RATIO, B2T_TR_INNER, B2T_TR_SUCCESS, B2T_TRACE_FIELDS };
+
+/* arrays b2t_fetch can return (knot-major, doubles): name -> shape per instance */
+typedef enum {
+  B2T_ARR_X = 0,        /* [N][nx]   current iterate */
+  B2T_ARR_U,            /* [N][nu]   (row N-1 unused) */
+  B2T_ARR_XKP1,         /* [N][nx]   integrator(x_k,u_k) (row N-1 unused) */
+  B2T_ARR_DQDD,         /* [N][n*3n] forward_dynamics_gradient */
+  B2T_ARR_GHAT,         /* [N][m*m]  inv(G_k + rho I) */
+  B2T_ARR_G,            /* [N][m]    gradient g_k */
+  B2T_ARR_SD,           /* [N][nx*nx] diagonal blocks of S */
+  B2T_ARR_SO,           /* [N][nx*nx] S_{k,k-1} (row 0 unused) */
+  B2T_ARR_PD,           /* [N][nx*nx] diagonal blocks of the preconditioner */
+  B2T_ARR_GAMMA,        /* [N][nx] */
+  B2T_ARR_L,            /* [N][nx]   multipliers from PCG */
+  B2T_ARR_DZ,           /* [N][m]    step [dx_k; du_k] */
+  B2T_ARR_XN,           /* [N][nx]   line-search trial point */
+  B2T_ARR_UN            /* [N][nu] */
+} b2t_array;
+
+typedef struct b2t_solver b2t_solver;
+
+int b2t_abi_version(void);
+const char* b2t_model_name(void);
+const char* b2t_model_digest(void);
+int b2t_model_dims(int* nq, int* nx, int* nu);
+const char* b2t_last_error(void);
+void b2t_default_options(b2t_options* o);
+
+int b2t_solver_create(const b2t_problem_desc* desc, int device, b2t_solver** out);
+int b2t_solver_destroy(b2t_solver* s);
+size_t b2t_workspace_bytes(const b2t_solver* s);
+int b2t_set_stream(b2t_solver* s, void* cuda_stream);
+
+/* inputs (host pointers unless on_device != 0, then device pointers of the same layout and type double) */
+int b2t_set_trajectory(b2t_solver* s, const double* x, const double* u, int on_device);
+int b2t_set_goals(b2t_solver* s, const double* xg, int on_device);
+/* xs [batch][nx] host: initial-state target of the first constraint row c_0 = x_0 - xs; b2t_set_trajectory sets xs = x[:,0]
+ * like SQP() does (TrajoptMPCReference.py:527) */
+int b2t_set_initial_state(b2t_solver* s, const double* xs);
+int b2t_set_multipliers(b2t_solver* s, const double* mu, const double* lam, const double* phi);   /* [batch][2m][N] host */
+int b2t_reset_multipliers(b2t_solver* s);
+
+int b2t_sqp_solve(b2t_solver* s, int method, const b2t_options* opts);
+
+int b2t_get_trajectory(b2t_solver* s, double* x, double* u, int on_device);
+int b2t_get_status(b2t_solver* s, int* status);
+int b2t_get_scalars(b2t_solver* s, double* scalars);
+int b2t_get_trace(b2t_solver* s, double* trace, int trace_cap);
+int b2t_get_multipliers(b2t_solver* s, double* mu, double* lam, double* phi);
+/* number of kernels launched and seconds spent (CUDA events) by the last b2t_sqp_solve */
+int b2t_get_launch_stats(b2t_solver* s, long long* launches, double* device_seconds);
+/* CUDA-event time of each kernel family accumulated over the last solve: [B2T_KERNEL_FAMILIES] seconds and launch counts */
+enum { B2T_K_FD = 0, B2T_K_FDGRAD, B2T_K_KKT, B2T_K_SCHUR, B2T_K_PCG, B2T_K_RECOVER, B2T_K_TRIAL, B2T_K_MERIT, B2T_K_CTRL, B2T_KERNEL_FAMILIES };
+int b2t_set_profiling(b2t_solver* s, int enabled);
+int b2t_get_kernel_times(b2t_solver* s, double* seconds, long long* launches);
+
+/* host -> device, solve, device -> host in one call (pinned staging inside the handle) */
+int b2t_sqp_solve_host(b2t_solver* s, const double* x0, const double* u0, const double* xg, int method, const b2t_options* opts,
+                       double* x_out, double* u_out, int* status_out);
+
+/* single stages on the handle's current (x, u), all instances; results via b2t_fetch */
+int b2t_stage_dynamics(b2t_solver* s);
+int b2t_stage_kkt(b2t_solver* s, double rho, int method);
+int b2t_stage_pcg(b2t_solver* s, int method, double tol, int max_iter, int* iters_out /* [batch] host */);
+int b2t_stage_recover(b2t_solver* s);
+int b2t_stage_merit(b2t_solver* s, double alpha, double* J, double* c, double* D /* [batch] host each */);
+int b2t_fetch(b2t_solver* s, int which, double* out);
+
+#ifdef __cplusplus
+}
+#endif
+#endif

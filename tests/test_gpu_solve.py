@@ -1,0 +1,135 @@
+"""-m gpu: complete SQP solves through the drop-in API against the reference's recorded results and the oracle."""
+import numpy as np
+import pytest
+
+import trajoptmpcreference_b200 as t
+from conftest import load_npz
+from gpu_common import make_pair, solve_meta
+from oracle import sqp
+
+pytestmark = pytest.mark.gpu
+
+PCG_TAGS = [k for k, v in solve_meta().items() if v["method"].startswith("PCG")]
+LONG = {"pend_N20_SS_al01", "pend_N20_SS_qp01"}     # hundreds of QP solves: chaotic amplification, compared loosely
+
+
+@pytest.mark.parametrize("tag", PCG_TAGS)
+def test_sqp_vs_reference_golden(tag, oracle_models):
+    """Same call as the reference's examples; exits / iteration counts / alpha sequence identical, J, x, u within the
+    measured parity floor (a 1-ulp change of S moves the reference's own result by 1e-9..6e-8)."""
+    S = load_npz("solve.npz")
+    mt = solve_meta()[tag]
+    N = mt["N"]
+    (plant, pc, pcons), _ = make_pair(mt["robot"], N, oracle_models, xg=S[tag + "/xg"], limits=mt["limits"], integrator=mt["integrator"])
+    solver = t.TrajoptMPCReference(plant, pc, pcons) if pcons is not None else t.TrajoptMPCReference(plant, pc)
+    n = plant.get_num_pos()
+    opts = dict(mt["options"]); opts["overloading"] = False
+    x, u, e1, e2, outer, it = solver.SQP(np.zeros((2 * n, N)), np.zeros((n, N - 1)), N, 0.1, getattr(t.SQPSolverMethods, mt["method"]), options=opts)
+    if tag in LONG:
+        assert [e1, e2, outer] == S[tag + "/exits"].tolist()[:3]
+        assert abs(solver.last_result.J[0] - float(S[tag + "/J"])) < 1e-3 * abs(float(S[tag + "/J"]))
+        assert np.max(np.abs(u)) < 0.2
+        return
+    assert [e1, e2, outer, it] == S[tag + "/exits"].tolist()
+    rows = solver.trace[1:]
+    k = len(rows)
+    assert [r["pcg_iters"] for r in rows] == S[tag + "/pcg_iters"].tolist()[-k:]
+    assert [r["line_search_iteration"] for r in rows] == S[tag + "/tr_ls"].tolist()[-k:]
+    assert np.allclose([r["alpha"] for r in rows], S[tag + "/tr_alpha"][-k:])
+    assert np.allclose([r["rho"] for r in rows], S[tag + "/tr_rho"][-k:], rtol=1e-12)
+    assert np.allclose([r["J"] for r in rows], S[tag + "/tr_J"][-k:], rtol=2e-7)
+    assert abs(solver.last_result.J[0] - float(S[tag + "/J"])) < 2e-7 * abs(float(S[tag + "/J"]))
+    assert np.max(np.abs(x - S[tag + "/x"])) < 2e-5
+    assert np.max(np.abs(u - S[tag + "/u"])) < 2e-5
+    if pcons is not None:
+        assert np.allclose(pcons.torque_limits.quadratic_penalty_mu, S[tag + "/mu"], rtol=1e-12)
+
+
+@pytest.mark.parametrize("run", ["4", "3"])
+def test_recorded_author_runs(run, oracle_models):
+    """data/4 (= examples/twolinks.py) and data/3 as recorded by the reference's authors."""
+    D = load_npz("ref_data.npz")
+    N = 10
+    (plant, pc, _), _ = make_pair("arm2", N, oracle_models, xg=D[run + "/xg"])
+    solver = t.TrajoptMPCReference(plant, pc)
+    x, u, e1, e2, outer, it = solver.SQP(np.zeros((4, N)), np.zeros((2, N - 1)), N, 0.1, t.SQPSolverMethods.PCG_SS,
+                                         options={"expected_reduction_min_SQP_DDP": -100, "overloading": False})
+    assert [e1, e2, outer, it] == D[run + "/exits"].tolist()
+    assert solver.pcg_iters == D[run + "/pcg_iters"].tolist()
+    rows = solver.trace[1:]
+    assert [r["line_search_iteration"] for r in rows] == D[run + "/tr_ls"].tolist()
+    assert np.allclose([r["alpha"] for r in rows], D[run + "/tr_alpha"])
+    assert np.allclose([r["J"] for r in rows], D[run + "/tr_J"], rtol=1e-6)
+    assert np.max(np.abs(x - D[run + "/final_x"])) < 1e-4 and np.max(np.abs(u - D[run + "/final_u"])) < 1e-4
+
+
+def _batch_goals(n, B, seed):
+    rng = np.random.default_rng(seed)
+    xg = np.zeros((B, 2 * n))
+    xg[:, :n] = rng.uniform(-0.5, 0.5, (B, n))
+    return xg
+
+
+@pytest.mark.parametrize("name,N,B,limits", [
+    ("arm6", 16, 24, None),
+    ("arm3", 12, 16, {"torque": ([0.4], [-0.4], "QUADRATIC_PENALTY"), "joint": ([0.45], [-0.45], "AUGMENTED_LAGRANGIAN")}),
+    ("arm6", 16, 12, {"torque": ([1.0], [-1.0], "QUADRATIC_PENALTY"), "joint": ([0.45], [-0.45], "QUADRATIC_PENALTY")}),
+])
+def test_batch_vs_oracle(name, N, B, limits, oracle_models):
+    """Independent instances with different goals in one batch; each compared with the oracle run on its own
+    (multi-coordinate box limits are UNPINNED in the reference: the oracle's element-wise restatement is the spec)."""
+    (plant, pc, pcons), (m, oc, ocn) = make_pair(name, N, oracle_models, limits=limits)
+    n = m.n
+    xg = _batch_goals(n, B, 11)
+    solver = t.TrajoptMPCReference(plant, pc, pcons) if pcons is not None else t.TrajoptMPCReference(plant, pc)
+    opts = {"expected_reduction_min_SQP_DDP": -100, "max_iter_softConstraints": 4}
+    r = solver.solve_batch(np.zeros((B, 2 * n, N)), np.zeros((B, n, N - 1)), xg, N, 0.1, t.SQPSolverMethods.PCG_SS, dict(opts))
+    same_iters = 0
+    for b in range(B):
+        import copy
+        oc_b = copy.copy(oc); oc_b.xg = xg[b]
+        ocn_b = copy.deepcopy(ocn)
+        ro = sqp.sqp(m, oc_b, ocn_b, np.zeros((2 * n, N)), np.zeros((n, N - 1)), N, 0.1, "PCG-SS", dict(opts))
+        same = (ro["exit_sqp"], ro["exit_soft"], ro["outer_iter"], ro["sqp_iter"]) == (r.exit_sqp[b], r.exit_soft[b], r.outer_iter[b], r.sqp_iter[b]) \
+            and sum(ro["pcg_iters"]) == r.total_pcg[b] and sum(ro["ls_trials"]) == r.total_trials[b]
+        same_iters += int(same)
+        if same:
+            assert abs(ro["J"] - r.J[b]) < 1e-6 * max(1.0, abs(ro["J"]))
+            assert np.max(np.abs(ro["x"] - r.x[b])) < 1e-4
+    assert same_iters >= int(0.9 * B), "only %d of %d instances reproduce the oracle's iteration counts" % (same_iters, B)
+
+
+def test_full_size_properties(oracle_models):
+    """BASELINE config shape (arm6, N=64, penalty box limits) at a reduced batch: size-independent properties."""
+    N, B = 64, 96
+    limits = {"torque": ([1.0], [-1.0], "QUADRATIC_PENALTY"), "joint": ([0.45], [-0.45], "QUADRATIC_PENALTY")}
+    (plant, pc, pcons), _ = make_pair("arm6", N, oracle_models, limits=limits)
+    n = 6
+    rng = np.random.default_rng(1)
+    xg = np.zeros((B, 12)); xg[:, :6] = rng.uniform(-0.5, 0.5, (B, 6))
+    opts = {"expected_reduction_min_SQP_DDP": -100}
+    solver = t.TrajoptMPCReference(plant, pc, pcons)
+    x0 = np.zeros((B, 12, N)); u0 = np.zeros((B, 6, N - 1))
+    r1 = solver.solve_batch(x0, u0, xg, N, 0.1, t.SQPSolverMethods.PCG_SS, dict(opts))
+    r1 = {k: np.array(v) for k, v in r1.items()}
+    # (a) run-to-run determinism: bitwise
+    r2 = solver.solve_batch(x0, u0, xg, N, 0.1, t.SQPSolverMethods.PCG_SS, dict(opts))
+    assert np.array_equal(r1["x"], r2.x) and np.array_equal(r1["u"], r2.u) and np.array_equal(r1["total_pcg"], r2.total_pcg)
+    # (b) an instance's result does not depend on its position in the batch or on its neighbours
+    perm = rng.permutation(B)
+    r3 = solver.solve_batch(x0, u0, xg[perm], N, 0.1, t.SQPSolverMethods.PCG_SS, dict(opts))
+    assert np.array_equal(r1["x"][perm], r3.x) and np.array_equal(r1["sqp_iter"][perm], r3.sqp_iter)
+    # (c) every instance terminated with a legal exit code; the start point is kept (x_0 = xs up to the PCG tolerance)
+    assert set(np.unique(r1["exit_sqp"])) <= {1, 2, 3} and set(np.unique(r1["exit_soft"])) <= {1, 2, 3}
+    assert np.max(np.abs(r1["x"][:, :, 0])) < 1e-3
+    # (d) reported J, c equal a fresh evaluation of the merit kernel at the returned trajectory
+    s = solver.batch_solver(N, 0.1, B)
+    s.stage_dynamics()
+    J, c, _ = s.stage_merit(0.0)
+    assert np.allclose(J, r3.J, rtol=1e-12) and np.allclose(c, r3.c, rtol=1e-9, atol=1e-12)
+    # (e) the unconstrained anchor instance of BASELINE.md inside a batch: 6 SQP iterations, 563 PCG iterations, 16 trials
+    solver2 = t.TrajoptMPCReference(plant, pc)
+    xg2 = xg.copy(); xg2[5, :6] = np.linspace(0.5, -0.5, 6)
+    r4 = solver2.solve_batch(x0, u0, xg2, N, 0.1, t.SQPSolverMethods.PCG_SS, dict(opts))
+    assert (r4.sqp_iter[5], r4.total_pcg[5], r4.total_trials[5]) == (6, 563, 16)
+    assert abs(r4.J[5] - 6.50929423656) < 1e-8

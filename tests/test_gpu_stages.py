@@ -1,0 +1,101 @@
+"""-m gpu: every kernel stage through the C ABI against the oracle / reference golden vectors (fp64, tight tolerances)."""
+import numpy as np
+import pytest
+
+import trajoptmpcreference_b200 as t
+from conftest import load_npz, relerr
+from gpu_common import make_pair
+from oracle import kkt, sqp, dense
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.mark.parametrize("name", ["pend", "arm2", "arm3", "arm6"])
+@pytest.mark.parametrize("integ", [0, 1])
+def test_dynamics_kernels_vs_reference(name, integ, oracle_models):
+    """k_fd + k_fd_grad against values recorded from the unmodified reference (tests/golden/dynamics.npz)."""
+    D = load_npz("dynamics.npz")
+    n = oracle_models[name].n
+    q, qd, u = D[name + "/q"], D[name + "/qd"], D[name + "/u"]
+    P = q.shape[0]
+    (plant, pc, _), _ = make_pair(name, 2, oracle_models, integrator=integ, cost_kind="quadratic")
+    s = t.BatchSolver(plant, pc, None, N=2, dt=0.1, batch=P)
+    x = np.zeros((P, 2 * n, 2)); uu = np.zeros((P, n, 1))
+    x[:, :n, 0] = q; x[:, n:, 0] = qd; uu[:, :, 0] = u
+    s.set_trajectory(x, uu)
+    s.stage_dynamics()
+    dq = s.fetch("dqdd")[:, 0].reshape(P, n, 3 * n)
+    assert relerr(dq, D[name + "/dqdd"]) < 1e-12
+    assert relerr(s.fetch("xkp1")[:, 0], D[name + "/xn%d" % integ]) < 1e-13
+    # reference-API callbacks of the plant object
+    A, B = plant.integrator(x[0, :, 0], uu[0, :, 0], 0.1, return_gradient=True)
+    assert relerr(A, D[name + "/A%d" % integ][0]) < 1e-12 and relerr(B, D[name + "/B%d" % integ][0]) < 1e-13
+    assert relerr(plant.forward_dynamics(x[0, :, 0], uu[0, :, 0]), D[name + "/qdd"][0]) < 1e-12
+
+
+def _kkt_case(tag, oracle_models):
+    K = load_npz("kkt.npz")
+    robot = {"arm2_urdf": "arm2", "arm3_qc": "arm3", "arm6_qc": "arm6", "pend_al": "pend"}[tag]
+    x, u, xs, xg = K[tag + "/x"], K[tag + "/u"], K[tag + "/xs"], K[tag + "/xg"]
+    N = x.shape[1]
+    limits = {"torque": ([0.3], [-0.3], "AUGMENTED_LAGRANGIAN")} if tag == "pend_al" else None
+    (plant, pc, pcons), (m, oc, ocn) = make_pair(robot, N, oracle_models, xg=xg, limits=limits)
+    if tag == "pend_al":
+        ocn.limits["torque"].lam[:] = K[tag + "/lam"]; ocn.limits["torque"].mu[:] = K[tag + "/mu"]
+        pcons.torque_limits.augmented_lagrangian_lambda[:] = K[tag + "/lam"]; pcons.torque_limits.quadratic_penalty_mu[:] = K[tag + "/mu"]
+    return K, plant, pc, pcons, m, oc, ocn, x, u, xs, N
+
+
+@pytest.mark.parametrize("tag", ["arm2_urdf", "arm3_qc", "arm6_qc", "pend_al"])
+@pytest.mark.parametrize("batch", [1, 3])
+def test_kkt_schur_pcg_recover_merit(tag, batch, oracle_models):
+    K, plant, pc, pcons, m, oc, ocn, x, u, xs, N = _kkt_case(tag, oracle_models)
+    n = m.n; nx = 2 * n; mm = 3 * n
+    s = t.BatchSolver(plant, pc, pcons, N=N, dt=0.1, batch=batch)
+    s.set_trajectory(np.broadcast_to(x[None], (batch,) + x.shape), np.broadcast_to(u[None], (batch,) + u.shape))
+    s.set_initial_state(np.broadcast_to(xs[None], (batch, nx)))
+    if pcons is not None:
+        mu, lam, phi = pcons.pack(N)
+        s.set_multipliers(*[np.broadcast_to(a[None], (batch,) + a.shape) for a in (mu, lam, phi)])
+    rho = 1e-3
+    X, U = x.T.copy(), u.T.copy()
+    blocks = kkt.form_blocks(m, oc, ocn, X, U, xs, 0.1)
+    sch = kkt.schur(blocks, rho, nx)
+    for method, kind in ((t.SQPSolverMethods.PCG_SS, "SS"), (t.SQPSolverMethods.PCG_BJ, "BJ"), (t.SQPSolverMethods.PCG_J, "J")):
+        s.stage_kkt(rho, method)
+        for b in range(batch):
+            assert relerr(s.fetch("g")[b], blocks["g"]) < 1e-12
+            Gh = s.fetch("Ghat")[b].reshape(N, mm, mm)
+            assert relerr(Gh, sch["Ghat"]) < 1e-11
+            assert relerr(s.fetch("Sd")[b].reshape(N, nx, nx), sch["Sd"]) < 1e-11
+            assert relerr(s.fetch("So")[b].reshape(N, nx, nx)[1:], sch["So"]) < 1e-11
+            assert relerr(s.fetch("gamma")[b], sch["gamma"]) < 1e-10
+        Pd, Po = kkt.preconditioner(sch["Sd"], sch["So"], kind)
+        assert relerr(s.fetch("Pd")[0].reshape(N, nx, nx), Pd) < 1e-9
+        # reference dense matrices as recorded from the unmodified reference
+        assert relerr(dense.assemble_bt(s.fetch("Sd")[0].reshape(N, nx, nx), s.fetch("So")[0].reshape(N, nx, nx)[1:]), K[tag + "/S"]) < 1e-11
+        it = s.stage_pcg(method)
+        l_or, trace = kkt.pcg(sch["Sd"], sch["So"], sch["gamma"], Pd, Po)
+        if kind != "J":
+            assert it.tolist() == [len(trace) - 1] * batch, (kind, it, len(trace) - 1)
+            assert len(trace) == len(K["%s/trace_%s" % (tag, kind)])
+            s.stage_recover()
+            dz_or = kkt.recover(blocks, sch, l_or, nx)
+            for b in range(batch):
+                assert np.max(np.abs(s.fetch("l")[b] - l_or)) < 1e-5 * max(1.0, np.max(np.abs(l_or)))
+                assert np.max(np.abs(s.fetch("dz")[b] - dz_or)) < 1e-5 * max(1.0, np.max(np.abs(dz_or)))
+    # merit terms of the trial point x - alpha dz (dz from the last recover = BJ): compare with the oracle on the SAME dz
+    s.stage_kkt(rho, t.SQPSolverMethods.PCG_SS); s.stage_pcg(t.SQPSolverMethods.PCG_SS); s.stage_recover()
+    dz = s.fetch("dz")[0]
+    for alpha in (1.0, 0.25):
+        J, c, D = s.stage_merit(alpha)
+        Xn = X - alpha * dz[:, :nx]; Un = U - alpha * dz[:N - 1, nx:]
+        J_or = sqp.total_cost(oc, ocn, Xn, Un)
+        c_or = sqp.total_violation(m, Xn, Un, xs, 0.1)
+        g_or = oc.gradients(Xn, Un)
+        D_or = float(np.sum(g_or[:N - 1] * dz[:N - 1]) + np.sum(g_or[N - 1, :nx] * dz[N - 1, :nx]))
+        if ocn is not None:
+            sg = ocn.gradients(Xn, Un)
+            D_or += float(np.sum(sg[:N - 1] * dz[:N - 1]) + np.sum(sg[N - 1, :nx] * dz[N - 1, :nx]))
+        assert np.allclose(J, J_or, rtol=1e-12) and np.allclose(c, c_or, rtol=1e-11) and np.allclose(D, D_or, rtol=1e-10, atol=1e-12)
+        assert relerr(s.fetch("xn")[0], Xn) < 1e-14

@@ -1,0 +1,101 @@
+"""Per-knot device math (csrc/b2t_core.cuh + generated model header) compiled for the host and checked against the
+oracle / the reference golden vectors.  Catches arithmetic bugs without a GPU; the kernels proper are tested with -m gpu."""
+import ctypes
+
+import numpy as np
+import pytest
+
+from conftest import load_npz, relerr
+from oracle import rbd, plant, cost as ocost, constraint as ocons
+
+hostemu = pytest.importorskip("hostemu")
+dp = ctypes.POINTER(ctypes.c_double)
+ip = ctypes.POINTER(ctypes.c_int)
+
+
+def P(a):
+    return a.ctypes.data_as(dp)
+
+
+def PI(a):
+    return a.ctypes.data_as(ip)
+
+
+@pytest.mark.parametrize("name", ["pend", "arm2", "arm3", "arm6"])
+@pytest.mark.parametrize("integ", [0, 1])
+def test_dynamics_math(name, integ, oracle_models):
+    lib = hostemu.load(name)
+    D = load_npz("dynamics.npz")
+    m = oracle_models[name]
+    n = m.n
+    q, qd, u = D[name + "/q"], D[name + "/qd"], D[name + "/u"]
+    x = np.ascontiguousarray(np.concatenate([q, qd], -1))
+    u = np.ascontiguousarray(u)
+    cnt = x.shape[0]
+    qdd = np.zeros((cnt, n)); Minv = np.zeros((cnt, n * n)); dqdd = np.zeros((cnt, n * 3 * n)); xn = np.zeros((cnt, 2 * n))
+    AB = np.zeros((cnt, 2 * n * 3 * n))
+    lib.he_dynamics(cnt, P(x), P(u), ctypes.c_double(0.1), ctypes.c_double(-9.81), integ, P(qdd), P(Minv), P(dqdd), P(xn), P(AB))
+    assert relerr(qdd, D[name + "/qdd"]) < 1e-13
+    assert relerr(Minv.reshape(cnt, n, n), D[name + "/Minv"]) < 1e-13
+    assert relerr(dqdd.reshape(cnt, n, 3 * n), D[name + "/dqdd"]) < 1e-12
+    assert relerr(xn, D[name + "/xn%d" % integ]) < 1e-13
+    ABr = AB.reshape(cnt, 2 * n, 3 * n)
+    assert relerr(ABr[:, :, :2 * n], D[name + "/A%d" % integ]) < 1e-12
+    assert relerr(ABr[:, :, 2 * n:], D[name + "/B%d" % integ]) < 1e-13
+
+
+@pytest.mark.parametrize("name,kind", [("arm2", 1), ("arm2", 0), ("arm6", 0)])
+def test_cost_math(name, kind, oracle_models):
+    lib = hostemu.load(name)
+    m = oracle_models[name]
+    n = m.n; nx = 2 * n; nm = 3 * n
+    rng = np.random.default_rng(5)
+    A = rng.uniform(-1, 1, (nx, nx)); Q = A @ A.T + np.eye(nx)
+    A = rng.uniform(-1, 1, (nx, nx)); QF = 10 * (A @ A.T) + np.eye(nx)
+    A = rng.uniform(-1, 1, (n, n)); R = A @ A.T + 0.1 * np.eye(n)
+    xg = rng.uniform(-1, 1, nx)
+    N = 7
+    X = rng.uniform(-1.5, 1.5, (N, nx)); U = rng.uniform(-1, 1, (N - 1, n))
+    c = ocost.UrdfCost(m, Q, QF, R, xg, QF_start=4) if kind == 1 else ocost.QuadraticCost(Q, QF, R, xg, QF_start=4)
+    Upad = np.zeros((N, n)); Upad[:N - 1] = U
+    val = np.zeros(N); grad = np.zeros((N, nm)); hess = np.zeros((N, nm * nm))
+    kidx = np.arange(N, dtype=np.int32); term = np.zeros(N, dtype=np.int32); term[-1] = 1
+    lib.he_cost(N, kind, 4, P(np.ascontiguousarray(Q)), P(np.ascontiguousarray(QF)), P(np.ascontiguousarray(R)), P(xg), P(X), P(Upad),
+                PI(kidx), PI(term), P(val), P(grad), P(hess))
+    assert relerr(val, c.values(X, U)) < 1e-13
+    assert relerr(grad, c.gradients(X, U)) < 1e-13
+    assert relerr(hess.reshape(N, nm, nm), c.hessians(X, U)) < 1e-13
+
+
+def test_soft_math():
+    lib = hostemu.load("arm3")
+    n = 3; nx = 6; nm = 9; N = 6
+    rng = np.random.default_rng(3)
+    cons = ocons.SoftConstraints(n, n, n, N)
+    cons.set_joint_limits([0.4, 0.5, 0.6], [-0.4, -0.3, -0.2], "AUGMENTED_LAGRANGIAN")
+    cons.set_torque_limits([0.5], [-0.5], "QUADRATIC_PENALTY")
+    for lim in cons.limits.values():
+        lim.mu[:] = rng.uniform(0.5, 2, lim.mu.shape); lim.lam[:] = rng.uniform(-0.1, 0.1, lim.lam.shape)
+    X = rng.uniform(-1, 1, (N, nx)); U = rng.uniform(-1, 1, (N - 1, n))
+    Z = np.zeros((N, nm)); Z[:, :nx] = X; Z[:N - 1, nx:] = U
+    mode = np.array([2, 2, 2, 0, 0, 0, 1, 1, 1], dtype=np.int32)
+    lb = np.array([-0.4, -0.3, -0.2, 0, 0, 0, -0.5, -0.5, -0.5]); ub = np.array([0.4, 0.5, 0.6, 0, 0, 0, 0.5, 0.5, 0.5])
+    mu = np.ones((N, 2 * nm)); lam = np.zeros((N, 2 * nm))
+    j, tq = cons.limits["joint"], cons.limits["torque"]
+    mu[:, 0:3] = j.mu[:3].T; mu[:, nm:nm + 3] = j.mu[3:].T; lam[:, 0:3] = j.lam[:3].T; lam[:, nm:nm + 3] = j.lam[3:].T
+    mu[:N - 1, 6:9] = tq.mu[:3].T; mu[:N - 1, nm + 6:nm + 9] = tq.mu[3:].T
+    lam[:N - 1, 6:9] = tq.lam[:3].T; lam[:N - 1, nm + 6:nm + 9] = tq.lam[3:].T
+    term = np.zeros(N, dtype=np.int32); term[-1] = 1
+    val = np.zeros(N); gck = np.zeros((N, nm))
+    lib.he_soft(N, PI(mode), P(lb), P(ub), P(Z), P(mu), P(lam), PI(term), P(val), P(gck))
+    assert relerr(val, cons.values(X, U)) < 1e-13
+    assert relerr(gck, cons.gradients(X, U)) < 1e-13
+
+
+def test_spd_inverse():
+    lib = hostemu.load("arm2")
+    rng = np.random.default_rng(1)
+    A = rng.uniform(-1, 1, (12, 12)); A = A @ A.T + 0.5 * np.eye(12)
+    B = np.ascontiguousarray(A.copy())
+    lib.he_spd_inverse(12, P(B))
+    assert relerr(B, np.linalg.inv(A)) < 1e-11

@@ -1,0 +1,741 @@
+"""Drop-in Python API of the reference (TrajoptPlant / TrajoptCost / TrajoptConstraint / TrajoptMPCReference) on top of
+the per-robot CUDA libraries.  Same class names, constructor signatures, option keys and return values as
+/root/reference/{TrajoptPlant,TrajoptCost,TrajoptConstraint,TrajoptMPCReference}.py for the SQP-PCG path; everything
+numerical happens on the GPU through the C ABI (include/b2t.h).  No CPU fallback.
+
+Differences from the reference, all deliberate:
+  * invalid arguments raise ValueError instead of print() + exit()   (TrajoptMPCReference.py:32-39, 596)
+  * the solver is re-entrant: no class-level counters, no unbounded saved_* lists
+  * costs are described by their parameters (Q, QF, R, xg); arbitrary Python callbacks cannot run inside a kernel
+  * `solve_batch` solves many independent instances (different goals / initial trajectories) in one launch sequence
+"""
+import ctypes
+import enum
+import os
+
+import numpy as np
+
+from . import _lib
+from .model import extract_model, model_digest, URDF_DIR
+
+
+class SQPSolverMethods(enum.Enum):          # TrajoptMPCReference.py:13-18
+    N = "N"
+    S = "S"
+    PCG_J = "PCG-J"
+    PCG_BJ = "PCG-BJ"
+    PCG_SS = "PCG-SS"
+
+
+class MPCSolverMethods(enum.Enum):          # TrajoptMPCReference.py:21-27
+    iLQR = "iLQR"
+    QP_N = "QP-N"
+    QP_S = "QP-S"
+    QP_PCG_J = "QP-PCG-J"
+    QP_PCG_BJ = "QP-PCG-BJ"
+    QP_PCG_SS = "QP-PCG-SS"
+
+
+_METHOD_CODE = {SQPSolverMethods.PCG_J: _lib.METHOD_PCG_J, SQPSolverMethods.PCG_BJ: _lib.METHOD_PCG_BJ,
+                SQPSolverMethods.PCG_SS: _lib.METHOD_PCG_SS}
+
+
+# --------------------------------------------------------------------------------------------------- plant
+class _RbdHandle:
+    """The solver and UrdfCost read / write `plant.rbdReference.overloading` (TrajoptMPCReference.py:97, TrajoptCost.py:389)."""
+
+    def __init__(self, model):
+        self.model = model
+        self.overloading = False
+
+
+class TrajoptPlant:
+    def __init__(self, integrator_type: int = 0, options=None, need_path: bool = False):
+        options = {} if options is None else options
+        if integrator_type not in (0, 1, 2, 3, 4, -1):
+            raise ValueError("Invalid integrator options are [0 : euler, 1 : semi-implicit euler, 2 : midpoint, 3 : rk3, 4 : rk4, -1 : hard-coded as dynamics")
+        if integrator_type not in (0, 1):
+            raise ValueError("integrator types 2-4 of the reference are inconsistent or crash (SURVEY.md 0.9); only 0 and 1 are supported")
+        self.integrator_type = integrator_type
+        options.setdefault("path_to_urdf", None)
+        options.setdefault("gravity", -9.81)
+        if need_path and not options.get("path_to_urdf"):
+            raise ValueError("You must include the 'path_to_urdf' in the options.")
+        self.options = options
+
+    def forward_dynamics(self, *a, **k):
+        raise NotImplementedError
+
+    def forward_dynamics_gradient(self, *a, **k):
+        raise NotImplementedError
+
+    def get_num_pos(self):
+        raise NotImplementedError
+
+    def get_num_vel(self):
+        raise NotImplementedError
+
+    def get_num_cntrl(self):
+        raise NotImplementedError
+
+
+class URDFPlant(TrajoptPlant):
+    """URDFPlant (TrajoptPlant.py:274-331).  `options['path_to_urdf']` may also be a built-in name ('arm6', 'pend', ...)."""
+
+    def __init__(self, integrator_type=0, options=None):
+        options = {} if options is None else options
+        super().__init__(integrator_type, options, True)
+        path = options["path_to_urdf"]
+        if not os.path.isfile(path):
+            cand = os.path.join(URDF_DIR, path + ".urdf")
+            if os.path.isfile(cand):
+                path = cand
+            else:
+                raise ValueError("Failed to parse URDF file at the given path.")
+        self.urdf_path = path
+        self.model = extract_model(path)
+        base = os.path.splitext(os.path.basename(path))[0]
+        builtin = os.path.join(URDF_DIR, base + ".urdf")
+        same = os.path.isfile(builtin) and model_digest(extract_model(builtin)) == model_digest(self.model)
+        self.tag = base if same else "%s_%s" % ("".join(ch if ch.isalnum() else "_" for ch in base), model_digest(self.model))
+        self.rbdReference = _RbdHandle(self.model)
+        self._lib = None
+        self._probe = None
+
+    @property
+    def lib(self):
+        if self._lib is None:
+            self._lib = _lib.load_library(self.model, self.tag)
+        return self._lib
+
+    def get_num_pos(self):
+        return self.model["n"]
+
+    def get_num_vel(self):
+        return self.model["n"]
+
+    def get_num_cntrl(self):
+        return self.model["n"]
+
+    # per-knot callbacks of the reference API, evaluated on the GPU (batch 1, 2 knots)
+    def _probe_solver(self):
+        if self._probe is None:
+            n = self.model["n"]
+            cost = QuadraticCost(np.eye(2 * n), np.eye(2 * n), np.eye(n), np.zeros(2 * n))
+            self._probe = BatchSolver(self, cost, None, N=2, dt=1.0, batch=1)
+        return self._probe
+
+    def _eval(self, xk, uk, dt):
+        p = self._probe_solver()
+        if p.dt != dt:
+            self._probe = None
+            n = self.model["n"]
+            cost = QuadraticCost(np.eye(2 * n), np.eye(2 * n), np.eye(n), np.zeros(2 * n))
+            self._probe = p = BatchSolver(self, cost, None, N=2, dt=dt, batch=1)
+        n = self.model["n"]
+        x = np.zeros((1, 2 * n, 2)); u = np.zeros((1, n, 1))
+        x[0, :, 0] = np.asarray(xk, dtype=np.float64).reshape(-1); u[0, :, 0] = np.asarray(uk, dtype=np.float64).reshape(-1)
+        p.set_trajectory(x, u)
+        p.stage_dynamics()
+        return p.fetch("dqdd")[0, 0].reshape(n, 3 * n), p.fetch("xkp1")[0, 0]
+
+    def forward_dynamics_gradient(self, x, u, iter_1=0, iter_2=0, iter_3=0):
+        return self._eval(x, u, 1.0)[0]
+
+    def forward_dynamics(self, x, u, iter_1=0, iter_2=0, iter_3=0):
+        n = self.model["n"]
+        big = 2.0 ** 40         # v+ = qd + dt*qdd for both integrators; a power-of-two dt makes the division exact
+        xn = self._eval(x, u, big)[1]
+        return (xn[n:] - np.asarray(x, dtype=np.float64).reshape(-1)[n:]) / big
+
+    def integrator(self, xk, uk, dt, return_gradient=False, iter_1=0, iter_2=0, iter_3=0):
+        n = self.model["n"]
+        dqdd, xn = self._eval(xk, uk, dt)
+        if not return_gradient:
+            return xn
+        top = np.hstack((np.zeros((n, n)), np.eye(n), np.zeros((n, n))))
+        if self.integrator_type == 0:
+            dxdot = np.vstack((top, dqdd))
+            return np.eye(2 * n) + dt * dxdot[:, :2 * n], dt * dxdot[:, 2 * n:]
+        Iz = np.hstack((np.eye(2 * n), np.zeros((2 * n, n))))
+        AB = Iz + dt * np.vstack((top + dt * dqdd, dqdd))
+        return AB[:, :2 * n], AB[:, 2 * n:]
+
+
+# --------------------------------------------------------------------------------------------------- costs
+class TrajoptCost:
+    def value(self, *a, **k):
+        raise NotImplementedError
+
+    def gradient(self, *a, **k):
+        raise NotImplementedError
+
+    def hessian(self, *a, **k):
+        raise NotImplementedError
+
+
+class QuadraticCost(TrajoptCost):
+    """QuadraticCost (TrajoptCost.py:24-104); value/gradient/hessian accept the 3-argument form and the iter_1..3 kwargs."""
+    _kind = _lib.COST_QUADRATIC
+
+    def __init__(self, Q_in, QF_in, R_in, xg_in, QF_start=None):
+        self.Q = Q_in
+        self.QF = QF_in
+        self.R = R_in
+        self.xg = xg_in
+        self.increaseCount_Q = 0
+        self.increaseCount_QF = 0
+        self.QF_start = QF_start
+
+    def get_currQ(self, u=None, timestep=None):
+        use_QF = (u is None) or (timestep is not None and self.QF_start is not None and timestep >= self.QF_start)
+        return self.QF if use_QF else self.Q
+
+    def value(self, x, u=None, timestep=None, iter_1=0, iter_2=0, iter_3=0):
+        dx = np.asarray(x) - self.xg
+        cost = 0.5 * np.matmul(dx.transpose(), np.matmul(self.get_currQ(u, timestep), dx))
+        if u is not None:
+            cost += 0.5 * np.matmul(np.asarray(u).transpose(), np.matmul(self.R, u))
+        return cost
+
+    def gradient(self, x, u=None, timestep=None, iter_1=0, iter_2=0, iter_3=0):
+        dx = np.asarray(x) - self.xg
+        top = np.matmul(dx.transpose(), self.get_currQ(u, timestep))
+        if u is None:
+            return top
+        return np.hstack((top, np.matmul(np.asarray(u).transpose(), self.R)))
+
+    def hessian(self, x, u=None, timestep=None, iter_1=0, iter_2=0, iter_3=0):
+        nx, nu = np.asarray(self.Q).shape[0], np.asarray(self.R).shape[0]
+        currQ = self.get_currQ(u, timestep)
+        if u is None:
+            return currQ
+        return np.vstack((np.hstack((currQ, np.zeros((nx, nu)))), np.hstack((np.zeros((nu, nx)), self.R))))
+
+    def increase_QF(self, multiplier: float = 2.0):
+        self.QF *= multiplier
+        self.increaseCount_QF += 1
+        return self.increaseCount_QF
+
+    def increase_Q(self, multiplier: float = 2.0):
+        self.Q *= multiplier
+        self.increaseCount_Q += 1
+        return self.increaseCount_Q
+
+    def reset_increase_count_QF(self):
+        self.increaseCount_QF = 0
+
+    def reset_increase_count_Q(self):
+        self.increaseCount_Q = 0
+
+    def shift_QF_start(self, shift: float = -1.0):
+        self.QF_start += shift
+        self.QF_start = max(self.QF_start, 0)
+        return self.QF_start
+
+
+class UrdfCost(QuadraticCost):
+    """UrdfCost (TrajoptCost.py:371-519): quadratic cost on the planar end-effector state (x, y, vx, vy), Gauss-Newton
+    Hessian (hess_mode 0).  2-joint robots only, like the reference."""
+    _kind = _lib.COST_URDF_EE
+
+    def __init__(self, plant, Q_in, QF_in, R_in, xg_in, QF_start=None, overloading=False):
+        super().__init__(Q_in, QF_in, R_in, xg_in, QF_start)
+        if plant.get_num_pos() != 2:
+            raise ValueError("UrdfCost is defined for 2-joint robots only (RBDReference.py:263)")
+        self.plant = plant
+        self.n = plant.get_num_pos()
+        self.offsets = [np.matrix([[0, 1, 0, 1]])]
+        self.plant.rbdReference.overloading = overloading
+        self.overloading = overloading
+        self.hess_mode = 0
+
+    def value(self, x, u=None, timestep=None, iter_1=0, iter_2=0, iter_3=0):
+        raise NotImplementedError("UrdfCost.value is evaluated inside the solver kernels; use TrajoptMPCReference.totalCost")
+
+    gradient = value
+    hessian = value
+
+
+# --------------------------------------------------------------------------------------------------- constraints
+_MODES = {"QUADRATIC_PENALTY": _lib.LIMIT_QUADRATIC_PENALTY, "AUGMENTED_LAGRANGIAN": _lib.LIMIT_AUGMENTED_LAGRANGIAN}
+
+
+class BoxConstraint:
+    """BoxConstraint (TrajoptConstraint.py:5-176) state holder: bounds, mode, options and the (mu, lambda, phi) arrays.
+    Soft modes only; the arithmetic lives in the kernels (csrc/b2t_core.cuh soft_value / soft_grad, k_outer)."""
+
+    def __init__(self, constraint_size=0, num_timesteps=0, upper_bounds=(), lower_bounds=(), mode="NONE", options=None):
+        options = {} if options is None else options
+        self.constraint_size = constraint_size
+        self.num_timesteps = num_timesteps
+        self.num_constraints = 2 * constraint_size * num_timesteps
+        lblen, ublen = len(lower_bounds), len(upper_bounds)
+        if (lblen != constraint_size and lblen != 1) or (ublen != constraint_size and ublen != 1):
+            raise ValueError("[!]ERROR please enter bounds of the size of constraint or constant 1")
+        self.bounds = np.zeros(2 * constraint_size)
+        self.bounds[:constraint_size] = lower_bounds
+        self.bounds[constraint_size:] = upper_bounds
+        if mode in ("ACTIVE_SET", "FULL_SET"):
+            raise ValueError("hard constraint modes change the size of the Schur system and are not supported on the GPU path; use QUADRATIC_PENALTY or AUGMENTED_LAGRANGIAN")
+        if mode == "ADMM_PROJECTION":
+            raise ValueError("[!] ERROR NOT IMPLEMENTED YET")            # same as the reference (TrajoptConstraint.py:87-89)
+        if mode not in _MODES:
+            raise ValueError("[!Error] Invalid Constraint Mode. Options are [ACTIVE_SET, FULL_SET, QUADRATIC_PENALTY, AUGMENTED_LAGRANGIAN, ADMM_PROJECTION]")
+        self.mode = mode
+        options.setdefault("quadratic_penalty_mu_init", 1e-2)
+        options.setdefault("quadratic_penalty_mu_factor", 10.0)
+        options.setdefault("quadratic_penalty_mu_max", 1e12)
+        options.setdefault("augmentated_lagrangian_phi_init", 1e-2)
+        options.setdefault("augmentated_lagrangian_phi_factor", 10.0)
+        options.setdefault("jacobian_extra_columns_head", 0)
+        options.setdefault("jacobian_extra_columns_tail", 0)
+        self.options = options
+        self.quadratic_penalty_mu = options["quadratic_penalty_mu_init"] * np.ones((2 * constraint_size, num_timesteps))
+        self.augmented_lagrangian_lambda = np.zeros((2 * constraint_size, num_timesteps))
+        self.augmented_lagrangian_phi = options["augmentated_lagrangian_phi_init"] * np.ones((2 * constraint_size, num_timesteps))
+
+    def is_hard_constraint_mode(self, mode=None):
+        return (mode or self.mode) in ["ACTIVE_SET", "FULL_SET"]
+
+    def is_soft_constraint_mode(self, mode=None):
+        return (mode or self.mode) in ["QUADRATIC_PENALTY", "AUGMENTED_LAGRANGIAN", "ADMM_PROJECTION"]
+
+    def shift_soft_constraint_constants(self, shift_steps: int):
+        """TrajoptConstraint.py:168-176 (literal, including which columns are re-initialised)."""
+        self.quadratic_penalty_mu[:, :-shift_steps] = self.quadratic_penalty_mu[:, shift_steps:]
+        self.augmented_lagrangian_lambda[:, :-shift_steps] = self.augmented_lagrangian_lambda[:, shift_steps:]
+        self.augmented_lagrangian_phi[:, :-shift_steps] = self.augmented_lagrangian_phi[:, shift_steps:]
+        self.quadratic_penalty_mu[:, shift_steps:] = self.options["quadratic_penalty_mu_init"]
+        self.augmented_lagrangian_lambda[:, shift_steps:] = 0.0
+        self.augmented_lagrangian_phi[:, shift_steps:] = self.options["augmentated_lagrangian_phi_init"]
+
+
+class TrajoptConstraint:
+    """TrajoptConstraint (TrajoptConstraint.py:178-387).  Joint and velocity limits carry N columns of multipliers, torque
+    limits N-1 (the reference allocates N-1 for joint limits and then indexes column N-1)."""
+
+    def __init__(self, nq: int = 0, nv: int = 0, nu: int = 0, num_timesteps: int = 0):
+        self.nq, self.nv, self.nu, self.num_timesteps = nq, nv, nu, num_timesteps
+        self.joint_limits = None
+        self.velocity_limits = None
+        self.torque_limits = None
+
+    def set_joint_limits(self, upper_bounds, lower_bounds, mode, options=None):
+        options = {} if options is None else options
+        options["jacobian_extra_columns_tail"] = self.nv + self.nu
+        self.joint_limits = BoxConstraint(self.nq, self.num_timesteps, upper_bounds, lower_bounds, mode, options)
+
+    def set_velocity_limits(self, upper_bounds, lower_bounds, mode, options=None):
+        options = {} if options is None else options
+        options["jacobian_extra_columns_head"] = self.nq
+        options["jacobian_extra_columns_tail"] = self.nu
+        self.velocity_limits = BoxConstraint(self.nv, self.num_timesteps, upper_bounds, lower_bounds, mode, options)
+
+    def set_torque_limits(self, upper_bounds, lower_bounds, mode, options=None):
+        options = {} if options is None else options
+        options["jacobian_extra_columns_head"] = self.nq + self.nv
+        self.torque_limits = BoxConstraint(self.nu, self.num_timesteps - 1, upper_bounds, lower_bounds, mode, options)
+
+    def _types(self):
+        return [(0, self.joint_limits, 0, self.nq), (1, self.velocity_limits, self.nq, self.nv),
+                (2, self.torque_limits, self.nq + self.nv, self.nu)]
+
+    def total_soft_constraints(self, timestep=None):
+        total = 0
+        for ty, lim, off, cs in self._types():
+            if lim is None:
+                continue
+            if timestep is None:
+                total += lim.num_constraints
+            elif not (ty == 2 and timestep >= self.num_timesteps - 1):
+                total += lim.constraint_size
+        return total
+
+    def shift_soft_constraint_constants(self, shift_steps: int):
+        for _, lim, _, _ in self._types():
+            if lim is not None:
+                lim.shift_soft_constraint_constants(shift_steps)
+
+    # ---- device layout helpers: [2m][N] per instance, lower coordinate i -> row i, upper -> row m + i
+    def pack(self, N):
+        m = self.nq + self.nv + self.nu
+        mu = np.zeros((2 * m, N)); lam = np.zeros((2 * m, N)); phi = np.ones((2 * m, N))
+        for ty, lim, off, cs in self._types():
+            if lim is None:
+                continue
+            T = lim.num_timesteps
+            for arr, src in ((mu, lim.quadratic_penalty_mu), (lam, lim.augmented_lagrangian_lambda), (phi, lim.augmented_lagrangian_phi)):
+                arr[off:off + cs, :T] = src[:cs]
+                arr[m + off:m + off + cs, :T] = src[cs:]
+        return mu, lam, phi
+
+    def unpack(self, mu, lam, phi):
+        m = self.nq + self.nv + self.nu
+        for ty, lim, off, cs in self._types():
+            if lim is None:
+                continue
+            T = lim.num_timesteps
+            for arr, dst in ((mu, lim.quadratic_penalty_mu), (lam, lim.augmented_lagrangian_lambda), (phi, lim.augmented_lagrangian_phi)):
+                dst[:cs] = arr[off:off + cs, :T]
+                dst[cs:] = arr[m + off:m + off + cs, :T]
+
+
+# --------------------------------------------------------------------------------------------------- batched solver
+def _dptr(a):
+    return a.ctypes.data_as(ctypes.c_void_p)
+
+
+def _as_f64(a, shape=None):
+    a = np.ascontiguousarray(np.asarray(a, dtype=np.float64))
+    if shape is not None and a.shape != tuple(shape):
+        raise ValueError("expected array of shape %r, got %r" % (tuple(shape), a.shape))
+    return a
+
+
+class BatchResult(dict):
+    __getattr__ = dict.__getitem__
+
+
+class BatchSolver:
+    """One device workspace for `batch` independent instances of (plant, cost, constraints, N, dt)."""
+
+    def __init__(self, plant, cost, constraints, N, dt, batch=1, dtype="f64", device=0, qf_start_override=None):
+        if not isinstance(plant, URDFPlant):
+            raise ValueError("Must pass in a URDFPlant: the dynamics kernels are generated from the URDF")
+        if not isinstance(cost, QuadraticCost):
+            raise ValueError("cost must be a QuadraticCost or UrdfCost (Python callbacks cannot run inside the kernels)")
+        n = plant.get_num_pos()
+        self.plant, self.cost, self.constraints = plant, cost, constraints
+        self.n, self.nx, self.nu, self.m = n, 2 * n, n, 3 * n
+        self.N, self.dt, self.batch, self.dtype, self.device = int(N), float(dt), int(batch), dtype, int(device)
+        self.lib = plant.lib
+        d = _lib.ProblemDesc()
+        d.batch, d.knots, d.integrator_type = self.batch, self.N, plant.integrator_type
+        d.dtype = {"f64": _lib.F64, "f32": _lib.F32}[dtype]
+        d.dt, d.gravity = self.dt, float(plant.options["gravity"])
+        d.cost_kind = cost._kind
+        qs = cost.QF_start if qf_start_override is None else qf_start_override
+        d.qf_start = -1 if qs is None else int(qs)
+        self._keep = [_as_f64(cost.Q, (self.nx, self.nx)), _as_f64(cost.QF, (self.nx, self.nx)), _as_f64(cost.R, (self.nu, self.nu))]
+        d.Q, d.QF, d.R = [a.ctypes.data_as(ctypes.POINTER(ctypes.c_double)) for a in self._keep]
+        lower = np.zeros(self.m); upper = np.zeros(self.m)
+        self.has_limits = False
+        for ty in range(3):
+            d.limit_mode[ty] = _lib.LIMIT_NONE
+            d.mu_init[ty], d.mu_factor[ty], d.mu_max[ty], d.phi_init[ty], d.phi_factor[ty] = 1e-2, 10.0, 1e12, 1e-2, 10.0
+        if constraints is not None:
+            if constraints.num_timesteps != self.N:
+                raise ValueError("TrajoptConstraint.num_timesteps must equal N")
+            for ty, lim, off, cs in constraints._types():
+                if lim is None:
+                    continue
+                self.has_limits = True
+                d.limit_mode[ty] = _MODES[lim.mode]
+                lower[off:off + cs] = lim.bounds[:cs]; upper[off:off + cs] = lim.bounds[cs:]
+                o = lim.options
+                d.mu_init[ty], d.mu_factor[ty], d.mu_max[ty] = o["quadratic_penalty_mu_init"], o["quadratic_penalty_mu_factor"], o["quadratic_penalty_mu_max"]
+                d.phi_init[ty], d.phi_factor[ty] = o["augmentated_lagrangian_phi_init"], o["augmentated_lagrangian_phi_factor"]
+        self._keep += [lower, upper]
+        d.lower = lower.ctypes.data_as(ctypes.POINTER(ctypes.c_double)); d.upper = upper.ctypes.data_as(ctypes.POINTER(ctypes.c_double))
+        self._h = ctypes.c_void_p()
+        _lib.check(self.lib, self.lib.b2t_solver_create(ctypes.byref(d), self.device, ctypes.byref(self._h)))
+        xg = np.broadcast_to(_as_f64(cost.xg).reshape(1, -1), (self.batch, self.nx))
+        self.set_goals(xg)
+
+    def close(self):
+        if getattr(self, "_h", None) is not None and self._h.value:
+            self.lib.b2t_solver_destroy(self._h)
+            self._h = ctypes.c_void_p()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    @property
+    def workspace_bytes(self):
+        return int(self.lib.b2t_workspace_bytes(self._h))
+
+    # ---- inputs
+    def set_trajectory(self, x, u):
+        """x (batch, nx, N), u (batch, nu, N-1): numpy (host) or torch CUDA float64 tensors (device, zero-copy)."""
+        if hasattr(x, "data_ptr"):
+            assert x.is_cuda and u.is_cuda and x.is_contiguous() and u.is_contiguous() and str(x.dtype) == "torch.float64"
+            assert tuple(x.shape) == (self.batch, self.nx, self.N) and tuple(u.shape) == (self.batch, self.nu, self.N - 1)
+            _lib.check(self.lib, self.lib.b2t_set_trajectory(self._h, ctypes.c_void_p(x.data_ptr()), ctypes.c_void_p(u.data_ptr()), 1))
+            return
+        x = _as_f64(x, (self.batch, self.nx, self.N)); u = _as_f64(u, (self.batch, self.nu, self.N - 1))
+        _lib.check(self.lib, self.lib.b2t_set_trajectory(self._h, _dptr(x), _dptr(u), 0))
+        self._sync_keep = (x, u)
+
+    def set_goals(self, xg):
+        if hasattr(xg, "data_ptr"):
+            assert xg.is_cuda and xg.is_contiguous() and tuple(xg.shape) == (self.batch, self.nx)
+            _lib.check(self.lib, self.lib.b2t_set_goals(self._h, ctypes.c_void_p(xg.data_ptr()), 1))
+            return
+        xg = _as_f64(xg, (self.batch, self.nx))
+        _lib.check(self.lib, self.lib.b2t_set_goals(self._h, _dptr(xg), 0))
+        self._goal_keep = xg
+
+    def set_initial_state(self, xs):
+        xs = _as_f64(xs, (self.batch, self.nx))
+        _lib.check(self.lib, self.lib.b2t_set_initial_state(self._h, _dptr(xs)))
+
+    def set_multipliers(self, mu, lam, phi):
+        args = [_as_f64(a, (self.batch, 2 * self.m, self.N)) for a in (mu, lam, phi)]
+        _lib.check(self.lib, self.lib.b2t_set_multipliers(self._h, *[_dptr(a) for a in args]))
+
+    def get_multipliers(self):
+        out = [np.zeros((self.batch, 2 * self.m, self.N)) for _ in range(3)]
+        _lib.check(self.lib, self.lib.b2t_get_multipliers(self._h, *[_dptr(a) for a in out]))
+        return out
+
+    def reset_multipliers(self):
+        _lib.check(self.lib, self.lib.b2t_reset_multipliers(self._h))
+
+    # ---- solve
+    def make_options(self, options=None):
+        o = _lib.Options()
+        self.lib.b2t_default_options(ctypes.byref(o))
+        options = options or {}
+        mapping = {"exit_tolerance_linSys": "exit_tolerance_linSys", "max_iter_linSys": "max_iter_linSys",
+                   "exit_tolerance_SQP_DDP": "exit_tolerance_SQP", "max_iter_SQP_DDP": "max_iter_SQP",
+                   "alpha_factor_SQP_DDP": "alpha_factor", "alpha_min_SQP_DDP": "alpha_min", "rho_factor_SQP_DDP": "rho_factor",
+                   "rho_min_SQP_DDP": "rho_min", "rho_max_SQP_DDP": "rho_max", "rho_init_SQP_DDP": "rho_init",
+                   "expected_reduction_min_SQP_DDP": "expected_reduction_min", "expected_reduction_max_SQP_DDP": "expected_reduction_max",
+                   "exit_tolerance_softConstraints": "exit_tolerance_soft", "max_iter_softConstraints": "max_iter_soft"}
+        for k, f in mapping.items():
+            if k in options:
+                setattr(o, f, type(getattr(o, f))(options[k]))
+        return o
+
+    def solve(self, method=SQPSolverMethods.PCG_SS, options=None):
+        """Runs SQP on the trajectories / goals currently in the workspace."""
+        if method not in _METHOD_CODE:
+            raise ValueError("the GPU path implements the PCG methods (PCG-J, PCG-BJ, PCG-SS); N and S are exact solves of the same system")
+        o = self.make_options(options)
+        _lib.check(self.lib, self.lib.b2t_sqp_solve(self._h, _METHOD_CODE[method], ctypes.byref(o)))
+
+    def solve_host(self, x0, u0, xg, x_out, u_out, status_out, method=SQPSolverMethods.PCG_SS, options=None):
+        """One call: host buffers in, host buffers out (pinned buffers make the copies asynchronous)."""
+        o = self.make_options(options)
+        _lib.check(self.lib, self.lib.b2t_sqp_solve_host(self._h, _dptr(x0), _dptr(u0), None if xg is None else _dptr(xg),
+                                                        _METHOD_CODE[method], ctypes.byref(o), _dptr(x_out), _dptr(u_out), _dptr(status_out)))
+
+    def get_trajectory(self, x_out=None, u_out=None):
+        if x_out is not None and hasattr(x_out, "data_ptr"):
+            _lib.check(self.lib, self.lib.b2t_get_trajectory(self._h, ctypes.c_void_p(x_out.data_ptr()), ctypes.c_void_p(u_out.data_ptr()), 1))
+            return x_out, u_out
+        x = np.zeros((self.batch, self.nx, self.N)) if x_out is None else x_out
+        u = np.zeros((self.batch, self.nu, self.N - 1)) if u_out is None else u_out
+        _lib.check(self.lib, self.lib.b2t_get_trajectory(self._h, _dptr(x), _dptr(u), 0))
+        return x, u
+
+    def get_status(self):
+        st = np.zeros((self.batch, _lib.STATUS_FIELDS), dtype=np.int32)
+        _lib.check(self.lib, self.lib.b2t_get_status(self._h, _dptr(st)))
+        return st
+
+    def get_scalars(self):
+        sc = np.zeros((self.batch, _lib.SCALAR_FIELDS))
+        _lib.check(self.lib, self.lib.b2t_get_scalars(self._h, _dptr(sc)))
+        return sc
+
+    def get_trace(self, cap=104):
+        tr = np.zeros((self.batch, cap, _lib.TRACE_FIELDS))
+        _lib.check(self.lib, self.lib.b2t_get_trace(self._h, _dptr(tr), cap))
+        return tr
+
+    def launch_stats(self):
+        n = ctypes.c_longlong(); s = ctypes.c_double()
+        _lib.check(self.lib, self.lib.b2t_get_launch_stats(self._h, ctypes.byref(n), ctypes.byref(s)))
+        return int(n.value), float(s.value)
+
+    def set_profiling(self, enabled):
+        _lib.check(self.lib, self.lib.b2t_set_profiling(self._h, int(bool(enabled))))
+
+    def kernel_times(self):
+        sec = (ctypes.c_double * _lib.KERNEL_FAMILIES)(); cnt = (ctypes.c_longlong * _lib.KERNEL_FAMILIES)()
+        _lib.check(self.lib, self.lib.b2t_get_kernel_times(self._h, sec, cnt))
+        return {name: (float(sec[i]), int(cnt[i])) for i, name in enumerate(_lib.KERNEL_FAMILY_NAMES)}
+
+    def result(self):
+        x, u = self.get_trajectory()
+        st = self.get_status(); sc = self.get_scalars()
+        return BatchResult(x=x, u=u, exit_sqp=st[:, 0], exit_soft=st[:, 1], outer_iter=st[:, 2], sqp_iter=st[:, 3], total_qp=st[:, 4],
+                           total_pcg=st[:, 5], total_trials=st[:, 6], trace_rows=st[:, 7], J=sc[:, 0], c=sc[:, 1], merit=sc[:, 2], rho=sc[:, 3])
+
+    # ---- stages (parity tests)
+    def stage_dynamics(self):
+        _lib.check(self.lib, self.lib.b2t_stage_dynamics(self._h))
+
+    def stage_kkt(self, rho, method=SQPSolverMethods.PCG_SS):
+        _lib.check(self.lib, self.lib.b2t_stage_kkt(self._h, float(rho), _METHOD_CODE[method]))
+
+    def stage_pcg(self, method=SQPSolverMethods.PCG_SS, tol=1e-6, max_iter=100):
+        it = np.zeros(self.batch, dtype=np.int32)
+        _lib.check(self.lib, self.lib.b2t_stage_pcg(self._h, _METHOD_CODE[method], float(tol), int(max_iter), _dptr(it)))
+        return it
+
+    def stage_recover(self):
+        _lib.check(self.lib, self.lib.b2t_stage_recover(self._h))
+
+    def stage_merit(self, alpha):
+        J = np.zeros(self.batch); c = np.zeros(self.batch); D = np.zeros(self.batch)
+        _lib.check(self.lib, self.lib.b2t_stage_merit(self._h, float(alpha), _dptr(J), _dptr(c), _dptr(D)))
+        return J, c, D
+
+    def fetch(self, name):
+        """Knot-major copy of an internal array: (batch, N, elems)."""
+        E = {"x": self.nx, "u": self.nu, "xkp1": self.nx, "dqdd": self.n * 3 * self.n, "Ghat": self.m * self.m, "g": self.m,
+             "Sd": self.nx * self.nx, "So": self.nx * self.nx, "Pd": self.nx * self.nx, "gamma": self.nx, "l": self.nx, "dz": self.m,
+             "xn": self.nx, "un": self.nu}[name]
+        out = np.zeros((self.batch, self.N, E))
+        _lib.check(self.lib, self.lib.b2t_fetch(self._h, _lib.ARR[name], _dptr(out)))
+        return out
+
+
+_TRACE_KEYS = ["outer_iteration", "iteration", "line_search_iteration", "alpha", "rho", "J", "c", "merit", "D", "reduction_ratio",
+               "inner_iters", "succeeded_line_search"]
+
+
+class TrajoptMPCReference:
+    """TrajoptMPCReference (TrajoptMPCReference.py:29-760), SQP with the Schur-complement / GBD-PCG linear solve."""
+
+    def __init__(self, plantObj, costObj, constraintObj=None):
+        if not isinstance(plantObj, TrajoptPlant) or not isinstance(costObj, TrajoptCost):
+            raise ValueError("Must pass in a TrajoptPlant and TrajoptCost object to TrajoptMPCReference.")
+        if constraintObj is None:
+            constraintObj = TrajoptConstraint()
+        elif not isinstance(constraintObj, TrajoptConstraint):
+            raise ValueError("If passing in additional constraints must pass in a TrajoptConstraint object to TrajoptMPCReference.")
+        self.plant, self.cost, self.other_constraints = plantObj, costObj, constraintObj
+        self.trace = []
+        self.exit_soft = 0
+        self.exit_sqp = 0
+        self.singular = False
+        self.n_inner_iter = 0
+        self.pcg_iters = []
+        self._solvers = {}
+
+    def update_cost(self, costObj):
+        assert isinstance(costObj, TrajoptCost), "Must pass in a TrajoptCost object to update_cost in TrajoptMPCReference."
+        self.cost = costObj
+        self._solvers.clear()
+
+    def update_plant(self, plantObj):
+        assert isinstance(plantObj, TrajoptPlant), "Must pass in a TrajoptPlant object to update_plant in TrajoptMPCReference."
+        self.plant = plantObj
+        self._solvers.clear()
+
+    def update_constraints(self, constraintObj):
+        assert isinstance(constraintObj, TrajoptConstraint), "Must pass in a TrajoptConstraint object to update_constraints in TrajoptMPCReference."
+        self.other_constraints = constraintObj
+        self._solvers.clear()
+
+    def set_default_options(self, options: dict):
+        """TrajoptMPCReference.set_default_options (:91-115): fills the caller's dict in place."""
+        options.setdefault("exit_tolerance_linSys", 1e-6)
+        options.setdefault("max_iter_linSys", 100)
+        options.setdefault("DEBUG_MODE_linSys", False)
+        options.setdefault("RETURN_TRACE_linSys", False)
+        options.setdefault("overloading", self.plant.rbdReference.overloading)
+        options.setdefault("exit_tolerance_SQP_DDP", 1e-6)
+        options.setdefault("max_iter_SQP_DDP", 100)
+        options.setdefault("DEBUG_MODE_SQP_DDP", False)
+        options.setdefault("alpha_factor_SQP_DDP", 0.5)
+        options.setdefault("alpha_min_SQP_DDP", 0.005)
+        options.setdefault("rho_factor_SQP_DDP", 4)
+        options.setdefault("rho_min_SQP_DDP", 1e-3)
+        options.setdefault("rho_max_SQP_DDP", 1e3)
+        options.setdefault("rho_init_SQP_DDP", 0.001)
+        options.setdefault("expected_reduction_min_SQP_DDP", 0.05)
+        options.setdefault("expected_reduction_max_SQP_DDP", 3)
+        options.setdefault("merit_factor_SQP", 1.5)
+        options.setdefault("exit_tolerance_softConstraints", 1e-6)
+        options.setdefault("max_iter_softConstraints", 10)
+        options.setdefault("DEBUG_MODE_Soft_Constraints", False)
+
+    def _constraints_or_none(self):
+        c = self.other_constraints
+        if c is None or all(l is None for l in (c.joint_limits, c.velocity_limits, c.torque_limits)):
+            return None
+        return c
+
+    def batch_solver(self, N, dt, batch, dtype="f64", device=0):
+        key = (N, float(dt), batch, dtype, device, id(self.cost), id(self.other_constraints))
+        if key not in self._solvers:
+            self._solvers[key] = BatchSolver(self.plant, self.cost, self._constraints_or_none(), N, dt, batch, dtype, device)
+        return self._solvers[key]
+
+    def SQP(self, x, u, N, dt, LINEAR_SYSTEM_SOLVER_METHOD=SQPSolverMethods.N, options=None, dtype="f64"):
+        """Same call and return value as the reference (:510, :760): (x, u, exit_sqp, exit_soft, outer_iter, sqp_iter)."""
+        options = {} if options is None else options
+        self.set_default_options(options)
+        if not isinstance(LINEAR_SYSTEM_SOLVER_METHOD, SQPSolverMethods):
+            raise ValueError("Invalid QP Solver options are: N, S, PCG-J, PCG-BJ, PCG-SS")
+        if options.get("overloading"):
+            raise ValueError("the operator-overloading tracer (overloading.py) is research instrumentation and is not supported")
+        s = self.batch_solver(N, dt, 1, dtype)
+        cons = self._constraints_or_none()
+        x = _as_f64(x, (s.nx, N)); u = _as_f64(u, (s.nu, N - 1))
+        s.set_goals(_as_f64(self.cost.xg).reshape(1, -1))
+        s.set_trajectory(x[None], u[None])
+        if cons is not None:
+            mu, lam, phi = cons.pack(N)
+            s.set_multipliers(mu[None], lam[None], phi[None])
+        s.solve(LINEAR_SYSTEM_SOLVER_METHOD, options)
+        r = s.result()
+        if cons is not None:
+            mu, lam, phi = s.get_multipliers()
+            cons.unpack(mu[0], lam[0], phi[0])
+        self.exit_sqp, self.exit_soft = int(r.exit_sqp[0]), int(r.exit_soft[0])
+        rows = int(r.trace_rows[0])
+        tr = s.get_trace()[0][:min(rows, 104)]
+        self.trace = []
+        self.pcg_iters = []
+        for i, row in enumerate(tr):
+            dct = {k: row[j] for j, k in enumerate(_TRACE_KEYS)}
+            for k in ("outer_iteration", "iteration", "line_search_iteration"):
+                dct[k] = int(dct[k])
+            dct["pcg_iters"] = int(dct["inner_iters"])
+            dct["inner_iters"] = 0 if (i == 0 and dct["outer_iteration"] == 0) else 2      # reference quirk (:445): len of a 2-tuple
+            dct["succeeded_line_search"] = bool(dct["succeeded_line_search"])
+            dct["singular"] = False
+            if i == 0:
+                dct["D"] = None
+                dct["reduction_ratio"] = None
+                dct["alpha"] = 1
+            else:
+                self.pcg_iters.append(dct["pcg_iters"])
+            self.trace.append(dct)
+        self.n_inner_iter = 2
+        self.last_result = r
+        return r.x[0], r.u[0], self.exit_sqp, self.exit_soft, int(r.outer_iter[0]), int(r.sqp_iter[0])
+
+    def solve_batch(self, x0, u0, xg, N, dt, LINEAR_SYSTEM_SOLVER_METHOD=SQPSolverMethods.PCG_SS, options=None, dtype="f64", device=0):
+        """Batched SQP: x0 (B, nx, N), u0 (B, nu, N-1), xg (B, nx).  Returns a BatchResult of per-instance arrays."""
+        options = {} if options is None else options
+        self.set_default_options(options)
+        B = x0.shape[0]
+        s = self.batch_solver(N, dt, B, dtype, device)
+        s.set_goals(xg)
+        s.set_trajectory(x0, u0)
+        cons = self._constraints_or_none()
+        if cons is not None:
+            mu, lam, phi = cons.pack(N)
+            s.set_multipliers(*[np.broadcast_to(a[None], (B,) + a.shape) for a in (mu, lam, phi)])
+        s.solve(LINEAR_SYSTEM_SOLVER_METHOD, options)
+        return s.result()
+
+    def totalCost(self, x, u, N):
+        """totalCost (:296-310) of one trajectory, evaluated by the merit kernel."""
+        s = self.batch_solver(N, 0.1, 1)
+        s.set_goals(_as_f64(self.cost.xg).reshape(1, -1))
+        s.set_trajectory(_as_f64(x)[None], _as_f64(u)[None])
+        # alpha = 0 with dz = 0: the trial point equals (x, u)
+        s.stage_dynamics()
+        J, c, D = s.stage_merit(0.0)
+        return float(J[0])

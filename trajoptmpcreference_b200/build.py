@@ -1,0 +1,71 @@
+"""Build the per-robot CUDA libraries (libb2t_<robot>.so) in-tree with nvcc for sm_100a.
+
+  python -m trajoptmpcreference_b200.build [robot ...]        (default: every built-in URDF)
+
+Each library = generated model header (codegen.py) + csrc/b2t_lib.cu.  nvcc cross-compiles without a GPU.
+"""
+import os
+import subprocess
+import sys
+import hashlib
+
+from .model import extract_model, builtin_urdf, model_digest
+from .codegen import write_header
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+CSRC = os.path.join(HERE, "csrc")
+LIBDIR = os.path.join(HERE, "_lib")
+BUILTIN = ["pend", "arm1", "arm2", "arm3", "arm4", "arm6"]
+NVCC = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")
+NVCC_FLAGS = ["-O3", "-std=c++17", "-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "--expt-relaxed-constexpr",
+              "-Xcompiler", "-fPIC", "-shared", "-Xptxas", "-v"]
+
+
+def lib_path(tag: str) -> str:
+    return os.path.join(LIBDIR, "libb2t_%s.so" % tag)
+
+
+def _sources_digest(header: str) -> str:
+    h = hashlib.sha1()
+    for p in (header, os.path.join(CSRC, "b2t_core.cuh"), os.path.join(CSRC, "b2t_kernels.cuh"), os.path.join(CSRC, "b2t_lib.cu"),
+              os.path.join(os.path.dirname(HERE), "include", "b2t.h")):
+        with open(p, "rb") as f:
+            h.update(f.read())
+    h.update(" ".join(NVCC_FLAGS).encode())
+    return h.hexdigest()
+
+
+def build_model(model: dict, tag: str, force: bool = False, verbose: bool = False) -> str:
+    """Generate the header for `model`, compile libb2t_<tag>.so if stale, return its path."""
+    os.makedirs(LIBDIR, exist_ok=True)
+    header = write_header(model, tag)
+    out = lib_path(tag)
+    stamp = out + ".stamp"
+    dig = _sources_digest(header)
+    if not force and os.path.isfile(out) and os.path.isfile(stamp) and open(stamp).read().strip() == dig:
+        return out
+    cmd = [NVCC] + NVCC_FLAGS + ['-DB2T_MODEL_HEADER="gen/model_%s.h"' % tag, "-I", CSRC, os.path.join(CSRC, "b2t_lib.cu"), "-o", out]
+    res = subprocess.run(cmd, capture_output=True, text=True)
+    log = res.stdout + res.stderr
+    with open(out + ".buildlog", "w") as f:
+        f.write(" ".join(cmd) + "\n" + log)
+    if res.returncode != 0:
+        raise RuntimeError("nvcc failed for %s:\n%s" % (tag, log[-6000:]))
+    if verbose:
+        print(log)
+    with open(stamp, "w") as f:
+        f.write(dig)
+    return out
+
+
+def build_builtin(names=None, force=False, verbose=False):
+    outs = []
+    for name in (names or BUILTIN):
+        outs.append(build_model(extract_model(builtin_urdf(name)), name, force, verbose))
+    return outs
+
+
+if __name__ == "__main__":
+    names = [a for a in sys.argv[1:] if not a.startswith("-")]
+    for p in build_builtin(names or None, force="--force" in sys.argv, verbose="-v" in sys.argv):
+        print(p)

@@ -1,0 +1,868 @@
+// b2t_kernels.cuh -- CUDA kernels of the batched SQP / Schur / GBD-PCG path (sm_100a).
+//
+// Data layout in HBM (K = batch * N knot points, t = b * N + k):
+//   per-knot arrays are element-major ("SoA over knots"):  a[e][t]  -> thread t of a per-knot kernel reads a
+//   coalesced 8-byte stream for every element e;
+//   the block-tridiagonal Schur complement and preconditioner blocks are instance-major, column-major over the
+//   row index r = k*nx + i:  S[b][c][r]  -> thread r of the per-instance PCG block reads coalesced columns, and an
+//   instance's matrices are one contiguous range (bulk-copyable into shared memory).
+// Control flow (outer AL loop, SQP loop, line search) lives on the device in per-instance state words; the host
+// only launches the fixed kernel sequence and reads one counter per SQP iteration.
+#pragma once
+#include <cuda_runtime.h>
+#include "b2t_core.cuh"
+
+namespace b2t {
+
+enum Phase { PH_SQP = 0, PH_OUTER = 1, PH_DONE = 2 };
+enum { TRACE_FIELDS = 12 };
+enum { MAX_LS_TRIALS = 32 };
+
+template <typename T>
+struct Opts {
+  T tol_lin; int max_iter_lin;
+  T tol_sqp; int max_iter_sqp;
+  T alpha_factor, alpha_min;
+  T rho_factor, rho_min, rho_max, rho_init;
+  T er_min, er_max;
+  T tol_soft; int max_iter_soft;
+  T merit_mu;
+};
+
+template <typename T>
+struct Dev {
+  int B, N, integrator;
+  T dt, gravity;
+  size_t K;
+  // per-knot SoA
+  T *x, *u, *xn, *un, *xkp1, *xkp1n, *dyn, *vaf, *Gh, *g, *Gg, *dz, *mu, *lam, *phi;
+  // instance-major
+  T *Sd, *So, *Pd, *gam, *l;
+  // per-instance
+  T *xs, *xg;
+  CostParams<T> cost;
+  LimitParams<T> lim;
+  T mu_factor[3], mu_max[3], phi_factor[3], mu_init[3], phi_init[3];
+  T *rho, *drho, *J, *c, *merit, *alpha, *deltaJ, *D, *ratio;
+  int *ls_iter, *sqp_iter, *outer_iter, *exit_sqp, *exit_soft, *phase, *err, *pcg_iters, *tot_qp, *tot_pcg, *tot_trials;
+  int *act, *n_act;
+  int *ls_list0, *ls_list1;
+  int *restart_list, *n_restart;
+  int *n_ls;          // [MAX_LS_TRIALS + 1]
+  T* trace;           // [B][trace_cap][TRACE_FIELDS]
+  int* trace_rows;
+  int trace_cap;
+};
+
+template <typename T>
+__device__ __forceinline__ void load_xu(const T* xs_, const T* us_, size_t K, size_t t, bool terminal, T* x, T* u) {
+  for (int i = 0; i < NX; ++i) x[i] = xs_[(size_t)i * K + t];
+  for (int i = 0; i < NU; ++i) u[i] = terminal ? T(0) : us_[(size_t)i * K + t];
+}
+
+// -----------------------------------------------------------------------------------------------------------------
+// k_fd: forward dynamics + integrator step of one knot per thread.
+//   TRIAL = false: reads (x,u); writes xkp1, Minv block of dyn, v/a/f of rnea(q,qd,qdd) (inputs of k_fd_grad)
+//   TRIAL = true : first forms the trial point xn = x - alpha dz_x, un = u - alpha dz_u (SQP :617-622), then xkp1n
+// -----------------------------------------------------------------------------------------------------------------
+template <typename T, bool TRIAL>
+__global__ void __launch_bounds__(128) k_fd(Dev<T> d, const int* list, const int* count) {
+  const size_t gt = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  const int slot = (int)(gt / d.N);
+  if (slot >= *count) return;
+  const int k = (int)(gt % d.N);
+  const int b = list[slot];
+  const size_t t = (size_t)b * d.N + k;
+  const size_t K = d.K;
+  const bool terminal = (k == d.N - 1);
+  T x[NX], u[NU];
+  load_xu(d.x, d.u, K, t, terminal, x, u);
+  if constexpr (TRIAL) {
+    const T al = d.alpha[b];
+    for (int i = 0; i < NX; ++i) { x[i] = x[i] - al * d.dz[(size_t)i * K + t]; d.xn[(size_t)i * K + t] = x[i]; }
+    if (!terminal)
+      for (int i = 0; i < NU; ++i) { u[i] = u[i] - al * d.dz[(size_t)(NX + i) * K + t]; d.un[(size_t)i * K + t] = u[i]; }
+  }
+  if (terminal) return;
+  T qdd[NJ], Minv[NJ * NJ], v[NJ][6], a[NJ][6], f[NJ][6], xnext[NX];
+  forward_dynamics<T, !TRIAL>(x, x + NJ, u, d.gravity, qdd, Minv, v, a, f);
+  integrate(d.integrator, x, qdd, d.dt, xnext);
+  T* outp = TRIAL ? d.xkp1n : d.xkp1;
+  for (int i = 0; i < NX; ++i) outp[(size_t)i * K + t] = xnext[i];
+  if constexpr (!TRIAL) {
+    for (int i = 0; i < NJ; ++i)
+      for (int j = 0; j < NJ; ++j) d.dyn[(size_t)(i * 3 * NJ + 2 * NJ + j) * K + t] = Minv[i * NJ + j];
+    for (int j = 0; j < NJ; ++j)
+      for (int i = 0; i < 6; ++i) {
+        d.vaf[(size_t)(j * 6 + i) * K + t] = v[j][i];
+        d.vaf[(size_t)(6 * NJ + j * 6 + i) * K + t] = a[j][i];
+        d.vaf[(size_t)(12 * NJ + j * 6 + i) * K + t] = f[j][i];
+      }
+  }
+}
+
+// -----------------------------------------------------------------------------------------------------------------
+// k_fd_grad: one column of dqdd/d(q,qd) per thread.  Thread index = col-major over (column, slot, knot) so that a warp
+// shares the column (uniform branches) and reads consecutive knots (coalesced).
+// -----------------------------------------------------------------------------------------------------------------
+template <typename T>
+__global__ void __launch_bounds__(128) k_fd_grad(Dev<T> d, const int* list, const int* count) {
+  const size_t per_col = (size_t)gridDim.x * blockDim.x;
+  (void)per_col;
+  const size_t gt = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  const int slot = (int)(gt / d.N);
+  if (slot >= *count) return;
+  const int k = (int)(gt % d.N);
+  if (k == d.N - 1) return;
+  const int colid = blockIdx.y;                 // 0 .. 2*NJ-1
+  const bool is_qd = colid >= NJ;
+  const int col = is_qd ? colid - NJ : colid;
+  const int b = list[slot];
+  const size_t t = (size_t)b * d.N + k;
+  const size_t K = d.K;
+  T q[NJ], qd[NJ], Minv[NJ * NJ], v[NJ][6], a[NJ][6], f[NJ][6];
+  for (int i = 0; i < NJ; ++i) { q[i] = d.x[(size_t)i * K + t]; qd[i] = d.x[(size_t)(NJ + i) * K + t]; }
+  for (int i = 0; i < NJ; ++i)
+    for (int j = 0; j < NJ; ++j) Minv[i * NJ + j] = d.dyn[(size_t)(i * 3 * NJ + 2 * NJ + j) * K + t];
+  for (int j = 0; j < NJ; ++j)
+    for (int i = 0; i < 6; ++i) {
+      v[j][i] = d.vaf[(size_t)(j * 6 + i) * K + t];
+      a[j][i] = d.vaf[(size_t)(6 * NJ + j * 6 + i) * K + t];
+      f[j][i] = d.vaf[(size_t)(12 * NJ + j * 6 + i) * K + t];
+    }
+  T out[NJ];
+  fd_grad_column(q, qd, v, a, f, Minv, d.gravity, col, is_qd, out);
+  for (int i = 0; i < NJ; ++i) d.dyn[(size_t)(i * 3 * NJ + colid) * K + t] = out[i];
+}
+
+// -----------------------------------------------------------------------------------------------------------------
+// k_kkt: per knot  G_k = hess + gck gck^T + rho I,  Ghat_k = G_k^-1,  g_k = grad + gck,  Gg_k = Ghat_k g_k
+// (formKKTSystemBlocks :216-225,252-260; solveKKTSystem_Schur :419-422)
+// -----------------------------------------------------------------------------------------------------------------
+template <typename T>
+__global__ void __launch_bounds__(64) k_kkt(Dev<T> d, const int* list, const int* count) {
+  const size_t gt = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  const int slot = (int)(gt / d.N);
+  if (slot >= *count) return;
+  const int k = (int)(gt % d.N);
+  const int b = list[slot];
+  const size_t t = (size_t)b * d.N + k;
+  const size_t K = d.K;
+  const bool terminal = (k == d.N - 1);
+  T z[NM], xg[NX];
+  load_xu(d.x, d.u, K, t, terminal, z, z + NX);
+  for (int i = 0; i < NX; ++i) xg[i] = d.xg[(size_t)i * d.B + b];
+  T g[NM], G[NM * NM];
+  cost_grad_hess<T, true>(d.cost, z, z + NX, xg, k, terminal, g, G);
+  if (d.lim.any) {
+    T gck[NM];
+    soft_grad(d.lim, z, d.mu + t, d.lam + t, K, terminal, gck);
+    for (int i = 0; i < NM; ++i) g[i] += gck[i];
+    for (int i = 0; i < NM; ++i)
+      for (int j = 0; j < NM; ++j) G[i * NM + j] += gck[i] * gck[j];
+  }
+  const T rho = d.rho[b];
+  const int M = terminal ? NX : NM;
+  for (int i = 0; i < NM; ++i) G[i * NM + i] += rho;
+  spd_inverse_inplace(G, M, NM);
+  if (terminal)
+    for (int i = 0; i < NM; ++i)
+      for (int j = 0; j < NM; ++j)
+        if (i >= NX || j >= NX) G[i * NM + j] = T(0);
+  for (int i = 0; i < NM; ++i) {
+    T acc = T(0);
+    for (int j = 0; j < M; ++j) acc += G[i * NM + j] * g[j];
+    d.Gg[(size_t)i * K + t] = (i < M) ? acc : T(0);
+    d.g[(size_t)i * K + t] = (i < M) ? g[i] : T(0);
+  }
+  for (int i = 0; i < NM * NM; ++i) d.Gh[(size_t)i * K + t] = G[i];
+}
+
+// -----------------------------------------------------------------------------------------------------------------
+// k_schur: per block row j  S_jj, S_j,j-1, gamma_j and the preconditioner diagonal block (block form of
+// S = -C Ghat C^T, gamma = c - C Ghat g, :423-424; PCG.compute_preconditioner PCG.py:166-212).
+//   precond: 0 = Jacobi (diag(S)^-1), 1 = block Jacobi / symmetric stair (S_jj^-1)
+// -----------------------------------------------------------------------------------------------------------------
+template <typename T>
+__global__ void __launch_bounds__(64) k_schur(Dev<T> d, const int* list, const int* count, int jacobi) {
+  const size_t gt = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  const int slot = (int)(gt / d.N);
+  if (slot >= *count) return;
+  const int j = (int)(gt % d.N);
+  const int b = list[slot];
+  const size_t t = (size_t)b * d.N + j;
+  const size_t K = d.K;
+  const int R = d.N * NX;
+  T Sd[NX * NX], gam[NX];
+  T* Sd_o = d.Sd + (size_t)b * R * NX;
+  T* So_o = d.So + (size_t)b * R * NX;
+  T* Pd_o = d.Pd + (size_t)b * R * NX;
+  if (j == 0) {
+    for (int i = 0; i < NX; ++i)
+      for (int c = 0; c < NX; ++c) {
+        Sd[i * NX + c] = -d.Gh[(size_t)(i * NM + c) * K + t];
+        So_o[(size_t)c * R + i] = T(0);
+      }
+    for (int i = 0; i < NX; ++i) gam[i] = (d.x[(size_t)i * K + t] - d.xs[(size_t)i * d.B + b]) - d.Gg[(size_t)i * K + t];
+  } else {
+    const size_t tp = t - 1;
+    T dq[NDYN], AB[NX * NM];
+    for (int i = 0; i < NDYN; ++i) dq[i] = d.dyn[(size_t)i * K + tp];
+    build_AB(d.integrator, dq, d.dt, AB);
+    // W = Ghat_{j-1} AB^T  (NM x NX)
+    T W[NM * NX];
+    for (int r = 0; r < NM; ++r) {
+      T grow[NM];
+      for (int c = 0; c < NM; ++c) grow[c] = d.Gh[(size_t)(r * NM + c) * K + tp];
+      for (int i = 0; i < NX; ++i) {
+        T acc = T(0);
+        for (int c = 0; c < NM; ++c) acc += grow[c] * AB[i * NM + c];
+        W[r * NX + i] = acc;
+      }
+    }
+    for (int i = 0; i < NX; ++i)
+      for (int c = 0; c < NX; ++c) {
+        T acc = T(0);
+        for (int r = 0; r < NM; ++r) acc += AB[i * NM + r] * W[r * NX + c];
+        Sd[i * NX + c] = -(acc + d.Gh[(size_t)(i * NM + c) * K + t]);
+      }
+    // S_{j,j-1} = AB Ghat_{j-1}[:, :NX]
+    for (int c = 0; c < NX; ++c) {
+      T gcol[NM];
+      for (int r = 0; r < NM; ++r) gcol[r] = d.Gh[(size_t)(r * NM + c) * K + tp];
+      for (int i = 0; i < NX; ++i) {
+        T acc = T(0);
+        for (int r = 0; r < NM; ++r) acc += AB[i * NM + r] * gcol[r];
+        So_o[(size_t)c * R + j * NX + i] = acc;
+      }
+    }
+    T Ggp[NM];
+    for (int r = 0; r < NM; ++r) Ggp[r] = d.Gg[(size_t)r * K + tp];
+    for (int i = 0; i < NX; ++i) {
+      T acc = T(0);
+      for (int r = 0; r < NM; ++r) acc += AB[i * NM + r] * Ggp[r];
+      T ck = d.x[(size_t)i * K + t] - d.xkp1[(size_t)i * K + tp];
+      gam[i] = (ck + acc) - d.Gg[(size_t)i * K + t];
+    }
+  }
+  for (int i = 0; i < NX; ++i) {
+    d.gam[(size_t)b * R + j * NX + i] = gam[i];
+    for (int c = 0; c < NX; ++c) Sd_o[(size_t)c * R + j * NX + i] = Sd[i * NX + c];
+  }
+  if (jacobi) {
+    for (int i = 0; i < NX; ++i)
+      for (int c = 0; c < NX; ++c) Pd_o[(size_t)c * R + j * NX + i] = (i == c) ? T(1) / Sd[i * NX + i] : T(0);
+  } else {
+    for (int i = 0; i < NX * NX; ++i) Sd[i] = -Sd[i];     // -S_jj is SPD
+    spd_inverse_inplace(Sd, NX, NX);
+    for (int i = 0; i < NX; ++i)
+      for (int c = 0; c < NX; ++c) Pd_o[(size_t)c * R + j * NX + i] = -Sd[i * NX + c];
+  }
+}
+
+// -----------------------------------------------------------------------------------------------------------------
+// k_pcg: one thread block per instance, one thread per row of the block-tridiagonal system (PCG.pcg, PCG.py:66-111).
+// Preconditioners (PCG.py:166-212): J / BJ use the diagonal blocks; SS (symmetric stair) is applied in factored form
+//   Pinv r = y - D^-1 (O y),  y = D^-1 r,  O = off-diagonal part of S     (== the reference's explicit
+//   Pinv_{k,k-1} = -S_kk^-1 S_{k,k-1} S_{k-1,k-1}^-1).
+// Dot products: warp-shuffle tree + fixed-order cross-warp sum (deterministic).
+// -----------------------------------------------------------------------------------------------------------------
+template <typename T>
+__device__ __forceinline__ T block_sum(T v, T* red, int tid, int nthreads) {
+  for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+  const int w = tid >> 5, nw = (nthreads + 31) >> 5;
+  __syncthreads();                    // red[] free to overwrite
+  if ((tid & 31) == 0) red[w] = v;
+  __syncthreads();
+  T s = T(0);
+  for (int i = 0; i < nw; ++i) s += red[i];
+  return s;
+}
+
+template <typename T>
+__device__ __forceinline__ T bt_diag_row(const T* Md, const T* vec, int r, int j, int R) {
+  T acc = T(0);
+#pragma unroll
+  for (int c = 0; c < NX; ++c) acc += Md[(size_t)c * R + r] * vec[j * NX + c];
+  return acc;
+}
+template <typename T>
+__device__ __forceinline__ T bt_off_row(const T* Mo, const T* vec, int r, int j, int i, int R, int N) {
+  T acc = T(0);
+  if (j > 0) {
+#pragma unroll
+    for (int c = 0; c < NX; ++c) acc += Mo[(size_t)c * R + r] * vec[(j - 1) * NX + c];
+  }
+  if (j < N - 1) {
+#pragma unroll
+    for (int c = 0; c < NX; ++c) acc += Mo[(size_t)i * R + (j + 1) * NX + c] * vec[(j + 1) * NX + c];
+  }
+  return acc;
+}
+
+enum { PCG_MAX_RPT = 4 };   // rows per thread (R <= 4096)
+
+template <typename T>
+__global__ void __launch_bounds__(1024) k_pcg(Dev<T> d, const int* list, const int* count, int stair, T tol, int max_iter) {
+  if ((int)blockIdx.x >= *count) return;
+  const int b = list[blockIdx.x];
+  const int N = d.N, R = N * NX;
+  const int tid = threadIdx.x, nt = blockDim.x;
+  extern __shared__ unsigned char smem_raw[];
+  T* p_s = reinterpret_cast<T*>(smem_raw);
+  T* y_s = p_s + R;
+  T* w_s = y_s + R;
+  T* red = w_s + R;
+  const T* Sd = d.Sd + (size_t)b * R * NX;
+  const T* So = d.So + (size_t)b * R * NX;
+  const T* Pd = d.Pd + (size_t)b * R * NX;
+  const T* gam = d.gam + (size_t)b * R;
+  T rr[PCG_MAX_RPT], xx[PCG_MAX_RPT], pp[PCG_MAX_RPT], rt[PCG_MAX_RPT];
+#pragma unroll
+  for (int m = 0; m < PCG_MAX_RPT; ++m) { rr[m] = T(0); xx[m] = T(0); pp[m] = T(0); rt[m] = T(0); }
+
+  auto precond = [&]() {
+    // input r in rr[], output rt[]; uses y_s, w_s
+    for (int m = 0, r = tid; r < R; r += nt, ++m) y_s[r] = rr[m];
+    __syncthreads();
+    T yv[PCG_MAX_RPT];
+    for (int m = 0, r = tid; r < R; r += nt, ++m) yv[m] = bt_diag_row(Pd, y_s, r, r / NX, R);
+    if (!stair) {
+      for (int m = 0, r = tid; r < R; r += nt, ++m) rt[m] = yv[m];
+      __syncthreads();
+      return;
+    }
+    __syncthreads();
+    for (int m = 0, r = tid; r < R; r += nt, ++m) w_s[r] = yv[m];      // w_s = y
+    __syncthreads();
+    T ov[PCG_MAX_RPT];
+    for (int m = 0, r = tid; r < R; r += nt, ++m) ov[m] = bt_off_row(So, w_s, r, r / NX, r % NX, R, N);
+    __syncthreads();
+    for (int m = 0, r = tid; r < R; r += nt, ++m) y_s[r] = ov[m];      // y_s = O y
+    __syncthreads();
+    for (int m = 0, r = tid; r < R; r += nt, ++m) rt[m] = yv[m] - bt_diag_row(Pd, y_s, r, r / NX, R);
+    __syncthreads();
+  };
+
+  // x0 = 0  ->  r = b
+  for (int m = 0, r = tid; r < R; r += nt, ++m) { rr[m] = gam[r]; xx[m] = T(0); }
+  precond();
+  T part = T(0);
+  for (int m = 0, r = tid; r < R; r += nt, ++m) { pp[m] = rt[m]; part += rr[m] * rt[m]; }
+  T nu = block_sum(part, red, tid, nt);
+  int iters = 0;
+  for (int it = 0; it < max_iter; ++it) {
+    for (int m = 0, r = tid; r < R; r += nt, ++m) p_s[r] = pp[m];
+    __syncthreads();
+    T ap[PCG_MAX_RPT];
+    part = T(0);
+    for (int m = 0, r = tid; r < R; r += nt, ++m) {
+      const int j = r / NX, i = r % NX;
+      ap[m] = bt_diag_row(Sd, p_s, r, j, R) + bt_off_row(So, p_s, r, j, i, R, N);
+      part += pp[m] * ap[m];
+    }
+    const T pAp = block_sum(part, red, tid, nt);
+    const T alpha = nu / pAp;
+    for (int m = 0, r = tid; r < R; r += nt, ++m) { rr[m] -= ap[m] * alpha; xx[m] += pp[m] * alpha; }
+    precond();
+    part = T(0);
+    for (int m = 0, r = tid; r < R; r += nt, ++m) part += rr[m] * rt[m];
+    const T nu_prime = block_sum(part, red, tid, nt);
+    iters = it + 1;
+    if (fabs(nu_prime) < tol) break;
+    const T beta = nu_prime / nu;
+    for (int m = 0, r = tid; r < R; r += nt, ++m) pp[m] = rt[m] + pp[m] * beta;
+    nu = nu_prime;
+  }
+  for (int m = 0, r = tid; r < R; r += nt, ++m) d.l[(size_t)b * R + r] = xx[m];
+  if (tid == 0) {
+    d.pcg_iters[b] = iters;
+    d.tot_pcg[b] += iters;
+    d.tot_qp[b] += 1;
+  }
+}
+
+// -----------------------------------------------------------------------------------------------------------------
+// k_recover: dz_k = Ghat_k (g_k - [l_k; 0] + AB_k^T l_{k+1})     (:449-452)
+// -----------------------------------------------------------------------------------------------------------------
+template <typename T>
+__global__ void __launch_bounds__(128) k_recover(Dev<T> d, const int* list, const int* count) {
+  const size_t gt = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  const int slot = (int)(gt / d.N);
+  if (slot >= *count) return;
+  const int k = (int)(gt % d.N);
+  const int b = list[slot];
+  const size_t t = (size_t)b * d.N + k;
+  const size_t K = d.K;
+  const int R = d.N * NX;
+  const bool terminal = (k == d.N - 1);
+  T rhs[NM];
+  for (int i = 0; i < NM; ++i) rhs[i] = d.g[(size_t)i * K + t];
+  const T* l = d.l + (size_t)b * R;
+  for (int i = 0; i < NX; ++i) rhs[i] -= l[k * NX + i];
+  if (!terminal) {
+    T dq[NDYN], AB[NX * NM];
+    for (int i = 0; i < NDYN; ++i) dq[i] = d.dyn[(size_t)i * K + t];
+    build_AB(d.integrator, dq, d.dt, AB);
+    for (int c = 0; c < NM; ++c) {
+      T acc = T(0);
+      for (int i = 0; i < NX; ++i) acc += AB[i * NM + c] * l[(k + 1) * NX + i];
+      rhs[c] += acc;
+    }
+  }
+  for (int i = 0; i < NM; ++i) {
+    T acc = T(0);
+    for (int c = 0; c < NM; ++c) acc += d.Gh[(size_t)(i * NM + c) * K + t] * rhs[c];
+    d.dz[(size_t)i * K + t] = acc;
+  }
+}
+
+// -----------------------------------------------------------------------------------------------------------------
+// merit evaluation of one instance (block): J = totalCost (:296-310), c = totalHardConstraintViolation (:273-294),
+// D = directional derivative (:635-648).  Per-knot terms in parallel, then summed by thread 0 in the reference's
+// sequential order.  TRIAL selects (xn, un, xkp1n) instead of (x, u, xkp1).
+// smem: 5 * N scalars.
+// -----------------------------------------------------------------------------------------------------------------
+template <typename T, bool TRIAL, bool WITH_D, bool WITH_C>
+__device__ __forceinline__ void merit_terms(const Dev<T>& d, int b, T* sm, T* J_out, T* c_out, T* D_out) {
+  const int N = d.N;
+  const size_t K = d.K;
+  T* s_cost = sm; T* s_soft = sm + N; T* s_c = sm + 2 * N; T* s_D = sm + 3 * N; T* s_Ds = sm + 4 * N;
+  const T* X = TRIAL ? d.xn : d.x;
+  const T* U = TRIAL ? d.un : d.u;
+  const T* XK = TRIAL ? d.xkp1n : d.xkp1;
+  for (int k = threadIdx.x; k < N; k += blockDim.x) {
+    const size_t t = (size_t)b * N + k;
+    const bool terminal = (k == N - 1);
+    T z[NM], xg[NX];
+    load_xu(X, U, K, t, terminal, z, z + NX);
+    for (int i = 0; i < NX; ++i) xg[i] = d.xg[(size_t)i * d.B + b];
+    s_cost[k] = cost_value(d.cost, z, z + NX, xg, k, terminal);
+    s_soft[k] = d.lim.any ? soft_value(d.lim, z, d.mu + t, d.lam + t, K, terminal) : T(0);
+    if constexpr (WITH_C) {
+      T acc = T(0);
+      if (k == 0) {
+        for (int i = 0; i < NX; ++i) acc += fabs(z[i] - d.xs[(size_t)i * d.B + b]);
+      } else {
+        for (int i = 0; i < NX; ++i) acc += fabs(z[i] - XK[(size_t)i * K + t - 1]);
+      }
+      s_c[k] = acc;
+    }
+    if constexpr (WITH_D) {
+      T g[NM], dzk[NM];
+      cost_grad_hess<T, false>(d.cost, z, z + NX, xg, k, terminal, g, (T*)nullptr);
+      const int M = terminal ? NX : NM;
+      for (int i = 0; i < NM; ++i) dzk[i] = d.dz[(size_t)i * K + t];
+      T acc = T(0);
+      for (int i = 0; i < M; ++i) acc += g[i] * dzk[i];
+      s_D[k] = acc;
+      T accs = T(0);
+      if (d.lim.any) {
+        T gck[NM];
+        soft_grad(d.lim, z, d.mu + t, d.lam + t, K, terminal, gck);
+        for (int i = 0; i < M; ++i) accs += gck[i] * dzk[i];
+      }
+      s_Ds[k] = accs;
+    }
+  }
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    T J = T(0);
+    for (int k = 0; k < N; ++k) J += s_cost[k];
+    if (d.lim.any)
+      for (int k = 0; k < N; ++k) J += s_soft[k];
+    *J_out = J;
+    if constexpr (WITH_C) {
+      T c = T(0);
+      for (int k = 0; k < N; ++k) c += s_c[k];
+      *c_out = c;
+    }
+    if constexpr (WITH_D) {
+      T D = T(0);
+      for (int k = 0; k < N; ++k) {
+        D += s_D[k];
+        if (d.lim.any) D += s_Ds[k];
+      }
+      *D_out = D;
+    }
+  }
+  __syncthreads();
+}
+
+template <typename T>
+__device__ __forceinline__ void trace_row(const Dev<T>& d, int b, int ls, T alpha, T D, T ratio, int inner, int success) {
+  int row = d.trace_rows[b];
+  if (row < d.trace_cap) {
+    T* tr = d.trace + ((size_t)b * d.trace_cap + row) * TRACE_FIELDS;
+    tr[0] = (T)d.outer_iter[b]; tr[1] = (T)d.sqp_iter[b]; tr[2] = (T)ls; tr[3] = alpha; tr[4] = d.rho[b]; tr[5] = d.J[b];
+    tr[6] = d.c[b]; tr[7] = d.merit[b]; tr[8] = D; tr[9] = ratio; tr[10] = (T)inner; tr[11] = (T)success;
+  }
+  d.trace_rows[b] = row + 1;
+}
+
+// start of an outer (soft-constraint) iteration: rho, J, c, merit and the seed trace row (SQP :535-569)
+template <typename T>
+__global__ void k_outer_begin(Dev<T> d, const int* list, const int* count, Opts<T> o, int with_c) {
+  if ((int)blockIdx.x >= *count) return;
+  const int b = list[blockIdx.x];
+  extern __shared__ unsigned char smem_raw[];
+  T* sm = reinterpret_cast<T*>(smem_raw);
+  __shared__ T J, c, D;
+  if (with_c) merit_terms<T, false, false, true>(d, b, sm, &J, &c, &D);
+  else merit_terms<T, false, false, false>(d, b, sm, &J, &c, &D);
+  if (threadIdx.x == 0) {
+    if (with_c) d.c[b] = c;
+    d.J[b] = J;
+    d.rho[b] = o.rho_init;
+    d.drho[b] = T(1);
+    d.merit[b] = J + o.merit_mu * d.c[b];
+    d.sqp_iter[b] = 0;
+    d.trace_rows[b] = 0;
+    d.phase[b] = PH_SQP;
+    trace_row(d, b, 0, T(1), T(0), T(0), 0, 0);
+  }
+}
+
+// start of one SQP iteration for all active instances: line-search state
+template <typename T>
+__global__ void k_iter_begin(Dev<T> d) {
+  const int n = *d.n_act;
+  const int s = blockIdx.x * blockDim.x + threadIdx.x;
+  if (s == 0) {
+    d.n_ls[0] = n;
+    for (int i = 1; i <= MAX_LS_TRIALS; ++i) d.n_ls[i] = 0;
+    *d.n_restart = 0;
+  }
+  if (s >= n) return;
+  const int b = d.act[s];
+  d.alpha[b] = T(1);
+  d.ls_iter[b] = 0;
+  d.err[b] = 0;
+  d.ls_list0[s] = b;
+}
+
+// -----------------------------------------------------------------------------------------------------------------
+// k_merit: evaluates the trial point of every instance still in its line search and takes the accept / backtrack /
+// fail decision (SQP :629-744, reduce_regularization :457-461).
+// -----------------------------------------------------------------------------------------------------------------
+template <typename T>
+__global__ void k_merit(Dev<T> d, const int* list, const int* count, int* next_list, int* next_count, Opts<T> o) {
+  if ((int)blockIdx.x >= *count) return;
+  const int b = list[blockIdx.x];
+  extern __shared__ unsigned char smem_raw[];
+  T* sm = reinterpret_cast<T*>(smem_raw);
+  __shared__ T Jn, cn, D;
+  __shared__ int accept;
+  merit_terms<T, true, true, true>(d, b, sm, &Jn, &cn, &D);
+  if (threadIdx.x == 0) {
+    const T mu = o.merit_mu;
+    const T alpha = d.alpha[b];
+    const T merit_new = Jn + mu * cn;
+    const T delta_J = d.J[b] - Jn;
+    const T delta_merit = d.merit[b] - merit_new;
+    const T expected = alpha * (D - mu * cn);
+    const T ratio = delta_merit / expected;
+    d.deltaJ[b] = delta_J;
+    d.tot_trials[b] += 1;
+    accept = 0;
+    if (delta_merit >= T(0) && ratio >= o.er_min && ratio <= o.er_max) {
+      accept = 1;
+      d.J[b] = Jn; d.c[b] = cn; d.merit[b] = merit_new;
+      T drho = fmin(d.drho[b] / o.rho_factor, T(1) / o.rho_factor);
+      T rho = fmax(d.rho[b] * drho, o.rho_min);
+      d.drho[b] = drho; d.rho[b] = rho;
+      trace_row(d, b, d.ls_iter[b], alpha, D, ratio, d.pcg_iters[b], 1);
+    } else if (alpha > o.alpha_min) {
+      d.alpha[b] = alpha * o.alpha_factor;
+      d.ls_iter[b] += 1;
+      const int pos = atomicAdd(next_count, 1);
+      next_list[pos] = b;
+    } else {
+      d.err[b] = 1;
+      trace_row(d, b, d.ls_iter[b], alpha, D, ratio, d.pcg_iters[b], 0);
+    }
+  }
+  __syncthreads();
+  if (accept) {
+    const int N = d.N;
+    const size_t K = d.K;
+    for (int idx = threadIdx.x; idx < N * NX; idx += blockDim.x) {
+      const int i = idx / N, k = idx % N;
+      const size_t t = (size_t)b * N + k;
+      d.x[(size_t)i * K + t] = d.xn[(size_t)i * K + t];
+    }
+    for (int idx = threadIdx.x; idx < (N - 1) * NU; idx += blockDim.x) {
+      const int i = idx / (N - 1), k = idx % (N - 1);
+      const size_t t = (size_t)b * N + k;
+      d.u[(size_t)i * K + t] = d.un[(size_t)i * K + t];
+    }
+  }
+}
+
+// stage entry point: J, c, D of the trial point for alpha (no decision)
+template <typename T>
+__global__ void k_merit_only(Dev<T> d, T* J, T* c, T* D) {
+  const int b = blockIdx.x;
+  extern __shared__ unsigned char smem_raw[];
+  T* sm = reinterpret_cast<T*>(smem_raw);
+  __shared__ T Jn, cn, Dn;
+  merit_terms<T, true, true, true>(d, b, sm, &Jn, &cn, &Dn);
+  if (threadIdx.x == 0) { J[b] = Jn; c[b] = cn; D[b] = Dn; }
+}
+
+// -----------------------------------------------------------------------------------------------------------------
+// k_sqp_ctrl: check_for_exit_or_error (:463-481) per active instance
+// -----------------------------------------------------------------------------------------------------------------
+template <typename T>
+__global__ void k_sqp_ctrl(Dev<T> d, Opts<T> o) {
+  const int n = *d.n_act;
+  const int s = blockIdx.x * blockDim.x + threadIdx.x;
+  if (s >= n) return;
+  const int b = d.act[s];
+  bool exit_flag = false;
+  if (d.err[b]) {
+    T drho = fmax(d.drho[b] * o.rho_factor, o.rho_factor);
+    T rho = fmax(d.rho[b] * drho, o.rho_min);
+    d.drho[b] = drho; d.rho[b] = rho;
+    if (rho > o.rho_max) { d.exit_sqp[b] = 2; exit_flag = true; }
+  } else if (d.deltaJ[b] < o.tol_sqp) {
+    d.exit_sqp[b] = 1; exit_flag = true;
+  }
+  if (d.sqp_iter[b] == o.max_iter_sqp - 1) { d.exit_sqp[b] = 3; exit_flag = true; }
+  else d.sqp_iter[b] += 1;
+  if (exit_flag) d.phase[b] = PH_OUTER;
+}
+
+// -----------------------------------------------------------------------------------------------------------------
+// k_outer: check_and_update_soft_constraints (:483-508) for instances whose SQP loop exited; BoxConstraint
+// max_soft_constraint_value (TrajoptConstraint.py:131-136) and update_soft_constraint_constants (:138-166).
+// Instances that continue re-enter the SQP loop through k_outer_begin (the host relaunches it on the `restart` list).
+// -----------------------------------------------------------------------------------------------------------------
+template <typename T>
+__global__ void k_outer(Dev<T> d, Opts<T> o) {
+  int* restart_list = d.restart_list;
+  int* restart_count = d.n_restart;
+  const int n = *d.n_act;
+  if ((int)blockIdx.x >= n) return;
+  const int b = d.act[blockIdx.x];
+  if (d.phase[b] != PH_OUTER) return;
+  const int N = d.N;
+  const size_t K = d.K;
+  __shared__ T s_max[3];
+  __shared__ int s_flag;
+  __shared__ int s_continue;
+  if (threadIdx.x == 0) { s_max[0] = s_max[1] = s_max[2] = T(0); s_flag = 1; s_continue = 0; }
+  __syncthreads();
+  T max_c = T(0);
+  if (d.lim.any) {
+    // per limit type: max over knots of | min over the type's 2*cs values |
+    extern __shared__ unsigned char smem_raw[];
+    T* sm = reinterpret_cast<T*>(smem_raw);     // [3][N]
+    for (int k = threadIdx.x; k < N; k += blockDim.x) {
+      const size_t t = (size_t)b * N + k;
+      const bool terminal = (k == N - 1);
+      T z[NM];
+      load_xu(d.x, d.u, K, t, terminal, z, z + NX);
+      const int lo[3] = {0, NJ, NX}, hi[3] = {NJ, NX, NM};
+      for (int ty = 0; ty < 3; ++ty) {
+        T mn = T(0);
+        bool has = false;
+        if (!(ty == 2 && terminal)) {
+          for (int i = lo[ty]; i < hi[ty]; ++i) {
+            if (d.lim.mode[i] == LIM_NONE) continue;
+            T vlo = z[i] - d.lim.lb[i], vhi = d.lim.ub[i] - z[i];
+            T m2 = fmin(vlo, vhi);
+            mn = has ? fmin(mn, m2) : m2;
+            has = true;
+          }
+        }
+        sm[ty * N + k] = has ? fabs(mn) : T(-1);
+      }
+    }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+      for (int ty = 0; ty < 3; ++ty)
+        for (int k = 0; k < N; ++k) max_c = fmax(max_c, sm[ty * N + k]);
+    }
+  }
+  if (threadIdx.x == 0) {
+    bool exit_flag = false;
+    if (max_c < o.tol_soft) { d.exit_soft[b] = 1; exit_flag = true; }
+    if (d.outer_iter[b] == o.max_iter_soft - 1) { d.exit_soft[b] = 2; exit_flag = true; }
+    else d.outer_iter[b] += 1;
+    s_continue = exit_flag ? 0 : 1;
+  }
+  __syncthreads();
+  if (!s_continue) {
+    if (threadIdx.x == 0) d.phase[b] = PH_DONE;
+    return;
+  }
+  // update mu / lambda / phi  (all limit types, every knot, both sides)
+  int changed = 0;
+  for (int k = threadIdx.x; k < N; k += blockDim.x) {
+    const size_t t = (size_t)b * N + k;
+    const bool terminal = (k == N - 1);
+    T z[NM];
+    load_xu(d.x, d.u, K, t, terminal, z, z + NX);
+    const int lim = terminal ? NX : NM;
+    for (int i = 0; i < lim; ++i) {
+      if (d.lim.mode[i] == LIM_NONE) continue;
+      const int ty = i < NJ ? 0 : (i < NX ? 1 : 2);
+      for (int side = 0; side < 2; ++side) {
+        const T v = side == 0 ? z[i] - d.lim.lb[i] : d.lim.ub[i] - z[i];
+        if (!(v < T(0))) continue;
+        const size_t idx = (size_t)(side * NM + i) * K + t;
+        if (!(fabs(v) < d.phi[idx])) {
+          const T cur = d.mu[idx];
+          if (cur < d.mu_max[ty]) { changed = 1; d.mu[idx] = fmin(d.mu_max[ty], cur * d.mu_factor[ty]); }
+        } else {
+          changed = 1;
+          d.lam[idx] += d.mu[idx] * v;
+          d.phi[idx] /= d.phi_factor[ty];
+        }
+      }
+    }
+  }
+  if (changed) atomicAnd(&s_flag, 0);
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    if (s_flag) { d.exit_soft[b] = 3; d.phase[b] = PH_DONE; }
+    else {
+      const int pos = atomicAdd(restart_count, 1);
+      restart_list[pos] = b;
+    }
+  }
+}
+
+// rebuild the active list (order-preserving, single block) and zero the restart counter
+template <typename T>
+__global__ void k_compact(Dev<T> d, int* scratch) {
+  __shared__ int s_n;
+  const int n = *d.n_act;
+  if (threadIdx.x == 0) {
+    int m = 0;
+    for (int s = 0; s < n; ++s) {
+      const int b = d.act[s];
+      if (d.phase[b] != PH_DONE) scratch[m++] = b;
+    }
+    s_n = m;
+  }
+  __syncthreads();
+  for (int s = threadIdx.x; s < s_n; s += blockDim.x) d.act[s] = scratch[s];
+  __syncthreads();
+  if (threadIdx.x == 0) *d.n_act = s_n;
+}
+
+// -----------------------------------------------------------------------------------------------------------------
+// layout conversion between the ABI (reference) layouts and the SoA workspace
+// -----------------------------------------------------------------------------------------------------------------
+template <typename T>
+__global__ void k_pack_traj(Dev<T> d, const double* x, const double* u) {   // x [B][NX][N], u [B][NU][N-1]
+  const size_t gt = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (gt >= d.K) return;
+  const int b = (int)(gt / d.N), k = (int)(gt % d.N);
+  for (int i = 0; i < NX; ++i) d.x[(size_t)i * d.K + gt] = (T)x[((size_t)b * NX + i) * d.N + k];
+  for (int i = 0; i < NU; ++i) d.u[(size_t)i * d.K + gt] = (k < d.N - 1) ? (T)u[((size_t)b * NU + i) * (d.N - 1) + k] : T(0);
+  if (k == 0)
+    for (int i = 0; i < NX; ++i) d.xs[(size_t)i * d.B + b] = (T)x[((size_t)b * NX + i) * d.N];
+}
+template <typename T>
+__global__ void k_unpack_traj(Dev<T> d, double* x, double* u) {
+  const size_t gt = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (gt >= d.K) return;
+  const int b = (int)(gt / d.N), k = (int)(gt % d.N);
+  for (int i = 0; i < NX; ++i) x[((size_t)b * NX + i) * d.N + k] = (double)d.x[(size_t)i * d.K + gt];
+  if (k < d.N - 1)
+    for (int i = 0; i < NU; ++i) u[((size_t)b * NU + i) * (d.N - 1) + k] = (double)d.u[(size_t)i * d.K + gt];
+}
+template <typename T>
+__global__ void k_pack_goals(Dev<T> d, const double* xg) {   // [B][NX]
+  const int b = blockIdx.x * blockDim.x + threadIdx.x;
+  if (b >= d.B) return;
+  for (int i = 0; i < NX; ++i) d.xg[(size_t)i * d.B + b] = (T)xg[(size_t)b * NX + i];
+}
+// generic fetch of a per-knot SoA array a[E][K] into knot-major doubles out[K][E]
+template <typename T>
+__global__ void k_fetch_soa(const T* a, size_t K, int E, double* out) {
+  const size_t gt = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (gt >= K) return;
+  for (int e = 0; e < E; ++e) out[gt * E + e] = (double)a[(size_t)e * K + gt];
+}
+// fetch of an instance-major block array M[b][c][r] (r = k*NX+i) into out[b][k][i*ncol + c]
+template <typename T>
+__global__ void k_fetch_blocks(const T* M, int B, int N, int ncol, double* out) {
+  const size_t gt = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (gt >= (size_t)B * N) return;
+  const int b = (int)(gt / N), k = (int)(gt % N);
+  const int R = N * NX;
+  for (int i = 0; i < NX; ++i)
+    for (int c = 0; c < ncol; ++c) out[(gt * NX + i) * ncol + c] = (double)M[((size_t)b * ncol + c) * R + k * NX + i];
+}
+template <typename T>
+__global__ void k_fill(T* p, size_t n, T v) {
+  const size_t gt = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (gt < n) p[gt] = v;
+}
+// multipliers: ABI layout [B][2m][N] <-> SoA [2m][K]
+template <typename T>
+__global__ void k_pack_mult(Dev<T> d, const double* src, T* dst) {
+  const size_t gt = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (gt >= d.K) return;
+  const int b = (int)(gt / d.N), k = (int)(gt % d.N);
+  for (int e = 0; e < 2 * NM; ++e) dst[(size_t)e * d.K + gt] = (T)src[((size_t)b * 2 * NM + e) * d.N + k];
+}
+template <typename T>
+__global__ void k_unpack_mult(Dev<T> d, const T* src, double* dst) {
+  const size_t gt = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (gt >= d.K) return;
+  const int b = (int)(gt / d.N), k = (int)(gt % d.N);
+  for (int e = 0; e < 2 * NM; ++e) dst[((size_t)b * 2 * NM + e) * d.N + k] = (double)src[(size_t)e * d.K + gt];
+}
+template <typename T>
+__global__ void k_init_mult(Dev<T> d) {
+  const size_t gt = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (gt >= d.K) return;
+  for (int e = 0; e < 2 * NM; ++e) {
+    const int i = e % NM;
+    const int ty = i < NJ ? 0 : (i < NX ? 1 : 2);
+    d.mu[(size_t)e * d.K + gt] = d.mu_init[ty];
+    d.lam[(size_t)e * d.K + gt] = T(0);
+    d.phi[(size_t)e * d.K + gt] = d.phi_init[ty];
+  }
+}
+template <typename T>
+__global__ void k_init_state(Dev<T> d) {
+  const int b = blockIdx.x * blockDim.x + threadIdx.x;
+  if (b == 0) *d.n_act = d.B;
+  if (b >= d.B) return;
+  d.act[b] = b;
+  d.outer_iter[b] = 0; d.sqp_iter[b] = 0; d.exit_sqp[b] = 0; d.exit_soft[b] = 0; d.phase[b] = PH_SQP; d.err[b] = 0;
+  d.pcg_iters[b] = 0; d.tot_qp[b] = 0; d.tot_pcg[b] = 0; d.tot_trials[b] = 0; d.trace_rows[b] = 0; d.ls_iter[b] = 0;
+  d.alpha[b] = T(1); d.deltaJ[b] = T(0); d.c[b] = T(0); d.J[b] = T(0); d.merit[b] = T(0); d.rho[b] = T(0); d.drho[b] = T(1);
+}
+
+}  // namespace b2t
+
+namespace b2t {
+template <typename T>
+__global__ void k_pack_status(Dev<T> d, int* st, double* sc) {
+  const int b = blockIdx.x * blockDim.x + threadIdx.x;
+  if (b >= d.B) return;
+  int* o = st + (size_t)b * 8;
+  o[0] = d.exit_sqp[b]; o[1] = d.exit_soft[b]; o[2] = d.outer_iter[b]; o[3] = d.sqp_iter[b];
+  o[4] = d.tot_qp[b]; o[5] = d.tot_pcg[b]; o[6] = d.tot_trials[b]; o[7] = d.trace_rows[b];
+  double* s = sc + (size_t)b * 4;
+  s[0] = (double)d.J[b]; s[1] = (double)d.c[b]; s[2] = (double)d.merit[b]; s[3] = (double)d.rho[b];
+}
+template <typename T>
+__global__ void k_fetch_trace(Dev<T> d, double* out, int cap) {
+  const size_t gt = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  const size_t n = (size_t)d.B * cap * TRACE_FIELDS;
+  if (gt >= n) return;
+  const int f = (int)(gt % TRACE_FIELDS);
+  const size_t br = gt / TRACE_FIELDS;
+  const int row = (int)(br % cap);
+  const int b = (int)(br / cap);
+  out[gt] = (row < d.trace_cap) ? (double)d.trace[((size_t)b * d.trace_cap + row) * TRACE_FIELDS + f] : 0.0;
+}
+}  // namespace b2t

@@ -1,0 +1,615 @@
+// b2t_lib.cu -- host side of libb2t_<robot>.so: workspace, launch sequence of one batched SQP solve, C ABI (include/b2t.h).
+#include <cstdio>
+#include <cstring>
+#include <string>
+#include <vector>
+#include <algorithm>
+#include <cuda_runtime.h>
+#include "b2t_kernels.cuh"
+#include "../../include/b2t.h"
+
+namespace {
+thread_local std::string g_err;
+int fail(int code, const std::string& msg) { g_err = msg; return code; }
+
+#define B2T_CUDA(call)                                                                              \
+  do {                                                                                              \
+    cudaError_t e__ = (call);                                                                       \
+    if (e__ != cudaSuccess)                                                                         \
+      return fail(B2T_ERR_CUDA, std::string(#call) + ": " + cudaGetErrorString(e__));               \
+  } while (0)
+
+inline unsigned cdiv(size_t a, size_t b) { return (unsigned)((a + b - 1) / b); }
+
+struct SolverBase {
+  virtual ~SolverBase() {}
+  virtual int init(const b2t_problem_desc* d, int device) = 0;
+  virtual int set_trajectory(const double* x, const double* u, int on_device) = 0;
+  virtual int set_goals(const double* xg, int on_device) = 0;
+  virtual int set_initial_state(const double* xs) = 0;
+  virtual int set_multipliers(const double* mu, const double* lam, const double* phi) = 0;
+  virtual int reset_multipliers() = 0;
+  virtual int solve(int method, const b2t_options* o) = 0;
+  virtual int get_trajectory(double* x, double* u, int on_device) = 0;
+  virtual int get_status(int* st) = 0;
+  virtual int get_scalars(double* sc) = 0;
+  virtual int get_trace(double* tr, int cap) = 0;
+  virtual int get_multipliers(double* mu, double* lam, double* phi) = 0;
+  virtual int solve_host(const double* x0, const double* u0, const double* xg, int method, const b2t_options* o, double* xo,
+                         double* uo, int* st) = 0;
+  virtual int stage_dynamics() = 0;
+  virtual int stage_kkt(double rho, int method) = 0;
+  virtual int stage_pcg(int method, double tol, int max_iter, int* iters) = 0;
+  virtual int stage_recover() = 0;
+  virtual int stage_merit(double alpha, double* J, double* c, double* D) = 0;
+  virtual int fetch(int which, double* out) = 0;
+  size_t ws_bytes = 0;
+  cudaStream_t stream = 0;
+  long long launches = 0;
+  double device_seconds = 0;
+  bool profiling = false;
+  double fam_seconds[B2T_KERNEL_FAMILIES] = {0};
+  long long fam_launches[B2T_KERNEL_FAMILIES] = {0};
+};
+
+template <typename T>
+struct SolverT : SolverBase {
+  b2t::Dev<T> d;
+  int device = 0;
+  std::vector<void*> allocs;
+  double* stage_x = nullptr; double* stage_u = nullptr; double* stage_g = nullptr; double* stage_out = nullptr;
+  size_t stage_out_bytes = 0;
+  int* h_count = nullptr;        // pinned
+  int* d_status = nullptr; double* d_scalars = nullptr;
+  int* d_scratch = nullptr;
+  cudaEvent_t ev0 = nullptr, ev1 = nullptr;
+  std::vector<cudaEvent_t> ev_pool; size_t ev_used = 0;
+  std::vector<int> ev_family;
+
+  ~SolverT() override {
+    cudaSetDevice(device);
+    for (void* p : allocs) cudaFree(p);
+    if (h_count) cudaFreeHost(h_count);
+    if (ev0) cudaEventDestroy(ev0);
+    if (ev1) cudaEventDestroy(ev1);
+    for (auto e : ev_pool) cudaEventDestroy(e);
+  }
+
+  template <typename U>
+  int alloc(U** p, size_t n) {
+    void* q = nullptr;
+    size_t bytes = std::max<size_t>(n, 1) * sizeof(U);
+    cudaError_t e = cudaMalloc(&q, bytes);
+    if (e != cudaSuccess) return fail(B2T_ERR_NOMEM, std::string("cudaMalloc: ") + cudaGetErrorString(e));
+    cudaMemsetAsync(q, 0, bytes, stream);
+    allocs.push_back(q);
+    ws_bytes += bytes;
+    *p = (U*)q;
+    return 0;
+  }
+#define B2T_ALLOC(p, n) do { int r__ = alloc(&(p), (n)); if (r__) return r__; } while (0)
+
+  template <typename U>
+  int upload(U** dst, const double* src, size_t n) {
+    std::vector<U> h(n);
+    for (size_t i = 0; i < n; ++i) h[i] = (U)src[i];
+    B2T_ALLOC(*dst, n);
+    B2T_CUDA(cudaMemcpy(*dst, h.data(), n * sizeof(U), cudaMemcpyHostToDevice));
+    return 0;
+  }
+
+  int init(const b2t_problem_desc* p, int dev) override {
+    using namespace b2t;
+    if (!p || p->batch < 1 || p->knots < 2) return fail(B2T_ERR_INVALID, "batch >= 1 and knots >= 2 required");
+    if (p->integrator_type != 0 && p->integrator_type != 1)
+      return fail(B2T_ERR_UNSUPPORTED, "integrator types 0 (euler) and 1 (semi-implicit euler) only");
+    if (p->cost_kind == B2T_COST_URDF_EE && NJ != 2)
+      return fail(B2T_ERR_UNSUPPORTED, "UrdfCost needs a 2-joint robot (reference limitation, RBDReference.py:263)");
+    if (p->cost_kind != B2T_COST_QUADRATIC && p->cost_kind != B2T_COST_URDF_EE) return fail(B2T_ERR_INVALID, "cost_kind");
+    if (!p->Q || !p->QF || !p->R) return fail(B2T_ERR_INVALID, "Q, QF, R required");
+    if ((size_t)p->knots * NX > (size_t)PCG_MAX_RPT * 1024) return fail(B2T_ERR_UNSUPPORTED, "knots * nx too large for the PCG block");
+    device = dev;
+    B2T_CUDA(cudaSetDevice(device));
+    memset(&d, 0, sizeof(d));
+    d.B = p->batch; d.N = p->knots; d.integrator = p->integrator_type;
+    d.dt = (T)p->dt; d.gravity = (T)p->gravity;
+    d.K = (size_t)d.B * d.N;
+    const size_t K = d.K, B = d.B, R = (size_t)d.N * NX;
+    B2T_ALLOC(d.x, NX * K); B2T_ALLOC(d.u, NU * K); B2T_ALLOC(d.xn, NX * K); B2T_ALLOC(d.un, NU * K);
+    B2T_ALLOC(d.xkp1, NX * K); B2T_ALLOC(d.xkp1n, NX * K); B2T_ALLOC(d.dyn, (size_t)NDYN * K); B2T_ALLOC(d.vaf, (size_t)NVAF * K);
+    B2T_ALLOC(d.Gh, (size_t)NM * NM * K); B2T_ALLOC(d.g, NM * K); B2T_ALLOC(d.Gg, NM * K); B2T_ALLOC(d.dz, NM * K);
+    B2T_ALLOC(d.Sd, B * R * NX); B2T_ALLOC(d.So, B * R * NX); B2T_ALLOC(d.Pd, B * R * NX); B2T_ALLOC(d.gam, B * R); B2T_ALLOC(d.l, B * R);
+    B2T_ALLOC(d.xs, NX * B); B2T_ALLOC(d.xg, NX * B);
+    // cost
+    d.cost.kind = p->cost_kind; d.cost.qf_start = p->qf_start;
+    { T* q; int r; if ((r = upload(&q, p->Q, NX * NX))) return r; d.cost.Q = q; }
+    { T* q; int r; if ((r = upload(&q, p->QF, NX * NX))) return r; d.cost.QF = q; }
+    { T* q; int r; if ((r = upload(&q, p->R, NU * NU))) return r; d.cost.R = q; }
+    // limits
+    int mode[NM]; double lb[NM], ub[NM];
+    int any = 0;
+    for (int i = 0; i < NM; ++i) {
+      const int ty = i < NJ ? 0 : (i < NX ? 1 : 2);
+      mode[i] = p->limit_mode[ty];
+      if (mode[i] < 0 || mode[i] > 2) return fail(B2T_ERR_INVALID, "limit_mode");
+      if (mode[i] != B2T_LIMIT_NONE) {
+        if (!p->lower || !p->upper) return fail(B2T_ERR_INVALID, "lower/upper bounds required");
+        any = 1; lb[i] = p->lower[i]; ub[i] = p->upper[i];
+      } else { lb[i] = 0; ub[i] = 0; }
+    }
+    d.lim.any = any;
+    { int* m; B2T_ALLOC(m, NM); B2T_CUDA(cudaMemcpy(m, mode, sizeof(mode), cudaMemcpyHostToDevice)); d.lim.mode = m; }
+    { T* q; int r; if ((r = upload(&q, lb, NM))) return r; d.lim.lb = q; }
+    { T* q; int r; if ((r = upload(&q, ub, NM))) return r; d.lim.ub = q; }
+    for (int ty = 0; ty < 3; ++ty) {
+      d.mu_init[ty] = (T)p->mu_init[ty]; d.mu_factor[ty] = (T)p->mu_factor[ty]; d.mu_max[ty] = (T)p->mu_max[ty];
+      d.phi_init[ty] = (T)p->phi_init[ty]; d.phi_factor[ty] = (T)p->phi_factor[ty];
+    }
+    const size_t nmult = any ? (size_t)2 * NM * K : 1;
+    B2T_ALLOC(d.mu, nmult); B2T_ALLOC(d.lam, nmult); B2T_ALLOC(d.phi, nmult);
+    // per-instance state
+    B2T_ALLOC(d.rho, B); B2T_ALLOC(d.drho, B); B2T_ALLOC(d.J, B); B2T_ALLOC(d.c, B); B2T_ALLOC(d.merit, B); B2T_ALLOC(d.alpha, B);
+    B2T_ALLOC(d.deltaJ, B); B2T_ALLOC(d.D, B); B2T_ALLOC(d.ratio, B);
+    B2T_ALLOC(d.ls_iter, B); B2T_ALLOC(d.sqp_iter, B); B2T_ALLOC(d.outer_iter, B); B2T_ALLOC(d.exit_sqp, B); B2T_ALLOC(d.exit_soft, B);
+    B2T_ALLOC(d.phase, B); B2T_ALLOC(d.err, B); B2T_ALLOC(d.pcg_iters, B); B2T_ALLOC(d.tot_qp, B); B2T_ALLOC(d.tot_pcg, B); B2T_ALLOC(d.tot_trials, B);
+    B2T_ALLOC(d.act, B); B2T_ALLOC(d.n_act, 1); B2T_ALLOC(d.ls_list0, B); B2T_ALLOC(d.ls_list1, B); B2T_ALLOC(d.restart_list, B); B2T_ALLOC(d.n_restart, 1);
+    B2T_ALLOC(d.n_ls, MAX_LS_TRIALS + 1);
+    d.trace_cap = 104;
+    B2T_ALLOC(d.trace, B * d.trace_cap * TRACE_FIELDS); B2T_ALLOC(d.trace_rows, B);
+    B2T_ALLOC(d_scratch, B); B2T_ALLOC(d_status, B * 8); B2T_ALLOC(d_scalars, B * 4);
+    B2T_ALLOC(stage_x, (size_t)B * NX * d.N); B2T_ALLOC(stage_u, (size_t)B * NU * (d.N - 1)); B2T_ALLOC(stage_g, (size_t)B * NX);
+    stage_out_bytes = std::max<size_t>({(size_t)NM * NM * K, (size_t)NDYN * K, (size_t)2 * NM * K, B * (size_t)d.trace_cap * TRACE_FIELDS}) * sizeof(double);
+    { void* q; cudaError_t e = cudaMalloc(&q, stage_out_bytes); if (e != cudaSuccess) return fail(B2T_ERR_NOMEM, "cudaMalloc stage_out"); allocs.push_back(q); ws_bytes += stage_out_bytes; stage_out = (double*)q; }
+    B2T_CUDA(cudaMallocHost((void**)&h_count, 64));
+    B2T_CUDA(cudaEventCreate(&ev0)); B2T_CUDA(cudaEventCreate(&ev1));
+    // kernels that need > 48 KB of dynamic shared memory
+    B2T_CUDA(cudaFuncSetAttribute(b2t::k_pcg<T>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+    int r = reset_multipliers();
+    if (r) return r;
+    k_init_state<T><<<cdiv(B, 128), 128, 0, stream>>>(d);
+    B2T_CUDA(cudaGetLastError());
+    B2T_CUDA(cudaStreamSynchronize(stream));
+    return 0;
+  }
+
+  // ------------------------------------------------------------------ launch bookkeeping
+  void tick(int family) {
+    ++launches;
+    ++fam_launches[family];
+  }
+  struct Scope {
+    SolverT* s; int fam; cudaEvent_t a = nullptr, b = nullptr;
+    Scope(SolverT* s_, int fam_) : s(s_), fam(fam_) {
+      if (s->profiling) { a = s->next_event(); b = s->next_event(); s->ev_family.push_back(fam); cudaEventRecord(a, s->stream); }
+    }
+    ~Scope() { if (s->profiling) cudaEventRecord(b, s->stream); }
+  };
+  cudaEvent_t next_event() {
+    if (ev_used == ev_pool.size()) { cudaEvent_t e; cudaEventCreate(&e); ev_pool.push_back(e); }
+    return ev_pool[ev_used++];
+  }
+  void collect_profile() {
+    if (!profiling) return;
+    cudaStreamSynchronize(stream);
+    for (size_t i = 0; i < ev_family.size(); ++i) {
+      float ms = 0;
+      cudaEventElapsedTime(&ms, ev_pool[2 * i], ev_pool[2 * i + 1]);
+      fam_seconds[ev_family[i]] += ms * 1e-3;
+    }
+    ev_used = 0; ev_family.clear();
+  }
+
+  // ------------------------------------------------------------------ inputs / outputs
+  int set_trajectory(const double* x, const double* u, int on_device) override {
+    using namespace b2t;
+    if (!x || !u) return fail(B2T_ERR_INVALID, "x, u required");
+    B2T_CUDA(cudaSetDevice(device));
+    const double *dx = x, *du = u;
+    if (!on_device) {
+      B2T_CUDA(cudaMemcpyAsync(stage_x, x, (size_t)d.B * NX * d.N * sizeof(double), cudaMemcpyHostToDevice, stream));
+      B2T_CUDA(cudaMemcpyAsync(stage_u, u, (size_t)d.B * NU * (d.N - 1) * sizeof(double), cudaMemcpyHostToDevice, stream));
+      dx = stage_x; du = stage_u;
+    }
+    k_pack_traj<T><<<cdiv(d.K, 128), 128, 0, stream>>>(d, dx, du);
+    B2T_CUDA(cudaGetLastError());
+    return 0;
+  }
+  int set_goals(const double* xg, int on_device) override {
+    using namespace b2t;
+    if (!xg) return fail(B2T_ERR_INVALID, "xg required");
+    B2T_CUDA(cudaSetDevice(device));
+    const double* dg = xg;
+    if (!on_device) {
+      B2T_CUDA(cudaMemcpyAsync(stage_g, xg, (size_t)d.B * NX * sizeof(double), cudaMemcpyHostToDevice, stream));
+      dg = stage_g;
+    }
+    k_pack_goals<T><<<cdiv(d.B, 128), 128, 0, stream>>>(d, dg);
+    B2T_CUDA(cudaGetLastError());
+    return 0;
+  }
+  int set_initial_state(const double* xs) override {
+    using namespace b2t;
+    if (!xs) return fail(B2T_ERR_INVALID, "xs required");
+    B2T_CUDA(cudaSetDevice(device));
+    std::vector<T> h((size_t)NX * d.B);
+    for (int b = 0; b < d.B; ++b)
+      for (int i = 0; i < NX; ++i) h[(size_t)i * d.B + b] = (T)xs[(size_t)b * NX + i];
+    B2T_CUDA(cudaStreamSynchronize(stream));
+    B2T_CUDA(cudaMemcpy(d.xs, h.data(), h.size() * sizeof(T), cudaMemcpyHostToDevice));
+    return 0;
+  }
+  int set_multipliers(const double* mu, const double* lam, const double* phi) override {
+    using namespace b2t;
+    if (!d.lim.any) return fail(B2T_ERR_INVALID, "no soft limits configured");
+    B2T_CUDA(cudaSetDevice(device));
+    const size_t bytes = (size_t)2 * NM * d.K * sizeof(double);
+    const double* src[3] = {mu, lam, phi};
+    T* dst[3] = {d.mu, d.lam, d.phi};
+    for (int i = 0; i < 3; ++i) {
+      if (!src[i]) continue;
+      B2T_CUDA(cudaMemcpyAsync(stage_out, src[i], bytes, cudaMemcpyHostToDevice, stream));
+      k_pack_mult<T><<<cdiv(d.K, 128), 128, 0, stream>>>(d, stage_out, dst[i]);
+      B2T_CUDA(cudaGetLastError());
+      B2T_CUDA(cudaStreamSynchronize(stream));
+    }
+    return 0;
+  }
+  int get_multipliers(double* mu, double* lam, double* phi) override {
+    using namespace b2t;
+    if (!d.lim.any) return fail(B2T_ERR_INVALID, "no soft limits configured");
+    B2T_CUDA(cudaSetDevice(device));
+    const size_t bytes = (size_t)2 * NM * d.K * sizeof(double);
+    double* dst[3] = {mu, lam, phi};
+    T* src[3] = {d.mu, d.lam, d.phi};
+    for (int i = 0; i < 3; ++i) {
+      if (!dst[i]) continue;
+      k_unpack_mult<T><<<cdiv(d.K, 128), 128, 0, stream>>>(d, src[i], stage_out);
+      B2T_CUDA(cudaGetLastError());
+      B2T_CUDA(cudaMemcpyAsync(dst[i], stage_out, bytes, cudaMemcpyDeviceToHost, stream));
+      B2T_CUDA(cudaStreamSynchronize(stream));
+    }
+    return 0;
+  }
+  int reset_multipliers() override {
+    using namespace b2t;
+    if (!d.lim.any) return 0;
+    B2T_CUDA(cudaSetDevice(device));
+    k_init_mult<T><<<cdiv(d.K, 128), 128, 0, stream>>>(d);
+    B2T_CUDA(cudaGetLastError());
+    return 0;
+  }
+  int get_trajectory(double* x, double* u, int on_device) override {
+    using namespace b2t;
+    if (!x || !u) return fail(B2T_ERR_INVALID, "x, u required");
+    B2T_CUDA(cudaSetDevice(device));
+    double* dx = on_device ? x : stage_x;
+    double* du = on_device ? u : stage_u;
+    k_unpack_traj<T><<<cdiv(d.K, 128), 128, 0, stream>>>(d, dx, du);
+    B2T_CUDA(cudaGetLastError());
+    if (!on_device) {
+      B2T_CUDA(cudaMemcpyAsync(x, stage_x, (size_t)d.B * NX * d.N * sizeof(double), cudaMemcpyDeviceToHost, stream));
+      B2T_CUDA(cudaMemcpyAsync(u, stage_u, (size_t)d.B * NU * (d.N - 1) * sizeof(double), cudaMemcpyDeviceToHost, stream));
+    }
+    B2T_CUDA(cudaStreamSynchronize(stream));
+    return 0;
+  }
+  int pack_status() {
+    using namespace b2t;
+    k_pack_status<T><<<cdiv(d.B, 128), 128, 0, stream>>>(d, d_status, d_scalars);
+    B2T_CUDA(cudaGetLastError());
+    return 0;
+  }
+  int get_status(int* st) override {
+    if (!st) return fail(B2T_ERR_INVALID, "status required");
+    B2T_CUDA(cudaSetDevice(device));
+    int r = pack_status(); if (r) return r;
+    B2T_CUDA(cudaMemcpyAsync(st, d_status, (size_t)d.B * 8 * sizeof(int), cudaMemcpyDeviceToHost, stream));
+    B2T_CUDA(cudaStreamSynchronize(stream));
+    return 0;
+  }
+  int get_scalars(double* sc) override {
+    if (!sc) return fail(B2T_ERR_INVALID, "scalars required");
+    B2T_CUDA(cudaSetDevice(device));
+    int r = pack_status(); if (r) return r;
+    B2T_CUDA(cudaMemcpyAsync(sc, d_scalars, (size_t)d.B * 4 * sizeof(double), cudaMemcpyDeviceToHost, stream));
+    B2T_CUDA(cudaStreamSynchronize(stream));
+    return 0;
+  }
+  int get_trace(double* tr, int cap) override {
+    using namespace b2t;
+    if (!tr || cap < 1) return fail(B2T_ERR_INVALID, "trace buffer required");
+    B2T_CUDA(cudaSetDevice(device));
+    const size_t n = (size_t)d.B * cap * TRACE_FIELDS;
+    if (n * sizeof(double) > stage_out_bytes) return fail(B2T_ERR_INVALID, "trace_cap too large");
+    k_fetch_trace<T><<<cdiv(n, 256), 256, 0, stream>>>(d, stage_out, cap);
+    B2T_CUDA(cudaGetLastError());
+    B2T_CUDA(cudaMemcpyAsync(tr, stage_out, n * sizeof(double), cudaMemcpyDeviceToHost, stream));
+    B2T_CUDA(cudaStreamSynchronize(stream));
+    return 0;
+  }
+
+  // ------------------------------------------------------------------ kernels of one QP solve
+  static b2t::Opts<T> convert(const b2t_options* o) {
+    b2t::Opts<T> r;
+    r.tol_lin = (T)o->exit_tolerance_linSys; r.max_iter_lin = o->max_iter_linSys;
+    r.tol_sqp = (T)o->exit_tolerance_SQP; r.max_iter_sqp = o->max_iter_SQP;
+    r.alpha_factor = (T)o->alpha_factor; r.alpha_min = (T)o->alpha_min;
+    r.rho_factor = (T)o->rho_factor; r.rho_min = (T)o->rho_min; r.rho_max = (T)o->rho_max; r.rho_init = (T)o->rho_init;
+    r.er_min = (T)o->expected_reduction_min; r.er_max = (T)o->expected_reduction_max;
+    r.tol_soft = (T)o->exit_tolerance_soft; r.max_iter_soft = o->max_iter_soft;
+    r.merit_mu = (T)o->merit_mu;
+    return r;
+  }
+  size_t pcg_smem() const { return ((size_t)3 * d.N * b2t::NX + 64) * sizeof(T); }
+  int pcg_threads() const {
+    int R = d.N * b2t::NX;
+    int t = ((R + 31) / 32) * 32;
+    return std::min(t, 1024);
+  }
+  int merit_threads() const { return std::min(256, ((d.N + 31) / 32) * 32); }
+
+  int launch_dynamics(const int* list, const int* count, int bound) {
+    using namespace b2t;
+    const size_t nthreads = (size_t)bound * d.N;
+    { Scope sc(this, B2T_K_FD); k_fd<T, false><<<cdiv(nthreads, 128), 128, 0, stream>>>(d, list, count); tick(B2T_K_FD); }
+    { Scope sc(this, B2T_K_FDGRAD); dim3 grid(cdiv(nthreads, 128), 2 * NJ); k_fd_grad<T><<<grid, 128, 0, stream>>>(d, list, count); tick(B2T_K_FDGRAD); }
+    return 0;
+  }
+  int launch_kkt(const int* list, const int* count, int bound, int method) {
+    using namespace b2t;
+    const size_t nthreads = (size_t)bound * d.N;
+    { Scope sc(this, B2T_K_KKT); k_kkt<T><<<cdiv(nthreads, 64), 64, 0, stream>>>(d, list, count); tick(B2T_K_KKT); }
+    { Scope sc(this, B2T_K_SCHUR); k_schur<T><<<cdiv(nthreads, 64), 64, 0, stream>>>(d, list, count, method == B2T_METHOD_PCG_J ? 1 : 0); tick(B2T_K_SCHUR); }
+    return 0;
+  }
+  int launch_pcg(const int* list, const int* count, int bound, int method, T tol, int max_iter) {
+    using namespace b2t;
+    Scope sc(this, B2T_K_PCG);
+    k_pcg<T><<<bound, pcg_threads(), pcg_smem(), stream>>>(d, list, count, method == B2T_METHOD_PCG_SS ? 1 : 0, tol, max_iter);
+    tick(B2T_K_PCG);
+    return 0;
+  }
+  int launch_recover(const int* list, const int* count, int bound) {
+    using namespace b2t;
+    Scope sc(this, B2T_K_RECOVER);
+    k_recover<T><<<cdiv((size_t)bound * d.N, 128), 128, 0, stream>>>(d, list, count);
+    tick(B2T_K_RECOVER);
+    return 0;
+  }
+
+  int solve(int method, const b2t_options* o) override {
+    using namespace b2t;
+    if (!o) return fail(B2T_ERR_INVALID, "options required");
+    if (method != B2T_METHOD_PCG_J && method != B2T_METHOD_PCG_BJ && method != B2T_METHOD_PCG_SS)
+      return fail(B2T_ERR_UNSUPPORTED, "method must be PCG-J, PCG-BJ or PCG-SS");
+    if (o->max_iter_SQP + 1 > d.trace_cap) return fail(B2T_ERR_UNSUPPORTED, "max_iter_SQP_DDP > 103");
+    B2T_CUDA(cudaSetDevice(device));
+    Opts<T> op = convert(o);
+    int max_trials = 1;
+    { double a = 1.0; while (a > o->alpha_min && max_trials < MAX_LS_TRIALS) { a *= o->alpha_factor; ++max_trials; } }
+    launches = 0; device_seconds = 0;
+    for (int i = 0; i < B2T_KERNEL_FAMILIES; ++i) { fam_seconds[i] = 0; fam_launches[i] = 0; }
+    B2T_CUDA(cudaEventRecord(ev0, stream));
+    const int B = d.B;
+    const size_t msmem = (size_t)5 * d.N * sizeof(T);
+    const int mt = merit_threads();
+    k_init_state<T><<<cdiv(B, 128), 128, 0, stream>>>(d); tick(B2T_K_CTRL);
+    { Scope sc(this, B2T_K_FD); k_fd<T, false><<<cdiv((size_t)B * d.N, 128), 128, 0, stream>>>(d, d.act, d.n_act); tick(B2T_K_FD); }
+    { Scope sc(this, B2T_K_MERIT); k_outer_begin<T><<<B, mt, msmem, stream>>>(d, d.act, d.n_act, op, 1); tick(B2T_K_MERIT); }
+    B2T_CUDA(cudaGetLastError());
+    int n = B;
+    const long long cap = (long long)o->max_iter_soft * o->max_iter_SQP + 8;
+    for (long long iter = 0; n > 0 && iter < cap; ++iter) {
+      { Scope sc(this, B2T_K_CTRL); k_iter_begin<T><<<cdiv(n, 128), 128, 0, stream>>>(d); tick(B2T_K_CTRL); }
+      launch_dynamics(d.act, d.n_act, n);
+      launch_kkt(d.act, d.n_act, n, method);
+      launch_pcg(d.act, d.n_act, n, method, op.tol_lin, op.max_iter_lin);
+      launch_recover(d.act, d.n_act, n);
+      for (int t = 0; t < max_trials; ++t) {
+        int* cur = (t % 2) ? d.ls_list1 : d.ls_list0;
+        int* nxt = (t % 2) ? d.ls_list0 : d.ls_list1;
+        { Scope sc(this, B2T_K_TRIAL); k_fd<T, true><<<cdiv((size_t)n * d.N, 128), 128, 0, stream>>>(d, cur, d.n_ls + t); tick(B2T_K_TRIAL); }
+        { Scope sc(this, B2T_K_MERIT); k_merit<T><<<n, mt, msmem, stream>>>(d, cur, d.n_ls + t, nxt, d.n_ls + t + 1, op); tick(B2T_K_MERIT); }
+      }
+      { Scope sc(this, B2T_K_CTRL); k_sqp_ctrl<T><<<cdiv(n, 128), 128, 0, stream>>>(d, op); tick(B2T_K_CTRL); }
+      { Scope sc(this, B2T_K_CTRL); k_outer<T><<<n, mt, (size_t)3 * d.N * sizeof(T), stream>>>(d, op); tick(B2T_K_CTRL); }
+      { Scope sc(this, B2T_K_MERIT); k_outer_begin<T><<<n, mt, msmem, stream>>>(d, d.restart_list, d.n_restart, op, 0); tick(B2T_K_MERIT); }
+      { Scope sc(this, B2T_K_CTRL); k_compact<T><<<1, 256, 0, stream>>>(d, d_scratch); tick(B2T_K_CTRL); }
+      B2T_CUDA(cudaMemcpyAsync(h_count, d.n_act, sizeof(int), cudaMemcpyDeviceToHost, stream));
+      B2T_CUDA(cudaStreamSynchronize(stream));
+      n = h_count[0];
+    }
+    B2T_CUDA(cudaEventRecord(ev1, stream));
+    B2T_CUDA(cudaEventSynchronize(ev1));
+    float ms = 0;
+    B2T_CUDA(cudaEventElapsedTime(&ms, ev0, ev1));
+    device_seconds = ms * 1e-3;
+    collect_profile();
+    B2T_CUDA(cudaGetLastError());
+    return 0;
+  }
+
+  int solve_host(const double* x0, const double* u0, const double* xg, int method, const b2t_options* o, double* xo, double* uo,
+                 int* st) override {
+    int r;
+    if ((r = set_trajectory(x0, u0, 0))) return r;
+    if (xg && (r = set_goals(xg, 0))) return r;
+    if ((r = solve(method, o))) return r;
+    if ((r = get_trajectory(xo, uo, 0))) return r;
+    if (st && (r = get_status(st))) return r;
+    return 0;
+  }
+
+  // ------------------------------------------------------------------ stages (parity tests)
+  int all_list() {   // act = 0..B-1
+    using namespace b2t;
+    k_init_state<T><<<cdiv(d.B, 128), 128, 0, stream>>>(d);
+    B2T_CUDA(cudaGetLastError());
+    return 0;
+  }
+  int stage_dynamics() override {
+    B2T_CUDA(cudaSetDevice(device));
+    int r = all_list(); if (r) return r;
+    launch_dynamics(d.act, d.n_act, d.B);
+    B2T_CUDA(cudaGetLastError());
+    B2T_CUDA(cudaStreamSynchronize(stream));
+    return 0;
+  }
+  int stage_kkt(double rho, int method) override {
+    using namespace b2t;
+    B2T_CUDA(cudaSetDevice(device));
+    int r = all_list(); if (r) return r;
+    k_fill<T><<<cdiv(d.B, 128), 128, 0, stream>>>(d.rho, (size_t)d.B, (T)rho);
+    launch_dynamics(d.act, d.n_act, d.B);
+    launch_kkt(d.act, d.n_act, d.B, method);
+    B2T_CUDA(cudaGetLastError());
+    B2T_CUDA(cudaStreamSynchronize(stream));
+    return 0;
+  }
+  int stage_pcg(int method, double tol, int max_iter, int* iters) override {
+    B2T_CUDA(cudaSetDevice(device));
+    launch_pcg(d.act, d.n_act, d.B, method, (T)tol, max_iter);
+    B2T_CUDA(cudaGetLastError());
+    if (iters) B2T_CUDA(cudaMemcpyAsync(iters, d.pcg_iters, (size_t)d.B * sizeof(int), cudaMemcpyDeviceToHost, stream));
+    B2T_CUDA(cudaStreamSynchronize(stream));
+    return 0;
+  }
+  int stage_recover() override {
+    B2T_CUDA(cudaSetDevice(device));
+    launch_recover(d.act, d.n_act, d.B);
+    B2T_CUDA(cudaGetLastError());
+    B2T_CUDA(cudaStreamSynchronize(stream));
+    return 0;
+  }
+  int stage_merit(double alpha, double* J, double* c, double* D) override {
+    using namespace b2t;
+    B2T_CUDA(cudaSetDevice(device));
+    k_fill<T><<<cdiv(d.B, 128), 128, 0, stream>>>(d.alpha, (size_t)d.B, (T)alpha);
+    k_fd<T, true><<<cdiv(d.K, 128), 128, 0, stream>>>(d, d.act, d.n_act);
+    k_merit_only<T><<<d.B, merit_threads(), (size_t)5 * d.N * sizeof(T), stream>>>(d, d.J, d.c, d.D);
+    B2T_CUDA(cudaGetLastError());
+    std::vector<T> h(d.B);
+    T* src[3] = {d.J, d.c, d.D};
+    double* dst[3] = {J, c, D};
+    for (int i = 0; i < 3; ++i) {
+      if (!dst[i]) continue;
+      B2T_CUDA(cudaMemcpy(h.data(), src[i], (size_t)d.B * sizeof(T), cudaMemcpyDeviceToHost));
+      for (int b = 0; b < d.B; ++b) dst[i][b] = (double)h[b];
+    }
+    return 0;
+  }
+  int fetch(int which, double* out) override {
+    using namespace b2t;
+    if (!out) return fail(B2T_ERR_INVALID, "out required");
+    B2T_CUDA(cudaSetDevice(device));
+    const size_t K = d.K;
+    const T* src = nullptr; int E = 0; bool blocks = false; bool flat = false;
+    switch (which) {
+      case B2T_ARR_X: src = d.x; E = NX; break;
+      case B2T_ARR_U: src = d.u; E = NU; break;
+      case B2T_ARR_XKP1: src = d.xkp1; E = NX; break;
+      case B2T_ARR_DQDD: src = d.dyn; E = NDYN; break;
+      case B2T_ARR_GHAT: src = d.Gh; E = NM * NM; break;
+      case B2T_ARR_G: src = d.g; E = NM; break;
+      case B2T_ARR_DZ: src = d.dz; E = NM; break;
+      case B2T_ARR_XN: src = d.xn; E = NX; break;
+      case B2T_ARR_UN: src = d.un; E = NU; break;
+      case B2T_ARR_SD: src = d.Sd; E = NX * NX; blocks = true; break;
+      case B2T_ARR_SO: src = d.So; E = NX * NX; blocks = true; break;
+      case B2T_ARR_PD: src = d.Pd; E = NX * NX; blocks = true; break;
+      case B2T_ARR_GAMMA: src = d.gam; E = NX; flat = true; break;
+      case B2T_ARR_L: src = d.l; E = NX; flat = true; break;
+      default: return fail(B2T_ERR_INVALID, "unknown array id");
+    }
+    const size_t n = K * E;
+    if (n * sizeof(double) > stage_out_bytes) return fail(B2T_ERR_INVALID, "array too large for staging");
+    if (blocks) k_fetch_blocks<T><<<cdiv(K, 128), 128, 0, stream>>>(src, d.B, d.N, NX, stage_out);
+    else if (flat) k_fetch_soa<T><<<cdiv(n, 128), 128, 0, stream>>>(src, n, 1, stage_out);
+    else k_fetch_soa<T><<<cdiv(K, 128), 128, 0, stream>>>(src, K, E, stage_out);
+    B2T_CUDA(cudaGetLastError());
+    B2T_CUDA(cudaMemcpyAsync(out, stage_out, n * sizeof(double), cudaMemcpyDeviceToHost, stream));
+    B2T_CUDA(cudaStreamSynchronize(stream));
+    return 0;
+  }
+};
+}  // namespace
+
+struct b2t_solver { SolverBase* impl; };
+
+extern "C" {
+int b2t_abi_version(void) { return B2T_ABI_VERSION; }
+const char* b2t_model_name(void) { return B2T_MODEL_NAME; }
+const char* b2t_model_digest(void) { return B2T_MODEL_DIGEST; }
+int b2t_model_dims(int* nq, int* nx, int* nu) {
+  if (nq) *nq = b2t::NQ;
+  if (nx) *nx = b2t::NX;
+  if (nu) *nu = b2t::NU;
+  return 0;
+}
+const char* b2t_last_error(void) { return g_err.c_str(); }
+void b2t_default_options(b2t_options* o) {
+  if (!o) return;
+  o->exit_tolerance_linSys = 1e-6; o->max_iter_linSys = 100;
+  o->exit_tolerance_SQP = 1e-6; o->max_iter_SQP = 100;
+  o->alpha_factor = 0.5; o->alpha_min = 0.005;
+  o->rho_factor = 4; o->rho_min = 1e-3; o->rho_max = 1e3; o->rho_init = 1e-3;
+  o->expected_reduction_min = 0.05; o->expected_reduction_max = 3;
+  o->exit_tolerance_soft = 1e-6; o->max_iter_soft = 10;
+  o->merit_mu = 10;
+}
+int b2t_solver_create(const b2t_problem_desc* desc, int device, b2t_solver** out) {
+  if (!desc || !out) return fail(B2T_ERR_INVALID, "desc and out required");
+  int ndev = 0;
+  if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0)
+    return fail(B2T_ERR_CUDA, "no CUDA device: this library has no CPU fallback");
+  if (device < 0 || device >= ndev) return fail(B2T_ERR_INVALID, "bad device index");
+  SolverBase* impl = nullptr;
+  if (desc->dtype == B2T_F64) impl = new SolverT<double>();
+  else if (desc->dtype == B2T_F32) impl = new SolverT<float>();
+  else return fail(B2T_ERR_INVALID, "dtype");
+  int r = impl->init(desc, device);
+  if (r) { delete impl; return r; }
+  *out = new b2t_solver{impl};
+  return 0;
+}
+int b2t_solver_destroy(b2t_solver* s) {
+  if (!s) return 0;
+  delete s->impl;
+  delete s;
+  return 0;
+}
+size_t b2t_workspace_bytes(const b2t_solver* s) { return s ? s->impl->ws_bytes : 0; }
+int b2t_set_stream(b2t_solver* s, void* st) { if (!s) return fail(B2T_ERR_INVALID, "null"); s->impl->stream = (cudaStream_t)st; return 0; }
+#define B2T_FWD(call) do { if (!s) return fail(B2T_ERR_INVALID, "null solver"); return s->impl->call; } while (0)
+int b2t_set_trajectory(b2t_solver* s, const double* x, const double* u, int od) { B2T_FWD(set_trajectory(x, u, od)); }
+int b2t_set_goals(b2t_solver* s, const double* xg, int od) { B2T_FWD(set_goals(xg, od)); }
+int b2t_set_initial_state(b2t_solver* s, const double* xs) { B2T_FWD(set_initial_state(xs)); }
+int b2t_set_multipliers(b2t_solver* s, const double* mu, const double* lam, const double* phi) { B2T_FWD(set_multipliers(mu, lam, phi)); }
+int b2t_reset_multipliers(b2t_solver* s) { B2T_FWD(reset_multipliers()); }
+int b2t_sqp_solve(b2t_solver* s, int method, const b2t_options* o) { B2T_FWD(solve(method, o)); }
+int b2t_get_trajectory(b2t_solver* s, double* x, double* u, int od) { B2T_FWD(get_trajectory(x, u, od)); }
+int b2t_get_status(b2t_solver* s, int* st) { B2T_FWD(get_status(st)); }
+int b2t_get_scalars(b2t_solver* s, double* sc) { B2T_FWD(get_scalars(sc)); }
+int b2t_get_trace(b2t_solver* s, double* tr, int cap) { B2T_FWD(get_trace(tr, cap)); }
+int b2t_get_multipliers(b2t_solver* s, double* mu, double* lam, double* phi) { B2T_FWD(get_multipliers(mu, lam, phi)); }
+int b2t_get_launch_stats(b2t_solver* s, long long* l, double* sec) {
+  if (!s) return fail(B2T_ERR_INVALID, "null solver");
+  if (l) *l = s->impl->launches;
+  if (sec) *sec = s->impl->device_seconds;
+  return 0;
+}
+int b2t_set_profiling(b2t_solver* s, int en) { if (!s) return fail(B2T_ERR_INVALID, "null solver"); s->impl->profiling = en != 0; return 0; }
+int b2t_get_kernel_times(b2t_solver* s, double* sec, long long* l) {
+  if (!s) return fail(B2T_ERR_INVALID, "null solver");
+  for (int i = 0; i < B2T_KERNEL_FAMILIES; ++i) { if (sec) sec[i] = s->impl->fam_seconds[i]; if (l) l[i] = s->impl->fam_launches[i]; }
+  return 0;
+}
+int b2t_sqp_solve_host(b2t_solver* s, const double* x0, const double* u0, const double* xg, int method, const b2t_options* o,
+                       double* xo, double* uo, int* st) { B2T_FWD(solve_host(x0, u0, xg, method, o, xo, uo, st)); }
+int b2t_stage_dynamics(b2t_solver* s) { B2T_FWD(stage_dynamics()); }
+int b2t_stage_kkt(b2t_solver* s, double rho, int method) { B2T_FWD(stage_kkt(rho, method)); }
+int b2t_stage_pcg(b2t_solver* s, int method, double tol, int mi, int* it) { B2T_FWD(stage_pcg(method, tol, mi, it)); }
+int b2t_stage_recover(b2t_solver* s) { B2T_FWD(stage_recover()); }
+int b2t_stage_merit(b2t_solver* s, double a, double* J, double* c, double* D) { B2T_FWD(stage_merit(a, J, c, D)); }
+int b2t_fetch(b2t_solver* s, int which, double* out) { B2T_FWD(fetch(which, out)); }
+}
