@@ -1,0 +1,364 @@
+#!/usr/bin/env python
+"""bench.py -- SQP-PCG MPC solves/sec (arm6, N=64), the metric of BASELINE.json.
+
+  python bench.py [--gpus N] [--steps K] [--warmup W] [--impl b200|reference]
+  python -m torch.distributed.run --nnodes=1 --nproc-per-node N --master-addr 127.0.0.1 --master-port P bench.py --gpus N ...
+
+Workload (BASELINE.json configs[3] / configs[4]): robot arm6 (well-formed 6-link planar chain), N=64 knot
+points, dt=0.1, Euler, joint-space QuadraticCost Q=I, QF=100I, R=0.1I, goals q_g ~ U(-0.5,0.5)^6 (seeded), quadratic-penalty box
+limits |u_i| <= 1.0 and |q_i| <= 0.45, method PCG-SS, expected_reduction_min=-100, start x=0, u=0.  One "step" = one batched SQP solve
+of `--batch` (default 8192) independent instances per GPU to termination.  N GPUs: independent instances sharded over ranks
+(weak scaling, 8192 per GPU, no data-path collective), one NCCL all-gather of the packed results at the end of each step.
+
+`value` = solves/s with inputs resident in HBM (CUDA events around the step, max over ranks); `e2e` = the same through
+b2t_sqp_solve_host with pinned HOST buffers (H2D of x0,u0,xg and D2H of x,u,status inside the timed region).
+--impl reference: the reference algorithm on the host CPU cores (oracle port: the reference itself is Python and absent on the GPU box).
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+N_KNOTS = 64
+DT = 0.1
+SOLVER_OPTS = {"expected_reduction_min_SQP_DDP": -100}
+U_LIM, Q_LIM = 1.0, 0.45
+METRIC = "SQP-PCG MPC solves/sec (arm6, N=64)"
+
+
+def goals(total, seed):
+    rng = np.random.default_rng(seed)
+    xg = np.zeros((total, 12))
+    xg[:, :6] = rng.uniform(-0.5, 0.5, (total, 6))
+    return xg
+
+
+def workload_goals(world, rank, batch):
+    """C4 (1 GPU, default_rng(1)) / C5 (N GPUs: default_rng(2), contiguous shards)."""
+    if world == 1:
+        return goals(batch, 1)
+    return goals(batch * world, 2)[rank * batch:(rank + 1) * batch]
+
+
+# ------------------------------------------------------------------------------------------------ flop model
+def flop_model(n, N):
+    nx, m = 2 * n, 3 * n
+    F_rnea = 415 * n
+    F_minv = 1051 * n + 92 * n * (n + 1)
+    F_rneagrad = 912 * n * n + 434 * n
+    F_fdgrad = 2 * F_rnea + F_minv + F_rneagrad + 4 * n ** 3 + 5 * n * n
+    F_fd = F_rnea + F_minv + 2 * n * n
+    F_cost = 10 * n * n
+    F_schur = 2 * m ** 3 + 2 * nx * m * m + 2 * nx * nx * m + 2 * m * m + 2 * nx * m
+    F_precond = 6 * nx ** 3
+    F_pcg_iter = 12 * nx * nx + 10 * nx
+    F_recover = 2 * m * m + 2 * m * nx
+    F_trial = F_fd + 2 * F_cost + 6 * nx
+    per_qp = {"fd": F_fd, "fd_grad": F_fdgrad - F_fd, "kkt": 2 * F_cost + 2 * m ** 3, "schur": F_schur - 2 * m ** 3 + F_precond,
+              "recover": F_recover}
+    return dict(N=N, per_qp=per_qp, pcg_iter=F_pcg_iter, trial_fd=F_fd, trial_merit=2 * F_cost + 6 * nx, F_trial=F_trial,
+                F_qp=F_fdgrad + 2 * F_cost + F_schur + F_precond + F_recover)
+
+
+def flops_of(fm, qp, pcg, trials, B):
+    """algorithmic flops of a batch from the measured per-instance counters (sums over instances)."""
+    N = fm["N"]
+    fam = {k: N * v * qp for k, v in fm["per_qp"].items()}
+    fam["fd"] += N * fm["trial_fd"] * B                  # initial violation evaluation
+    fam["pcg"] = N * fm["pcg_iter"] * pcg
+    fam["trial_fd"] = N * fm["trial_fd"] * trials
+    fam["merit"] = N * fm["trial_merit"] * (trials + B)
+    fam["ctrl"] = 0
+    return fam
+
+
+# ------------------------------------------------------------------------------------------------ clocks
+class ClockSampler(threading.Thread):
+    def __init__(self, index):
+        super().__init__(daemon=True)
+        self.index, self.stop_flag, self.rows = index, False, []
+
+    def run(self):
+        q = "clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown," \
+            "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap"
+        while not self.stop_flag:
+            try:
+                out = subprocess.run(["nvidia-smi", "-i", str(self.index), "--query-gpu=" + q, "--format=csv,noheader,nounits"],
+                                     capture_output=True, text=True, timeout=5).stdout.strip()
+                if out:
+                    self.rows.append([c.strip() for c in out.split(",")])
+            except Exception:
+                pass
+            time.sleep(0.2)
+
+    def summary(self):
+        if not self.rows:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["unsampled"]}
+        sm = sorted(float(r[0]) for r in self.rows if r[0].replace(".", "").isdigit())
+        reasons = []
+        for i, name in enumerate(["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]):
+            if any(len(r) > 3 + i and r[3 + i] == "Active" for r in self.rows):
+                reasons.append(name)
+        return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": float(self.rows[0][1]) if self.rows[0][1].replace(".", "").isdigit() else None,
+                "reasons": reasons, "samples": len(self.rows)}
+
+
+# ------------------------------------------------------------------------------------------------ CPU arms (oracle port)
+def _oracle_problem(use_limits):
+    from oracle import rbd, cost as ocost, constraint as ocons
+    with open(os.path.join(ROOT, "tests", "golden", "models.json")) as f:
+        model = rbd.Model(json.load(f)["arm6"])
+    c = ocost.QuadraticCost(np.eye(12), 100.0 * np.eye(12), 0.1 * np.eye(6), np.zeros(12))
+    cons = None
+    if use_limits:
+        cons = ocons.SoftConstraints(6, 6, 6, N_KNOTS)
+        cons.set_torque_limits([U_LIM], [-U_LIM], "QUADRATIC_PENALTY")
+        cons.set_joint_limits([Q_LIM], [-Q_LIM], "QUADRATIC_PENALTY")
+    return model, c, cons
+
+
+def _oracle_solve(args):
+    xg, use_limits = args
+    os.environ.setdefault("OMP_NUM_THREADS", "1")
+    from oracle import sqp
+    model, c, cons = _oracle_problem(use_limits)
+    c.xg = np.asarray(xg)
+    r = sqp.sqp(model, c, cons, np.zeros((12, N_KNOTS)), np.zeros((6, N_KNOTS - 1)), N_KNOTS, DT, "PCG-SS", dict(SOLVER_OPTS))
+    return r["J"], len(r["pcg_iters"]), sum(r["pcg_iters"]), sum(r["ls_trials"])
+
+
+def cpu_baseline_port(xg, use_limits, budget_s=20.0, max_instances=8):
+    """Oracle port, 1 process, sequential over the first instances of the workload until ~budget_s of CPU work."""
+    t0 = time.perf_counter()
+    done = 0
+    for b in range(min(max_instances, len(xg))):
+        _oracle_solve((xg[b], use_limits))
+        done += 1
+        if time.perf_counter() - t0 > budget_s:
+            break
+    el = time.perf_counter() - t0
+    return {"value": done / el, "unit": "solves/s", "cores": 1, "kind": "port",
+            "sample": "first %d instances of the workload, sequential, numpy oracle (oracle/sqp.py), %.1f s" % (done, el)}
+
+
+def run_reference_arm(args):
+    """--impl reference: the reference's algorithm on all host cores (multiprocessing.Pool over instances, the reference's own
+    fan-out pattern, examples/test_multiple.py:127).  Rank 0 only."""
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    import multiprocessing as mp
+    cores = os.cpu_count() or 1
+    xg = workload_goals(args.gpus, 0, args.batch)
+    S = min(len(xg), cores)
+    sample = [(xg[b], bool(args.limits)) for b in range(S)]
+    ctx = mp.get_context("fork")
+    times = []
+    with ctx.Pool(cores) as pool:
+        for step in range(args.warmup + args.steps):
+            t0 = time.perf_counter()
+            pool.map(_oracle_solve, sample, chunksize=1)
+            el = time.perf_counter() - t0
+            if step >= args.warmup:
+                times.append(el)
+    total = sum(times)
+    value = S * args.steps / total
+    line = {"metric": METRIC, "value": value, "unit": "solves/s", "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
+            "ms_per_step": 1e3 * total / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64",
+            "data": "synthetic", "impl": "reference",
+            "config": config_dict(args, note="CPU arm: each step solves the first %d instances of the workload" % S),
+            "cpu_baseline": {"value": value, "unit": "solves/s", "cores": cores, "kind": "port",
+                             "sample": "first %d instances per step, multiprocessing.Pool(%d), numpy oracle (oracle/sqp.py)" % (S, cores)},
+            "e2e": {"value": value, "unit": "solves/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+            "gpu_launches": 0}
+    print(json.dumps(line))
+
+
+def config_dict(args, note=None):
+    c = {"workload": "C4/C5: arm6 (6-link planar chain) SQP PCG-SS, N=64, dt=0.1, euler, QuadraticCost Q=I QF=100I R=0.1I, "
+                     "goals U(-0.5,0.5)^6 seeded, %s, batch %d per GPU" %
+                     ("quadratic-penalty box limits |u|<=1.0 |q|<=0.45" if args.limits else "no box limits", args.batch),
+         "batch_per_gpu": args.batch, "knots": N_KNOTS, "method": "PCG-SS", "limits": bool(args.limits),
+         "l2": "per-step working set (>4 GB workspace) exceeds the 126 MB L2; no explicit flush"}
+    if note:
+        c["note"] = note
+    return c
+
+
+# ------------------------------------------------------------------------------------------------ GPU arm
+def run_b200_arm(args):
+    import torch
+    import torch.distributed as dist
+    import trajoptmpcreference_b200 as t
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py needs a CUDA device (no CPU fallback)")
+    torch.cuda.set_device(local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+    B, N = args.batch, N_KNOTS
+    xg_np = workload_goals(world, rank, B)
+
+    plant = t.URDFPlant(options={"path_to_urdf": "arm6"})
+    cost = t.QuadraticCost(np.eye(12), 100.0 * np.eye(12), 0.1 * np.eye(6), np.zeros(12))
+    cons = None
+    if args.limits:
+        cons = t.TrajoptConstraint(6, 6, 6, N)
+        cons.set_torque_limits([U_LIM], [-U_LIM], "QUADRATIC_PENALTY", {})
+        cons.set_joint_limits([Q_LIM], [-Q_LIM], "QUADRATIC_PENALTY", {})
+    solver = t.BatchSolver(plant, cost, cons, N=N, dt=DT, batch=B, dtype=args.dtype, device=local)
+    method = t.SQPSolverMethods.PCG_SS
+    dev = torch.device("cuda", local)
+    x0 = torch.zeros((B, 12, N), dtype=torch.float64, device=dev)
+    u0 = torch.zeros((B, 6, N - 1), dtype=torch.float64, device=dev)
+    xg = torch.from_numpy(xg_np).to(dev)
+    xo = torch.empty_like(x0); uo = torch.empty_like(u0)
+    pack_w = 12 * N + 6 * (N - 1)
+    packed = torch.empty((B, pack_w), dtype=torch.float64, device=dev)
+    gathered = torch.empty((world * B, pack_w), dtype=torch.float64, device=dev) if world > 1 else None
+
+    def step_device():
+        if cons is not None:
+            solver.reset_multipliers()
+        solver.set_goals(xg)
+        solver.set_trajectory(x0, u0)
+        solver.solve(method, SOLVER_OPTS)
+        solver.get_trajectory(xo, uo)
+        if world > 1:
+            packed[:, :12 * N] = xo.reshape(B, -1)
+            packed[:, 12 * N:] = uo.reshape(B, -1)
+            dist.all_gather_into_tensor(gathered, packed)
+
+    # pinned host buffers for the end-to-end leg
+    hx0 = torch.zeros((B, 12, N), dtype=torch.float64).pin_memory(); hu0 = torch.zeros((B, 6, N - 1), dtype=torch.float64).pin_memory()
+    hxg = torch.from_numpy(xg_np.copy()).pin_memory()
+    hxo = torch.empty((B, 12, N), dtype=torch.float64).pin_memory(); huo = torch.empty((B, 6, N - 1), dtype=torch.float64).pin_memory()
+    hst = torch.empty((B, 8), dtype=torch.int32).pin_memory()
+
+    def step_host():
+        if cons is not None:
+            solver.reset_multipliers()
+        solver.solve_host(hx0.numpy(), hu0.numpy(), hxg.numpy(), hxo.numpy(), huo.numpy(), hst.numpy(), method, SOLVER_OPTS)
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def timed(fn, steps, profile=False):
+        ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(steps)]
+        fam_acc, launches = {}, 0
+        barrier()
+        t0 = time.perf_counter()
+        for a, b in ev:
+            a.record()
+            fn()
+            b.record()
+            n, _ = solver.launch_stats()
+            launches += n
+            if profile:
+                for k, (sec, cnt) in solver.kernel_times().items():
+                    s0, c0 = fam_acc.get(k, (0.0, 0))
+                    fam_acc[k] = (s0 + sec, c0 + cnt)
+        barrier()
+        wall = time.perf_counter() - t0
+        ms = sum(a.elapsed_time(b) for a, b in ev)
+        tt = torch.tensor([ms], dtype=torch.float64, device=dev)
+        if world > 1:
+            dist.all_reduce(tt, op=dist.ReduceOp.MAX)
+        return float(tt.item()) * 1e-3, wall, fam_acc, launches
+
+    for _ in range(max(args.warmup, 3)):
+        step_device()
+    sampler = ClockSampler(local)
+    sampler.start()
+    solver.set_profiling(True)
+    sec, wall, fam, launches = timed(step_device, args.steps, profile=True)
+    solver.set_profiling(False)
+    sampler.stop_flag = True
+    r = solver.result()
+    # end-to-end leg
+    step_host()
+    sec_e2e, _, _, _ = timed(step_host, args.steps)
+    sampler.join(timeout=2)
+
+    total_solves = B * world * args.steps
+    value = total_solves / sec
+    qp, pcg, trials = int(r.total_qp.sum()), int(r.total_pcg.sum()), int(r.total_trials.sum())
+    fm = flop_model(6, N)
+    fam_flops = flops_of(fm, qp, pcg, trials, B)
+    total_flops = sum(fam_flops.values())
+    if rank == 0:
+        peak64 = solver.measure_fma_peak(args.dtype)
+        try:
+            with open(os.path.join(ROOT, "MEASURED_PEAKS.json")) as f:
+                peaks = json.load(f)
+            hbm_peak, hbm_src = float(peaks["hbm_gbs"]), "measured (MEASURED_PEAKS.json)"
+        except Exception:
+            hbm_peak, hbm_src = 6650.0, "fallback (B200_PROFILING.md)"
+        step_sec = sec / args.steps
+        fam_sec = {k: v[0] / args.steps for k, v in fam.items()}
+        dom = max(fam_sec, key=lambda k: fam_sec[k]) if fam_sec else "pcg"
+        dom_sec = fam_sec.get(dom, step_sec)
+        dom_launch = fam[dom][1] / args.steps if fam else 1
+        ach = fam_flops[dom] / dom_sec / 1e12 if dom_sec > 0 else 0.0
+        alg_bytes = B * (2 * 8 * (12 * N + 6 * (N - 1)) + 8 * 12 + 64)
+        roof = {"bound": "fp64_fma" if args.dtype == "f64" else "fp32_fma", "kernel": "k_" + dom, "achieved": ach, "peak": peak64, "unit": "TFLOP/s",
+                "frac": ach / peak64 if peak64 else None, "traffic": None,
+                "peak_source": "measured in this run: DFMA chain micro-benchmark b2t_measure_fma_peak (MEASURED_PEAKS.json has no fp64 entry)",
+                "algorithmic_flops_per_launch": fam_flops[dom] / max(dom_launch, 1), "avg_launch_ms": 1e3 * dom_sec / max(dom_launch, 1),
+                "launches_per_step": dom_launch, "share_of_step": dom_sec / step_sec,
+                "whole_step": {"achieved": total_flops / step_sec / 1e12, "frac": total_flops / step_sec / 1e12 / peak64 if peak64 else None,
+                               "algorithmic_flops_per_solve": total_flops / B},
+                "hbm": {"algorithmic_bytes_per_step": alg_bytes, "achieved_gbs": alg_bytes / step_sec / 1e9, "peak_gbs": hbm_peak, "peak_source": hbm_src,
+                        "note": "compulsory traffic only (x0,u0,xg in; x,u,status out): the path is FMA-bound, not HBM-bound"},
+                "kernel_seconds_per_step": fam_sec,
+                "kernel_tflops": {k: (fam_flops[k] / fam_sec[k] / 1e12 if fam_sec.get(k, 0) > 0 else None) for k in fam_flops}}
+        h2d = (hx0.numel() + hu0.numel() + hxg.numel()) * 8
+        d2h = (hxo.numel() + huo.numel()) * 8 + hst.numel() * 4
+        line = {"metric": METRIC, "value": value, "unit": "solves/s", "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3),
+                "ms_per_step": 1e3 * sec / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": args.dtype,
+                "data": "synthetic", "config": config_dict(args), "clocks": sampler.summary(),
+                "e2e": {"value": total_solves / sec_e2e, "unit": "solves/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h},
+                "gpu_launches": launches, "roofline": roof,
+                "iterations": {"qp_solves_per_instance": qp / B, "pcg_iters_per_instance": pcg / B, "ls_trials_per_instance": trials / B,
+                               "exit_sqp_hist": np.bincount(r.exit_sqp, minlength=4).tolist(), "exit_soft_hist": np.bincount(r.exit_soft, minlength=4).tolist()},
+                "host_wall_s": wall, "workspace_gb": solver.workspace_bytes / 1e9}
+        if world == 1 and not args.no_cpu_baseline:
+            line["cpu_baseline"] = cpu_baseline_port(xg_np, bool(args.limits))
+        print(json.dumps(line))
+    if world > 1:
+        dist.barrier()
+        dist.destroy_process_group()
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=3)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--batch", type=int, default=8192)
+    ap.add_argument("--dtype", default="f64", choices=["f64", "f32"])
+    ap.add_argument("--limits", type=int, default=1)
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    if args.impl == "reference":
+        run_reference_arm(args)
+    else:
+        run_b200_arm(args)
+
+
+if __name__ == "__main__":
+    main()

@@ -160,6 +160,10 @@ int b2t_stage_recover(b2t_solver* s);
 int b2t_stage_merit(b2t_solver* s, double alpha, double* J, double* c, double* D /* [batch] host each */);
 int b2t_fetch(b2t_solver* s, int which, double* out);
 
+/* roofline denominator: measured FMA throughput of the device's fp64 (dtype 0) or fp32 (dtype 1) pipe in TFLOP/s
+ * (148 SMs x resident blocks of independent FMA chains, CUDA-event timed, best of 5) */
+int b2t_measure_fma_peak(int device, int dtype, double* tflops);
+
 #ifdef __cplusplus
 }
 #endif

@@ -77,13 +77,26 @@ def test_kkt_schur_pcg_recover_merit(tag, batch, oracle_models):
         it = s.stage_pcg(method)
         l_or, trace = kkt.pcg(sch["Sd"], sch["So"], sch["gamma"], Pd, Po)
         if kind != "J":
-            assert it.tolist() == [len(trace) - 1] * batch, (kind, it, len(trace) - 1)
+            # the exit test |nu| < 1e-6 is a threshold on a rounding-sensitive quantity: on this random (non-converged)
+            # trajectory the count may differ by one, and then only if the oracle's |nu| sits at the threshold there
             assert len(trace) == len(K["%s/trace_%s" % (tag, kind)])
+            assert len(set(it.tolist())) == 1
+            dif = int(it[0]) - (len(trace) - 1)
+            assert abs(dif) <= 1, (kind, it, len(trace) - 1)
+            if dif != 0:
+                assert 0.25e-6 < trace[min(int(it[0]), len(trace) - 1)] < 4e-6, (kind, it, trace[-3:])
             s.stage_recover()
             dz_or = kkt.recover(blocks, sch, l_or, nx)
-            for b in range(batch):
-                assert np.max(np.abs(s.fetch("l")[b] - l_or)) < 1e-5 * max(1.0, np.max(np.abs(l_or)))
-                assert np.max(np.abs(s.fetch("dz")[b] - dz_or)) < 1e-5 * max(1.0, np.max(np.abs(dz_or)))
+            for b in range(batch):      # PCG stops at |r^T Pinv r| < 1e-6 (absolute): the iterate is only that accurate
+                assert np.max(np.abs(s.fetch("l")[b] - l_or)) < 2e-3 * max(1.0, np.max(np.abs(l_or)))
+                assert np.max(np.abs(s.fetch("dz")[b] - dz_or)) < 2e-3 * max(1.0, np.max(np.abs(dz_or)))
+            # converged PCG (tolerance far below rounding): the kernel must reach the exact solution of S l = gamma
+            s.stage_pcg(method, tol=1e-26, max_iter=100)
+            s.stage_recover()
+            l_ex = kkt.bt_solve_dense(sch["Sd"], sch["So"], sch["gamma"])
+            dz_ex = kkt.recover(blocks, sch, l_ex, nx)
+            assert np.max(np.abs(s.fetch("l")[0] - l_ex)) < 1e-7 * max(1.0, np.max(np.abs(l_ex)))
+            assert np.max(np.abs(s.fetch("dz")[batch - 1] - dz_ex)) < 1e-7 * max(1.0, np.max(np.abs(dz_ex)))
     # merit terms of the trial point x - alpha dz (dz from the last recover = BJ): compare with the oracle on the SAME dz
     s.stage_kkt(rho, t.SQPSolverMethods.PCG_SS); s.stage_pcg(t.SQPSolverMethods.PCG_SS); s.stage_recover()
     dz = s.fetch("dz")[0]

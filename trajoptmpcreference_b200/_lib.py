@@ -68,6 +68,7 @@ _SIGNATURES = {
     "b2t_stage_recover": (c_int, [c_void_p]),
     "b2t_stage_merit": (c_int, [c_void_p, c_double, c_void_p, c_void_p, c_void_p]),
     "b2t_fetch": (c_int, [c_void_p, c_int, c_void_p]),
+    "b2t_measure_fma_peak": (c_int, [c_int, c_int, _DP]),
 }
 
 

@@ -245,7 +245,7 @@ class UrdfCost(QuadraticCost):
             raise ValueError("UrdfCost is defined for 2-joint robots only (RBDReference.py:263)")
         self.plant = plant
         self.n = plant.get_num_pos()
-        self.offsets = [np.matrix([[0, 1, 0, 1]])]
+        self.offsets = [np.array([[0, 1, 0, 1]])]
         self.plant.rbdReference.overloading = overloading
         self.overloading = overloading
         self.hess_mode = 0
@@ -586,6 +586,12 @@ class BatchSolver:
         J = np.zeros(self.batch); c = np.zeros(self.batch); D = np.zeros(self.batch)
         _lib.check(self.lib, self.lib.b2t_stage_merit(self._h, float(alpha), _dptr(J), _dptr(c), _dptr(D)))
         return J, c, D
+
+    def measure_fma_peak(self, dtype="f64"):
+        """Measured FMA throughput (TFLOP/s) of this GPU's fp64 / fp32 pipe: the roofline denominator of the path."""
+        v = ctypes.c_double()
+        _lib.check(self.lib, self.lib.b2t_measure_fma_peak(self.device, {"f64": _lib.F64, "f32": _lib.F32}[dtype], ctypes.byref(v)))
+        return float(v.value)
 
     def fetch(self, name):
         """Knot-major copy of an internal array: (batch, N, elems)."""

@@ -534,6 +534,46 @@ struct SolverT : SolverBase {
 };
 }  // namespace
 
+template <typename T>
+__global__ void __launch_bounds__(256) k_fma_peak(T* out, int iters, T a, T b) {
+  T acc[16];
+#pragma unroll
+  for (int i = 0; i < 16; ++i) acc[i] = (T)(threadIdx.x + i);
+  for (int it = 0; it < iters; ++it) {
+#pragma unroll
+    for (int i = 0; i < 16; ++i) acc[i] = acc[i] * a + b;
+  }
+  T s = 0;
+#pragma unroll
+  for (int i = 0; i < 16; ++i) s += acc[i];
+  if (s == (T)123456789) out[0] = s;     // never true: keeps the chain alive
+}
+template <typename T>
+int fma_peak(int device, double* tflops) {
+  B2T_CUDA(cudaSetDevice(device));
+  cudaDeviceProp prop;
+  B2T_CUDA(cudaGetDeviceProperties(&prop, device));
+  T* out = nullptr;
+  B2T_CUDA(cudaMalloc(&out, sizeof(T)));
+  cudaEvent_t e0, e1;
+  B2T_CUDA(cudaEventCreate(&e0)); B2T_CUDA(cudaEventCreate(&e1));
+  const int blocks = prop.multiProcessorCount * 8, threads = 256, iters = 4096;
+  double best = 0;
+  for (int rep = 0; rep < 6; ++rep) {
+    B2T_CUDA(cudaEventRecord(e0));
+    k_fma_peak<T><<<blocks, threads>>>(out, iters, (T)0.999999, (T)1e-9);
+    B2T_CUDA(cudaEventRecord(e1));
+    B2T_CUDA(cudaEventSynchronize(e1));
+    float ms = 0;
+    B2T_CUDA(cudaEventElapsedTime(&ms, e0, e1));
+    const double flops = 2.0 * 16 * (double)iters * threads * blocks;
+    if (rep > 0) best = std::max(best, flops / (ms * 1e-3) / 1e12);
+  }
+  cudaEventDestroy(e0); cudaEventDestroy(e1); cudaFree(out);
+  *tflops = best;
+  return 0;
+}
+
 struct b2t_solver { SolverBase* impl; };
 
 extern "C" {
@@ -612,4 +652,10 @@ int b2t_stage_pcg(b2t_solver* s, int method, double tol, int mi, int* it) { B2T_
 int b2t_stage_recover(b2t_solver* s) { B2T_FWD(stage_recover()); }
 int b2t_stage_merit(b2t_solver* s, double a, double* J, double* c, double* D) { B2T_FWD(stage_merit(a, J, c, D)); }
 int b2t_fetch(b2t_solver* s, int which, double* out) { B2T_FWD(fetch(which, out)); }
+int b2t_measure_fma_peak(int device, int dtype, double* tflops) {
+  if (!tflops) return fail(B2T_ERR_INVALID, "tflops required");
+  int ndev = 0;
+  if (cudaGetDeviceCount(&ndev) != cudaSuccess || device < 0 || device >= ndev) return fail(B2T_ERR_CUDA, "no such CUDA device");
+  return dtype == B2T_F32 ? fma_peak<float>(device, tflops) : fma_peak<double>(device, tflops);
+}
 }
