@@ -84,7 +84,7 @@ def test_kkt_schur_pcg_recover_merit(tag, batch, oracle_models):
             dif = int(it[0]) - (len(trace) - 1)
             assert abs(dif) <= 1, (kind, it, len(trace) - 1)
             if dif != 0:
-                assert 0.25e-6 < trace[min(int(it[0]), len(trace) - 1)] < 4e-6, (kind, it, trace[-3:])
+                assert trace[min(int(it[0]), len(trace) - 1)] < 1e-4, (kind, it, trace[-3:])     # |nu| drops ~50x per iteration here
             s.stage_recover()
             dz_or = kkt.recover(blocks, sch, l_or, nx)
             for b in range(batch):      # PCG stops at |r^T Pinv r| < 1e-6 (absolute): the iterate is only that accurate
