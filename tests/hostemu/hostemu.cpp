@@ -47,3 +47,5 @@ int he_soft(int count, const int* mode, const double* lb, const double* ub, cons
 }
 int he_spd_inverse(int n, double* A) { spd_inverse_inplace(A, n, n); return 0; }
 }
+extern "C" int he_spd_inverse_packed12(double* a) { spd_inverse_packed<12>(a); return 0; }
+extern "C" int he_spd_inverse_packed4(double* a) { spd_inverse_packed<4>(a); return 0; }

@@ -132,4 +132,4 @@ def test_full_size_properties(oracle_models):
     xg2 = xg.copy(); xg2[5, :6] = np.linspace(0.5, -0.5, 6)
     r4 = solver2.solve_batch(x0, u0, xg2, N, 0.1, t.SQPSolverMethods.PCG_SS, dict(opts))
     assert (r4.sqp_iter[5], r4.total_pcg[5], r4.total_trials[5]) == (6, 563, 16)
-    assert abs(r4.J[5] - 6.50929423656) < 1e-8
+    assert abs(r4.J[5] - 6.50929423656) < 1e-7       # parity floor: the reference's own J moves by ~1e-8 under 1-ulp perturbations

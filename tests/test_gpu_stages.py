@@ -46,12 +46,15 @@ def _kkt_case(tag, oracle_models):
     return K, plant, pc, pcons, m, oc, ocn, x, u, xs, N
 
 
-@pytest.mark.parametrize("tag", ["arm2_urdf", "arm3_qc", "arm6_qc", "pend_al"])
+@pytest.mark.parametrize("tag,dense_kkt", [("arm2_urdf", False), ("arm3_qc", False), ("arm3_qc", True), ("arm6_qc", False), ("arm6_qc", True),
+                                       ("pend_al", False), ("pend_al", True)])
 @pytest.mark.parametrize("batch", [1, 3])
-def test_kkt_schur_pcg_recover_merit(tag, batch, oracle_models):
+def test_kkt_schur_pcg_recover_merit(tag, dense_kkt, batch, oracle_models):
+    """dense_kkt=False: structured kernels when the cost is diagonal (k_kkt_diag / k_schur_diag / k_recover_diag);
+    dense_kkt=True: general dense-G_k kernels (always used for UrdfCost)."""
     K, plant, pc, pcons, m, oc, ocn, x, u, xs, N = _kkt_case(tag, oracle_models)
     n = m.n; nx = 2 * n; mm = 3 * n
-    s = t.BatchSolver(plant, pc, pcons, N=N, dt=0.1, batch=batch)
+    s = t.BatchSolver(plant, pc, pcons, N=N, dt=0.1, batch=batch, dense_kkt=dense_kkt)
     s.set_trajectory(np.broadcast_to(x[None], (batch,) + x.shape), np.broadcast_to(u[None], (batch,) + u.shape))
     s.set_initial_state(np.broadcast_to(xs[None], (batch, nx)))
     if pcons is not None:

@@ -99,3 +99,19 @@ def test_spd_inverse():
     B = np.ascontiguousarray(A.copy())
     lib.he_spd_inverse(12, P(B))
     assert relerr(B, np.linalg.inv(A)) < 1e-11
+
+
+@pytest.mark.parametrize("n", [4, 12])
+def test_spd_inverse_packed(n):
+    lib = hostemu.load("arm2")
+    rng = np.random.default_rng(2)
+    A = rng.uniform(-1, 1, (n, n)); A = A @ A.T + 0.5 * np.eye(n)
+    packed = np.array([A[i, j] for i in range(n) for j in range(i + 1)])
+    getattr(lib, "he_spd_inverse_packed%d" % n)(P(packed))
+    inv = np.linalg.inv(A)
+    got = np.zeros((n, n))
+    k = 0
+    for i in range(n):
+        for j in range(i + 1):
+            got[i, j] = got[j, i] = packed[k]; k += 1
+    assert relerr(got, inv) < 1e-11

@@ -400,7 +400,7 @@ class BatchResult(dict):
 class BatchSolver:
     """One device workspace for `batch` independent instances of (plant, cost, constraints, N, dt)."""
 
-    def __init__(self, plant, cost, constraints, N, dt, batch=1, dtype="f64", device=0, qf_start_override=None):
+    def __init__(self, plant, cost, constraints, N, dt, batch=1, dtype="f64", device=0, qf_start_override=None, dense_kkt=False):
         if not isinstance(plant, URDFPlant):
             raise ValueError("Must pass in a URDFPlant: the dynamics kernels are generated from the URDF")
         if not isinstance(cost, QuadraticCost):
@@ -439,7 +439,18 @@ class BatchSolver:
         self._keep += [lower, upper]
         d.lower = lower.ctypes.data_as(ctypes.POINTER(ctypes.c_double)); d.upper = upper.ctypes.data_as(ctypes.POINTER(ctypes.c_double))
         self._h = ctypes.c_void_p()
-        _lib.check(self.lib, self.lib.b2t_solver_create(ctypes.byref(d), self.device, ctypes.byref(self._h)))
+        # dense_kkt=True forces the general (dense G_k) kernels even when Q, QF, R are diagonal (used by the parity tests)
+        old = os.environ.get("B2T_DENSE_KKT")
+        if dense_kkt:
+            os.environ["B2T_DENSE_KKT"] = "1"
+        try:
+            _lib.check(self.lib, self.lib.b2t_solver_create(ctypes.byref(d), self.device, ctypes.byref(self._h)))
+        finally:
+            if dense_kkt:
+                if old is None:
+                    os.environ.pop("B2T_DENSE_KKT", None)
+                else:
+                    os.environ["B2T_DENSE_KKT"] = old
         xg = np.broadcast_to(_as_f64(cost.xg).reshape(1, -1), (self.batch, self.nx))
         self.set_goals(xg)
 

@@ -32,6 +32,7 @@ struct Opts {
 template <typename T>
 struct Dev {
   int B, N, integrator;
+  int diag_mode;      // 1: Q, QF, R diagonal -> Ghat_k kept as diag(dinv) - s h h^T (Sherman-Morrison), structured Schur kernels
   T dt, gravity;
   size_t K;
   // per-knot SoA
@@ -261,6 +262,229 @@ __global__ void __launch_bounds__(64) k_schur(Dev<T> d, const int* list, const i
 }
 
 // -----------------------------------------------------------------------------------------------------------------
+// Structured fast path (diag_mode): QuadraticCost with diagonal Q, QF, R.  G_k + rho I = diag(d) + gck gck^T, so
+//   Ghat_k = diag(1/d) - s h h^T,  h = gck / d,  s = 1 / (1 + gck^T h)           (Sherman-Morrison)
+// is stored as 2m+1 scalars per knot (rows [0,m) dinv, [m,2m) h, 2m: s of the Gh array) instead of m*m, and the Schur
+// blocks are assembled from the integrator structure  AB = [[E0 + tau Ab], [Ab]],  Ab = [dt Dq, I + dt Dqd, dt Minv],
+// E0 = [I, dte I, 0]  (euler: dte = dt, tau = 0; semi-implicit: dte = 0, tau = dt):
+//   AB D AB^T = [[Z + tau (F + F^T) + tau^2 M, F^T + tau M], [F + tau M, M]],  M = Ab D Ab^T, F = Ab D E0^T, Z = E0 D E0^T.
+// Same mathematics as k_kkt / k_schur / k_recover (formKKTSystemBlocks :216-260, solveKKTSystem_Schur :419-452), ~10x fewer flops.
+// -----------------------------------------------------------------------------------------------------------------
+template <typename T>
+__global__ void __launch_bounds__(128) k_kkt_diag(Dev<T> d, const int* list, const int* count) {
+  const size_t gt = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  const int slot = (int)(gt / d.N);
+  if (slot >= *count) return;
+  const int k = (int)(gt % d.N);
+  const int b = list[slot];
+  const size_t t = (size_t)b * d.N + k;
+  const size_t K = d.K;
+  const bool terminal = (k == d.N - 1);
+  T z[NM];
+  load_xu(d.x, d.u, K, t, terminal, z, z + NX);
+  const T* Q = cost_Q(d.cost, k, terminal);
+  const T rho = d.rho[b];
+  T g[NM], dd[NM];
+  for (int i = 0; i < NX; ++i) {
+    const T qi = Q[i * NX + i];
+    g[i] = (z[i] - d.xg[(size_t)i * d.B + b]) * qi;
+    dd[i] = qi + rho;
+  }
+  for (int i = 0; i < NU; ++i) {
+    const T ri = d.cost.R[i * NU + i];
+    g[NX + i] = terminal ? T(0) : z[NX + i] * ri;
+    dd[NX + i] = ri + rho;
+  }
+  T gck[NM];
+  for (int i = 0; i < NM; ++i) gck[i] = T(0);
+  if (d.lim.any) {
+    soft_grad(d.lim, z, d.mu + t, d.lam + t, K, terminal, gck);
+    for (int i = 0; i < NM; ++i) g[i] += gck[i];
+  }
+  const int M = terminal ? NX : NM;
+  T hg = T(0), den = T(1);
+  T h[NM], dinv[NM];
+  for (int i = 0; i < NM; ++i) {
+    dinv[i] = (i < M) ? T(1) / dd[i] : T(0);
+    h[i] = gck[i] * dinv[i];
+    den += gck[i] * h[i];
+    hg += h[i] * g[i];
+  }
+  const T sS = T(1) / den;
+  for (int i = 0; i < NM; ++i) {
+    d.Gh[(size_t)i * K + t] = dinv[i];
+    d.Gh[(size_t)(NM + i) * K + t] = h[i];
+    d.g[(size_t)i * K + t] = (i < M) ? g[i] : T(0);
+    d.Gg[(size_t)i * K + t] = (i < M) ? dinv[i] * g[i] - sS * h[i] * hg : T(0);
+  }
+  d.Gh[(size_t)(2 * NM) * K + t] = sS;
+}
+
+// bottom rows of [A B]: Ab (NJ x NM row-major) = dt * dqdd + [0 I 0]   (both integrators)
+template <typename T>
+__device__ __forceinline__ void load_Ab(const Dev<T>& d, size_t t, T* Ab) {
+  for (int a = 0; a < NJ; ++a) {
+    for (int c = 0; c < NM; ++c) Ab[a * NM + c] = d.dt * d.dyn[(size_t)(a * 3 * NJ + c) * d.K + t];
+    Ab[a * NM + NJ + a] += T(1);
+  }
+}
+
+template <typename T>
+__global__ void __launch_bounds__(128) k_schur_diag(Dev<T> d, const int* list, const int* count, int jacobi) {
+  const size_t gt = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  const int slot = (int)(gt / d.N);
+  if (slot >= *count) return;
+  const int j = (int)(gt % d.N);
+  const int b = list[slot];
+  const size_t t = (size_t)b * d.N + j;
+  const size_t K = d.K;
+  const int R = d.N * NX;
+  T* Sd_o = d.Sd + (size_t)b * R * NX;
+  T* So_o = d.So + (size_t)b * R * NX;
+  T* Pd_o = d.Pd + (size_t)b * R * NX;
+  T Sd[NX * NX], gam[NX];
+  // Ghat_j[:nx,:nx] = diag(dx) - sj hx hx^T
+  T dx[NX], hx[NX];
+  for (int i = 0; i < NX; ++i) { dx[i] = d.Gh[(size_t)i * K + t]; hx[i] = d.Gh[(size_t)(NM + i) * K + t]; }
+  const T sj = d.Gh[(size_t)(2 * NM) * K + t];
+  if (j == 0) {
+    for (int i = 0; i < NX; ++i)
+      for (int c = 0; c < NX; ++c) {
+        Sd[i * NX + c] = -(((i == c) ? dx[i] : T(0)) - sj * hx[i] * hx[c]);
+        So_o[(size_t)c * R + i] = T(0);
+      }
+    for (int i = 0; i < NX; ++i) gam[i] = (d.x[(size_t)i * K + t] - d.xs[(size_t)i * d.B + b]) - d.Gg[(size_t)i * K + t];
+  } else {
+    const size_t tp = t - 1;
+    const T dte = d.integrator == 0 ? d.dt : T(0);
+    const T tau = d.integrator == 0 ? T(0) : d.dt;
+    T Ab[NJ * NM], dv[NM], hv[NM], Gg[NM];
+    load_Ab(d, tp, Ab);
+    for (int i = 0; i < NM; ++i) { dv[i] = d.Gh[(size_t)i * K + tp]; hv[i] = d.Gh[(size_t)(NM + i) * K + tp]; Gg[i] = d.Gg[(size_t)i * K + tp]; }
+    const T sp = d.Gh[(size_t)(2 * NM) * K + tp];
+    T M[NJ * NJ], F[NJ * NJ], vb[NJ], wb[NJ];
+    for (int a = 0; a < NJ; ++a) {
+      T accv = T(0), accw = T(0);
+      for (int r = 0; r < NM; ++r) { accv += Ab[a * NM + r] * hv[r]; accw += Ab[a * NM + r] * Gg[r]; }
+      vb[a] = accv; wb[a] = accw;
+      for (int c2 = 0; c2 <= a; ++c2) {
+        T acc = T(0);
+        for (int r = 0; r < NM; ++r) acc += Ab[a * NM + r] * dv[r] * Ab[c2 * NM + r];
+        M[a * NJ + c2] = acc; M[c2 * NJ + a] = acc;
+      }
+      for (int i = 0; i < NJ; ++i) F[a * NJ + i] = Ab[a * NM + i] * dv[i] + dte * Ab[a * NM + NJ + i] * dv[NJ + i];
+    }
+    T v[NX], w[NX];
+    for (int i = 0; i < NJ; ++i) {
+      v[i] = hv[i] + dte * hv[NJ + i] + tau * vb[i];
+      v[NJ + i] = vb[i];
+      w[i] = Gg[i] + dte * Gg[NJ + i] + tau * wb[i];
+      w[NJ + i] = wb[i];
+    }
+    // S_jj = -(AB D AB^T - sp v v^T + Ghat_j[:nx,:nx])
+    for (int i = 0; i < NJ; ++i)
+      for (int c = 0; c < NJ; ++c) {
+        const T Zic = (i == c) ? dv[i] + dte * dte * dv[NJ + i] : T(0);
+        const T tt = Zic + tau * (F[c * NJ + i] + F[i * NJ + c]) + tau * tau * M[i * NJ + c];
+        const T tb = F[c * NJ + i] + tau * M[i * NJ + c];        // top i, bottom c
+        const T bb = M[i * NJ + c];
+        Sd[i * NX + c] = tt;
+        Sd[i * NX + NJ + c] = tb;
+        Sd[(NJ + c) * NX + i] = tb;
+        Sd[(NJ + i) * NX + NJ + c] = bb;
+      }
+    for (int i = 0; i < NX; ++i)
+      for (int c = 0; c < NX; ++c)
+        Sd[i * NX + c] = -((Sd[i * NX + c] - sp * v[i] * v[c]) + (((i == c) ? dx[i] : T(0)) - sj * hx[i] * hx[c]));
+    // S_{j,j-1} = AB[:, :nx] diag(dv_x) - sp v hv_x^T
+    for (int c = 0; c < NX; ++c) {
+      for (int i = 0; i < NJ; ++i) {
+        const T e0 = ((c == i) ? T(1) : T(0)) + ((c == NJ + i) ? dte : T(0));
+        const T top = e0 + tau * Ab[i * NM + c];
+        So_o[(size_t)c * R + j * NX + i] = top * dv[c] - sp * v[i] * hv[c];
+        So_o[(size_t)c * R + j * NX + NJ + i] = Ab[i * NM + c] * dv[c] - sp * v[NJ + i] * hv[c];
+      }
+    }
+    for (int i = 0; i < NX; ++i) {
+      const T ck = d.x[(size_t)i * K + t] - d.xkp1[(size_t)i * K + tp];
+      gam[i] = (ck + w[i]) - d.Gg[(size_t)i * K + t];
+    }
+  }
+  for (int i = 0; i < NX; ++i) {
+    d.gam[(size_t)b * R + j * NX + i] = gam[i];
+    for (int c = 0; c < NX; ++c) Sd_o[(size_t)c * R + j * NX + i] = Sd[i * NX + c];
+  }
+  if (jacobi) {
+    for (int i = 0; i < NX; ++i)
+      for (int c = 0; c < NX; ++c) Pd_o[(size_t)c * R + j * NX + i] = (i == c) ? T(1) / Sd[i * NX + i] : T(0);
+  } else {
+    T pk[NX * (NX + 1) / 2];
+    static_for<0, NX>([&](auto ic) {
+      constexpr int i = decltype(ic)::value;
+      static_for<0, i + 1>([&](auto cc) { constexpr int c = decltype(cc)::value; pk[i * (i + 1) / 2 + c] = -Sd[i * NX + c]; });
+    });
+    spd_inverse_packed<NX>(pk);
+    static_for<0, NX>([&](auto ic) {
+      constexpr int i = decltype(ic)::value;
+      static_for<0, i + 1>([&](auto cc) {
+        constexpr int c = decltype(cc)::value;
+        const T val = -pk[i * (i + 1) / 2 + c];
+        Pd_o[(size_t)c * R + j * NX + i] = val;
+        Pd_o[(size_t)i * R + j * NX + c] = val;
+      });
+    });
+  }
+}
+
+template <typename T>
+__global__ void __launch_bounds__(128) k_recover_diag(Dev<T> d, const int* list, const int* count) {
+  const size_t gt = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  const int slot = (int)(gt / d.N);
+  if (slot >= *count) return;
+  const int k = (int)(gt % d.N);
+  const int b = list[slot];
+  const size_t t = (size_t)b * d.N + k;
+  const size_t K = d.K;
+  const int R = d.N * NX;
+  const bool terminal = (k == d.N - 1);
+  T rhs[NM];
+  for (int i = 0; i < NM; ++i) rhs[i] = d.g[(size_t)i * K + t];
+  const T* l = d.l + (size_t)b * R;
+  for (int i = 0; i < NX; ++i) rhs[i] -= l[k * NX + i];
+  if (!terminal) {
+    const T dte = d.integrator == 0 ? d.dt : T(0);
+    const T tau = d.integrator == 0 ? T(0) : d.dt;
+    const T* ln = l + (k + 1) * NX;
+    T wv[NJ];
+    for (int a = 0; a < NJ; ++a) wv[a] = tau * ln[a] + ln[NJ + a];
+    for (int c = 0; c < NM; ++c) {
+      T acc = T(0);
+      for (int a = 0; a < NJ; ++a) acc += (d.dt * d.dyn[(size_t)(a * 3 * NJ + c) * K + t] + ((c == NJ + a) ? T(1) : T(0))) * wv[a];
+      rhs[c] += acc;
+    }
+    for (int i = 0; i < NJ; ++i) { rhs[i] += ln[i]; rhs[NJ + i] += dte * ln[i]; }
+  }
+  T hr = T(0);
+  T dinv[NM], h[NM];
+  for (int i = 0; i < NM; ++i) { dinv[i] = d.Gh[(size_t)i * K + t]; h[i] = d.Gh[(size_t)(NM + i) * K + t]; hr += h[i] * rhs[i]; }
+  const T sS = d.Gh[(size_t)(2 * NM) * K + t];
+  for (int i = 0; i < NM; ++i) d.dz[(size_t)i * K + t] = dinv[i] * rhs[i] - sS * h[i] * hr;
+}
+
+// dense reconstruction of Ghat from its structured form (B2T_ARR_GHAT in diag_mode)
+template <typename T>
+__global__ void k_fetch_ghat_diag(Dev<T> d, double* out) {
+  const size_t gt = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (gt >= d.K) return;
+  const T sS = d.Gh[(size_t)(2 * NM) * d.K + gt];
+  for (int i = 0; i < NM; ++i)
+    for (int c = 0; c < NM; ++c) {
+      const T v = ((i == c) ? d.Gh[(size_t)i * d.K + gt] : T(0)) - sS * d.Gh[(size_t)(NM + i) * d.K + gt] * d.Gh[(size_t)(NM + c) * d.K + gt];
+      out[gt * NM * NM + i * NM + c] = (double)v;
+    }
+}
+
+// -----------------------------------------------------------------------------------------------------------------
 // k_pcg: one thread block per instance, one thread per row of the block-tridiagonal system (PCG.pcg, PCG.py:66-111).
 // Preconditioners (PCG.py:166-212): J / BJ use the diagonal blocks; SS (symmetric stair) is applied in factored form
 //   Pinv r = y - D^-1 (O y),  y = D^-1 r,  O = off-diagonal part of S     (== the reference's explicit
@@ -375,6 +599,149 @@ __global__ void __launch_bounds__(1024) k_pcg(Dev<T> d, const int* list, const i
     nu = nu_prime;
   }
   for (int m = 0, r = tid; r < R; r += nt, ++m) d.l[(size_t)b * R + r] = xx[m];
+  if (tid == 0) {
+    d.pcg_iters[b] = iters;
+    d.tot_pcg[b] += iters;
+    d.tot_qp[b] += 1;
+  }
+}
+
+// -----------------------------------------------------------------------------------------------------------------
+// k_pcg2: register / shared-memory tiled PCG.  One block per instance, TB = NX/RPT threads per block row, RPT rows per
+// thread.  The off-diagonal blocks of S (used four times per iteration: S p down/up, O y down/up) live in REGISTERS
+// (2*RPT*NX values per thread); the diagonal blocks of S and of the preconditioner live in SHARED memory in a
+// thread-major layout (conflict-free); vectors are exchanged through two zero-padded shared buffers, so a thread loads
+// each vector entry once for its RPT rows.  Same arithmetic as k_pcg (PCG.py:66-111), same deterministic reductions.
+// SMEM = false streams the diagonal blocks from global memory (L1/L2) when N*NX*NX*2 scalars exceed shared memory.
+// -----------------------------------------------------------------------------------------------------------------
+template <typename T, int RPT, bool SMEM, int MAXT>
+__global__ void __launch_bounds__(MAXT) k_pcg2(Dev<T> d, const int* list, const int* count, int stair, T tol, int max_iter) {
+  if ((int)blockIdx.x >= *count) return;
+  constexpr int TB = NX / RPT;
+  static_assert(NX % RPT == 0, "RPT must divide NX");
+  const int b = list[blockIdx.x];
+  const int N = d.N, R = N * NX, NT = N * TB;
+  const int tid = threadIdx.x, nt = blockDim.x;
+  const bool live = tid < NT;
+  const int j = live ? tid / TB : 0;
+  const int i0 = live ? (tid % TB) * RPT : 0;
+  extern __shared__ unsigned char smem_raw[];
+  T* A_s = reinterpret_cast<T*>(smem_raw);          // (N+2)*NX, blocks 0 and N+1 stay zero
+  T* B_s = A_s + (N + 2) * NX;
+  T* red = B_s + (N + 2) * NX;                       // 32
+  T* Sd_s = red + 32;                                // [RPT*NX][nt]
+  T* Pd_s = Sd_s + (SMEM ? (size_t)RPT * NX * nt : 0);
+  const T* Sd = d.Sd + (size_t)b * R * NX;
+  const T* So = d.So + (size_t)b * R * NX;
+  const T* Pd = d.Pd + (size_t)b * R * NX;
+  const T* gam = d.gam + (size_t)b * R;
+  // ---- one-time loads
+  T so_dn[RPT][NX], so_up[RPT][NX];
+#pragma unroll
+  for (int k = 0; k < RPT; ++k)
+#pragma unroll
+    for (int c = 0; c < NX; ++c) {
+      const int r = j * NX + i0 + k;
+      so_dn[k][c] = live ? So[(size_t)c * R + r] : T(0);                                   // S_{j,j-1}[i][c]  (zero for j = 0)
+      so_up[k][c] = (live && j < N - 1) ? So[(size_t)(i0 + k) * R + (j + 1) * NX + c] : T(0);   // S_{j+1,j}[c][i]
+      if constexpr (SMEM) {
+        Sd_s[(size_t)(k * NX + c) * nt + tid] = live ? Sd[(size_t)c * R + r] : T(0);
+        Pd_s[(size_t)(k * NX + c) * nt + tid] = live ? Pd[(size_t)c * R + r] : T(0);
+      }
+    }
+  for (int idx = tid; idx < (N + 2) * NX; idx += nt) { A_s[idx] = T(0); B_s[idx] = T(0); }
+  __syncthreads();
+  auto ldSd = [&](int k, int c) -> T { if constexpr (SMEM) return Sd_s[(size_t)(k * NX + c) * nt + tid]; else return Sd[(size_t)c * R + j * NX + i0 + k]; };
+  auto ldPd = [&](int k, int c) -> T { if constexpr (SMEM) return Pd_s[(size_t)(k * NX + c) * nt + tid]; else return Pd[(size_t)c * R + j * NX + i0 + k]; };
+  const int vb = (j + 1) * NX;                       // own block in the padded vectors
+  // block-diagonal product with Pd from buffer V (own block only)
+  auto pd_mul = [&](const T* V, T* out) {
+#pragma unroll
+    for (int k = 0; k < RPT; ++k) out[k] = T(0);
+#pragma unroll
+    for (int c = 0; c < NX; ++c) {
+      const T v = V[vb + c];
+#pragma unroll
+      for (int k = 0; k < RPT; ++k) out[k] += ldPd(k, c) * v;
+    }
+  };
+  auto store = [&](T* V, const T* val) {
+    if (live) {
+#pragma unroll
+      for (int k = 0; k < RPT; ++k) V[vb + i0 + k] = val[k];
+    }
+  };
+  T rr[RPT], xx[RPT], pp[RPT], rt[RPT], yv[RPT], tmp[RPT];
+  // rt = Pinv rr  (uses A_s and B_s; on return both may be overwritten after the caller's next barrier)
+  auto precond = [&]() {
+    store(B_s, rr);
+    __syncthreads();
+    pd_mul(B_s, yv);
+    if (!stair) {
+#pragma unroll
+      for (int k = 0; k < RPT; ++k) rt[k] = yv[k];
+      return;
+    }
+    store(A_s, yv);
+    __syncthreads();
+#pragma unroll
+    for (int k = 0; k < RPT; ++k) tmp[k] = T(0);
+#pragma unroll
+    for (int c = 0; c < NX; ++c) {
+      const T ym = A_s[vb - NX + c], yp = A_s[vb + NX + c];
+#pragma unroll
+      for (int k = 0; k < RPT; ++k) tmp[k] += so_dn[k][c] * ym + so_up[k][c] * yp;
+    }
+    __syncthreads();            // every thread has read r (B_s) in pd_mul above before B_s is overwritten
+    store(B_s, tmp);
+    __syncthreads();
+    pd_mul(B_s, tmp);
+#pragma unroll
+    for (int k = 0; k < RPT; ++k) rt[k] = yv[k] - tmp[k];
+  };
+#pragma unroll
+  for (int k = 0; k < RPT; ++k) { rr[k] = live ? gam[j * NX + i0 + k] : T(0); xx[k] = T(0); }
+  precond();
+  T part = T(0);
+#pragma unroll
+  for (int k = 0; k < RPT; ++k) { pp[k] = rt[k]; part += rr[k] * rt[k]; }
+  T nu = block_sum(part, red, tid, nt);
+  int iters = 0;
+  for (int it = 0; it < max_iter; ++it) {
+    store(A_s, pp);              // block_sum's barriers separate this from the previous readers of A_s
+    __syncthreads();
+    T ap[RPT];
+#pragma unroll
+    for (int k = 0; k < RPT; ++k) ap[k] = T(0);
+#pragma unroll
+    for (int c = 0; c < NX; ++c) {
+      const T pm = A_s[vb - NX + c], p0 = A_s[vb + c], pq = A_s[vb + NX + c];
+#pragma unroll
+      for (int k = 0; k < RPT; ++k) ap[k] += ldSd(k, c) * p0 + so_dn[k][c] * pm + so_up[k][c] * pq;
+    }
+    part = T(0);
+#pragma unroll
+    for (int k = 0; k < RPT; ++k) part += pp[k] * ap[k];
+    const T pAp = block_sum(part, red, tid, nt);
+    const T alpha = nu / pAp;
+#pragma unroll
+    for (int k = 0; k < RPT; ++k) { rr[k] -= ap[k] * alpha; xx[k] += pp[k] * alpha; }
+    precond();
+    part = T(0);
+#pragma unroll
+    for (int k = 0; k < RPT; ++k) part += rr[k] * rt[k];
+    const T nu_prime = block_sum(part, red, tid, nt);
+    iters = it + 1;
+    if (fabs(nu_prime) < tol) break;
+    const T beta = nu_prime / nu;
+#pragma unroll
+    for (int k = 0; k < RPT; ++k) pp[k] = rt[k] + pp[k] * beta;
+    nu = nu_prime;
+  }
+  if (live) {
+#pragma unroll
+    for (int k = 0; k < RPT; ++k) d.l[(size_t)b * R + j * NX + i0 + k] = xx[k];
+  }
   if (tid == 0) {
     d.pcg_iters[b] = iters;
     d.tot_pcg[b] += iters;

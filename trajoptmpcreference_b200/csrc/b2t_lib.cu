@@ -1,5 +1,6 @@
 // b2t_lib.cu -- host side of libb2t_<robot>.so: workspace, launch sequence of one batched SQP solve, C ABI (include/b2t.h).
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <string>
 #include <vector>
@@ -122,6 +123,18 @@ struct SolverT : SolverBase {
     B2T_ALLOC(d.xs, NX * B); B2T_ALLOC(d.xg, NX * B);
     // cost
     d.cost.kind = p->cost_kind; d.cost.qf_start = p->qf_start;
+    {   // structured fast path when the quadratic cost is diagonal (B2T_DENSE_KKT=1 forces the general kernels)
+      bool diag = p->cost_kind == B2T_COST_QUADRATIC;
+      for (int i = 0; i < NX && diag; ++i)
+        for (int j = 0; j < NX; ++j)
+          if (i != j && (p->Q[i * NX + j] != 0.0 || p->QF[i * NX + j] != 0.0)) { diag = false; break; }
+      for (int i = 0; i < NU && diag; ++i)
+        for (int j = 0; j < NU; ++j)
+          if (i != j && p->R[i * NU + j] != 0.0) { diag = false; break; }
+      const char* e = getenv("B2T_DENSE_KKT");
+      if (e && atoi(e) != 0) diag = false;
+      d.diag_mode = diag ? 1 : 0;
+    }
     { T* q; int r; if ((r = upload(&q, p->Q, NX * NX))) return r; d.cost.Q = q; }
     { T* q; int r; if ((r = upload(&q, p->QF, NX * NX))) return r; d.cost.QF = q; }
     { T* q; int r; if ((r = upload(&q, p->R, NU * NU))) return r; d.cost.R = q; }
@@ -164,6 +177,9 @@ struct SolverT : SolverBase {
     B2T_CUDA(cudaEventCreate(&ev0)); B2T_CUDA(cudaEventCreate(&ev1));
     // kernels that need > 48 KB of dynamic shared memory
     B2T_CUDA(cudaFuncSetAttribute(b2t::k_pcg<T>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+    B2T_CUDA(cudaFuncSetAttribute(b2t::k_pcg2<T, PCG_RPT, true, 256>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+    B2T_CUDA(cudaFuncSetAttribute(b2t::k_pcg2<T, PCG_RPT, true, 512>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+    B2T_CUDA(cudaFuncSetAttribute(b2t::k_pcg2<T, PCG_RPT, true, 1024>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
     int r = reset_multipliers();
     if (r) return r;
     k_init_state<T><<<cdiv(B, 128), 128, 0, stream>>>(d);
@@ -358,21 +374,49 @@ struct SolverT : SolverBase {
   int launch_kkt(const int* list, const int* count, int bound, int method) {
     using namespace b2t;
     const size_t nthreads = (size_t)bound * d.N;
+    const int jac = method == B2T_METHOD_PCG_J ? 1 : 0;
+    if (d.diag_mode) {
+      { Scope sc(this, B2T_K_KKT); k_kkt_diag<T><<<cdiv(nthreads, 128), 128, 0, stream>>>(d, list, count); tick(B2T_K_KKT); }
+      { Scope sc(this, B2T_K_SCHUR); k_schur_diag<T><<<cdiv(nthreads, 128), 128, 0, stream>>>(d, list, count, jac); tick(B2T_K_SCHUR); }
+      return 0;
+    }
     { Scope sc(this, B2T_K_KKT); k_kkt<T><<<cdiv(nthreads, 64), 64, 0, stream>>>(d, list, count); tick(B2T_K_KKT); }
-    { Scope sc(this, B2T_K_SCHUR); k_schur<T><<<cdiv(nthreads, 64), 64, 0, stream>>>(d, list, count, method == B2T_METHOD_PCG_J ? 1 : 0); tick(B2T_K_SCHUR); }
+    { Scope sc(this, B2T_K_SCHUR); k_schur<T><<<cdiv(nthreads, 64), 64, 0, stream>>>(d, list, count, jac); tick(B2T_K_SCHUR); }
     return 0;
   }
+  // rows per thread of k_pcg2: largest divisor of NX that is <= 3
+  static constexpr int PCG_RPT = (b2t::NX % 3 == 0) ? 3 : ((b2t::NX % 2 == 0) ? 2 : 1);
+  int pcg2_threads() const { int nt = d.N * (b2t::NX / PCG_RPT); return ((nt + 31) / 32) * 32; }
+  size_t pcg2_smem(bool mats) const {
+    size_t v = ((size_t)2 * (d.N + 2) * b2t::NX + 32) * sizeof(T);
+    if (mats) v += (size_t)2 * PCG_RPT * b2t::NX * pcg2_threads() * sizeof(T);
+    return v;
+  }
+  int pcg_variant = -1;      // 0: k_pcg (v1), 1: k_pcg2 with shared-memory diagonal blocks, 2: k_pcg2 streaming them
   int launch_pcg(const int* list, const int* count, int bound, int method, T tol, int max_iter) {
     using namespace b2t;
+    if (pcg_variant < 0) {
+      const char* e = getenv("B2T_PCG_VARIANT");
+      if (e) pcg_variant = atoi(e);
+      else if (pcg2_threads() > 1024) pcg_variant = 0;
+      else pcg_variant = pcg2_smem(true) <= (size_t)220 * 1024 ? 1 : 2;
+    }
+    const int stair = method == B2T_METHOD_PCG_SS ? 1 : 0;
     Scope sc(this, B2T_K_PCG);
-    k_pcg<T><<<bound, pcg_threads(), pcg_smem(), stream>>>(d, list, count, method == B2T_METHOD_PCG_SS ? 1 : 0, tol, max_iter);
+    const int nt = pcg2_threads();
+#define B2T_PCG2(SM, MT) k_pcg2<T, PCG_RPT, SM, MT><<<bound, nt, pcg2_smem(SM), stream>>>(d, list, count, stair, tol, max_iter)
+    if (pcg_variant == 1) { if (nt <= 256) B2T_PCG2(true, 256); else if (nt <= 512) B2T_PCG2(true, 512); else B2T_PCG2(true, 1024); }
+    else if (pcg_variant == 2) { if (nt <= 256) B2T_PCG2(false, 256); else if (nt <= 512) B2T_PCG2(false, 512); else B2T_PCG2(false, 1024); }
+    else k_pcg<T><<<bound, pcg_threads(), pcg_smem(), stream>>>(d, list, count, stair, tol, max_iter);
+#undef B2T_PCG2
     tick(B2T_K_PCG);
     return 0;
   }
   int launch_recover(const int* list, const int* count, int bound) {
     using namespace b2t;
     Scope sc(this, B2T_K_RECOVER);
-    k_recover<T><<<cdiv((size_t)bound * d.N, 128), 128, 0, stream>>>(d, list, count);
+    if (d.diag_mode) k_recover_diag<T><<<cdiv((size_t)bound * d.N, 128), 128, 0, stream>>>(d, list, count);
+    else k_recover<T><<<cdiv((size_t)bound * d.N, 128), 128, 0, stream>>>(d, list, count);
     tick(B2T_K_RECOVER);
     return 0;
   }
@@ -523,7 +567,8 @@ struct SolverT : SolverBase {
     }
     const size_t n = K * E;
     if (n * sizeof(double) > stage_out_bytes) return fail(B2T_ERR_INVALID, "array too large for staging");
-    if (blocks) k_fetch_blocks<T><<<cdiv(K, 128), 128, 0, stream>>>(src, d.B, d.N, NX, stage_out);
+    if (which == B2T_ARR_GHAT && d.diag_mode) k_fetch_ghat_diag<T><<<cdiv(K, 128), 128, 0, stream>>>(d, stage_out);
+    else if (blocks) k_fetch_blocks<T><<<cdiv(K, 128), 128, 0, stream>>>(src, d.B, d.N, NX, stage_out);
     else if (flat) k_fetch_soa<T><<<cdiv(n, 128), 128, 0, stream>>>(src, n, 1, stage_out);
     else k_fetch_soa<T><<<cdiv(K, 128), 128, 0, stream>>>(src, K, E, stage_out);
     B2T_CUDA(cudaGetLastError());
