@@ -614,68 +614,103 @@ __global__ void __launch_bounds__(1024) k_pcg(Dev<T> d, const int* list, const i
 // each vector entry once for its RPT rows.  Same arithmetic as k_pcg (PCG.py:66-111), same deterministic reductions.
 // SMEM = false streams the diagonal blocks from global memory (L1/L2) when N*NX*NX*2 scalars exceed shared memory.
 // -----------------------------------------------------------------------------------------------------------------
-template <typename T, int RPT, bool SMEM, int MAXT>
+template <typename T, int RPT, int CS, bool SMEM, int MAXT>
 __global__ void __launch_bounds__(MAXT) k_pcg2(Dev<T> d, const int* list, const int* count, int stair, T tol, int max_iter) {
   if ((int)blockIdx.x >= *count) return;
-  constexpr int TB = NX / RPT;
-  static_assert(NX % RPT == 0, "RPT must divide NX");
+  // thread (j, g, h): block row j, rows i0 = g*RPT .. i0+RPT-1, columns c0 = h*NXC .. c0+NXC-1 of every 1 x NX row slice.
+  // CS = 2 halves the registers per thread (more resident warps, room for the compiler to pipeline loads); the CS partial
+  // sums of a row are combined with one butterfly shuffle.
+  constexpr int TB = NX / RPT;                      // row groups per block row
+  constexpr int TBC = TB * CS;                      // threads per block row (all in one warp)
+  constexpr int NXC = NX / CS;                      // columns per thread
+  static_assert(NX % RPT == 0 && NX % CS == 0 && NXC % 2 == 0, "tile shape");
+  static_assert(32 % TBC == 0, "the threads of a block row must share a warp");
+  static_assert(CS == 1 || CS == 2, "column split");
   const int b = list[blockIdx.x];
-  const int N = d.N, R = N * NX, NT = N * TB;
+  const int N = d.N, R = N * NX, NT = N * TBC;
   const int tid = threadIdx.x, nt = blockDim.x;
   const bool live = tid < NT;
-  const int j = live ? tid / TB : 0;
-  const int i0 = live ? (tid % TB) * RPT : 0;
+  const int j = live ? tid / TBC : 0;
+  const int i0 = live ? ((tid % TBC) / CS) * RPT : 0;
+  const int h = tid % CS;
+  const int c0 = h * NXC;
+  const bool lead = live && h == 0;                  // the lane that stores / contributes to dot products
   extern __shared__ unsigned char smem_raw[];
-  T* A_s = reinterpret_cast<T*>(smem_raw);          // (N+2)*NX, blocks 0 and N+1 stay zero
-  T* B_s = A_s + (N + 2) * NX;
-  T* red = B_s + (N + 2) * NX;                       // 32
-  T* Sd_s = red + 32;                                // [RPT*NX][nt]
-  T* Pd_s = Sd_s + (SMEM ? (size_t)RPT * NX * nt : 0);
+  const int VL = (N + 2) * NX;                       // padded vector length: blocks 0 and N+1 stay zero
+  T* A_s = reinterpret_cast<T*>(smem_raw);          // neighbour exchange (p, y)
+  T* B_s = A_s + VL;                                 // own-block exchange (r)
+  T* C_s = B_s + VL;                                 // own-block exchange (O y)
+  T* red = C_s + VL;                                 // 32
+  // diagonal blocks: [RPT][NXC/2][MAXT] pairs (columns c, c+1 of this thread's slice) -> one 128-bit load per pair, conflict-free
+  using T2 = typename std::conditional<sizeof(T) == 8, double2, float2>::type;
+  T2* Sd_s = reinterpret_cast<T2*>(red + 32);
+  T2* Pd_s = Sd_s + (SMEM ? (size_t)RPT * (NXC / 2) * MAXT : 0);
   const T* Sd = d.Sd + (size_t)b * R * NX;
   const T* So = d.So + (size_t)b * R * NX;
   const T* Pd = d.Pd + (size_t)b * R * NX;
   const T* gam = d.gam + (size_t)b * R;
-  // ---- one-time loads
-  T so_dn[RPT][NX], so_up[RPT][NX];
+  // ---- one-time loads: off-diagonal blocks into registers, diagonal blocks into shared memory
+  T so_dn[RPT][NXC], so_up[RPT][NXC];
 #pragma unroll
   for (int k = 0; k < RPT; ++k)
 #pragma unroll
-    for (int c = 0; c < NX; ++c) {
+    for (int cc = 0; cc < NXC; ++cc) {
       const int r = j * NX + i0 + k;
-      so_dn[k][c] = live ? So[(size_t)c * R + r] : T(0);                                   // S_{j,j-1}[i][c]  (zero for j = 0)
-      so_up[k][c] = (live && j < N - 1) ? So[(size_t)(i0 + k) * R + (j + 1) * NX + c] : T(0);   // S_{j+1,j}[c][i]
+      const int c = c0 + cc;
+      so_dn[k][cc] = live ? So[(size_t)c * R + r] : T(0);                                        // S_{j,j-1}[i][c]  (zero for j = 0)
+      so_up[k][cc] = (live && j < N - 1) ? So[(size_t)(i0 + k) * R + (j + 1) * NX + c] : T(0);   // S_{j+1,j}[c][i]
       if constexpr (SMEM) {
-        Sd_s[(size_t)(k * NX + c) * nt + tid] = live ? Sd[(size_t)c * R + r] : T(0);
-        Pd_s[(size_t)(k * NX + c) * nt + tid] = live ? Pd[(size_t)c * R + r] : T(0);
+        if (cc % 2 == 0) {
+          T2 sv, pv;
+          sv.x = live ? Sd[(size_t)c * R + r] : T(0); sv.y = live ? Sd[(size_t)(c + 1) * R + r] : T(0);
+          pv.x = live ? Pd[(size_t)c * R + r] : T(0); pv.y = live ? Pd[(size_t)(c + 1) * R + r] : T(0);
+          Sd_s[(k * (NXC / 2) + cc / 2) * MAXT + tid] = sv;
+          Pd_s[(k * (NXC / 2) + cc / 2) * MAXT + tid] = pv;
+        }
       }
     }
-  for (int idx = tid; idx < (N + 2) * NX; idx += nt) { A_s[idx] = T(0); B_s[idx] = T(0); }
+  for (int idx = tid; idx < 3 * VL; idx += nt) A_s[idx] = T(0);
   __syncthreads();
-  auto ldSd = [&](int k, int c) -> T { if constexpr (SMEM) return Sd_s[(size_t)(k * NX + c) * nt + tid]; else return Sd[(size_t)c * R + j * NX + i0 + k]; };
-  auto ldPd = [&](int k, int c) -> T { if constexpr (SMEM) return Pd_s[(size_t)(k * NX + c) * nt + tid]; else return Pd[(size_t)c * R + j * NX + i0 + k]; };
+  // pair (cc, cc+1) of this thread's column slice, cc even
+  auto ldSd2 = [&](int k, int cc) -> T2 {
+    if constexpr (SMEM) return Sd_s[(k * (NXC / 2) + cc / 2) * MAXT + tid];
+    else { T2 v; v.x = Sd[(size_t)(c0 + cc) * R + j * NX + i0 + k]; v.y = Sd[(size_t)(c0 + cc + 1) * R + j * NX + i0 + k]; return v; }
+  };
+  auto ldPd2 = [&](int k, int cc) -> T2 {
+    if constexpr (SMEM) return Pd_s[(k * (NXC / 2) + cc / 2) * MAXT + tid];
+    else { T2 v; v.x = Pd[(size_t)(c0 + cc) * R + j * NX + i0 + k]; v.y = Pd[(size_t)(c0 + cc + 1) * R + j * NX + i0 + k]; return v; }
+  };
+  auto ldV2 = [&](const T* V, int idx) -> T2 { return *reinterpret_cast<const T2*>(V + idx); };   // idx even -> 16-byte aligned
+  auto combine = [&](T v) -> T {
+    if constexpr (CS == 2) v += __shfl_xor_sync(0xffffffffu, v, 1);
+    return v;
+  };
   const int vb = (j + 1) * NX;                       // own block in the padded vectors
-  // block-diagonal product with Pd from buffer V (own block only)
+  // out = Pd_jj * V[own block]; the block's entries were written by lanes of this warp (-> __syncwarp suffices)
   auto pd_mul = [&](const T* V, T* out) {
+    T o0[RPT], o1[RPT];
 #pragma unroll
-    for (int k = 0; k < RPT; ++k) out[k] = T(0);
+    for (int k = 0; k < RPT; ++k) { o0[k] = T(0); o1[k] = T(0); }
 #pragma unroll
-    for (int c = 0; c < NX; ++c) {
-      const T v = V[vb + c];
+    for (int cc = 0; cc < NXC; cc += 2) {
+      const T2 v = ldV2(V, vb + c0 + cc);
 #pragma unroll
-      for (int k = 0; k < RPT; ++k) out[k] += ldPd(k, c) * v;
+      for (int k = 0; k < RPT; ++k) { const T2 m2 = ldPd2(k, cc); o0[k] += m2.x * v.x; o1[k] += m2.y * v.y; }
     }
+#pragma unroll
+    for (int k = 0; k < RPT; ++k) out[k] = combine(o0[k] + o1[k]);
   };
   auto store = [&](T* V, const T* val) {
-    if (live) {
+    if (lead) {
 #pragma unroll
       for (int k = 0; k < RPT; ++k) V[vb + i0 + k] = val[k];
     }
   };
   T rr[RPT], xx[RPT], pp[RPT], rt[RPT], yv[RPT], tmp[RPT];
-  // rt = Pinv rr  (uses A_s and B_s; on return both may be overwritten after the caller's next barrier)
+  // rt = Pinv rr.  Block barriers: one (stair only), before the neighbour reads of y.
   auto precond = [&]() {
     store(B_s, rr);
-    __syncthreads();
+    __syncwarp();
     pd_mul(B_s, yv);
     if (!stair) {
 #pragma unroll
@@ -684,18 +719,23 @@ __global__ void __launch_bounds__(MAXT) k_pcg2(Dev<T> d, const int* list, const 
     }
     store(A_s, yv);
     __syncthreads();
+    T t1[RPT], t2[RPT];
 #pragma unroll
-    for (int k = 0; k < RPT; ++k) tmp[k] = T(0);
+    for (int k = 0; k < RPT; ++k) { t1[k] = T(0); t2[k] = T(0); }
 #pragma unroll
-    for (int c = 0; c < NX; ++c) {
-      const T ym = A_s[vb - NX + c], yp = A_s[vb + NX + c];
+    for (int cc = 0; cc < NXC; cc += 2) {
+      const T2 ym = ldV2(A_s, vb - NX + c0 + cc), yp = ldV2(A_s, vb + NX + c0 + cc);
 #pragma unroll
-      for (int k = 0; k < RPT; ++k) tmp[k] += so_dn[k][c] * ym + so_up[k][c] * yp;
+      for (int k = 0; k < RPT; ++k) {
+        t1[k] += so_dn[k][cc] * ym.x; t2[k] += so_up[k][cc] * yp.x;
+        t1[k] += so_dn[k][cc + 1] * ym.y; t2[k] += so_up[k][cc + 1] * yp.y;
+      }
     }
-    __syncthreads();            // every thread has read r (B_s) in pd_mul above before B_s is overwritten
-    store(B_s, tmp);
-    __syncthreads();
-    pd_mul(B_s, tmp);
+#pragma unroll
+    for (int k = 0; k < RPT; ++k) tmp[k] = combine(t1[k] + t2[k]);
+    store(C_s, tmp);
+    __syncwarp();
+    pd_mul(C_s, tmp);
 #pragma unroll
     for (int k = 0; k < RPT; ++k) rt[k] = yv[k] - tmp[k];
   };
@@ -705,24 +745,28 @@ __global__ void __launch_bounds__(MAXT) k_pcg2(Dev<T> d, const int* list, const 
   T part = T(0);
 #pragma unroll
   for (int k = 0; k < RPT; ++k) { pp[k] = rt[k]; part += rr[k] * rt[k]; }
-  T nu = block_sum(part, red, tid, nt);
+  T nu = block_sum(lead ? part : T(0), red, tid, nt);   // its barriers also order the y reads above before the p store below
   int iters = 0;
   for (int it = 0; it < max_iter; ++it) {
-    store(A_s, pp);              // block_sum's barriers separate this from the previous readers of A_s
+    store(A_s, pp);
     __syncthreads();
-    T ap[RPT];
+    T a0[RPT], a1[RPT], a2[RPT], ap[RPT];
 #pragma unroll
-    for (int k = 0; k < RPT; ++k) ap[k] = T(0);
+    for (int k = 0; k < RPT; ++k) { a0[k] = T(0); a1[k] = T(0); a2[k] = T(0); }
 #pragma unroll
-    for (int c = 0; c < NX; ++c) {
-      const T pm = A_s[vb - NX + c], p0 = A_s[vb + c], pq = A_s[vb + NX + c];
+    for (int cc = 0; cc < NXC; cc += 2) {
+      const T2 pm = ldV2(A_s, vb - NX + c0 + cc), p0 = ldV2(A_s, vb + c0 + cc), pq = ldV2(A_s, vb + NX + c0 + cc);
 #pragma unroll
-      for (int k = 0; k < RPT; ++k) ap[k] += ldSd(k, c) * p0 + so_dn[k][c] * pm + so_up[k][c] * pq;
+      for (int k = 0; k < RPT; ++k) {
+        const T2 m2 = ldSd2(k, cc);
+        a0[k] += m2.x * p0.x; a1[k] += so_dn[k][cc] * pm.x; a2[k] += so_up[k][cc] * pq.x;
+        a0[k] += m2.y * p0.y; a1[k] += so_dn[k][cc + 1] * pm.y; a2[k] += so_up[k][cc + 1] * pq.y;
+      }
     }
     part = T(0);
 #pragma unroll
-    for (int k = 0; k < RPT; ++k) part += pp[k] * ap[k];
-    const T pAp = block_sum(part, red, tid, nt);
+    for (int k = 0; k < RPT; ++k) { ap[k] = combine(a0[k] + a1[k] + a2[k]); part += pp[k] * ap[k]; }
+    const T pAp = block_sum(lead ? part : T(0), red, tid, nt);     // barriers: all reads of p from A_s are complete
     const T alpha = nu / pAp;
 #pragma unroll
     for (int k = 0; k < RPT; ++k) { rr[k] -= ap[k] * alpha; xx[k] += pp[k] * alpha; }
@@ -730,7 +774,7 @@ __global__ void __launch_bounds__(MAXT) k_pcg2(Dev<T> d, const int* list, const 
     part = T(0);
 #pragma unroll
     for (int k = 0; k < RPT; ++k) part += rr[k] * rt[k];
-    const T nu_prime = block_sum(part, red, tid, nt);
+    const T nu_prime = block_sum(lead ? part : T(0), red, tid, nt);
     iters = it + 1;
     if (fabs(nu_prime) < tol) break;
     const T beta = nu_prime / nu;
@@ -738,7 +782,7 @@ __global__ void __launch_bounds__(MAXT) k_pcg2(Dev<T> d, const int* list, const 
     for (int k = 0; k < RPT; ++k) pp[k] = rt[k] + pp[k] * beta;
     nu = nu_prime;
   }
-  if (live) {
+  if (lead) {
 #pragma unroll
     for (int k = 0; k < RPT; ++k) d.l[(size_t)b * R + j * NX + i0 + k] = xx[k];
   }
@@ -966,6 +1010,139 @@ __global__ void k_merit(Dev<T> d, const int* list, const int* count, int* next_l
   }
 }
 
+// -----------------------------------------------------------------------------------------------------------------
+// k_linesearch: the whole backtracking line search of one SQP iteration (SQP :606-744) plus check_for_exit_or_error
+// (:463-481), one block per active instance, one thread per knot point.  Each trial: trial point x - alpha dz (kept
+// in registers), forward dynamics, cost / penalty / defect / directional-derivative terms per knot in parallel, then
+// thread 0 sums them in the reference's sequential order and decides accept / halve alpha / fail.  Replaces the
+// 2 x max_trials launches of k_fd<TRIAL> + k_merit and the k_sqp_ctrl launch.
+// smem: (5 + NX) * N scalars.
+// -----------------------------------------------------------------------------------------------------------------
+template <typename T>
+__global__ void __launch_bounds__(128) k_linesearch(Dev<T> d, Opts<T> o) {
+  if ((int)blockIdx.x >= *d.n_act) return;
+  const int b = d.act[blockIdx.x];
+  const int N = d.N;
+  const size_t K = d.K;
+  extern __shared__ unsigned char smem_raw[];
+  T* sm = reinterpret_cast<T*>(smem_raw);
+  T* s_cost = sm; T* s_soft = sm + N; T* s_c = sm + 2 * N; T* s_D = sm + 3 * N; T* s_Ds = sm + 4 * N; T* s_xn = sm + 5 * N;   // [N][NX]
+  __shared__ int s_state;     // 0: accepted, 1: try a smaller alpha, 2: failed
+  T alpha = T(1);
+  int ls = 0;
+  for (;;) {
+    for (int k = threadIdx.x; k < N; k += blockDim.x) {
+      const size_t t = (size_t)b * N + k;
+      const bool terminal = (k == N - 1);
+      T z[NM], dzk[NM], xg[NX];
+      load_xu(d.x, d.u, K, t, terminal, z, z + NX);
+      for (int i = 0; i < NM; ++i) dzk[i] = d.dz[(size_t)i * K + t];
+      for (int i = 0; i < NX; ++i) { z[i] = z[i] - alpha * dzk[i]; d.xn[(size_t)i * K + t] = z[i]; xg[i] = d.xg[(size_t)i * d.B + b]; }
+      if (!terminal)
+        for (int i = 0; i < NU; ++i) { z[NX + i] = z[NX + i] - alpha * dzk[NX + i]; d.un[(size_t)i * K + t] = z[NX + i]; }
+      if (!terminal) {
+        T qdd[NJ], Minv[NJ * NJ], v[NJ][6], a[NJ][6], f[NJ][6], xnext[NX];
+        forward_dynamics<T, false>(z, z + NJ, z + NX, d.gravity, qdd, Minv, v, a, f);
+        integrate(d.integrator, z, qdd, d.dt, xnext);
+        for (int i = 0; i < NX; ++i) s_xn[k * NX + i] = xnext[i];
+      }
+      s_cost[k] = cost_value(d.cost, z, z + NX, xg, k, terminal);
+      s_soft[k] = d.lim.any ? soft_value(d.lim, z, d.mu + t, d.lam + t, K, terminal) : T(0);
+      T g[NM];
+      cost_grad_hess<T, false>(d.cost, z, z + NX, xg, k, terminal, g, (T*)nullptr);
+      const int M = terminal ? NX : NM;
+      T acc = T(0);
+      for (int i = 0; i < M; ++i) acc += g[i] * dzk[i];
+      s_D[k] = acc;
+      T accs = T(0);
+      if (d.lim.any) {
+        T gck[NM];
+        soft_grad(d.lim, z, d.mu + t, d.lam + t, K, terminal, gck);
+        for (int i = 0; i < M; ++i) accs += gck[i] * dzk[i];
+      }
+      s_Ds[k] = accs;
+      if (k == 0) {
+        T cc = T(0);
+        for (int i = 0; i < NX; ++i) cc += fabs(z[i] - d.xs[(size_t)i * d.B + b]);
+        s_c[0] = cc;
+      }
+    }
+    __syncthreads();
+    for (int k = threadIdx.x; k < N; k += blockDim.x) {         // defect of knot k against the step from knot k-1
+      if (k == 0) continue;
+      const size_t t = (size_t)b * N + k;
+      T cc = T(0);
+      for (int i = 0; i < NX; ++i) cc += fabs(d.xn[(size_t)i * K + t] - s_xn[(k - 1) * NX + i]);
+      s_c[k] = cc;
+    }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+      T Jn = T(0), cn = T(0), D = T(0);
+      for (int k = 0; k < N; ++k) Jn += s_cost[k];
+      if (d.lim.any)
+        for (int k = 0; k < N; ++k) Jn += s_soft[k];
+      for (int k = 0; k < N; ++k) cn += s_c[k];
+      for (int k = 0; k < N; ++k) { D += s_D[k]; if (d.lim.any) D += s_Ds[k]; }
+      const T mu = o.merit_mu;
+      const T merit_new = Jn + mu * cn;
+      const T delta_J = d.J[b] - Jn;
+      const T delta_merit = d.merit[b] - merit_new;
+      const T expected = alpha * (D - mu * cn);
+      const T ratio = delta_merit / expected;
+      d.deltaJ[b] = delta_J;
+      d.tot_trials[b] += 1;
+      if (delta_merit >= T(0) && ratio >= o.er_min && ratio <= o.er_max) {
+        s_state = 0;
+        d.J[b] = Jn; d.c[b] = cn; d.merit[b] = merit_new;
+        const T drho = fmin(d.drho[b] / o.rho_factor, T(1) / o.rho_factor);     // reduce_regularization (:457-461)
+        d.drho[b] = drho; d.rho[b] = fmax(d.rho[b] * drho, o.rho_min);
+        trace_row(d, b, ls, alpha, D, ratio, d.pcg_iters[b], 1);
+      } else if (alpha > o.alpha_min) {
+        s_state = 1;
+      } else {
+        s_state = 2;
+        trace_row(d, b, ls, alpha, D, ratio, d.pcg_iters[b], 0);
+      }
+    }
+    __syncthreads();
+    const int st = s_state;
+    if (st == 0) {
+      for (int idx = threadIdx.x; idx < N * NX; idx += blockDim.x) {
+        const int i = idx / N, k = idx % N;
+        const size_t t = (size_t)b * N + k;
+        d.x[(size_t)i * K + t] = d.xn[(size_t)i * K + t];
+      }
+      for (int idx = threadIdx.x; idx < (N - 1) * NU; idx += blockDim.x) {
+        const int i = idx / (N - 1), k = idx % (N - 1);
+        const size_t t = (size_t)b * N + k;
+        d.u[(size_t)i * K + t] = d.un[(size_t)i * K + t];
+      }
+    }
+    if (st != 1) {
+      if (threadIdx.x == 0) {           // check_for_exit_or_error (:463-481)
+        bool exit_flag = false;
+        if (st == 2) {
+          const T drho = fmax(d.drho[b] * o.rho_factor, o.rho_factor);
+          const T rho = fmax(d.rho[b] * drho, o.rho_min);
+          d.drho[b] = drho; d.rho[b] = rho;
+          if (rho > o.rho_max) { d.exit_sqp[b] = 2; exit_flag = true; }
+        } else if (d.deltaJ[b] < o.tol_sqp) {
+          d.exit_sqp[b] = 1; exit_flag = true;
+        }
+        if (d.sqp_iter[b] == o.max_iter_sqp - 1) { d.exit_sqp[b] = 3; exit_flag = true; }
+        else d.sqp_iter[b] += 1;
+        if (exit_flag) d.phase[b] = PH_OUTER;
+        d.ls_iter[b] = ls;
+        d.alpha[b] = alpha;
+      }
+      return;
+    }
+    alpha *= o.alpha_factor;
+    ls += 1;
+    __syncthreads();      // s_state / shared terms are rewritten by the next trial
+  }
+}
+
 // stage entry point: J, c, D of the trial point for alpha (no decision)
 template <typename T>
 __global__ void k_merit_only(Dev<T> d, T* J, T* c, T* D) {
@@ -1006,7 +1183,7 @@ __global__ void k_sqp_ctrl(Dev<T> d, Opts<T> o) {
 // Instances that continue re-enter the SQP loop through k_outer_begin (the host relaunches it on the `restart` list).
 // -----------------------------------------------------------------------------------------------------------------
 template <typename T>
-__global__ void k_outer(Dev<T> d, Opts<T> o) {
+__global__ void k_outer(Dev<T> d, Opts<T> o, int fused_restart) {
   int* restart_list = d.restart_list;
   int* restart_count = d.n_restart;
   const int n = *d.n_act;
@@ -1092,32 +1269,65 @@ __global__ void k_outer(Dev<T> d, Opts<T> o) {
   }
   if (changed) atomicAnd(&s_flag, 0);
   __syncthreads();
-  if (threadIdx.x == 0) {
-    if (s_flag) { d.exit_soft[b] = 3; d.phase[b] = PH_DONE; }
-    else {
+  if (s_flag) {
+    if (threadIdx.x == 0) { d.exit_soft[b] = 3; d.phase[b] = PH_DONE; }
+    return;
+  }
+  if (!fused_restart) {
+    if (threadIdx.x == 0) {
       const int pos = atomicAdd(restart_count, 1);
       restart_list[pos] = b;
+    }
+    return;
+  }
+  // next outer iteration (SQP :535-569): J with the updated penalties, rho, merit, seed trace row; c is unchanged
+  __threadfence_block();
+  __syncthreads();
+  {
+    extern __shared__ unsigned char smem_raw2[];
+    T* sm2 = reinterpret_cast<T*>(smem_raw2);
+    __shared__ T Jb, cb, Db;
+    merit_terms<T, false, false, false>(d, b, sm2, &Jb, &cb, &Db);
+    if (threadIdx.x == 0) {
+      d.J[b] = Jb;
+      d.rho[b] = o.rho_init;
+      d.drho[b] = T(1);
+      d.merit[b] = Jb + o.merit_mu * d.c[b];
+      d.sqp_iter[b] = 0;
+      d.trace_rows[b] = 0;
+      d.phase[b] = PH_SQP;
+      trace_row(d, b, 0, T(1), T(0), T(0), 0, 0);
     }
   }
 }
 
-// rebuild the active list (order-preserving, single block) and zero the restart counter
+// rebuild the active list (order-preserving, single block of 1024 threads: per-thread chunk counts + block scan)
 template <typename T>
-__global__ void k_compact(Dev<T> d, int* scratch) {
-  __shared__ int s_n;
+__global__ void __launch_bounds__(1024) k_compact(Dev<T> d, int* scratch) {
+  __shared__ int s_cnt[1024];
   const int n = *d.n_act;
-  if (threadIdx.x == 0) {
-    int m = 0;
-    for (int s = 0; s < n; ++s) {
-      const int b = d.act[s];
-      if (d.phase[b] != PH_DONE) scratch[m++] = b;
-    }
-    s_n = m;
+  const int chunk = (n + blockDim.x - 1) / blockDim.x;
+  const int lo = min(n, (int)threadIdx.x * chunk), hi = min(n, lo + chunk);
+  int cnt = 0;
+  for (int s = lo; s < hi; ++s) cnt += (d.phase[d.act[s]] != PH_DONE) ? 1 : 0;
+  s_cnt[threadIdx.x] = cnt;
+  __syncthreads();
+  for (int off = 1; off < (int)blockDim.x; off <<= 1) {       // inclusive Hillis-Steele scan
+    int v = (threadIdx.x >= (unsigned)off) ? s_cnt[threadIdx.x - off] : 0;
+    __syncthreads();
+    s_cnt[threadIdx.x] += v;
+    __syncthreads();
   }
+  int pos = s_cnt[threadIdx.x] - cnt;
+  for (int s = lo; s < hi; ++s) {
+    const int b = d.act[s];
+    if (d.phase[b] != PH_DONE) scratch[pos++] = b;
+  }
+  const int total = s_cnt[blockDim.x - 1];
   __syncthreads();
-  for (int s = threadIdx.x; s < s_n; s += blockDim.x) d.act[s] = scratch[s];
+  for (int s = threadIdx.x; s < total; s += blockDim.x) d.act[s] = scratch[s];
   __syncthreads();
-  if (threadIdx.x == 0) *d.n_act = s_n;
+  if (threadIdx.x == 0) { *d.n_act = total; *d.n_restart = 0; }
 }
 
 // -----------------------------------------------------------------------------------------------------------------

@@ -177,9 +177,14 @@ struct SolverT : SolverBase {
     B2T_CUDA(cudaEventCreate(&ev0)); B2T_CUDA(cudaEventCreate(&ev1));
     // kernels that need > 48 KB of dynamic shared memory
     B2T_CUDA(cudaFuncSetAttribute(b2t::k_pcg<T>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
-    B2T_CUDA(cudaFuncSetAttribute(b2t::k_pcg2<T, PCG_RPT, true, 256>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
-    B2T_CUDA(cudaFuncSetAttribute(b2t::k_pcg2<T, PCG_RPT, true, 512>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
-    B2T_CUDA(cudaFuncSetAttribute(b2t::k_pcg2<T, PCG_RPT, true, 1024>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+    B2T_CUDA(cudaFuncSetAttribute(b2t::k_pcg2<T, PCG_RPT, 1, true, 256>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+    B2T_CUDA(cudaFuncSetAttribute(b2t::k_pcg2<T, PCG_RPT, 1, true, 512>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+    B2T_CUDA(cudaFuncSetAttribute(b2t::k_pcg2<T, PCG_RPT, 1, true, 1024>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+    if constexpr (PCG_CS_MAX == 2) {
+      B2T_CUDA(cudaFuncSetAttribute(b2t::k_pcg2<T, PCG_RPT, 2, true, 256>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+      B2T_CUDA(cudaFuncSetAttribute(b2t::k_pcg2<T, PCG_RPT, 2, true, 512>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+      B2T_CUDA(cudaFuncSetAttribute(b2t::k_pcg2<T, PCG_RPT, 2, true, 1024>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+    }
     int r = reset_multipliers();
     if (r) return r;
     k_init_state<T><<<cdiv(B, 128), 128, 0, stream>>>(d);
@@ -385,11 +390,31 @@ struct SolverT : SolverBase {
     return 0;
   }
   // rows per thread of k_pcg2: largest divisor of NX that is <= 3
-  static constexpr int PCG_RPT = (b2t::NX % 3 == 0) ? 3 : ((b2t::NX % 2 == 0) ? 2 : 1);
-  int pcg2_threads() const { int nt = d.N * (b2t::NX / PCG_RPT); return ((nt + 31) / 32) * 32; }
-  size_t pcg2_smem(bool mats) const {
-    size_t v = ((size_t)2 * (d.N + 2) * b2t::NX + 32) * sizeof(T);
-    if (mats) v += (size_t)2 * PCG_RPT * b2t::NX * pcg2_threads() * sizeof(T);
+  static constexpr bool pcg_rpt_ok(int r) { int tb = b2t::NX / r; return b2t::NX % r == 0 && (tb & (tb - 1)) == 0 && tb <= 32; }
+  static constexpr int pick_rpt() {
+    if (pcg_rpt_ok(3)) return 3;
+    for (int r = 2; r <= b2t::NX; ++r) if (pcg_rpt_ok(r)) return r;
+    return b2t::NX;
+  }
+  static constexpr int PCG_RPT = pick_rpt();
+  // column split: 2 when every thread still gets an even number of columns and the block fits 1024 threads
+  static constexpr int PCG_CS_MAX = (b2t::NX % 4 == 0 && 32 % ((b2t::NX / PCG_RPT) * 2) == 0) ? 2 : 1;
+  int pcg_cs = 0;
+  int pcg2_cs() {
+    if (!pcg_cs) {
+      const char* e = getenv("B2T_PCG_CS");
+      int want = e ? atoi(e) : 1;      // measured on B200 (arm6, N=64): CS=1 22.3 ms vs CS=2 28.3 ms per 2048-instance step
+      if (want > PCG_CS_MAX) want = PCG_CS_MAX;
+      if (want == 2 && d.N * (b2t::NX / PCG_RPT) * 2 > 1024) want = 1;
+      pcg_cs = want < 1 ? 1 : want;
+    }
+    return pcg_cs;
+  }
+  int pcg2_threads() { int nt = d.N * (b2t::NX / PCG_RPT) * pcg2_cs(); return ((nt + 31) / 32) * 32; }
+  int pcg2_maxt() { int nt = pcg2_threads(); return nt <= 256 ? 256 : (nt <= 512 ? 512 : 1024); }
+  size_t pcg2_smem(bool mats) {
+    size_t v = ((size_t)3 * (d.N + 2) * b2t::NX + 32) * sizeof(T);
+    if (mats) v += (size_t)2 * PCG_RPT * (b2t::NX / pcg2_cs()) * pcg2_maxt() * sizeof(T);
     return v;
   }
   int pcg_variant = -1;      // 0: k_pcg (v1), 1: k_pcg2 with shared-memory diagonal blocks, 2: k_pcg2 streaming them
@@ -404,10 +429,15 @@ struct SolverT : SolverBase {
     const int stair = method == B2T_METHOD_PCG_SS ? 1 : 0;
     Scope sc(this, B2T_K_PCG);
     const int nt = pcg2_threads();
-#define B2T_PCG2(SM, MT) k_pcg2<T, PCG_RPT, SM, MT><<<bound, nt, pcg2_smem(SM), stream>>>(d, list, count, stair, tol, max_iter)
-    if (pcg_variant == 1) { if (nt <= 256) B2T_PCG2(true, 256); else if (nt <= 512) B2T_PCG2(true, 512); else B2T_PCG2(true, 1024); }
-    else if (pcg_variant == 2) { if (nt <= 256) B2T_PCG2(false, 256); else if (nt <= 512) B2T_PCG2(false, 512); else B2T_PCG2(false, 1024); }
-    else k_pcg<T><<<bound, pcg_threads(), pcg_smem(), stream>>>(d, list, count, stair, tol, max_iter);
+    const int cs = pcg2_cs();
+#define B2T_PCG2(CSV, SM, MT) k_pcg2<T, PCG_RPT, CSV, SM, MT><<<bound, nt, pcg2_smem(SM), stream>>>(d, list, count, stair, tol, max_iter)
+#define B2T_PCG2_MT(CSV, SM) do { if (nt <= 256) B2T_PCG2(CSV, SM, 256); else if (nt <= 512) B2T_PCG2(CSV, SM, 512); else B2T_PCG2(CSV, SM, 1024); } while (0)
+    if (pcg_variant == 1 || pcg_variant == 2) {
+      const bool sm = pcg_variant == 1;
+      if (cs == 2) { if constexpr (PCG_CS_MAX == 2) { if (sm) B2T_PCG2_MT(2, true); else B2T_PCG2_MT(2, false); } }
+      else { if (sm) B2T_PCG2_MT(1, true); else B2T_PCG2_MT(1, false); }
+    } else k_pcg<T><<<bound, pcg_threads(), pcg_smem(), stream>>>(d, list, count, stair, tol, max_iter);
+#undef B2T_PCG2_MT
 #undef B2T_PCG2
     tick(B2T_K_PCG);
     return 0;
@@ -443,22 +473,31 @@ struct SolverT : SolverBase {
     B2T_CUDA(cudaGetLastError());
     int n = B;
     const long long cap = (long long)o->max_iter_soft * o->max_iter_SQP + 8;
+    const bool legacy_ls = getenv("B2T_LEGACY_LS") && atoi(getenv("B2T_LEGACY_LS")) != 0;
+    const size_t lsmem = (size_t)(5 + NX) * d.N * sizeof(T);
+    const int lst = std::min(128, ((d.N + 31) / 32) * 32);
+    const size_t osmem = std::max((size_t)3 * d.N * sizeof(T), msmem);
     for (long long iter = 0; n > 0 && iter < cap; ++iter) {
-      { Scope sc(this, B2T_K_CTRL); k_iter_begin<T><<<cdiv(n, 128), 128, 0, stream>>>(d); tick(B2T_K_CTRL); }
       launch_dynamics(d.act, d.n_act, n);
       launch_kkt(d.act, d.n_act, n, method);
       launch_pcg(d.act, d.n_act, n, method, op.tol_lin, op.max_iter_lin);
       launch_recover(d.act, d.n_act, n);
-      for (int t = 0; t < max_trials; ++t) {
-        int* cur = (t % 2) ? d.ls_list1 : d.ls_list0;
-        int* nxt = (t % 2) ? d.ls_list0 : d.ls_list1;
-        { Scope sc(this, B2T_K_TRIAL); k_fd<T, true><<<cdiv((size_t)n * d.N, 128), 128, 0, stream>>>(d, cur, d.n_ls + t); tick(B2T_K_TRIAL); }
-        { Scope sc(this, B2T_K_MERIT); k_merit<T><<<n, mt, msmem, stream>>>(d, cur, d.n_ls + t, nxt, d.n_ls + t + 1, op); tick(B2T_K_MERIT); }
+      if (!legacy_ls) {
+        { Scope sc(this, B2T_K_TRIAL); k_linesearch<T><<<n, lst, lsmem, stream>>>(d, op); tick(B2T_K_TRIAL); }
+        { Scope sc(this, B2T_K_CTRL); k_outer<T><<<n, mt, osmem, stream>>>(d, op, 1); tick(B2T_K_CTRL); }
+      } else {
+        { Scope sc(this, B2T_K_CTRL); k_iter_begin<T><<<cdiv(n, 128), 128, 0, stream>>>(d); tick(B2T_K_CTRL); }
+        for (int t = 0; t < max_trials; ++t) {
+          int* cur = (t % 2) ? d.ls_list1 : d.ls_list0;
+          int* nxt = (t % 2) ? d.ls_list0 : d.ls_list1;
+          { Scope sc(this, B2T_K_TRIAL); k_fd<T, true><<<cdiv((size_t)n * d.N, 128), 128, 0, stream>>>(d, cur, d.n_ls + t); tick(B2T_K_TRIAL); }
+          { Scope sc(this, B2T_K_MERIT); k_merit<T><<<n, mt, msmem, stream>>>(d, cur, d.n_ls + t, nxt, d.n_ls + t + 1, op); tick(B2T_K_MERIT); }
+        }
+        { Scope sc(this, B2T_K_CTRL); k_sqp_ctrl<T><<<cdiv(n, 128), 128, 0, stream>>>(d, op); tick(B2T_K_CTRL); }
+        { Scope sc(this, B2T_K_CTRL); k_outer<T><<<n, mt, osmem, stream>>>(d, op, 0); tick(B2T_K_CTRL); }
+        { Scope sc(this, B2T_K_MERIT); k_outer_begin<T><<<n, mt, msmem, stream>>>(d, d.restart_list, d.n_restart, op, 0); tick(B2T_K_MERIT); }
       }
-      { Scope sc(this, B2T_K_CTRL); k_sqp_ctrl<T><<<cdiv(n, 128), 128, 0, stream>>>(d, op); tick(B2T_K_CTRL); }
-      { Scope sc(this, B2T_K_CTRL); k_outer<T><<<n, mt, (size_t)3 * d.N * sizeof(T), stream>>>(d, op); tick(B2T_K_CTRL); }
-      { Scope sc(this, B2T_K_MERIT); k_outer_begin<T><<<n, mt, msmem, stream>>>(d, d.restart_list, d.n_restart, op, 0); tick(B2T_K_MERIT); }
-      { Scope sc(this, B2T_K_CTRL); k_compact<T><<<1, 256, 0, stream>>>(d, d_scratch); tick(B2T_K_CTRL); }
+      { Scope sc(this, B2T_K_CTRL); k_compact<T><<<1, 1024, 0, stream>>>(d, d_scratch); tick(B2T_K_CTRL); }
       B2T_CUDA(cudaMemcpyAsync(h_count, d.n_act, sizeof(int), cudaMemcpyDeviceToHost, stream));
       B2T_CUDA(cudaStreamSynchronize(stream));
       n = h_count[0];
