@@ -3,9 +3,9 @@
 // Data layout in HBM (K = batch * N knot points, t = b * N + k):
 //   per-knot arrays are element-major ("SoA over knots"):  a[e][t]  -> thread t of a per-knot kernel reads a
 //   coalesced 8-byte stream for every element e;
-//   the block-tridiagonal Schur complement and preconditioner blocks are instance-major, column-major over the
-//   row index r = k*nx + i:  S[b][c][r]  -> thread r of the per-instance PCG block reads coalesced columns, and an
-//   instance's matrices are one contiguous range (bulk-copyable into shared memory).
+//   the block-tridiagonal Schur complement and preconditioner blocks use the same layout, one nx*nx block per knot:
+//   Sd[i*nx+c][t] = S_kk[i][c], So[i*nx+c][t] = S_{k,k-1}[i][c], Pd likewise; gamma[i][t], l[i][t].  The per-knot
+//   assembly kernels write them fully coalesced; the per-instance PCG block loads them once into registers / shared memory.
 // Control flow (outer AL loop, SQP loop, line search) lives on the device in per-instance state words; the host
 // only launches the fixed kernel sequence and reads one counter per SQP iteration.
 #pragma once
@@ -37,7 +37,7 @@ struct Dev {
   size_t K;
   // per-knot SoA
   T *x, *u, *xn, *un, *xkp1, *xkp1n, *dyn, *vaf, *Gh, *g, *Gg, *dz, *mu, *lam, *phi;
-  // instance-major
+  // block-tridiagonal system, per-knot SoA: [nx*nx][K] and [nx][K]
   T *Sd, *So, *Pd, *gam, *l;
   // per-instance
   T *xs, *xg;
@@ -193,16 +193,16 @@ __global__ void __launch_bounds__(64) k_schur(Dev<T> d, const int* list, const i
   const int b = list[slot];
   const size_t t = (size_t)b * d.N + j;
   const size_t K = d.K;
-  const int R = d.N * NX;
+  (void)0;
   T Sd[NX * NX], gam[NX];
-  T* Sd_o = d.Sd + (size_t)b * R * NX;
-  T* So_o = d.So + (size_t)b * R * NX;
-  T* Pd_o = d.Pd + (size_t)b * R * NX;
+  T* Sd_o = d.Sd + (size_t)b * d.N;
+  T* So_o = d.So + (size_t)b * d.N;
+  T* Pd_o = d.Pd + (size_t)b * d.N;
   if (j == 0) {
     for (int i = 0; i < NX; ++i)
       for (int c = 0; c < NX; ++c) {
         Sd[i * NX + c] = -d.Gh[(size_t)(i * NM + c) * K + t];
-        So_o[(size_t)c * R + i] = T(0);
+        So_o[(size_t)(i * NX + c) * K] = T(0);
       }
     for (int i = 0; i < NX; ++i) gam[i] = (d.x[(size_t)i * K + t] - d.xs[(size_t)i * d.B + b]) - d.Gg[(size_t)i * K + t];
   } else {
@@ -234,7 +234,7 @@ __global__ void __launch_bounds__(64) k_schur(Dev<T> d, const int* list, const i
       for (int i = 0; i < NX; ++i) {
         T acc = T(0);
         for (int r = 0; r < NM; ++r) acc += AB[i * NM + r] * gcol[r];
-        So_o[(size_t)c * R + j * NX + i] = acc;
+        So_o[(size_t)(i * NX + c) * K + j] = acc;
       }
     }
     T Ggp[NM];
@@ -247,17 +247,17 @@ __global__ void __launch_bounds__(64) k_schur(Dev<T> d, const int* list, const i
     }
   }
   for (int i = 0; i < NX; ++i) {
-    d.gam[(size_t)b * R + j * NX + i] = gam[i];
-    for (int c = 0; c < NX; ++c) Sd_o[(size_t)c * R + j * NX + i] = Sd[i * NX + c];
+    d.gam[(size_t)i * K + t] = gam[i];
+    for (int c = 0; c < NX; ++c) Sd_o[(size_t)(i * NX + c) * K + j] = Sd[i * NX + c];
   }
   if (jacobi) {
     for (int i = 0; i < NX; ++i)
-      for (int c = 0; c < NX; ++c) Pd_o[(size_t)c * R + j * NX + i] = (i == c) ? T(1) / Sd[i * NX + i] : T(0);
+      for (int c = 0; c < NX; ++c) Pd_o[(size_t)(i * NX + c) * K + j] = (i == c) ? T(1) / Sd[i * NX + i] : T(0);
   } else {
     for (int i = 0; i < NX * NX; ++i) Sd[i] = -Sd[i];     // -S_jj is SPD
     spd_inverse_inplace(Sd, NX, NX);
     for (int i = 0; i < NX; ++i)
-      for (int c = 0; c < NX; ++c) Pd_o[(size_t)c * R + j * NX + i] = -Sd[i * NX + c];
+      for (int c = 0; c < NX; ++c) Pd_o[(size_t)(i * NX + c) * K + j] = -Sd[i * NX + c];
   }
 }
 
@@ -329,8 +329,15 @@ __device__ __forceinline__ void load_Ab(const Dev<T>& d, size_t t, T* Ab) {
   }
 }
 
+// k_schur_diag: one thread per block row j.  The knot's Ab (NJ x NM) is staged in shared memory ([entry][thread], conflict-free);
+// M, F, v, w are accumulated in registers by streaming over the columns r of Ab (rank-1 updates M += d_r a_r a_r^T), and every
+// entry of S_jj / S_j,j-1 / gamma_j is written straight to global memory -- no per-thread local arrays.
+enum { SCHUR_THREADS = 64 };
 template <typename T>
-__global__ void __launch_bounds__(128) k_schur_diag(Dev<T> d, const int* list, const int* count, int jacobi) {
+__global__ void __launch_bounds__(SCHUR_THREADS) k_schur_diag(Dev<T> d, const int* list, const int* count, int jacobi) {
+  extern __shared__ unsigned char smem_raw[];
+  T* sAb = reinterpret_cast<T*>(smem_raw);            // [NJ*NM][SCHUR_THREADS]
+  const int tx = threadIdx.x;
   const size_t gt = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
   const int slot = (int)(gt / d.N);
   if (slot >= *count) return;
@@ -338,102 +345,145 @@ __global__ void __launch_bounds__(128) k_schur_diag(Dev<T> d, const int* list, c
   const int b = list[slot];
   const size_t t = (size_t)b * d.N + j;
   const size_t K = d.K;
-  const int R = d.N * NX;
-  T* Sd_o = d.Sd + (size_t)b * R * NX;
-  T* So_o = d.So + (size_t)b * R * NX;
-  T* Pd_o = d.Pd + (size_t)b * R * NX;
-  T Sd[NX * NX], gam[NX];
-  // Ghat_j[:nx,:nx] = diag(dx) - sj hx hx^T
-  T dx[NX], hx[NX];
-  for (int i = 0; i < NX; ++i) { dx[i] = d.Gh[(size_t)i * K + t]; hx[i] = d.Gh[(size_t)(NM + i) * K + t]; }
-  const T sj = d.Gh[(size_t)(2 * NM) * K + t];
+  (void)0;
+  T* Sd_o = d.Sd + (size_t)b * d.N;
+  T* So_o = d.So + (size_t)b * d.N;
+  T* gm_o = d.gam + (size_t)b * d.N;
+  auto GH = [&](int e, size_t tt) -> T { return d.Gh[(size_t)e * K + tt]; };
+  const T sj = GH(2 * NM, t);
+  (void)jacobi;
   if (j == 0) {
-    for (int i = 0; i < NX; ++i)
-      for (int c = 0; c < NX; ++c) {
-        Sd[i * NX + c] = -(((i == c) ? dx[i] : T(0)) - sj * hx[i] * hx[c]);
-        So_o[(size_t)c * R + i] = T(0);
-      }
-    for (int i = 0; i < NX; ++i) gam[i] = (d.x[(size_t)i * K + t] - d.xs[(size_t)i * d.B + b]) - d.Gg[(size_t)i * K + t];
-  } else {
-    const size_t tp = t - 1;
-    const T dte = d.integrator == 0 ? d.dt : T(0);
-    const T tau = d.integrator == 0 ? T(0) : d.dt;
-    T Ab[NJ * NM], dv[NM], hv[NM], Gg[NM];
-    load_Ab(d, tp, Ab);
-    for (int i = 0; i < NM; ++i) { dv[i] = d.Gh[(size_t)i * K + tp]; hv[i] = d.Gh[(size_t)(NM + i) * K + tp]; Gg[i] = d.Gg[(size_t)i * K + tp]; }
-    const T sp = d.Gh[(size_t)(2 * NM) * K + tp];
-    T M[NJ * NJ], F[NJ * NJ], vb[NJ], wb[NJ];
-    for (int a = 0; a < NJ; ++a) {
-      T accv = T(0), accw = T(0);
-      for (int r = 0; r < NM; ++r) { accv += Ab[a * NM + r] * hv[r]; accw += Ab[a * NM + r] * Gg[r]; }
-      vb[a] = accv; wb[a] = accw;
-      for (int c2 = 0; c2 <= a; ++c2) {
-        T acc = T(0);
-        for (int r = 0; r < NM; ++r) acc += Ab[a * NM + r] * dv[r] * Ab[c2 * NM + r];
-        M[a * NJ + c2] = acc; M[c2 * NJ + a] = acc;
-      }
-      for (int i = 0; i < NJ; ++i) F[a * NJ + i] = Ab[a * NM + i] * dv[i] + dte * Ab[a * NM + NJ + i] * dv[NJ + i];
-    }
-    T v[NX], w[NX];
-    for (int i = 0; i < NJ; ++i) {
-      v[i] = hv[i] + dte * hv[NJ + i] + tau * vb[i];
-      v[NJ + i] = vb[i];
-      w[i] = Gg[i] + dte * Gg[NJ + i] + tau * wb[i];
-      w[NJ + i] = wb[i];
-    }
-    // S_jj = -(AB D AB^T - sp v v^T + Ghat_j[:nx,:nx])
-    for (int i = 0; i < NJ; ++i)
-      for (int c = 0; c < NJ; ++c) {
-        const T Zic = (i == c) ? dv[i] + dte * dte * dv[NJ + i] : T(0);
-        const T tt = Zic + tau * (F[c * NJ + i] + F[i * NJ + c]) + tau * tau * M[i * NJ + c];
-        const T tb = F[c * NJ + i] + tau * M[i * NJ + c];        // top i, bottom c
-        const T bb = M[i * NJ + c];
-        Sd[i * NX + c] = tt;
-        Sd[i * NX + NJ + c] = tb;
-        Sd[(NJ + c) * NX + i] = tb;
-        Sd[(NJ + i) * NX + NJ + c] = bb;
-      }
-    for (int i = 0; i < NX; ++i)
-      for (int c = 0; c < NX; ++c)
-        Sd[i * NX + c] = -((Sd[i * NX + c] - sp * v[i] * v[c]) + (((i == c) ? dx[i] : T(0)) - sj * hx[i] * hx[c]));
-    // S_{j,j-1} = AB[:, :nx] diag(dv_x) - sp v hv_x^T
-    for (int c = 0; c < NX; ++c) {
-      for (int i = 0; i < NJ; ++i) {
-        const T e0 = ((c == i) ? T(1) : T(0)) + ((c == NJ + i) ? dte : T(0));
-        const T top = e0 + tau * Ab[i * NM + c];
-        So_o[(size_t)c * R + j * NX + i] = top * dv[c] - sp * v[i] * hv[c];
-        So_o[(size_t)c * R + j * NX + NJ + i] = Ab[i * NM + c] * dv[c] - sp * v[NJ + i] * hv[c];
-      }
-    }
-    for (int i = 0; i < NX; ++i) {
-      const T ck = d.x[(size_t)i * K + t] - d.xkp1[(size_t)i * K + tp];
-      gam[i] = (ck + w[i]) - d.Gg[(size_t)i * K + t];
-    }
+    static_for<0, NX>([&](auto ic) {
+      constexpr int i = decltype(ic)::value;
+      const T hi = GH(NM + i, t);
+      static_for<0, NX>([&](auto cc) {
+        constexpr int c = decltype(cc)::value;
+        const T val = -(((i == c) ? GH(i, t) : T(0)) - sj * hi * GH(NM + c, t));
+        Sd_o[(size_t)(i * NX + c) * K + j] = val;
+        So_o[(size_t)(i * NX + c) * K + j] = T(0);
+      });
+      gm_o[(size_t)i * K + j] = (d.x[(size_t)i * K + t] - d.xs[(size_t)i * d.B + b]) - d.Gg[(size_t)i * K + t];
+    });
+    return;
   }
-  for (int i = 0; i < NX; ++i) {
-    d.gam[(size_t)b * R + j * NX + i] = gam[i];
-    for (int c = 0; c < NX; ++c) Sd_o[(size_t)c * R + j * NX + i] = Sd[i * NX + c];
-  }
+  const size_t tp = t - 1;
+  const T dte = d.integrator == 0 ? d.dt : T(0);
+  const T tau = d.integrator == 0 ? T(0) : d.dt;
+  const T sp = GH(2 * NM, tp);
+  // stage Ab = dt * dqdd + [0 I 0] of knot j-1
+  static_for<0, NJ>([&](auto ac) {
+    constexpr int a = decltype(ac)::value;
+    static_for<0, NM>([&](auto cc) {
+      constexpr int c = decltype(cc)::value;
+      sAb[(a * NM + c) * SCHUR_THREADS + tx] = d.dt * d.dyn[(size_t)(a * 3 * NJ + c) * K + tp] + ((c == NJ + a) ? T(1) : T(0));
+    });
+  });
+  auto AB = [&](int a, int c) -> T { return sAb[(a * NM + c) * SCHUR_THREADS + tx]; };
+  // stream over the columns r of Ab
+  T Mp[NJ * (NJ + 1) / 2], F[NJ][NJ], vb[NJ], wb[NJ];      // Mp: packed lower triangle of M
+  auto MI = [](int a, int c) { return a >= c ? a * (a + 1) / 2 + c : c * (c + 1) / 2 + a; };
+  static_for<0, NJ>([&](auto ac) {
+    constexpr int a = decltype(ac)::value;
+    vb[a] = T(0); wb[a] = T(0);
+    static_for<0, NJ>([&](auto cc) { constexpr int c = decltype(cc)::value; F[a][c] = T(0); });
+    static_for<0, a + 1>([&](auto cc) { constexpr int c = decltype(cc)::value; Mp[a * (a + 1) / 2 + c] = T(0); });
+  });
+  static_for<0, NM>([&](auto rc) {
+    constexpr int r = decltype(rc)::value;
+    const T dr = GH(r, tp), hr = GH(NM + r, tp), gr = d.Gg[(size_t)r * K + tp];
+    T col[NJ];
+    static_for<0, NJ>([&](auto ac) { constexpr int a = decltype(ac)::value; col[a] = AB(a, r); });
+    static_for<0, NJ>([&](auto ac) {
+      constexpr int a = decltype(ac)::value;
+      vb[a] += col[a] * hr;
+      wb[a] += col[a] * gr;
+      const T cd = col[a] * dr;
+      static_for<0, a + 1>([&](auto cc) { constexpr int c = decltype(cc)::value; Mp[a * (a + 1) / 2 + c] += cd * col[c]; });
+      if constexpr (r < NJ) F[a][r] += cd;                       // Ab[a][i] d_i
+      else if constexpr (r < NX) F[a][r - NJ] += dte * cd;       // dte Ab[a][n+i] d_{n+i}
+    });
+  });
+  // gamma_j = c_j + AB (Ghat g)_{j-1} - (Ghat g)_j[:nx]
+  static_for<0, NJ>([&](auto ic) {
+    constexpr int i = decltype(ic)::value;
+    const T wt = d.Gg[(size_t)i * K + tp] + dte * d.Gg[(size_t)(NJ + i) * K + tp] + tau * wb[i];
+    const T ckt = d.x[(size_t)i * K + t] - d.xkp1[(size_t)i * K + tp];
+    gm_o[(size_t)i * K + j] = (ckt + wt) - d.Gg[(size_t)i * K + t];
+    const T ckb = d.x[(size_t)(NJ + i) * K + t] - d.xkp1[(size_t)(NJ + i) * K + tp];
+    gm_o[(size_t)(NJ + i) * K + j] = (ckb + wb[i]) - d.Gg[(size_t)(NJ + i) * K + t];
+  });
+  T v[NX];
+  static_for<0, NJ>([&](auto ic) {
+    constexpr int i = decltype(ic)::value;
+    v[i] = GH(NM + i, tp) + dte * GH(NM + NJ + i, tp) + tau * vb[i];
+    v[NJ + i] = vb[i];
+  });
+  // S_jj = -(AB D AB^T - sp v v^T + Ghat_j[:nx,:nx])
+  static_for<0, NJ>([&](auto ic) {
+    constexpr int i = decltype(ic)::value;
+    const T Zi = GH(i, tp) + dte * dte * GH(NJ + i, tp);
+    const T hxi = GH(NM + i, t), hxni = GH(NM + NJ + i, t);
+    static_for<0, NJ>([&](auto cc) {
+      constexpr int c = decltype(cc)::value;
+      const T hxc = GH(NM + c, t), hxnc = GH(NM + NJ + c, t);
+      const T mic = Mp[MI(i, c)];
+      const T tt = ((i == c) ? Zi : T(0)) + tau * (F[c][i] + F[i][c]) + tau * tau * mic;
+      const T tb = F[c][i] + tau * mic;                           // (top i, bottom c)
+      const T gtt = ((i == c) ? GH(i, t) : T(0)) - sj * hxi * hxc;
+      const T gtb = -sj * hxi * hxnc;
+      const T gbb = ((i == c) ? GH(NJ + i, t) : T(0)) - sj * hxni * hxnc;
+      Sd_o[(size_t)(i * NX + c) * K + j] = -((tt - sp * v[i] * v[c]) + gtt);
+      Sd_o[(size_t)(i * NX + NJ + c) * K + j] = -((tb - sp * v[i] * v[NJ + c]) + gtb);
+      Sd_o[(size_t)((NJ + c) * NX + i) * K + j] = -((tb - sp * v[NJ + c] * v[i]) + gtb);
+      Sd_o[(size_t)((NJ + i) * NX + NJ + c) * K + j] = -((mic - sp * v[NJ + i] * v[NJ + c]) + gbb);
+    });
+  });
+  // S_{j,j-1} = AB[:, :nx] diag(d_x) - sp v h_x^T
+  static_for<0, NX>([&](auto cc) {
+    constexpr int c = decltype(cc)::value;
+    const T dc = GH(c, tp), hc = GH(NM + c, tp);
+    static_for<0, NJ>([&](auto ic) {
+      constexpr int i = decltype(ic)::value;
+      const T ab = AB(i, c);
+      const T e0 = ((c == i) ? T(1) : T(0)) + ((c == NJ + i) ? dte : T(0));
+      So_o[(size_t)(i * NX + c) * K + j] = (e0 + tau * ab) * dc - sp * v[i] * hc;
+      So_o[(size_t)((NJ + i) * NX + c) * K + j] = ab * dc - sp * v[NJ + i] * hc;
+    });
+  });
+}
+
+// Pd_j = S_jj^-1 (block Jacobi / symmetric stair) or diag(S_jj)^-1 (Jacobi) -- PCG.compute_preconditioner (PCG.py:166-212).
+// One thread per block row; -S_jj (SPD) is inverted in packed storage with a fully unrolled Cholesky, all in registers.
+template <typename T>
+__global__ void __launch_bounds__(128) k_pinv(Dev<T> d, const int* list, const int* count, int jacobi) {
+  const size_t gt = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  const int slot = (int)(gt / d.N);
+  if (slot >= *count) return;
+  const int j = (int)(gt % d.N);
+  const int b = list[slot];
+  (void)0;
+  const T* Sd_o = d.Sd + (size_t)b * d.N;
+  T* Pd_o = d.Pd + (size_t)b * d.N;
   if (jacobi) {
     for (int i = 0; i < NX; ++i)
-      for (int c = 0; c < NX; ++c) Pd_o[(size_t)c * R + j * NX + i] = (i == c) ? T(1) / Sd[i * NX + i] : T(0);
-  } else {
-    T pk[NX * (NX + 1) / 2];
-    static_for<0, NX>([&](auto ic) {
-      constexpr int i = decltype(ic)::value;
-      static_for<0, i + 1>([&](auto cc) { constexpr int c = decltype(cc)::value; pk[i * (i + 1) / 2 + c] = -Sd[i * NX + c]; });
-    });
-    spd_inverse_packed<NX>(pk);
-    static_for<0, NX>([&](auto ic) {
-      constexpr int i = decltype(ic)::value;
-      static_for<0, i + 1>([&](auto cc) {
-        constexpr int c = decltype(cc)::value;
-        const T val = -pk[i * (i + 1) / 2 + c];
-        Pd_o[(size_t)c * R + j * NX + i] = val;
-        Pd_o[(size_t)i * R + j * NX + c] = val;
-      });
-    });
+      for (int c = 0; c < NX; ++c) Pd_o[(size_t)(i * NX + c) * d.K + j] = (i == c) ? T(1) / Sd_o[(size_t)(i * NX + i) * d.K + j] : T(0);
+    return;
   }
+  T pk[NX * (NX + 1) / 2];
+  static_for<0, NX>([&](auto ic) {
+    constexpr int i = decltype(ic)::value;
+    static_for<0, i + 1>([&](auto cc) { constexpr int c = decltype(cc)::value; pk[i * (i + 1) / 2 + c] = -Sd_o[(size_t)(i * NX + c) * d.K + j]; });
+  });
+  spd_inverse_packed<NX>(pk);
+  static_for<0, NX>([&](auto ic) {
+    constexpr int i = decltype(ic)::value;
+    static_for<0, i + 1>([&](auto cc) {
+      constexpr int c = decltype(cc)::value;
+      const T val = -pk[i * (i + 1) / 2 + c];
+      Pd_o[(size_t)(i * NX + c) * d.K + j] = val;
+      Pd_o[(size_t)(c * NX + i) * d.K + j] = val;
+    });
+  });
 }
 
 template <typename T>
@@ -445,16 +495,17 @@ __global__ void __launch_bounds__(128) k_recover_diag(Dev<T> d, const int* list,
   const int b = list[slot];
   const size_t t = (size_t)b * d.N + k;
   const size_t K = d.K;
-  const int R = d.N * NX;
+  (void)0;
   const bool terminal = (k == d.N - 1);
   T rhs[NM];
   for (int i = 0; i < NM; ++i) rhs[i] = d.g[(size_t)i * K + t];
-  const T* l = d.l + (size_t)b * R;
-  for (int i = 0; i < NX; ++i) rhs[i] -= l[k * NX + i];
+  const T* l = d.l + (size_t)b * d.N;
+  for (int i = 0; i < NX; ++i) rhs[i] -= l[(size_t)i * K + k];
   if (!terminal) {
     const T dte = d.integrator == 0 ? d.dt : T(0);
     const T tau = d.integrator == 0 ? T(0) : d.dt;
-    const T* ln = l + (k + 1) * NX;
+    T ln[NX];
+    for (int i = 0; i < NX; ++i) ln[i] = l[(size_t)i * K + k + 1];
     T wv[NJ];
     for (int a = 0; a < NJ; ++a) wv[a] = tau * ln[a] + ln[NJ + a];
     for (int c = 0; c < NM; ++c) {
@@ -504,22 +555,23 @@ __device__ __forceinline__ T block_sum(T v, T* red, int tid, int nthreads) {
 }
 
 template <typename T>
-__device__ __forceinline__ T bt_diag_row(const T* Md, const T* vec, int r, int j, int R) {
+__device__ __forceinline__ T bt_diag_row(const T* Md, const T* vec, int r, int j, size_t K) {
   T acc = T(0);
+  const int i = r % NX;
 #pragma unroll
-  for (int c = 0; c < NX; ++c) acc += Md[(size_t)c * R + r] * vec[j * NX + c];
+  for (int c = 0; c < NX; ++c) acc += Md[(size_t)(i * NX + c) * K + j] * vec[j * NX + c];
   return acc;
 }
 template <typename T>
-__device__ __forceinline__ T bt_off_row(const T* Mo, const T* vec, int r, int j, int i, int R, int N) {
+__device__ __forceinline__ T bt_off_row(const T* Mo, const T* vec, int r, int j, int i, size_t K, int N) {
   T acc = T(0);
   if (j > 0) {
 #pragma unroll
-    for (int c = 0; c < NX; ++c) acc += Mo[(size_t)c * R + r] * vec[(j - 1) * NX + c];
+    for (int c = 0; c < NX; ++c) acc += Mo[(size_t)(i * NX + c) * K + j] * vec[(j - 1) * NX + c];
   }
   if (j < N - 1) {
 #pragma unroll
-    for (int c = 0; c < NX; ++c) acc += Mo[(size_t)i * R + (j + 1) * NX + c] * vec[(j + 1) * NX + c];
+    for (int c = 0; c < NX; ++c) acc += Mo[(size_t)(c * NX + i) * K + j + 1] * vec[(j + 1) * NX + c];
   }
   return acc;
 }
@@ -537,10 +589,10 @@ __global__ void __launch_bounds__(1024) k_pcg(Dev<T> d, const int* list, const i
   T* y_s = p_s + R;
   T* w_s = y_s + R;
   T* red = w_s + R;
-  const T* Sd = d.Sd + (size_t)b * R * NX;
-  const T* So = d.So + (size_t)b * R * NX;
-  const T* Pd = d.Pd + (size_t)b * R * NX;
-  const T* gam = d.gam + (size_t)b * R;
+  const T* Sd = d.Sd + (size_t)b * d.N;
+  const T* So = d.So + (size_t)b * d.N;
+  const T* Pd = d.Pd + (size_t)b * d.N;
+  const T* gam = d.gam + (size_t)b * d.N;
   T rr[PCG_MAX_RPT], xx[PCG_MAX_RPT], pp[PCG_MAX_RPT], rt[PCG_MAX_RPT];
 #pragma unroll
   for (int m = 0; m < PCG_MAX_RPT; ++m) { rr[m] = T(0); xx[m] = T(0); pp[m] = T(0); rt[m] = T(0); }
@@ -550,7 +602,7 @@ __global__ void __launch_bounds__(1024) k_pcg(Dev<T> d, const int* list, const i
     for (int m = 0, r = tid; r < R; r += nt, ++m) y_s[r] = rr[m];
     __syncthreads();
     T yv[PCG_MAX_RPT];
-    for (int m = 0, r = tid; r < R; r += nt, ++m) yv[m] = bt_diag_row(Pd, y_s, r, r / NX, R);
+    for (int m = 0, r = tid; r < R; r += nt, ++m) yv[m] = bt_diag_row(Pd, y_s, r, r / NX, d.K);
     if (!stair) {
       for (int m = 0, r = tid; r < R; r += nt, ++m) rt[m] = yv[m];
       __syncthreads();
@@ -560,16 +612,16 @@ __global__ void __launch_bounds__(1024) k_pcg(Dev<T> d, const int* list, const i
     for (int m = 0, r = tid; r < R; r += nt, ++m) w_s[r] = yv[m];      // w_s = y
     __syncthreads();
     T ov[PCG_MAX_RPT];
-    for (int m = 0, r = tid; r < R; r += nt, ++m) ov[m] = bt_off_row(So, w_s, r, r / NX, r % NX, R, N);
+    for (int m = 0, r = tid; r < R; r += nt, ++m) ov[m] = bt_off_row(So, w_s, r, r / NX, r % NX, d.K, N);
     __syncthreads();
     for (int m = 0, r = tid; r < R; r += nt, ++m) y_s[r] = ov[m];      // y_s = O y
     __syncthreads();
-    for (int m = 0, r = tid; r < R; r += nt, ++m) rt[m] = yv[m] - bt_diag_row(Pd, y_s, r, r / NX, R);
+    for (int m = 0, r = tid; r < R; r += nt, ++m) rt[m] = yv[m] - bt_diag_row(Pd, y_s, r, r / NX, d.K);
     __syncthreads();
   };
 
   // x0 = 0  ->  r = b
-  for (int m = 0, r = tid; r < R; r += nt, ++m) { rr[m] = gam[r]; xx[m] = T(0); }
+  for (int m = 0, r = tid; r < R; r += nt, ++m) { rr[m] = gam[(size_t)(r % NX) * d.K + r / NX]; xx[m] = T(0); }
   precond();
   T part = T(0);
   for (int m = 0, r = tid; r < R; r += nt, ++m) { pp[m] = rt[m]; part += rr[m] * rt[m]; }
@@ -582,7 +634,7 @@ __global__ void __launch_bounds__(1024) k_pcg(Dev<T> d, const int* list, const i
     part = T(0);
     for (int m = 0, r = tid; r < R; r += nt, ++m) {
       const int j = r / NX, i = r % NX;
-      ap[m] = bt_diag_row(Sd, p_s, r, j, R) + bt_off_row(So, p_s, r, j, i, R, N);
+      ap[m] = bt_diag_row(Sd, p_s, r, j, d.K) + bt_off_row(So, p_s, r, j, i, d.K, N);
       part += pp[m] * ap[m];
     }
     const T pAp = block_sum(part, red, tid, nt);
@@ -598,7 +650,7 @@ __global__ void __launch_bounds__(1024) k_pcg(Dev<T> d, const int* list, const i
     for (int m = 0, r = tid; r < R; r += nt, ++m) pp[m] = rt[m] + pp[m] * beta;
     nu = nu_prime;
   }
-  for (int m = 0, r = tid; r < R; r += nt, ++m) d.l[(size_t)b * R + r] = xx[m];
+  for (int m = 0, r = tid; r < R; r += nt, ++m) d.l[(size_t)(r % NX) * d.K + (size_t)b * N + r / NX] = xx[m];
   if (tid == 0) {
     d.pcg_iters[b] = iters;
     d.tot_pcg[b] += iters;
@@ -627,7 +679,8 @@ __global__ void __launch_bounds__(MAXT) k_pcg2(Dev<T> d, const int* list, const 
   static_assert(32 % TBC == 0, "the threads of a block row must share a warp");
   static_assert(CS == 1 || CS == 2, "column split");
   const int b = list[blockIdx.x];
-  const int N = d.N, R = N * NX, NT = N * TBC;
+  const int N = d.N, NT = N * TBC;
+  const size_t K = d.K;
   const int tid = threadIdx.x, nt = blockDim.x;
   const bool live = tid < NT;
   const int j = live ? tid / TBC : 0;
@@ -645,25 +698,24 @@ __global__ void __launch_bounds__(MAXT) k_pcg2(Dev<T> d, const int* list, const 
   using T2 = typename std::conditional<sizeof(T) == 8, double2, float2>::type;
   T2* Sd_s = reinterpret_cast<T2*>(red + 32);
   T2* Pd_s = Sd_s + (SMEM ? (size_t)RPT * (NXC / 2) * MAXT : 0);
-  const T* Sd = d.Sd + (size_t)b * R * NX;
-  const T* So = d.So + (size_t)b * R * NX;
-  const T* Pd = d.Pd + (size_t)b * R * NX;
-  const T* gam = d.gam + (size_t)b * R;
+  const T* Sd = d.Sd + (size_t)b * d.N;
+  const T* So = d.So + (size_t)b * d.N;
+  const T* Pd = d.Pd + (size_t)b * d.N;
+  const T* gam = d.gam + (size_t)b * d.N;
   // ---- one-time loads: off-diagonal blocks into registers, diagonal blocks into shared memory
   T so_dn[RPT][NXC], so_up[RPT][NXC];
 #pragma unroll
   for (int k = 0; k < RPT; ++k)
 #pragma unroll
     for (int cc = 0; cc < NXC; ++cc) {
-      const int r = j * NX + i0 + k;
       const int c = c0 + cc;
-      so_dn[k][cc] = live ? So[(size_t)c * R + r] : T(0);                                        // S_{j,j-1}[i][c]  (zero for j = 0)
-      so_up[k][cc] = (live && j < N - 1) ? So[(size_t)(i0 + k) * R + (j + 1) * NX + c] : T(0);   // S_{j+1,j}[c][i]
+      so_dn[k][cc] = live ? So[(size_t)((i0 + k) * NX + c) * K + j] : T(0);                                        // S_{j,j-1}[i][c]  (zero for j = 0)
+      so_up[k][cc] = (live && j < N - 1) ? So[(size_t)(c * NX + i0 + k) * K + j + 1] : T(0);   // S_{j+1,j}[c][i]
       if constexpr (SMEM) {
         if (cc % 2 == 0) {
           T2 sv, pv;
-          sv.x = live ? Sd[(size_t)c * R + r] : T(0); sv.y = live ? Sd[(size_t)(c + 1) * R + r] : T(0);
-          pv.x = live ? Pd[(size_t)c * R + r] : T(0); pv.y = live ? Pd[(size_t)(c + 1) * R + r] : T(0);
+          sv.x = live ? Sd[(size_t)((i0 + k) * NX + c) * K + j] : T(0); sv.y = live ? Sd[(size_t)((i0 + k) * NX + c + 1) * K + j] : T(0);
+          pv.x = live ? Pd[(size_t)((i0 + k) * NX + c) * K + j] : T(0); pv.y = live ? Pd[(size_t)((i0 + k) * NX + c + 1) * K + j] : T(0);
           Sd_s[(k * (NXC / 2) + cc / 2) * MAXT + tid] = sv;
           Pd_s[(k * (NXC / 2) + cc / 2) * MAXT + tid] = pv;
         }
@@ -674,11 +726,11 @@ __global__ void __launch_bounds__(MAXT) k_pcg2(Dev<T> d, const int* list, const 
   // pair (cc, cc+1) of this thread's column slice, cc even
   auto ldSd2 = [&](int k, int cc) -> T2 {
     if constexpr (SMEM) return Sd_s[(k * (NXC / 2) + cc / 2) * MAXT + tid];
-    else { T2 v; v.x = Sd[(size_t)(c0 + cc) * R + j * NX + i0 + k]; v.y = Sd[(size_t)(c0 + cc + 1) * R + j * NX + i0 + k]; return v; }
+    else { T2 v; v.x = Sd[(size_t)((i0 + k) * NX + c0 + cc) * K + j]; v.y = Sd[(size_t)((i0 + k) * NX + c0 + cc + 1) * K + j]; return v; }
   };
   auto ldPd2 = [&](int k, int cc) -> T2 {
     if constexpr (SMEM) return Pd_s[(k * (NXC / 2) + cc / 2) * MAXT + tid];
-    else { T2 v; v.x = Pd[(size_t)(c0 + cc) * R + j * NX + i0 + k]; v.y = Pd[(size_t)(c0 + cc + 1) * R + j * NX + i0 + k]; return v; }
+    else { T2 v; v.x = Pd[(size_t)((i0 + k) * NX + c0 + cc) * K + j]; v.y = Pd[(size_t)((i0 + k) * NX + c0 + cc + 1) * K + j]; return v; }
   };
   auto ldV2 = [&](const T* V, int idx) -> T2 { return *reinterpret_cast<const T2*>(V + idx); };   // idx even -> 16-byte aligned
   auto combine = [&](T v) -> T {
@@ -740,7 +792,7 @@ __global__ void __launch_bounds__(MAXT) k_pcg2(Dev<T> d, const int* list, const 
     for (int k = 0; k < RPT; ++k) rt[k] = yv[k] - tmp[k];
   };
 #pragma unroll
-  for (int k = 0; k < RPT; ++k) { rr[k] = live ? gam[j * NX + i0 + k] : T(0); xx[k] = T(0); }
+  for (int k = 0; k < RPT; ++k) { rr[k] = live ? gam[(size_t)(i0 + k) * K + j] : T(0); xx[k] = T(0); }
   precond();
   T part = T(0);
 #pragma unroll
@@ -784,7 +836,226 @@ __global__ void __launch_bounds__(MAXT) k_pcg2(Dev<T> d, const int* list, const 
   }
   if (lead) {
 #pragma unroll
-    for (int k = 0; k < RPT; ++k) d.l[(size_t)b * R + j * NX + i0 + k] = xx[k];
+    for (int k = 0; k < RPT; ++k) d.l[(size_t)(i0 + k) * K + (size_t)b * N + j] = xx[k];
+  }
+  if (tid == 0) {
+    d.pcg_iters[b] = iters;
+    d.tot_pcg[b] += iters;
+    d.tot_qp[b] += 1;
+  }
+}
+
+// -----------------------------------------------------------------------------------------------------------------
+// k_pcg3: matrix-free, register-resident PCG for the structured (diag_mode) path.  S and the stair off-diagonal blocks
+// are never read: with  Ghat_k = diag(dinv) - s h h^T  and  AB_k = [[E0 + tau Ab],[Ab]]  (see k_kkt_diag)
+//     w_k = Ghat_k ([p_k;0] - AB_k^T p_{k+1}),     (S p)_{k+1} = AB_k w_k - w_{k+1}[:nx],   (S p)_0 = -w_0[:nx]
+//     q_k = Ghat_k [y_k;0],  q'_k = Ghat_k AB_k^T y_{k+1},   (O y)_{k+1} = AB_k q_k + q'_{k+1}[:nx],  (O y)_0 = q'_0[:nx]
+// (O = off-diagonal part of S, used by the symmetric-stair preconditioner  Pinv r = y - D^-1 O y,  y = D^-1 r).
+// Four lanes per knot k: lane g holds columns [g*MC, g*MC+MC) of Ab_k (all NJ rows), the matching entries of dinv_k, h_k,
+// and rows [g*RPT, g*RPT+RPT) of the preconditioner block of block row j = (k+1) mod N, whose PCG vector entries it owns.
+// Everything matrix-like stays in registers for all iterations; shared memory only carries the vectors between lanes.
+// Same PCG recurrence and exit test as PCG.pcg (PCG.py:66-111); the products are algebraically identical to S p / O y
+// (verified against the explicit form: identical iteration counts, SURVEY.md 7.2 parity floor).
+// -----------------------------------------------------------------------------------------------------------------
+template <typename T, int MAXT>
+__global__ void __launch_bounds__(MAXT) k_pcg3(Dev<T> d, const int* list, const int* count, int stair, T tol, int max_iter) {
+  if ((int)blockIdx.x >= *count) return;
+  // only launched when nx % 4 == 0 (the host falls back to k_pcg2 otherwise); RPT >= 1 keeps the definition well-formed
+  constexpr int RPT = (NX % 4 == 0) ? NX / 4 : 1;   // owned rows per lane
+  constexpr int MC = (NM + 3) / 4;            // Ab columns per lane
+  const int b = list[blockIdx.x];
+  const int N = d.N;
+  const size_t K = d.K;
+  const int tid = threadIdx.x, nt = blockDim.x;
+  const bool live = tid < 4 * N;
+  const int k = live ? tid >> 2 : 0;          // knot
+  const int g = tid & 3;                      // lane within the knot group
+  const bool has_next = live && (k < N - 1);  // knot N-1 has no dynamics; its group owns block row 0
+  const int jo = (k + 1 == N) ? 0 : k + 1;    // owned block row
+  const int c0 = g * MC, i0 = g * RPT;
+  const size_t tk = (size_t)b * N + k, tj = (size_t)b * N + jo;
+  const T dte = d.integrator == 0 ? d.dt : T(0);
+  const T tau = d.integrator == 0 ? T(0) : d.dt;
+  extern __shared__ unsigned char smem_raw[];
+  T* V = reinterpret_cast<T*>(smem_raw);      // [(N+1)][NX]  p / r / O y; block N stays zero
+  T* V2 = V + (N + 1) * NX;                   // [(N+1)][NX]  y; block N stays zero
+  T* W = V2 + (N + 1) * NX;                   // [N][NM]      w or q'
+  T* Wq = W + N * NM;                         // [N][NM]      q
+  T* red = Wq + N * NM;                       // 32
+  // ---- resident data
+  T ab[NJ][MC], dinv[MC], hh[MC], pd[RPT][NX];
+  bool cval[MC];
+#pragma unroll
+  for (int i = 0; i < MC; ++i) {
+    const int c = c0 + i;
+    cval[i] = live && c < NM;
+    dinv[i] = cval[i] ? d.Gh[(size_t)c * K + tk] : T(0);
+    hh[i] = cval[i] ? d.Gh[(size_t)(NM + c) * K + tk] : T(0);
+#pragma unroll
+    for (int a = 0; a < NJ; ++a)
+      ab[a][i] = (cval[i] && has_next) ? d.dt * d.dyn[(size_t)(a * 3 * NJ + c) * K + tk] + ((c == NJ + a) ? T(1) : T(0)) : T(0);
+  }
+  const T sS = live ? d.Gh[(size_t)(2 * NM) * K + tk] : T(0);
+#pragma unroll
+  for (int r = 0; r < RPT; ++r)
+#pragma unroll
+    for (int c = 0; c < NX; ++c) pd[r][c] = live ? d.Pd[(size_t)((i0 + r) * NX + c) * K + tj] : T(0);
+  for (int idx = tid; idx < 2 * (N + 1) * NX + 2 * N * NM; idx += nt) V[idx] = T(0);
+  __syncthreads();
+
+  auto quad = [&](T v) -> T {                 // sum over the 4 lanes of the knot group (all lanes get it)
+    v += __shfl_xor_sync(0xffffffffu, v, 1);
+    v += __shfl_xor_sync(0xffffffffu, v, 2);
+    return v;
+  };
+  auto publish = [&](T* buf, const T* val) {  // owned rows of block jo
+    if (live) {
+#pragma unroll
+      for (int r = 0; r < RPT; ++r) buf[jo * NX + i0 + r] = val[r];
+    }
+  };
+  // t_c = (AB_k^T z)_c for my columns, z = the nx-vector stored in block k+1 of `buf` (zero block for k = N-1)
+  auto abt = [&](const T* buf, T* tc) {
+    T pi[NJ], zq[NJ];
+    const T* z = buf + (k + 1) * NX;
+#pragma unroll
+    for (int a = 0; a < NJ; ++a) { zq[a] = z[a]; pi[a] = tau * zq[a] + z[NJ + a]; }
+#pragma unroll
+    for (int i = 0; i < MC; ++i) {
+      const int c = c0 + i;
+      T acc = T(0);
+#pragma unroll
+      for (int a = 0; a < NJ; ++a) acc += ab[a][i] * pi[a];
+      // E0^T z_q : identity on the q columns, dte on the qd columns (only where the knot has dynamics)
+      T e0 = T(0);
+#pragma unroll
+      for (int a = 0; a < NJ; ++a) { if (c == a) e0 = zq[a]; if (c == NJ + a) e0 = dte * zq[a]; }
+      tc[i] = has_next ? acc + e0 : T(0);
+    }
+  };
+  // out_r (owned rows of block jo) = AB_k zz + sign * Wn[jo][row], zz given by my columns (regs) and by smem copy `full` of knot k
+  auto abmul = [&](const T* zc, const T* full, const T* Wn, T sign, T* out) {
+    T pb[NJ];
+#pragma unroll
+    for (int a = 0; a < NJ; ++a) {
+      T acc = T(0);
+#pragma unroll
+      for (int i = 0; i < MC; ++i) acc += ab[a][i] * zc[i];
+      pb[a] = quad(acc);
+    }
+#pragma unroll
+    for (int r = 0; r < RPT; ++r) {
+      const int row = i0 + r;
+      T val = T(0);
+      if (has_next) {
+        T bot = T(0);
+#pragma unroll
+        for (int a = 0; a < NJ; ++a) if ((row % NJ) == a) bot = pb[a];
+        val = (row < NJ) ? full[k * NM + row] + dte * full[k * NM + NJ + row] + tau * bot : bot;
+      }
+      out[r] = live ? val + sign * Wn[jo * NM + row] : T(0);
+    }
+  };
+  // out = Pd_jo * buf[jo]  (entries published by the lanes of this group: __syncwarp suffices)
+  auto pd_mul = [&](const T* buf, T* out) {
+    T o0[RPT], o1[RPT];
+#pragma unroll
+    for (int r = 0; r < RPT; ++r) { o0[r] = T(0); o1[r] = T(0); }
+#pragma unroll
+    for (int c = 0; c < NX; c += 2) {
+      const T v0 = buf[jo * NX + c], v1 = buf[jo * NX + c + 1];
+#pragma unroll
+      for (int r = 0; r < RPT; ++r) { o0[r] += pd[r][c] * v0; o1[r] += pd[r][c + 1] * v1; }
+    }
+#pragma unroll
+    for (int r = 0; r < RPT; ++r) out[r] = o0[r] + o1[r];
+  };
+  T rr[RPT], xx[RPT], pp[RPT], rt[RPT], yv[RPT], tmp[RPT];
+  auto precond = [&]() {
+    publish(V, rr);
+    __syncwarp();
+    pd_mul(V, yv);
+    if (!stair) {
+#pragma unroll
+      for (int r = 0; r < RPT; ++r) rt[r] = yv[r];
+      return;
+    }
+    publish(V2, yv);
+    __syncthreads();
+    // q_c = Ghat [y_k;0], q'_c = Ghat AB^T y_{k+1}
+    T u1[MC], u2[MC], h1 = T(0), h2 = T(0);
+    abt(V2, u2);
+#pragma unroll
+    for (int i = 0; i < MC; ++i) {
+      const int c = c0 + i;
+      u1[i] = (cval[i] && c < NX) ? V2[k * NX + c] : T(0);
+      h1 += hh[i] * u1[i];
+      h2 += hh[i] * u2[i];
+    }
+    h1 = quad(h1); h2 = quad(h2);
+#pragma unroll
+    for (int i = 0; i < MC; ++i) {
+      u1[i] = dinv[i] * u1[i] - sS * hh[i] * h1;
+      u2[i] = dinv[i] * u2[i] - sS * hh[i] * h2;
+      if (cval[i]) { Wq[k * NM + c0 + i] = u1[i]; W[k * NM + c0 + i] = u2[i]; }
+    }
+    __syncthreads();
+    abmul(u1, Wq, W, T(1), tmp);
+    publish(V, tmp);
+    __syncwarp();
+    pd_mul(V, tmp);
+#pragma unroll
+    for (int r = 0; r < RPT; ++r) rt[r] = yv[r] - tmp[r];
+  };
+#pragma unroll
+  for (int r = 0; r < RPT; ++r) { rr[r] = live ? d.gam[(size_t)(i0 + r) * K + tj] : T(0); xx[r] = T(0); }
+  precond();
+  T part = T(0);
+#pragma unroll
+  for (int r = 0; r < RPT; ++r) { pp[r] = rt[r]; part += rr[r] * rt[r]; }
+  T nu = block_sum(part, red, tid, nt);
+  int iters = 0;
+  for (int it = 0; it < max_iter; ++it) {
+    publish(V, pp);
+    __syncthreads();
+    T uc[MC], hu = T(0), ap[RPT];
+    abt(V, uc);
+#pragma unroll
+    for (int i = 0; i < MC; ++i) {
+      const int c = c0 + i;
+      uc[i] = ((cval[i] && c < NX) ? V[k * NX + c] : T(0)) - uc[i];
+      hu += hh[i] * uc[i];
+    }
+    hu = quad(hu);
+#pragma unroll
+    for (int i = 0; i < MC; ++i) {
+      uc[i] = dinv[i] * uc[i] - sS * hh[i] * hu;
+      if (cval[i]) W[k * NM + c0 + i] = uc[i];
+    }
+    __syncthreads();
+    abmul(uc, W, W, T(-1), ap);
+    part = T(0);
+#pragma unroll
+    for (int r = 0; r < RPT; ++r) part += pp[r] * ap[r];
+    const T pAp = block_sum(part, red, tid, nt);
+    const T alpha = nu / pAp;
+#pragma unroll
+    for (int r = 0; r < RPT; ++r) { rr[r] -= ap[r] * alpha; xx[r] += pp[r] * alpha; }
+    precond();
+    part = T(0);
+#pragma unroll
+    for (int r = 0; r < RPT; ++r) part += rr[r] * rt[r];
+    const T nu_prime = block_sum(part, red, tid, nt);
+    iters = it + 1;
+    if (fabs(nu_prime) < tol) break;
+    const T beta = nu_prime / nu;
+#pragma unroll
+    for (int r = 0; r < RPT; ++r) pp[r] = rt[r] + pp[r] * beta;
+    nu = nu_prime;
+  }
+  if (live) {
+#pragma unroll
+    for (int r = 0; r < RPT; ++r) d.l[(size_t)(i0 + r) * K + tj] = xx[r];
   }
   if (tid == 0) {
     d.pcg_iters[b] = iters;
@@ -805,19 +1076,19 @@ __global__ void __launch_bounds__(128) k_recover(Dev<T> d, const int* list, cons
   const int b = list[slot];
   const size_t t = (size_t)b * d.N + k;
   const size_t K = d.K;
-  const int R = d.N * NX;
+  (void)0;
   const bool terminal = (k == d.N - 1);
   T rhs[NM];
   for (int i = 0; i < NM; ++i) rhs[i] = d.g[(size_t)i * K + t];
-  const T* l = d.l + (size_t)b * R;
-  for (int i = 0; i < NX; ++i) rhs[i] -= l[k * NX + i];
+  const T* l = d.l + (size_t)b * d.N;
+  for (int i = 0; i < NX; ++i) rhs[i] -= l[(size_t)i * K + k];
   if (!terminal) {
     T dq[NDYN], AB[NX * NM];
     for (int i = 0; i < NDYN; ++i) dq[i] = d.dyn[(size_t)i * K + t];
     build_AB(d.integrator, dq, d.dt, AB);
     for (int c = 0; c < NM; ++c) {
       T acc = T(0);
-      for (int i = 0; i < NX; ++i) acc += AB[i * NM + c] * l[(k + 1) * NX + i];
+      for (int i = 0; i < NX; ++i) acc += AB[i * NM + c] * l[(size_t)i * K + k + 1];
       rhs[c] += acc;
     }
   }
@@ -1365,16 +1636,7 @@ __global__ void k_fetch_soa(const T* a, size_t K, int E, double* out) {
   if (gt >= K) return;
   for (int e = 0; e < E; ++e) out[gt * E + e] = (double)a[(size_t)e * K + gt];
 }
-// fetch of an instance-major block array M[b][c][r] (r = k*NX+i) into out[b][k][i*ncol + c]
-template <typename T>
-__global__ void k_fetch_blocks(const T* M, int B, int N, int ncol, double* out) {
-  const size_t gt = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
-  if (gt >= (size_t)B * N) return;
-  const int b = (int)(gt / N), k = (int)(gt % N);
-  const int R = N * NX;
-  for (int i = 0; i < NX; ++i)
-    for (int c = 0; c < ncol; ++c) out[(gt * NX + i) * ncol + c] = (double)M[((size_t)b * ncol + c) * R + k * NX + i];
-}
+
 template <typename T>
 __global__ void k_fill(T* p, size_t n, T v) {
   const size_t gt = (size_t)blockIdx.x * blockDim.x + threadIdx.x;

@@ -177,9 +177,15 @@ struct SolverT : SolverBase {
     B2T_CUDA(cudaEventCreate(&ev0)); B2T_CUDA(cudaEventCreate(&ev1));
     // kernels that need > 48 KB of dynamic shared memory
     B2T_CUDA(cudaFuncSetAttribute(b2t::k_pcg<T>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+    B2T_CUDA(cudaFuncSetAttribute(b2t::k_schur_diag<T>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)((size_t)NJ * NM * SCHUR_THREADS * sizeof(T))));
     B2T_CUDA(cudaFuncSetAttribute(b2t::k_pcg2<T, PCG_RPT, 1, true, 256>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
     B2T_CUDA(cudaFuncSetAttribute(b2t::k_pcg2<T, PCG_RPT, 1, true, 512>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
     B2T_CUDA(cudaFuncSetAttribute(b2t::k_pcg2<T, PCG_RPT, 1, true, 1024>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+    if constexpr (b2t::NX % 4 == 0) {
+      B2T_CUDA(cudaFuncSetAttribute(b2t::k_pcg3<T, 256>, cudaFuncAttributeMaxDynamicSharedMemorySize, 160 * 1024));
+      B2T_CUDA(cudaFuncSetAttribute(b2t::k_pcg3<T, 512>, cudaFuncAttributeMaxDynamicSharedMemorySize, 160 * 1024));
+      B2T_CUDA(cudaFuncSetAttribute(b2t::k_pcg3<T, 1024>, cudaFuncAttributeMaxDynamicSharedMemorySize, 160 * 1024));
+    }
     if constexpr (PCG_CS_MAX == 2) {
       B2T_CUDA(cudaFuncSetAttribute(b2t::k_pcg2<T, PCG_RPT, 2, true, 256>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
       B2T_CUDA(cudaFuncSetAttribute(b2t::k_pcg2<T, PCG_RPT, 2, true, 512>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
@@ -382,7 +388,8 @@ struct SolverT : SolverBase {
     const int jac = method == B2T_METHOD_PCG_J ? 1 : 0;
     if (d.diag_mode) {
       { Scope sc(this, B2T_K_KKT); k_kkt_diag<T><<<cdiv(nthreads, 128), 128, 0, stream>>>(d, list, count); tick(B2T_K_KKT); }
-      { Scope sc(this, B2T_K_SCHUR); k_schur_diag<T><<<cdiv(nthreads, 128), 128, 0, stream>>>(d, list, count, jac); tick(B2T_K_SCHUR); }
+      { Scope sc(this, B2T_K_SCHUR); k_schur_diag<T><<<cdiv(nthreads, SCHUR_THREADS), SCHUR_THREADS, (size_t)NJ * NM * SCHUR_THREADS * sizeof(T), stream>>>(d, list, count, jac); tick(B2T_K_SCHUR); }
+      { Scope sc(this, B2T_K_SCHUR); k_pinv<T><<<cdiv(nthreads, 128), 128, 0, stream>>>(d, list, count, jac); tick(B2T_K_SCHUR); }
       return 0;
     }
     { Scope sc(this, B2T_K_KKT); k_kkt<T><<<cdiv(nthreads, 64), 64, 0, stream>>>(d, list, count); tick(B2T_K_KKT); }
@@ -417,7 +424,9 @@ struct SolverT : SolverBase {
     if (mats) v += (size_t)2 * PCG_RPT * (b2t::NX / pcg2_cs()) * pcg2_maxt() * sizeof(T);
     return v;
   }
-  int pcg_variant = -1;      // 0: k_pcg (v1), 1: k_pcg2 with shared-memory diagonal blocks, 2: k_pcg2 streaming them
+  // 0: k_pcg (v1), 1: k_pcg2 with shared-memory diagonal blocks (default), 2: k_pcg2 streaming them from L1/L2,
+  // 3: k_pcg3 matrix-free (opt-in with B2T_PCG_VARIANT=3; measured slower than variant 1 on B200: 30.7 vs 23.8 ms / 2048 instances)
+  int pcg_variant = -1;
   int launch_pcg(const int* list, const int* count, int bound, int method, T tol, int max_iter) {
     using namespace b2t;
     if (pcg_variant < 0) {
@@ -425,10 +434,22 @@ struct SolverT : SolverBase {
       if (e) pcg_variant = atoi(e);
       else if (pcg2_threads() > 1024) pcg_variant = 0;
       else pcg_variant = pcg2_smem(true) <= (size_t)220 * 1024 ? 1 : 2;
+      if (pcg_variant == 3 && !(d.diag_mode && b2t::NX % 4 == 0 && 4 * d.N <= 1024)) pcg_variant = 1;
     }
     const int stair = method == B2T_METHOD_PCG_SS ? 1 : 0;
     Scope sc(this, B2T_K_PCG);
     const int nt = pcg2_threads();
+    if (pcg_variant == 3) {
+      if constexpr (b2t::NX % 4 == 0) {
+        const int nt3 = ((4 * d.N + 31) / 32) * 32;
+        const size_t sm3 = ((size_t)2 * (d.N + 1) * NX + (size_t)2 * d.N * NM + 32) * sizeof(T);
+        if (nt3 <= 256) k_pcg3<T, 256><<<bound, nt3, sm3, stream>>>(d, list, count, stair, tol, max_iter);
+        else if (nt3 <= 512) k_pcg3<T, 512><<<bound, nt3, sm3, stream>>>(d, list, count, stair, tol, max_iter);
+        else k_pcg3<T, 1024><<<bound, nt3, sm3, stream>>>(d, list, count, stair, tol, max_iter);
+      }
+      tick(B2T_K_PCG);
+      return 0;
+    }
     const int cs = pcg2_cs();
 #define B2T_PCG2(CSV, SM, MT) k_pcg2<T, PCG_RPT, CSV, SM, MT><<<bound, nt, pcg2_smem(SM), stream>>>(d, list, count, stair, tol, max_iter)
 #define B2T_PCG2_MT(CSV, SM) do { if (nt <= 256) B2T_PCG2(CSV, SM, 256); else if (nt <= 512) B2T_PCG2(CSV, SM, 512); else B2T_PCG2(CSV, SM, 1024); } while (0)
@@ -586,7 +607,7 @@ struct SolverT : SolverBase {
     if (!out) return fail(B2T_ERR_INVALID, "out required");
     B2T_CUDA(cudaSetDevice(device));
     const size_t K = d.K;
-    const T* src = nullptr; int E = 0; bool blocks = false; bool flat = false;
+    const T* src = nullptr; int E = 0;
     switch (which) {
       case B2T_ARR_X: src = d.x; E = NX; break;
       case B2T_ARR_U: src = d.u; E = NU; break;
@@ -597,18 +618,16 @@ struct SolverT : SolverBase {
       case B2T_ARR_DZ: src = d.dz; E = NM; break;
       case B2T_ARR_XN: src = d.xn; E = NX; break;
       case B2T_ARR_UN: src = d.un; E = NU; break;
-      case B2T_ARR_SD: src = d.Sd; E = NX * NX; blocks = true; break;
-      case B2T_ARR_SO: src = d.So; E = NX * NX; blocks = true; break;
-      case B2T_ARR_PD: src = d.Pd; E = NX * NX; blocks = true; break;
-      case B2T_ARR_GAMMA: src = d.gam; E = NX; flat = true; break;
-      case B2T_ARR_L: src = d.l; E = NX; flat = true; break;
+      case B2T_ARR_SD: src = d.Sd; E = NX * NX; break;
+      case B2T_ARR_SO: src = d.So; E = NX * NX; break;
+      case B2T_ARR_PD: src = d.Pd; E = NX * NX; break;
+      case B2T_ARR_GAMMA: src = d.gam; E = NX; break;
+      case B2T_ARR_L: src = d.l; E = NX; break;
       default: return fail(B2T_ERR_INVALID, "unknown array id");
     }
     const size_t n = K * E;
     if (n * sizeof(double) > stage_out_bytes) return fail(B2T_ERR_INVALID, "array too large for staging");
     if (which == B2T_ARR_GHAT && d.diag_mode) k_fetch_ghat_diag<T><<<cdiv(K, 128), 128, 0, stream>>>(d, stage_out);
-    else if (blocks) k_fetch_blocks<T><<<cdiv(K, 128), 128, 0, stream>>>(src, d.B, d.N, NX, stage_out);
-    else if (flat) k_fetch_soa<T><<<cdiv(n, 128), 128, 0, stream>>>(src, n, 1, stage_out);
     else k_fetch_soa<T><<<cdiv(K, 128), 128, 0, stream>>>(src, K, E, stage_out);
     B2T_CUDA(cudaGetLastError());
     B2T_CUDA(cudaMemcpyAsync(out, stage_out, n * sizeof(double), cudaMemcpyDeviceToHost, stream));
