@@ -133,3 +133,26 @@ def test_full_size_properties(oracle_models):
     r4 = solver2.solve_batch(x0, u0, xg2, N, 0.1, t.SQPSolverMethods.PCG_SS, dict(opts))
     assert (r4.sqp_iter[5], r4.total_pcg[5], r4.total_trials[5]) == (6, 563, 16)
     assert abs(r4.J[5] - 6.50929423656) < 1e-7       # parity floor: the reference's own J moves by ~1e-8 under 1-ulp perturbations
+
+
+def test_fp32_mode(oracle_models):
+    """dtype='f32' instantiates the whole path in single precision.  Measured (scripts/fp32_probe.py):
+    on arm2 it tracks fp64 to ~1e-4; on arm6 the SQP iteration amplifies fp32 rounding (Ghat has entries ~1/rho = 1e3, the
+    PCG exit test is an absolute 1e-6) and the iterates take a different path, so only sanity is asserted there."""
+    N = 10
+    (plant, pc, _), _ = make_pair("arm2", N, oracle_models, cost_kind="quadratic", xg=np.array([0.4, -0.3, 0.0, 0.0]))
+    B = 8
+    xg = _batch_goals(2, B, 5)
+    solver = t.TrajoptMPCReference(plant, pc)
+    opts = {"expected_reduction_min_SQP_DDP": -100}
+    x0 = np.zeros((B, 4, N)); u0 = np.zeros((B, 2, N - 1))
+    r64 = solver.solve_batch(x0, u0, xg, N, 0.1, t.SQPSolverMethods.PCG_SS, dict(opts), dtype="f64")
+    r64 = {k: np.array(v) for k, v in r64.items()}
+    r32 = solver.solve_batch(x0, u0, xg, N, 0.1, t.SQPSolverMethods.PCG_SS, dict(opts), dtype="f32")
+    assert set(np.unique(r32.exit_sqp)) <= {1, 2, 3}
+    assert np.all(np.abs(r32.J - r64["J"]) <= 6e-4 * np.maximum(1.0, np.abs(r64["J"])))
+    assert np.max(np.abs(r32.x - r64["x"])) < 5e-3
+    (plant6, pc6, _), _ = make_pair("arm6", 16, oracle_models)
+    s6 = t.TrajoptMPCReference(plant6, pc6)
+    r = s6.solve_batch(np.zeros((B, 12, 16)), np.zeros((B, 6, 15)), _batch_goals(6, B, 5), 16, 0.1, t.SQPSolverMethods.PCG_SS, dict(opts), dtype="f32")
+    assert set(np.unique(r.exit_sqp)) <= {1, 2, 3} and np.all(np.isfinite(r.J)) and np.all(np.isfinite(r.x))
