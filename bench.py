@@ -74,8 +74,8 @@ def flops_of(fm, qp, pcg, trials, B):
     fam = {k: N * v * qp for k, v in fm["per_qp"].items()}
     fam["fd"] += N * fm["trial_fd"] * B                  # initial violation evaluation
     fam["pcg"] = N * fm["pcg_iter"] * pcg
-    fam["trial_fd"] = N * fm["trial_fd"] * trials
-    fam["merit"] = N * fm["trial_merit"] * (trials + B)
+    fam["trial_fd"] = N * fm["F_trial"] * trials         # k_linesearch: trial point, forward dynamics, merit terms
+    fam["merit"] = N * fm["trial_merit"] * B             # k_outer_begin: initial J, c
     fam["ctrl"] = 0
     return fam
 
@@ -187,7 +187,7 @@ def config_dict(args, note=None):
                      "goals U(-0.5,0.5)^6 seeded, %s, batch %d per GPU" %
                      ("quadratic-penalty box limits |u|<=1.0 |q|<=0.45" if args.limits else "no box limits", args.batch),
          "batch_per_gpu": args.batch, "knots": N_KNOTS, "method": "PCG-SS", "limits": bool(args.limits),
-         "l2": "per-step working set (>4 GB workspace) exceeds the 126 MB L2; no explicit flush"}
+         "l2": "no explicit flush: the per-step working set (solver workspace, see workspace_gb) exceeds the 126 MB L2 at the default batch"}
     if note:
         c["note"] = note
     return c
@@ -206,6 +206,7 @@ def run_b200_arm(args):
         raise SystemExit("bench.py needs a CUDA device (no CPU fallback)")
     torch.cuda.set_device(local)
     if world > 1:
+        os.environ["NCCL_DEBUG"] = os.environ.get("B2T_NCCL_DEBUG", "WARN")     # keep stdout to the single JSON line
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
     B, N = args.batch, N_KNOTS
     xg_np = workload_goals(world, rank, B)

@@ -47,8 +47,9 @@ typedef enum {
 
 typedef enum { B2T_COST_QUADRATIC = 0, B2T_COST_URDF_EE = 1 } b2t_cost_kind;
 typedef enum { B2T_LIMIT_NONE = 0, B2T_LIMIT_QUADRATIC_PENALTY = 1, B2T_LIMIT_AUGMENTED_LAGRANGIAN = 2 } b2t_limit_mode;
-/* SQPSolverMethods (TrajoptMPCReference.py:13-18); N and S are exact solves of the same system */
-typedef enum { B2T_METHOD_PCG_J = 2, B2T_METHOD_PCG_BJ = 3, B2T_METHOD_PCG_SS = 4 } b2t_method;
+/* SQPSolverMethods (TrajoptMPCReference.py:13-18).  N (dense KKT backslash, :313-359) and S (Schur backslash, :430-436) are
+ * exact solves of the same linear system; both run the block-tridiagonal factorisation of the Schur complement here. */
+typedef enum { B2T_METHOD_N = 0, B2T_METHOD_S = 1, B2T_METHOD_PCG_J = 2, B2T_METHOD_PCG_BJ = 3, B2T_METHOD_PCG_SS = 4 } b2t_method;
 typedef enum { B2T_F64 = 0, B2T_F32 = 1 } b2t_dtype;
 /* limit types, index into the per-type arrays below */
 enum { B2T_LIM_JOINT = 0, B2T_LIM_VELOCITY = 1, B2T_LIM_TORQUE = 2 };

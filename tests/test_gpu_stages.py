@@ -100,6 +100,13 @@ def test_kkt_schur_pcg_recover_merit(tag, dense_kkt, batch, oracle_models):
             dz_ex = kkt.recover(blocks, sch, l_ex, nx)
             assert np.max(np.abs(s.fetch("l")[0] - l_ex)) < 1e-7 * max(1.0, np.max(np.abs(l_ex)))
             assert np.max(np.abs(s.fetch("dz")[batch - 1] - dz_ex)) < 1e-7 * max(1.0, np.max(np.abs(dz_ex)))
+    # exact methods S / N (block-tridiagonal factorisation) against the reference's recorded np.linalg.solve results
+    for method, key in ((t.SQPSolverMethods.S, "dxul_S"), (t.SQPSolverMethods.N, "dxul_N")):
+        s.stage_kkt(rho, method); it = s.stage_pcg(method); s.stage_recover()
+        assert it.tolist() == [0] * batch
+        dzg, lg = s.fetch("dz")[batch - 1], s.fetch("l")[batch - 1]
+        packed = np.concatenate([dzg[:N - 1].reshape(-1), dzg[N - 1, :nx], lg.reshape(-1)])[:, None]
+        assert relerr(packed, K[tag + "/" + key]) < 1e-7
     # merit terms of the trial point x - alpha dz (dz from the last recover = BJ): compare with the oracle on the SAME dz
     s.stage_kkt(rho, t.SQPSolverMethods.PCG_SS); s.stage_pcg(t.SQPSolverMethods.PCG_SS); s.stage_recover()
     dz = s.fetch("dz")[0]

@@ -11,7 +11,7 @@ from .model import extract_model, builtin_urdf, model_digest
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 
 # ---- mirrors of include/b2t.h
-METHOD_PCG_J, METHOD_PCG_BJ, METHOD_PCG_SS = 2, 3, 4
+METHOD_N, METHOD_S, METHOD_PCG_J, METHOD_PCG_BJ, METHOD_PCG_SS = 0, 1, 2, 3, 4
 F64, F32 = 0, 1
 COST_QUADRATIC, COST_URDF_EE = 0, 1
 LIMIT_NONE, LIMIT_QUADRATIC_PENALTY, LIMIT_AUGMENTED_LAGRANGIAN = 0, 1, 2

@@ -36,8 +36,8 @@ class MPCSolverMethods(enum.Enum):          # TrajoptMPCReference.py:21-27
     QP_PCG_SS = "QP-PCG-SS"
 
 
-_METHOD_CODE = {SQPSolverMethods.PCG_J: _lib.METHOD_PCG_J, SQPSolverMethods.PCG_BJ: _lib.METHOD_PCG_BJ,
-                SQPSolverMethods.PCG_SS: _lib.METHOD_PCG_SS}
+_METHOD_CODE = {SQPSolverMethods.N: _lib.METHOD_N, SQPSolverMethods.S: _lib.METHOD_S, SQPSolverMethods.PCG_J: _lib.METHOD_PCG_J,
+                SQPSolverMethods.PCG_BJ: _lib.METHOD_PCG_BJ, SQPSolverMethods.PCG_SS: _lib.METHOD_PCG_SS}
 
 
 # --------------------------------------------------------------------------------------------------- plant
@@ -525,7 +525,7 @@ class BatchSolver:
     def solve(self, method=SQPSolverMethods.PCG_SS, options=None):
         """Runs SQP on the trajectories / goals currently in the workspace."""
         if method not in _METHOD_CODE:
-            raise ValueError("the GPU path implements the PCG methods (PCG-J, PCG-BJ, PCG-SS); N and S are exact solves of the same system")
+            raise ValueError("Invalid QP Solver options are: N, S, PCG-J, PCG-BJ, PCG-SS")
         o = self.make_options(options)
         _lib.check(self.lib, self.lib.b2t_sqp_solve(self._h, _METHOD_CODE[method], ctypes.byref(o)))
 

@@ -1065,6 +1065,76 @@ __global__ void __launch_bounds__(MAXT) k_pcg3(Dev<T> d, const int* list, const 
 }
 
 // -----------------------------------------------------------------------------------------------------------------
+// k_bt_solve: exact solve of S l = gamma (methods 'S' and 'N' of the reference: np.linalg.solve on the Schur system,
+// TrajoptMPCReference.py:430-436, resp. on the full KKT system :349-357 -- the same solution up to rounding).
+// Block Thomas algorithm on the SPD block-tridiagonal matrix T = -S, one thread per instance:
+//   Delta_0 = D_0,  Delta_j = D_j - O_j Delta_{j-1}^-1 O_j^T,  g_j = b_j - O_j Delta_{j-1}^-1 g_{j-1},
+//   l_{N-1} = Delta_{N-1}^-1 g_{N-1},  l_j = Delta_j^-1 (g_j - O_{j+1}^T l_{j+1}).
+// Delta_j^-1 is kept in the (otherwise unused) preconditioner array, g_j in l.  ~5 k FMA per knot: far less work than PCG,
+// so a latency-bound kernel is adequate here.
+// -----------------------------------------------------------------------------------------------------------------
+template <typename T>
+__global__ void __launch_bounds__(32) k_bt_solve(Dev<T> d, const int* list, const int* count) {
+  const int slot = blockIdx.x * blockDim.x + threadIdx.x;
+  if (slot >= *count) return;
+  const int b = list[slot];
+  const int N = d.N;
+  const size_t K = d.K;
+  const size_t t0 = (size_t)b * N;
+  T Dp[NX * NX], Dj[NX * NX], M[NX * NX], gp[NX], gj[NX];
+  for (int j = 0; j < N; ++j) {
+    const size_t t = t0 + j;
+    for (int e = 0; e < NX * NX; ++e) Dj[e] = -d.Sd[(size_t)e * K + t];
+    for (int i = 0; i < NX; ++i) gj[i] = -d.gam[(size_t)i * K + t];
+    if (j > 0) {
+      // M = O_j Dp   (O_j = -So_j)
+      for (int i = 0; i < NX; ++i)
+        for (int c = 0; c < NX; ++c) {
+          T acc = T(0);
+          for (int r = 0; r < NX; ++r) acc += (-d.So[(size_t)(i * NX + r) * K + t]) * Dp[r * NX + c];
+          M[i * NX + c] = acc;
+        }
+      for (int i = 0; i < NX; ++i) {
+        for (int c = 0; c < NX; ++c) {
+          T acc = T(0);
+          for (int r = 0; r < NX; ++r) acc += M[i * NX + r] * (-d.So[(size_t)(c * NX + r) * K + t]);
+          Dj[i * NX + c] -= acc;
+        }
+        T accg = T(0);
+        for (int r = 0; r < NX; ++r) accg += M[i * NX + r] * gp[r];
+        gj[i] -= accg;
+      }
+    }
+    spd_inverse_inplace(Dj, NX, NX);
+    for (int e = 0; e < NX * NX; ++e) { Dp[e] = Dj[e]; d.Pd[(size_t)e * K + t] = Dj[e]; }
+    for (int i = 0; i < NX; ++i) { gp[i] = gj[i]; d.l[(size_t)i * K + t] = gj[i]; }
+  }
+  // back substitution
+  T ln[NX];
+  for (int j = N - 1; j >= 0; --j) {
+    const size_t t = t0 + j;
+    T rhs[NX];
+    for (int i = 0; i < NX; ++i) rhs[i] = d.l[(size_t)i * K + t];
+    if (j < N - 1) {
+      for (int i = 0; i < NX; ++i) {
+        T acc = T(0);
+        for (int r = 0; r < NX; ++r) acc += (-d.So[(size_t)(r * NX + i) * K + t + 1]) * ln[r];     // O_{j+1}^T l_{j+1}
+        rhs[i] -= acc;
+      }
+    }
+    T lj[NX];
+    for (int i = 0; i < NX; ++i) {
+      T acc = T(0);
+      for (int c = 0; c < NX; ++c) acc += d.Pd[(size_t)(i * NX + c) * K + t] * rhs[c];
+      lj[i] = acc;
+    }
+    for (int i = 0; i < NX; ++i) { ln[i] = lj[i]; d.l[(size_t)i * K + t] = lj[i]; }
+  }
+  d.pcg_iters[b] = 0;
+  d.tot_qp[b] += 1;
+}
+
+// -----------------------------------------------------------------------------------------------------------------
 // k_recover: dz_k = Ghat_k (g_k - [l_k; 0] + AB_k^T l_{k+1})     (:449-452)
 // -----------------------------------------------------------------------------------------------------------------
 template <typename T>

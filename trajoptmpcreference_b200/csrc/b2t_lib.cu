@@ -389,7 +389,9 @@ struct SolverT : SolverBase {
     if (d.diag_mode) {
       { Scope sc(this, B2T_K_KKT); k_kkt_diag<T><<<cdiv(nthreads, 128), 128, 0, stream>>>(d, list, count); tick(B2T_K_KKT); }
       { Scope sc(this, B2T_K_SCHUR); k_schur_diag<T><<<cdiv(nthreads, SCHUR_THREADS), SCHUR_THREADS, (size_t)NJ * NM * SCHUR_THREADS * sizeof(T), stream>>>(d, list, count, jac); tick(B2T_K_SCHUR); }
-      { Scope sc(this, B2T_K_SCHUR); k_pinv<T><<<cdiv(nthreads, 128), 128, 0, stream>>>(d, list, count, jac); tick(B2T_K_SCHUR); }
+      if (method != B2T_METHOD_N && method != B2T_METHOD_S) {
+        Scope sc(this, B2T_K_SCHUR); k_pinv<T><<<cdiv(nthreads, 128), 128, 0, stream>>>(d, list, count, jac); tick(B2T_K_SCHUR);
+      }
       return 0;
     }
     { Scope sc(this, B2T_K_KKT); k_kkt<T><<<cdiv(nthreads, 64), 64, 0, stream>>>(d, list, count); tick(B2T_K_KKT); }
@@ -438,6 +440,11 @@ struct SolverT : SolverBase {
     }
     const int stair = method == B2T_METHOD_PCG_SS ? 1 : 0;
     Scope sc(this, B2T_K_PCG);
+    if (method == B2T_METHOD_N || method == B2T_METHOD_S) {
+      k_bt_solve<T><<<cdiv(bound, 32), 32, 0, stream>>>(d, list, count);
+      tick(B2T_K_PCG);
+      return 0;
+    }
     const int nt = pcg2_threads();
     if (pcg_variant == 3) {
       if constexpr (b2t::NX % 4 == 0) {
@@ -475,8 +482,9 @@ struct SolverT : SolverBase {
   int solve(int method, const b2t_options* o) override {
     using namespace b2t;
     if (!o) return fail(B2T_ERR_INVALID, "options required");
-    if (method != B2T_METHOD_PCG_J && method != B2T_METHOD_PCG_BJ && method != B2T_METHOD_PCG_SS)
-      return fail(B2T_ERR_UNSUPPORTED, "method must be PCG-J, PCG-BJ or PCG-SS");
+    if (method != B2T_METHOD_N && method != B2T_METHOD_S && method != B2T_METHOD_PCG_J && method != B2T_METHOD_PCG_BJ &&
+        method != B2T_METHOD_PCG_SS)
+      return fail(B2T_ERR_INVALID, "method must be N, S, PCG-J, PCG-BJ or PCG-SS");
     if (o->max_iter_SQP + 1 > d.trace_cap) return fail(B2T_ERR_UNSUPPORTED, "max_iter_SQP_DDP > 103");
     B2T_CUDA(cudaSetDevice(device));
     Opts<T> op = convert(o);
