@@ -109,7 +109,11 @@ typedef enum {
   B2T_ARR_L,            /* [N][nx]   multipliers from PCG */
   B2T_ARR_DZ,           /* [N][m]    step [dx_k; du_k] */
   B2T_ARR_XN,           /* [N][nx]   line-search trial point */
-  B2T_ARR_UN            /* [N][nu] */
+  B2T_ARR_UN,           /* [N][nu] */
+  /* per-knot cost terms at the current (x, u), evaluated on demand: TrajoptCost.value / gradient / hessian (TrajoptCost.py:49-83, 402-519) */
+  B2T_ARR_COST_VALUE,   /* [N][1] */
+  B2T_ARR_COST_GRAD,    /* [N][m]   (control part zero at the terminal knot) */
+  B2T_ARR_COST_HESS     /* [N][m*m] */
 } b2t_array;
 
 typedef struct b2t_solver b2t_solver;

@@ -122,3 +122,27 @@ def test_kkt_schur_pcg_recover_merit(tag, dense_kkt, batch, oracle_models):
             D_or += float(np.sum(sg[:N - 1] * dz[:N - 1]) + np.sum(sg[N - 1, :nx] * dz[N - 1, :nx]))
         assert np.allclose(J, J_or, rtol=1e-12) and np.allclose(c, c_or, rtol=1e-11) and np.allclose(D, D_or, rtol=1e-10, atol=1e-12)
         assert relerr(s.fetch("xn")[0], Xn) < 1e-14
+
+
+def test_urdf_cost_callbacks(oracle_models):
+    """UrdfCost.value / gradient / hessian (TrajoptCost.py:402-519) evaluated by the cost kernels vs the oracle."""
+    from oracle import cost as ocost
+    m = oracle_models["arm2"]
+    rng = np.random.default_rng(9)
+    A = rng.uniform(-1, 1, (4, 4)); Q = A @ A.T + np.eye(4); QF = 50 * Q; R = np.diag([0.1, 0.3]); xg = np.array([-1.0, 1.5, 0.1, -0.2])
+    plant = t.URDFPlant(options={"path_to_urdf": "arm2"})
+    pc = t.UrdfCost(plant, Q, QF, R, xg, QF_start=3)
+    oc = ocost.UrdfCost(m, Q, QF, R, xg, QF_start=3)
+    for k in (1, 4):
+        x = rng.uniform(-1, 1, 4); u = rng.uniform(-1, 1, 2)
+        X = np.stack([x, x]); U = u[None]
+        vals = oc.values(X, U); grads = oc.gradients(X, U); hess = oc.hessians(X, U)
+        # oracle arrays are for knots (0 running, 1 terminal); evaluate the running knot at timestep k explicitly
+        oc_k = ocost.UrdfCost(m, Q if k < 3 else QF, QF, R, xg)
+        v_run = oc_k.values(X, U)[0]; g_run = oc_k.gradients(X, U)[0]; h_run = oc_k.hessians(X, U)[0]
+        assert abs(pc.value(x, u, k) - v_run) < 1e-12 * max(1, abs(v_run))
+        assert relerr(pc.gradient(x, u, k), g_run) < 1e-12
+        assert relerr(pc.hessian(x, u, k), h_run) < 1e-12
+        assert abs(pc.value(x, None, 9) - vals[1]) < 1e-12 * max(1, abs(vals[1]))
+        assert relerr(pc.gradient(x, None, 9), grads[1][:4]) < 1e-12
+        assert relerr(pc.hessian(x, None, 9), hess[1][:4, :4]) < 1e-12

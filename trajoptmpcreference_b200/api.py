@@ -250,11 +250,43 @@ class UrdfCost(QuadraticCost):
         self.overloading = overloading
         self.hess_mode = 0
 
-    def value(self, x, u=None, timestep=None, iter_1=0, iter_2=0, iter_3=0):
-        raise NotImplementedError("UrdfCost.value is evaluated inside the solver kernels; use TrajoptMPCReference.totalCost")
+    def _knot(self, x, u, timestep):
+        """Evaluate this cost at one knot on the GPU (1 instance, 2 knots: knot 0 = (x,u) as a running knot, knot 1 = x as terminal)."""
+        n = self.n
+        use_qf_running = timestep is not None and self.QF_start is not None and timestep >= self.QF_start
+        key = ("probe", use_qf_running)
+        cache = self.__dict__.setdefault("_probe", {})
+        if key not in cache:
+            cache[key] = BatchSolver(self.plant, self, None, N=2, dt=0.1, batch=1, qf_start_override=(0 if use_qf_running else -1))
+        s = cache[key]
+        s.set_goals(_as_f64(self.xg).reshape(1, -1))
+        X = np.zeros((1, 2 * n, 2)); U = np.zeros((1, n, 1))
+        xv = np.asarray(x, dtype=np.float64).reshape(-1)
+        X[0, :, 0] = xv; X[0, :, 1] = xv
+        if u is not None:
+            U[0, :, 0] = np.asarray(u, dtype=np.float64).reshape(-1)
+        s.set_trajectory(X, U)
+        return s, (1 if u is None else 0)
 
-    gradient = value
-    hessian = value
+    def value(self, x, u=None, timestep=None, iter_1=0, iter_2=0, iter_3=0):
+        s, k = self._knot(x, u, timestep)
+        return float(s.fetch("cost_value")[0, k, 0])
+
+    def gradient(self, x, u=None, timestep=None, iter_1=0, iter_2=0, iter_3=0):
+        s, k = self._knot(x, u, timestep)
+        g = s.fetch("cost_grad")[0, k]
+        return g[:2 * self.n].copy() if u is None else g.copy()
+
+    def hessian(self, x, u=None, timestep=None, iter_1=0, iter_2=0, iter_3=0):
+        s, k = self._knot(x, u, timestep)
+        m = 3 * self.n
+        H = s.fetch("cost_hess")[0, k].reshape(m, m)
+        return H[:2 * self.n, :2 * self.n].copy() if u is None else H.copy()
+
+    def delta_x(self, x):
+        """End-effector state error (TrajoptCost.py:425-435), recovered from the gradient: e = Q^-1 J_tot^-T grad is not needed by the
+        solver; provided for exampleHelpers-style reporting through value(): 0.5 e^T Q e."""
+        raise NotImplementedError("delta_x is internal to the kernels (urdf_cost_terms); use value()/gradient()")
 
 
 # --------------------------------------------------------------------------------------------------- constraints
@@ -608,7 +640,7 @@ class BatchSolver:
         """Knot-major copy of an internal array: (batch, N, elems)."""
         E = {"x": self.nx, "u": self.nu, "xkp1": self.nx, "dqdd": self.n * 3 * self.n, "Ghat": self.m * self.m, "g": self.m,
              "Sd": self.nx * self.nx, "So": self.nx * self.nx, "Pd": self.nx * self.nx, "gamma": self.nx, "l": self.nx, "dz": self.m,
-             "xn": self.nx, "un": self.nu}[name]
+             "xn": self.nx, "un": self.nu, "cost_value": 1, "cost_grad": self.m, "cost_hess": self.m * self.m}[name]
         out = np.zeros((self.batch, self.N, E))
         _lib.check(self.lib, self.lib.b2t_fetch(self._h, _lib.ARR[name], _dptr(out)))
         return out

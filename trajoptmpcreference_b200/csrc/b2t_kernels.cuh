@@ -1707,6 +1707,22 @@ __global__ void k_fetch_soa(const T* a, size_t K, int E, double* out) {
   for (int e = 0; e < E; ++e) out[gt * E + e] = (double)a[(size_t)e * K + gt];
 }
 
+// per-knot cost value / gradient / Hessian at (x, u) -> knot-major doubles (what = 0, 1, 2)
+template <typename T>
+__global__ void k_cost_eval(Dev<T> d, int what, double* out) {
+  const size_t gt = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (gt >= d.K) return;
+  const int b = (int)(gt / d.N), k = (int)(gt % d.N);
+  const bool terminal = (k == d.N - 1);
+  T z[NM], xg[NX];
+  load_xu(d.x, d.u, d.K, gt, terminal, z, z + NX);
+  for (int i = 0; i < NX; ++i) xg[i] = d.xg[(size_t)i * d.B + b];
+  if (what == 0) { out[gt] = (double)cost_value(d.cost, z, z + NX, xg, k, terminal); return; }
+  T g[NM], H[NM * NM];
+  cost_grad_hess<T, true>(d.cost, z, z + NX, xg, k, terminal, g, H);
+  if (what == 1) { for (int i = 0; i < NM; ++i) out[gt * NM + i] = (double)g[i]; }
+  else { for (int i = 0; i < NM * NM; ++i) out[gt * NM * NM + i] = (double)H[i]; }
+}
 template <typename T>
 __global__ void k_fill(T* p, size_t n, T v) {
   const size_t gt = (size_t)blockIdx.x * blockDim.x + threadIdx.x;

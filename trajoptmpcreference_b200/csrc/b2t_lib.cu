@@ -631,11 +631,15 @@ struct SolverT : SolverBase {
       case B2T_ARR_PD: src = d.Pd; E = NX * NX; break;
       case B2T_ARR_GAMMA: src = d.gam; E = NX; break;
       case B2T_ARR_L: src = d.l; E = NX; break;
+      case B2T_ARR_COST_VALUE: E = 1; break;
+      case B2T_ARR_COST_GRAD: E = NM; break;
+      case B2T_ARR_COST_HESS: E = NM * NM; break;
       default: return fail(B2T_ERR_INVALID, "unknown array id");
     }
     const size_t n = K * E;
     if (n * sizeof(double) > stage_out_bytes) return fail(B2T_ERR_INVALID, "array too large for staging");
-    if (which == B2T_ARR_GHAT && d.diag_mode) k_fetch_ghat_diag<T><<<cdiv(K, 128), 128, 0, stream>>>(d, stage_out);
+    if (which >= B2T_ARR_COST_VALUE) k_cost_eval<T><<<cdiv(K, 64), 64, 0, stream>>>(d, which - B2T_ARR_COST_VALUE, stage_out);
+    else if (which == B2T_ARR_GHAT && d.diag_mode) k_fetch_ghat_diag<T><<<cdiv(K, 128), 128, 0, stream>>>(d, stage_out);
     else k_fetch_soa<T><<<cdiv(K, 128), 128, 0, stream>>>(src, K, E, stage_out);
     B2T_CUDA(cudaGetLastError());
     B2T_CUDA(cudaMemcpyAsync(out, stage_out, n * sizeof(double), cudaMemcpyDeviceToHost, stream));
