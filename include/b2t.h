@@ -14,6 +14,7 @@
  *   b2t_set_trajectory / b2t_set_goals / b2t_set_multipliers
  *                            arguments x, u of SQP() (:510), cost.xg, BoxConstraint mu/lambda/phi (:23-25)
  *   b2t_sqp_solve            TrajoptMPCReference.SQP (:510-760), batched over independent instances
+ *   b2t_ilqr_solve           the iLQR solver the reference names but does not ship (README.md:15-17, :21-27)
  *   b2t_get_trajectory / b2t_get_status / b2t_get_trace / b2t_get_multipliers
  *                            the 6-tuple SQP returns (:760), self.trace (:555-569), mu/lambda/phi state
  *   b2t_sqp_solve_host       one call from host buffers to host buffers (what examples/exampleHelpers.py:80 does)
@@ -140,6 +141,9 @@ int b2t_set_multipliers(b2t_solver* s, const double* mu, const double* lam, cons
 int b2t_reset_multipliers(b2t_solver* s);
 
 int b2t_sqp_solve(b2t_solver* s, int method, const b2t_options* opts);
+/* iLQR / DDP on the same problem description (MPCSolverMethods.iLQR, TrajoptMPCReference.py:21-27; the reference ships no
+ * implementation -- specification: oracle/ilqr.py).  x[:,0] is the start state, the state trajectory is re-rolled from u. */
+int b2t_ilqr_solve(b2t_solver* s, const b2t_options* opts);
 
 int b2t_get_trajectory(b2t_solver* s, double* x, double* u, int on_device);
 int b2t_get_status(b2t_solver* s, int* status);

@@ -561,6 +561,11 @@ class BatchSolver:
         o = self.make_options(options)
         _lib.check(self.lib, self.lib.b2t_sqp_solve(self._h, _METHOD_CODE[method], ctypes.byref(o)))
 
+    def solve_ilqr(self, options=None):
+        """iLQR on the trajectories / goals currently in the workspace (x[:,0] = start state, x re-rolled from u)."""
+        o = self.make_options(options)
+        _lib.check(self.lib, self.lib.b2t_ilqr_solve(self._h, ctypes.byref(o)))
+
     def solve_host(self, x0, u0, xg, x_out, u_out, status_out, method=SQPSolverMethods.PCG_SS, options=None):
         """One call: host buffers in, host buffers out (pinned buffers make the copies asynchronous)."""
         o = self.make_options(options)
@@ -763,6 +768,34 @@ class TrajoptMPCReference:
         self.n_inner_iter = 2
         self.last_result = r
         return r.x[0], r.u[0], self.exit_sqp, self.exit_soft, int(r.outer_iter[0]), int(r.sqp_iter[0])
+
+    def iLQR(self, x, u, N, dt, options=None, dtype="f64"):
+        """iLQR with soft (penalty / augmented-Lagrangian) box limits: MPCSolverMethods.iLQR, which the reference names
+        (README.md:15-17) but does not implement.  Same options and return tuple as SQP; specification: oracle/ilqr.py."""
+        options = {} if options is None else options
+        self.set_default_options(options)
+        r = self.ilqr_batch(_as_f64(x)[None], _as_f64(u)[None], _as_f64(self.cost.xg).reshape(1, -1), N, dt, options, dtype, single=True)
+        self.exit_sqp, self.exit_soft = int(r.exit_sqp[0]), int(r.exit_soft[0])
+        self.last_result = r
+        return r.x[0], r.u[0], self.exit_sqp, self.exit_soft, int(r.outer_iter[0]), int(r.sqp_iter[0])
+
+    def ilqr_batch(self, x0, u0, xg, N, dt, options=None, dtype="f64", single=False, device=0):
+        options = {} if options is None else options
+        self.set_default_options(options)
+        B = x0.shape[0]
+        s = self.batch_solver(N, dt, B, dtype, device)
+        s.set_goals(xg)
+        s.set_trajectory(x0, u0)
+        cons = self._constraints_or_none()
+        if cons is not None:
+            mu, lam, phi = cons.pack(N)
+            s.set_multipliers(*[np.broadcast_to(a[None], (B,) + a.shape) for a in (mu, lam, phi)])
+        s.solve_ilqr(options)
+        r = s.result()
+        if single and cons is not None:
+            mu, lam, phi = s.get_multipliers()
+            cons.unpack(mu[0], lam[0], phi[0])
+        return r
 
     def solve_batch(self, x0, u0, xg, N, dt, LINEAR_SYSTEM_SOLVER_METHOD=SQPSolverMethods.PCG_SS, options=None, dtype="f64", device=0):
         """Batched SQP: x0 (B, nx, N), u0 (B, nu, N-1), xg (B, nx).  Returns a BatchResult of per-instance arrays."""

@@ -15,7 +15,7 @@ from .codegen import write_header
 HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 LIBDIR = os.path.join(HERE, "_lib")
-BUILTIN = ["pend", "arm1", "arm2", "arm3", "arm4", "arm6"]
+BUILTIN = ["pend", "arm1", "arm2", "arm3", "arm4", "arm6", "cartpole"]
 NVCC = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")
 NVCC_FLAGS = ["-O3", "-std=c++17", "-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "--expt-relaxed-constexpr",
               "-Xcompiler", "-fPIC", "-shared", "-Xptxas", "-v"]
@@ -27,7 +27,7 @@ def lib_path(tag: str) -> str:
 
 def _sources_digest(header: str) -> str:
     h = hashlib.sha1()
-    for p in (header, os.path.join(CSRC, "b2t_core.cuh"), os.path.join(CSRC, "b2t_kernels.cuh"), os.path.join(CSRC, "b2t_lib.cu"),
+    for p in (header, os.path.join(CSRC, "b2t_core.cuh"), os.path.join(CSRC, "b2t_kernels.cuh"), os.path.join(CSRC, "b2t_ilqr.cuh"), os.path.join(CSRC, "b2t_lib.cu"),
               os.path.join(os.path.dirname(HERE), "include", "b2t.h")):
         with open(p, "rb") as f:
             h.update(f.read())

@@ -1,0 +1,271 @@
+// b2t_ilqr.cuh -- iLQR (Gauss-Newton DDP with soft box limits) kernels.  The reference ships no iLQR code (README.md:15-17 and
+// the enum MPCSolverMethods.iLQR, TrajoptMPCReference.py:21-27, only name it); the specification is oracle/ilqr.py in this
+// repository.  Shares the dynamics, cost, penalty, outer-loop and work-list kernels with the SQP path.
+//   k_ilqr_cost      thread / knot      l_x, l_u (g) and the Gauss-Newton Hessian incl. penalty terms (Gh, dense m x m)
+//   k_ilqr_backward  thread / instance  Riccati recursion over the knots: gains kff, K, expected-reduction terms dV1, dV2
+//   k_ilqr_search    thread / instance  backtracking over alpha: closed-loop rollout through the integrator, cost, accept / fail,
+//                                       regularisation schedule and exit tests (same formulas as the SQP path)
+//   k_ilqr_rollout0  thread / instance  initial state trajectory = rollout of the given controls
+#pragma once
+#include "b2t_kernels.cuh"
+
+namespace b2t {
+
+template <typename T>
+__global__ void __launch_bounds__(64) k_ilqr_cost(Dev<T> d, const int* list, const int* count) {
+  const size_t gt = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  const int slot = (int)(gt / d.N);
+  if (slot >= *count) return;
+  const int k = (int)(gt % d.N);
+  const int b = list[slot];
+  const size_t t = (size_t)b * d.N + k;
+  const size_t K = d.K;
+  const bool terminal = (k == d.N - 1);
+  T z[NM], xg[NX];
+  load_xu(d.x, d.u, K, t, terminal, z, z + NX);
+  for (int i = 0; i < NX; ++i) xg[i] = d.xg[(size_t)i * d.B + b];
+  T g[NM], G[NM * NM];
+  cost_grad_hess<T, true>(d.cost, z, z + NX, xg, k, terminal, g, G);
+  if (d.lim.any) {
+    T gck[NM];
+    soft_grad(d.lim, z, d.mu + t, d.lam + t, K, terminal, gck);
+    for (int i = 0; i < NM; ++i) g[i] += gck[i];
+    for (int i = 0; i < NM; ++i)
+      for (int j = 0; j < NM; ++j) G[i * NM + j] += gck[i] * gck[j];
+  }
+  for (int i = 0; i < NM; ++i) d.g[(size_t)i * K + t] = g[i];
+  for (int i = 0; i < NM * NM; ++i) d.Gh[(size_t)i * K + t] = G[i];
+}
+
+// gains are stored in the (otherwise unused) Schur arrays: K_k (NU x NX) in Sd[0 .. NU*NX), kff_k in gam[0 .. NU)
+template <typename T>
+__global__ void __launch_bounds__(32) k_ilqr_backward(Dev<T> d, const int* list, const int* count) {
+  const int slot = blockIdx.x * blockDim.x + threadIdx.x;
+  if (slot >= *count) return;
+  const int b = list[slot];
+  const int N = d.N;
+  const size_t K = d.K;
+  const size_t t0 = (size_t)b * N;
+  const T rho = d.rho[b];
+  T Vx[NX], Vxx[NX * NX];
+  {
+    const size_t t = t0 + N - 1;
+    for (int i = 0; i < NX; ++i) {
+      Vx[i] = d.g[(size_t)i * K + t];
+      for (int c = 0; c < NX; ++c) Vxx[i * NX + c] = d.Gh[(size_t)(i * NM + c) * K + t];
+    }
+  }
+  T dV1 = T(0), dV2 = T(0);
+  int ok = 1;
+  for (int k = N - 2; k >= 0 && ok; --k) {
+    const size_t t = t0 + k;
+    T dq[NDYN], AB[NX * NM];
+    for (int i = 0; i < NDYN; ++i) dq[i] = d.dyn[(size_t)i * K + t];
+    build_AB(d.integrator, dq, d.dt, AB);                 // [A B], NX x NM
+    // VAB = Vxx [A B]  (NX x NM)
+    T VAB[NX * NM];
+    for (int i = 0; i < NX; ++i)
+      for (int c = 0; c < NM; ++c) {
+        T acc = T(0);
+        for (int r = 0; r < NX; ++r) acc += Vxx[i * NX + r] * AB[r * NM + c];
+        VAB[i * NM + c] = acc;
+      }
+    // Q = H + [A B]^T Vxx [A B]  (NM x NM: blocks Qxx, Qxu; Qux, Quu),  q = g + [A B]^T Vx
+    T Q[NM * NM], q[NM];
+    for (int a = 0; a < NM; ++a) {
+      T accq = d.g[(size_t)a * K + t];
+      for (int r = 0; r < NX; ++r) accq += AB[r * NM + a] * Vx[r];
+      q[a] = accq;
+      for (int c = 0; c < NM; ++c) {
+        T acc = d.Gh[(size_t)(a * NM + c) * K + t];
+        for (int r = 0; r < NX; ++r) acc += AB[r * NM + a] * VAB[r * NM + c];
+        Q[a * NM + c] = acc;
+      }
+    }
+    // Quu + rho I, its inverse (SPD; a non-positive pivot flags failure -> the caller raises rho)
+    T Quu[NU * NU], Qi[NU * NU];
+    for (int i = 0; i < NU; ++i)
+      for (int c = 0; c < NU; ++c) {
+        Quu[i * NU + c] = Q[(NX + i) * NM + NX + c] + ((i == c) ? rho : T(0));
+        Qi[i * NU + c] = Quu[i * NU + c];
+      }
+    {   // Cholesky test for positive definiteness (mirrors np.linalg.cholesky in the oracle)
+      T L[NU * NU];
+      for (int i = 0; i < NU * NU; ++i) L[i] = Quu[i];
+      for (int j = 0; j < NU && ok; ++j) {
+        T s = L[j * NU + j];
+        for (int r = 0; r < j; ++r) s -= L[j * NU + r] * L[j * NU + r];
+        if (!(s > T(0))) { ok = 0; break; }
+        const T ljj = sqrt(s);
+        L[j * NU + j] = ljj;
+        for (int i = j + 1; i < NU; ++i) {
+          T s2 = L[i * NU + j];
+          for (int r = 0; r < j; ++r) s2 -= L[i * NU + r] * L[j * NU + r];
+          L[i * NU + j] = s2 / ljj;
+        }
+      }
+    }
+    if (!ok) break;
+    spd_inverse_inplace(Qi, NU, NU);
+    T kff[NU], Kg[NU * NX];
+    for (int i = 0; i < NU; ++i) {
+      T acc = T(0);
+      for (int c = 0; c < NU; ++c) acc += Qi[i * NU + c] * q[NX + c];
+      kff[i] = -acc;
+      for (int x = 0; x < NX; ++x) {
+        T a2 = T(0);
+        for (int c = 0; c < NU; ++c) a2 += Qi[i * NU + c] * Q[(NX + c) * NM + x];
+        Kg[i * NX + x] = -a2;
+      }
+    }
+    T Qk[NU];        // Quu kff
+    for (int i = 0; i < NU; ++i) {
+      T acc = T(0);
+      for (int c = 0; c < NU; ++c) acc += Quu[i * NU + c] * kff[c];
+      Qk[i] = acc;
+    }
+    T s1 = T(0), s2 = T(0);
+    for (int i = 0; i < NU; ++i) { s1 += kff[i] * q[NX + i]; s2 += kff[i] * Qk[i]; }
+    dV1 += s1;
+    dV2 += T(0.5) * s2;
+    // Vx = Qx + K^T Quu kff + K^T Qu + Qux^T kff ;  Vxx = Qxx + K^T Quu K + K^T Qux + Qux^T K
+    T QK[NU * NX];   // Quu K
+    for (int i = 0; i < NU; ++i)
+      for (int x = 0; x < NX; ++x) {
+        T acc = T(0);
+        for (int c = 0; c < NU; ++c) acc += Quu[i * NU + c] * Kg[c * NX + x];
+        QK[i * NX + x] = acc;
+      }
+    T Vn[NX * NX];
+    for (int x = 0; x < NX; ++x) {
+      T acc = q[x];
+      for (int i = 0; i < NU; ++i) acc += Kg[i * NX + x] * Qk[i] + Kg[i * NX + x] * q[NX + i] + Q[(NX + i) * NM + x] * kff[i];
+      Vx[x] = acc;
+      for (int y = 0; y < NX; ++y) {
+        T a2 = Q[x * NM + y];
+        for (int i = 0; i < NU; ++i) a2 += Kg[i * NX + x] * QK[i * NX + y] + Kg[i * NX + x] * Q[(NX + i) * NM + y] + Q[(NX + i) * NM + x] * Kg[i * NX + y];
+        Vn[x * NX + y] = a2;
+      }
+    }
+    for (int x = 0; x < NX; ++x)
+      for (int y = 0; y < NX; ++y) Vxx[x * NX + y] = T(0.5) * (Vn[x * NX + y] + Vn[y * NX + x]);
+    for (int i = 0; i < NU; ++i) {
+      d.gam[(size_t)i * K + t] = kff[i];
+      for (int x = 0; x < NX; ++x) d.Sd[(size_t)(i * NX + x) * K + t] = Kg[i * NX + x];
+    }
+  }
+  d.D[b] = dV1;
+  d.ratio[b] = dV2;
+  d.err[b] = ok ? 0 : 1;
+  d.tot_qp[b] += 1;
+}
+
+template <typename T>
+__global__ void __launch_bounds__(32) k_ilqr_rollout0(Dev<T> d) {
+  const int b = blockIdx.x * blockDim.x + threadIdx.x;
+  if (b >= d.B) return;
+  const int N = d.N;
+  const size_t K = d.K;
+  const size_t t0 = (size_t)b * N;
+  T x[NX];
+  for (int i = 0; i < NX; ++i) x[i] = d.x[(size_t)i * K + t0];
+  for (int k = 0; k < N - 1; ++k) {
+    T u[NU], qdd[NJ], Minv[NJ * NJ], v[NJ][6], a[NJ][6], f[NJ][6], xn[NX];
+    for (int i = 0; i < NU; ++i) u[i] = d.u[(size_t)i * K + t0 + k];
+    forward_dynamics<T, false>(x, x + NJ, u, d.gravity, qdd, Minv, v, a, f);
+    integrate(d.integrator, x, qdd, d.dt, xn);
+    for (int i = 0; i < NX; ++i) { x[i] = xn[i]; d.x[(size_t)i * K + t0 + k + 1] = xn[i]; }
+  }
+}
+
+enum { ILQR_MAX_KNOTS = 512 };
+
+template <typename T>
+__global__ void __launch_bounds__(32) k_ilqr_search(Dev<T> d, Opts<T> o) {
+  const int slot = blockIdx.x * blockDim.x + threadIdx.x;
+  if (slot >= *d.n_act) return;
+  const int b = d.act[slot];
+  const int N = d.N;
+  const size_t K = d.K;
+  const size_t t0 = (size_t)b * N;
+  T xg[NX];
+  for (int i = 0; i < NX; ++i) xg[i] = d.xg[(size_t)i * d.B + b];
+  const T dV1 = d.D[b], dV2 = d.ratio[b];
+  bool error = d.err[b] != 0;
+  T alpha = T(1);
+  int ls = 0;
+  T delta_J = T(0);
+  T soft[ILQR_MAX_KNOTS];
+  while (!error) {
+    T z[NM], Jc = T(0);
+    for (int i = 0; i < NX; ++i) z[i] = d.x[(size_t)i * K + t0];            // x_0 is fixed
+    for (int k = 0; k < N; ++k) {
+      const size_t t = t0 + k;
+      const bool terminal = (k == N - 1);
+      for (int i = 0; i < NX; ++i) d.xn[(size_t)i * K + t] = z[i];
+      if (!terminal) {
+        for (int i = 0; i < NU; ++i) {
+          T acc = d.u[(size_t)i * K + t] + alpha * d.gam[(size_t)i * K + t];
+          for (int x = 0; x < NX; ++x) acc += d.Sd[(size_t)(i * NX + x) * K + t] * (z[x] - d.x[(size_t)x * K + t]);
+          z[NX + i] = acc;
+          d.un[(size_t)i * K + t] = acc;
+        }
+      } else {
+        for (int i = 0; i < NU; ++i) z[NX + i] = T(0);
+      }
+      Jc += cost_value(d.cost, z, z + NX, xg, k, terminal);
+      soft[k] = d.lim.any ? soft_value(d.lim, z, d.mu + t, d.lam + t, K, terminal) : T(0);
+      if (!terminal) {
+        T qdd[NJ], Minv[NJ * NJ], v[NJ][6], a[NJ][6], f[NJ][6], xn[NX];
+        forward_dynamics<T, false>(z, z + NJ, z + NX, d.gravity, qdd, Minv, v, a, f);
+        integrate(d.integrator, z, qdd, d.dt, xn);
+        for (int i = 0; i < NX; ++i) z[i] = xn[i];
+      }
+    }
+    T Jn = Jc;
+    if (d.lim.any)
+      for (int k = 0; k < N; ++k) Jn += soft[k];
+    delta_J = d.J[b] - Jn;
+    const T expected = -(alpha * dV1 + alpha * alpha * dV2);
+    const T ratio = delta_J / expected;
+    d.tot_trials[b] += 1;
+    const bool finite = (Jn == Jn) && (fabs(Jn) < T(1e300));
+    if (expected > T(0) && finite && ratio >= o.er_min && ratio <= o.er_max) {
+      for (int k = 0; k < N; ++k) {
+        for (int i = 0; i < NX; ++i) d.x[(size_t)i * K + t0 + k] = d.xn[(size_t)i * K + t0 + k];
+        if (k < N - 1)
+          for (int i = 0; i < NU; ++i) d.u[(size_t)i * K + t0 + k] = d.un[(size_t)i * K + t0 + k];
+      }
+      d.J[b] = Jn;
+      d.merit[b] = Jn;
+      const T drho = fmin(d.drho[b] / o.rho_factor, T(1) / o.rho_factor);
+      d.drho[b] = drho; d.rho[b] = fmax(d.rho[b] * drho, o.rho_min);
+      trace_row(d, b, ls, alpha, dV1, ratio, 0, 1);
+      break;
+    } else if (alpha > o.alpha_min) {
+      alpha *= o.alpha_factor;
+      ls += 1;
+    } else {
+      error = true;
+      trace_row(d, b, ls, alpha, dV1, ratio, 0, 0);
+    }
+  }
+  // check_for_exit_or_error (TrajoptMPCReference.py:463-481)
+  bool exit_flag = false;
+  if (error) {
+    const T drho = fmax(d.drho[b] * o.rho_factor, o.rho_factor);
+    const T rho = fmax(d.rho[b] * drho, o.rho_min);
+    d.drho[b] = drho; d.rho[b] = rho;
+    if (rho > o.rho_max) { d.exit_sqp[b] = 2; exit_flag = true; }
+  } else if (delta_J < o.tol_sqp) {
+    d.exit_sqp[b] = 1; exit_flag = true;
+  }
+  if (d.sqp_iter[b] == o.max_iter_sqp - 1) { d.exit_sqp[b] = 3; exit_flag = true; }
+  else d.sqp_iter[b] += 1;
+  if (exit_flag) d.phase[b] = PH_OUTER;
+  d.deltaJ[b] = delta_J;
+  d.ls_iter[b] = ls;
+  d.alpha[b] = alpha;
+}
+
+}  // namespace b2t

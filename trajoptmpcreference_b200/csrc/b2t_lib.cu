@@ -7,6 +7,7 @@
 #include <algorithm>
 #include <cuda_runtime.h>
 #include "b2t_kernels.cuh"
+#include "b2t_ilqr.cuh"
 #include "../../include/b2t.h"
 
 namespace {
@@ -31,6 +32,7 @@ struct SolverBase {
   virtual int set_multipliers(const double* mu, const double* lam, const double* phi) = 0;
   virtual int reset_multipliers() = 0;
   virtual int solve(int method, const b2t_options* o) = 0;
+  virtual int solve_ilqr(const b2t_options* o) = 0;
   virtual int get_trajectory(double* x, double* u, int on_device) = 0;
   virtual int get_status(int* st) = 0;
   virtual int get_scalars(double* sc) = 0;
@@ -541,6 +543,48 @@ struct SolverT : SolverBase {
     return 0;
   }
 
+  // iLQR (oracle/ilqr.py is the specification): same work-list / outer-loop machinery as solve()
+  int solve_ilqr(const b2t_options* o) override {
+    using namespace b2t;
+    if (!o) return fail(B2T_ERR_INVALID, "options required");
+    if (o->max_iter_SQP + 1 > d.trace_cap) return fail(B2T_ERR_UNSUPPORTED, "max_iter_SQP_DDP > 103");
+    if (d.N > ILQR_MAX_KNOTS) return fail(B2T_ERR_UNSUPPORTED, "iLQR supports at most 512 knot points");
+    B2T_CUDA(cudaSetDevice(device));
+    Opts<T> op = convert(o);
+    launches = 0; device_seconds = 0;
+    for (int i = 0; i < B2T_KERNEL_FAMILIES; ++i) { fam_seconds[i] = 0; fam_launches[i] = 0; }
+    B2T_CUDA(cudaEventRecord(ev0, stream));
+    const int B = d.B;
+    const size_t msmem = (size_t)5 * d.N * sizeof(T);
+    const int mt = merit_threads();
+    k_init_state<T><<<cdiv(B, 128), 128, 0, stream>>>(d); tick(B2T_K_CTRL);
+    { Scope sc(this, B2T_K_TRIAL); k_ilqr_rollout0<T><<<cdiv(B, 32), 32, 0, stream>>>(d); tick(B2T_K_TRIAL); }
+    { Scope sc(this, B2T_K_MERIT); k_outer_begin<T><<<B, mt, msmem, stream>>>(d, d.act, d.n_act, op, 0); tick(B2T_K_MERIT); }
+    B2T_CUDA(cudaGetLastError());
+    int n = B;
+    const long long cap = (long long)o->max_iter_soft * o->max_iter_SQP + 8;
+    const size_t osmem = std::max((size_t)3 * d.N * sizeof(T), msmem);
+    for (long long iter = 0; n > 0 && iter < cap; ++iter) {
+      launch_dynamics(d.act, d.n_act, n);
+      { Scope sc(this, B2T_K_KKT); k_ilqr_cost<T><<<cdiv((size_t)n * d.N, 64), 64, 0, stream>>>(d, d.act, d.n_act); tick(B2T_K_KKT); }
+      { Scope sc(this, B2T_K_SCHUR); k_ilqr_backward<T><<<cdiv(n, 32), 32, 0, stream>>>(d, d.act, d.n_act); tick(B2T_K_SCHUR); }
+      { Scope sc(this, B2T_K_TRIAL); k_ilqr_search<T><<<cdiv(n, 32), 32, 0, stream>>>(d, op); tick(B2T_K_TRIAL); }
+      { Scope sc(this, B2T_K_CTRL); k_outer<T><<<n, mt, osmem, stream>>>(d, op, 1); tick(B2T_K_CTRL); }
+      { Scope sc(this, B2T_K_CTRL); k_compact<T><<<1, 1024, 0, stream>>>(d, d_scratch); tick(B2T_K_CTRL); }
+      B2T_CUDA(cudaMemcpyAsync(h_count, d.n_act, sizeof(int), cudaMemcpyDeviceToHost, stream));
+      B2T_CUDA(cudaStreamSynchronize(stream));
+      n = h_count[0];
+    }
+    B2T_CUDA(cudaEventRecord(ev1, stream));
+    B2T_CUDA(cudaEventSynchronize(ev1));
+    float ms = 0;
+    B2T_CUDA(cudaEventElapsedTime(&ms, ev0, ev1));
+    device_seconds = ms * 1e-3;
+    collect_profile();
+    B2T_CUDA(cudaGetLastError());
+    return 0;
+  }
+
   int solve_host(const double* x0, const double* u0, const double* xg, int method, const b2t_options* o, double* xo, double* uo,
                  int* st) override {
     int r;
@@ -742,6 +786,7 @@ int b2t_set_initial_state(b2t_solver* s, const double* xs) { B2T_FWD(set_initial
 int b2t_set_multipliers(b2t_solver* s, const double* mu, const double* lam, const double* phi) { B2T_FWD(set_multipliers(mu, lam, phi)); }
 int b2t_reset_multipliers(b2t_solver* s) { B2T_FWD(reset_multipliers()); }
 int b2t_sqp_solve(b2t_solver* s, int method, const b2t_options* o) { B2T_FWD(solve(method, o)); }
+int b2t_ilqr_solve(b2t_solver* s, const b2t_options* o) { B2T_FWD(solve_ilqr(o)); }
 int b2t_get_trajectory(b2t_solver* s, double* x, double* u, int od) { B2T_FWD(get_trajectory(x, u, od)); }
 int b2t_get_status(b2t_solver* s, int* st) { B2T_FWD(get_status(st)); }
 int b2t_get_scalars(b2t_solver* s, double* sc) { B2T_FWD(get_scalars(sc)); }

@@ -47,3 +47,48 @@ def main():
 
 if __name__ == "__main__":
     main()
+
+
+CARTPOLE = """<?xml version="1.0" ?>
+<robot name="cartpole">
+  <link name="world"/>
+  <joint name="slider" type="prismatic">
+    <parent link="world"/>
+    <child link="cart"/>
+    <origin rpy="0 0 0" xyz="0 0 0"/>
+    <axis xyz="1 0 0"/>
+  </joint>
+  <link name="cart">
+    <origin rpy="0 0 0" xyz="0 0 0"/>
+    <inertial>
+      <origin rpy="0 0 0" xyz="0 0 0"/>
+      <mass value="1.0"/>
+      <inertia ixx="0.01" ixy="0.0" ixz="0.0" iyy="0.01" iyz="0.0" izz="0.01"/>
+    </inertial>
+  </link>
+  <joint name="hinge" type="revolute">
+    <parent link="cart"/>
+    <child link="pole"/>
+    <origin rpy="0 0 0" xyz="0 0 0"/>
+    <axis xyz="0 1 0"/>
+  </joint>
+  <link name="pole">
+    <origin rpy="0 0 0" xyz="0 0 -0.5"/>
+    <inertial>
+      <origin rpy="0 0 0" xyz="0 0 -0.5"/>
+      <mass value="0.2"/>
+      <inertia ixx="0.016666666666666666" ixy="0.0" ixz="0.0" iyy="0.016666666666666666" iyz="0.0" izz="0.0005"/>
+    </inertial>
+  </link>
+</robot>
+"""
+
+
+def write_cartpole():
+    here = os.path.dirname(os.path.abspath(__file__))
+    with open(os.path.join(here, "cartpole.urdf"), "w") as f:
+        f.write(CARTPOLE)
+
+
+if __name__ == "__main__":
+    write_cartpole()
