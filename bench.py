@@ -182,6 +182,29 @@ def run_reference_arm(args):
     print(json.dumps(line))
 
 
+def ncu_traffic(family, batch, launches_per_step, qp_per_instance):
+    """DRAM bytes per launch of the dominant kernel from the committed `ncu --set full` capture (profiles/): the capture gives
+    dram__bytes_read.sum + dram__bytes_write.sum for ONE launch over `launch__grid_size` instances; scaled to the average number
+    of instances per launch of this run (the per-instance traffic of k_pcg2 does not depend on the batch: every instance's
+    S, Pinv and gamma blocks are read once, l is written once)."""
+    if family != "pcg":
+        return None, "no ncu capture for this kernel family"
+    path = os.path.join(ROOT, "profiles", "r01_v2_ncu_full_k_pcg2.csv")
+    try:
+        vals = {}
+        with open(path) as f:
+            for line in f:
+                parts = line.strip().split(",")
+                if len(parts) >= 2:
+                    vals[parts[0]] = parts[1]
+        grid = float(vals["launch__grid_size"])
+        per_inst = (float(vals["dram__bytes_read.sum"]) + float(vals["dram__bytes_write.sum"])) * 1e6 / grid
+        inst_per_launch = batch * qp_per_instance / max(launches_per_step, 1)
+        return per_inst * inst_per_launch, "profiles/r01_v2_ncu_full_k_pcg2.csv: %.0f bytes per instance x %.0f instances per launch (avg)" % (per_inst, inst_per_launch)
+    except Exception as e:      # noqa: BLE001
+        return None, "ncu capture unreadable: %s" % e
+
+
 def config_dict(args, note=None):
     c = {"workload": "C4/C5: arm6 (6-link planar chain) SQP PCG-SS, N=64, dt=0.1, euler, QuadraticCost Q=I QF=100I R=0.1I, "
                      "goals U(-0.5,0.5)^6 seeded, %s, batch %d per GPU" %
@@ -315,8 +338,9 @@ def run_b200_arm(args):
         dom_launch = fam[dom][1] / args.steps if fam else 1
         ach = fam_flops[dom] / dom_sec / 1e12 if dom_sec > 0 else 0.0
         alg_bytes = B * (2 * 8 * (12 * N + 6 * (N - 1)) + 8 * 12 + 64)
+        traffic, traffic_src = ncu_traffic(dom, B, dom_launch, qp / B if B else 0)
         roof = {"bound": "fp64_fma" if args.dtype == "f64" else "fp32_fma", "kernel": "k_" + dom, "achieved": ach, "peak": peak64, "unit": "TFLOP/s",
-                "frac": ach / peak64 if peak64 else None, "traffic": None,
+                "frac": ach / peak64 if peak64 else None, "traffic": traffic, "traffic_source": traffic_src,
                 "peak_source": "measured in this run: DFMA chain micro-benchmark b2t_measure_fma_peak (MEASURED_PEAKS.json has no fp64 entry)",
                 "algorithmic_flops_per_launch": fam_flops[dom] / max(dom_launch, 1), "avg_launch_ms": 1e3 * dom_sec / max(dom_launch, 1),
                 "launches_per_step": dom_launch, "share_of_step": dom_sec / step_sec,

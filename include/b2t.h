@@ -145,6 +145,12 @@ int b2t_sqp_solve(b2t_solver* s, int method, const b2t_options* opts);
  * implementation -- specification: oracle/ilqr.py).  x[:,0] is the start state, the state trajectory is re-rolled from u. */
 int b2t_ilqr_solve(b2t_solver* s, const b2t_options* opts);
 
+/* Receding-horizon step (MPC loop around SQP / iLQR): reports the current initial state x_0 and the control u_0
+ * that is applied, takes the next initial state from `x_next` ([batch][nx] host; NULL = simulate x_0, u_0 with the plant's own
+ * integrator), shifts x, u and the soft-constraint multipliers one knot to the left (TrajoptConstraint.shift_soft_constraint_constants,
+ * TrajoptConstraint.py:168-176) and sets xs.  The workspace then holds the warm start of the next solve.  Outputs may be NULL. */
+int b2t_mpc_shift(b2t_solver* s, const double* x_next, double* x0_out, double* u0_out, double* xnext_out);
+
 int b2t_get_trajectory(b2t_solver* s, double* x, double* u, int on_device);
 int b2t_get_status(b2t_solver* s, int* status);
 int b2t_get_scalars(b2t_solver* s, double* scalars);

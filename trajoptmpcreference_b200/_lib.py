@@ -55,6 +55,7 @@ _SIGNATURES = {
     "b2t_reset_multipliers": (c_int, [c_void_p]),
     "b2t_sqp_solve": (c_int, [c_void_p, c_int, POINTER(Options)]),
     "b2t_ilqr_solve": (c_int, [c_void_p, POINTER(Options)]),
+    "b2t_mpc_shift": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p]),
     "b2t_get_trajectory": (c_int, [c_void_p, c_void_p, c_void_p, c_int]),
     "b2t_get_status": (c_int, [c_void_p, c_void_p]),
     "b2t_get_scalars": (c_int, [c_void_p, c_void_p]),

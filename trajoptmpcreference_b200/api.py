@@ -566,6 +566,13 @@ class BatchSolver:
         o = self.make_options(options)
         _lib.check(self.lib, self.lib.b2t_ilqr_solve(self._h, ctypes.byref(o)))
 
+    def mpc_shift(self, x_next=None):
+        """Receding-horizon shift by one knot; returns (x_0, u_0 applied, next initial state).  x_next=None simulates the plant."""
+        x0 = np.zeros((self.batch, self.nx)); u0 = np.zeros((self.batch, self.nu)); xn = np.zeros((self.batch, self.nx))
+        arg = None if x_next is None else _dptr(_as_f64(x_next, (self.batch, self.nx)))
+        _lib.check(self.lib, self.lib.b2t_mpc_shift(self._h, arg, _dptr(x0), _dptr(u0), _dptr(xn)))
+        return x0, u0, xn
+
     def solve_host(self, x0, u0, xg, x_out, u_out, status_out, method=SQPSolverMethods.PCG_SS, options=None):
         """One call: host buffers in, host buffers out (pinned buffers make the copies asynchronous)."""
         o = self.make_options(options)
@@ -796,6 +803,41 @@ class TrajoptMPCReference:
             mu, lam, phi = s.get_multipliers()
             cons.unpack(mu[0], lam[0], phi[0])
         return r
+
+    def mpc_batch(self, x_start, xg, N, dt, steps, method=SQPSolverMethods.PCG_SS, options=None, use_ilqr=False, dtype="f64", device=0,
+                  measure=None):
+        """Receding-horizon MPC (README.md:15-17 names it; no reference code -- semantics in DESIGN.md section 9): `steps` times
+        {solve from the warm start, apply u_0, obtain the next state (simulated by the plant, or measure(step, x, u) -> (B,nx)),
+        shift trajectories and multipliers one knot}.  Everything stays on the device between solves.
+        x_start (B, nx), xg (B, nx).  Returns BatchResult(x_closed (B,nx,steps+1), u_applied (B,nu,steps), sqp_iter (B,steps), J (B,steps))."""
+        options = {} if options is None else options
+        self.set_default_options(options)
+        x_start = _as_f64(x_start); B = x_start.shape[0]
+        s = self.batch_solver(N, dt, B, dtype, device)
+        s.set_goals(xg)
+        X0 = np.repeat(x_start[:, :, None], N, axis=2); U0 = np.zeros((B, s.nu, N - 1))
+        s.set_trajectory(X0, U0)
+        cons = self._constraints_or_none()
+        if cons is not None:
+            mu, lam, phi = cons.pack(N)
+            s.set_multipliers(*[np.broadcast_to(a[None], (B,) + a.shape) for a in (mu, lam, phi)])
+        xc = np.zeros((B, s.nx, steps + 1)); ua = np.zeros((B, s.nu, steps)); its = np.zeros((B, steps), dtype=np.int64); Js = np.zeros((B, steps))
+        xc[:, :, 0] = x_start
+        for k in range(steps):
+            if use_ilqr:
+                s.solve_ilqr(options)
+            else:
+                s.solve(method, options)
+            st = s.get_status(); sc = s.get_scalars()
+            its[:, k] = st[:, 3]; Js[:, k] = sc[:, 0]
+            if measure is None:
+                x0, u0, xn = s.mpc_shift(None)
+            else:
+                xt, ut = s.get_trajectory()
+                xn = _as_f64(measure(k, xt[:, :, 0], ut[:, :, 0]), (B, s.nx))
+                x0, u0, _ = s.mpc_shift(xn)
+            ua[:, :, k] = u0; xc[:, :, k + 1] = xn
+        return BatchResult(x_closed=xc, u_applied=ua, sqp_iter=its, J=Js)
 
     def solve_batch(self, x0, u0, xg, N, dt, LINEAR_SYSTEM_SOLVER_METHOD=SQPSolverMethods.PCG_SS, options=None, dtype="f64", device=0):
         """Batched SQP: x0 (B, nx, N), u0 (B, nu, N-1), xg (B, nx).  Returns a BatchResult of per-instance arrays."""

@@ -1769,6 +1769,73 @@ __global__ void k_init_state(Dev<T> d) {
 }  // namespace b2t
 
 namespace b2t {
+// -----------------------------------------------------------------------------------------------------------------
+// k_mpc_shift: receding-horizon shift by one knot: the applied control is u_0, the next initial state is
+// either measured (x_next given) or simulated with the plant's own integrator; x, u move one knot to the left (last knot
+// repeated) as the warm start of the next solve; the soft-constraint multipliers move with them
+// (TrajoptConstraint.shift_soft_constraint_constants, TrajoptConstraint.py:168-176,380-387; the last column is re-initialised --
+// the reference's slice `[:, shift_steps:] = init` re-initialises every column but the first).
+// One block per instance, one thread per knot.  out_x0 / out_u0 (may be null): the state before the shift and the applied control.
+// -----------------------------------------------------------------------------------------------------------------
+template <typename T>
+__global__ void k_mpc_shift(Dev<T> d, const double* x_next, double* out_x0, double* out_u0, double* out_xnext) {
+  const int b = blockIdx.x;
+  const int N = d.N;
+  const size_t K = d.K;
+  const size_t t0 = (size_t)b * N;
+  __shared__ T s_xn[NX];
+  if (threadIdx.x == 0) {
+    T x[NX], u[NU];
+    for (int i = 0; i < NX; ++i) x[i] = d.x[(size_t)i * K + t0];
+    for (int i = 0; i < NU; ++i) u[i] = d.u[(size_t)i * K + t0];
+    if (out_x0) for (int i = 0; i < NX; ++i) out_x0[(size_t)b * NX + i] = (double)x[i];
+    if (out_u0) for (int i = 0; i < NU; ++i) out_u0[(size_t)b * NU + i] = (double)u[i];
+    if (x_next) {
+      for (int i = 0; i < NX; ++i) s_xn[i] = (T)x_next[(size_t)b * NX + i];
+    } else {
+      T qdd[NJ], Minv[NJ * NJ], v[NJ][6], a[NJ][6], f[NJ][6], xn[NX];
+      forward_dynamics<T, false>(x, x + NJ, u, d.gravity, qdd, Minv, v, a, f);
+      integrate(d.integrator, x, qdd, d.dt, xn);
+      for (int i = 0; i < NX; ++i) s_xn[i] = xn[i];
+    }
+    if (out_xnext) for (int i = 0; i < NX; ++i) out_xnext[(size_t)b * NX + i] = (double)s_xn[i];
+  }
+  __syncthreads();
+  for (int base = 0; base < N; base += blockDim.x) {          // chunks left to right: a chunk only reads knots >= its own
+    const int k = base + threadIdx.x;
+    T xv[NX], uv[NU], mv[3][2 * NM];
+    const bool live = k < N;
+    const int src = (k + 1 < N) ? k + 1 : N - 1;
+    if (live) {
+      for (int i = 0; i < NX; ++i) xv[i] = d.x[(size_t)i * K + t0 + src];
+      const int usrc = (k + 1 < N - 1) ? k + 1 : N - 2;
+      for (int i = 0; i < NU; ++i) uv[i] = d.u[(size_t)i * K + t0 + usrc];
+      if (d.lim.any)
+        for (int e = 0; e < 2 * NM; ++e) {
+          mv[0][e] = d.mu[(size_t)e * K + t0 + src]; mv[1][e] = d.lam[(size_t)e * K + t0 + src]; mv[2][e] = d.phi[(size_t)e * K + t0 + src];
+        }
+    }
+    __syncthreads();
+    if (live) {
+      for (int i = 0; i < NX; ++i) d.x[(size_t)i * K + t0 + k] = (k == 0) ? s_xn[i] : xv[i];
+      if (k < N - 1)
+        for (int i = 0; i < NU; ++i) d.u[(size_t)i * K + t0 + k] = uv[i];
+      if (d.lim.any)
+        for (int e = 0; e < 2 * NM; ++e) {
+          const int ci = e % NM;
+          const int ty = ci < NJ ? 0 : (ci < NX ? 1 : 2);
+          const bool last = (k == N - 1);
+          d.mu[(size_t)e * K + t0 + k] = last ? d.mu_init[ty] : mv[0][e];
+          d.lam[(size_t)e * K + t0 + k] = last ? T(0) : mv[1][e];
+          d.phi[(size_t)e * K + t0 + k] = last ? d.phi_init[ty] : mv[2][e];
+        }
+    }
+    __syncthreads();
+  }
+  if (threadIdx.x == 0)
+    for (int i = 0; i < NX; ++i) d.xs[(size_t)i * d.B + b] = s_xn[i];
+}
+
 template <typename T>
 __global__ void k_pack_status(Dev<T> d, int* st, double* sc) {
   const int b = blockIdx.x * blockDim.x + threadIdx.x;

@@ -33,6 +33,7 @@ struct SolverBase {
   virtual int reset_multipliers() = 0;
   virtual int solve(int method, const b2t_options* o) = 0;
   virtual int solve_ilqr(const b2t_options* o) = 0;
+  virtual int mpc_shift(const double* x_next, double* x0_out, double* u0_out, double* xnext_out) = 0;
   virtual int get_trajectory(double* x, double* u, int on_device) = 0;
   virtual int get_status(int* st) = 0;
   virtual int get_scalars(double* sc) = 0;
@@ -543,6 +544,25 @@ struct SolverT : SolverBase {
     return 0;
   }
 
+  int mpc_shift(const double* x_next, double* x0_out, double* u0_out, double* xnext_out) override {
+    using namespace b2t;
+    B2T_CUDA(cudaSetDevice(device));
+    const size_t nb = (size_t)d.B * NX * sizeof(double);
+    double* dxn = nullptr;
+    if (x_next) {
+      B2T_CUDA(cudaMemcpyAsync(stage_g, x_next, nb, cudaMemcpyHostToDevice, stream));
+      dxn = stage_g;
+    }
+    double* o0 = stage_out; double* o1 = stage_out + (size_t)d.B * NX; double* o2 = o1 + (size_t)d.B * NU;
+    k_mpc_shift<T><<<d.B, std::min(256, ((d.N + 31) / 32) * 32), 0, stream>>>(d, dxn, o0, o1, o2);
+    B2T_CUDA(cudaGetLastError());
+    if (x0_out) B2T_CUDA(cudaMemcpyAsync(x0_out, o0, nb, cudaMemcpyDeviceToHost, stream));
+    if (u0_out) B2T_CUDA(cudaMemcpyAsync(u0_out, o1, (size_t)d.B * NU * sizeof(double), cudaMemcpyDeviceToHost, stream));
+    if (xnext_out) B2T_CUDA(cudaMemcpyAsync(xnext_out, o2, nb, cudaMemcpyDeviceToHost, stream));
+    B2T_CUDA(cudaStreamSynchronize(stream));
+    return 0;
+  }
+
   // iLQR (oracle/ilqr.py is the specification): same work-list / outer-loop machinery as solve()
   int solve_ilqr(const b2t_options* o) override {
     using namespace b2t;
@@ -787,6 +807,7 @@ int b2t_set_multipliers(b2t_solver* s, const double* mu, const double* lam, cons
 int b2t_reset_multipliers(b2t_solver* s) { B2T_FWD(reset_multipliers()); }
 int b2t_sqp_solve(b2t_solver* s, int method, const b2t_options* o) { B2T_FWD(solve(method, o)); }
 int b2t_ilqr_solve(b2t_solver* s, const b2t_options* o) { B2T_FWD(solve_ilqr(o)); }
+int b2t_mpc_shift(b2t_solver* s, const double* xn, double* x0, double* u0, double* xno) { B2T_FWD(mpc_shift(xn, x0, u0, xno)); }
 int b2t_get_trajectory(b2t_solver* s, double* x, double* u, int od) { B2T_FWD(get_trajectory(x, u, od)); }
 int b2t_get_status(b2t_solver* s, int* st) { B2T_FWD(get_status(st)); }
 int b2t_get_scalars(b2t_solver* s, double* sc) { B2T_FWD(get_scalars(sc)); }
