@@ -18,6 +18,7 @@ def run(name, N, dt, B, mk_cost, mk_cons, xg, u0, steps=3):
     s = t.BatchSolver(plant, cost, cons, N=N, dt=dt, batch=B)
     x0 = np.zeros((B, 2 * n, N)); U0 = np.broadcast_to(u0.reshape(1, n, 1), (B, n, N - 1)).copy()
     times = []
+    s.set_profiling(True)
     for it in range(steps + 2):
         if cons is not None:
             s.reset_multipliers()

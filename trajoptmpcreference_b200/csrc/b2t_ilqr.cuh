@@ -160,6 +160,159 @@ __global__ void __launch_bounds__(32) k_ilqr_backward(Dev<T> d, const int* list,
   d.tot_qp[b] += 1;
 }
 
+// Block-parallel Riccati recursion: one block (ILQR_BW_THREADS threads) per instance, the knots are processed sequentially, every
+// matrix product of a knot is spread over the threads (entries of the result), operands staged in shared memory.
+// Same arithmetic as k_ilqr_backward (which is kept as the single-thread reference variant, B2T_ILQR_BW=1).
+enum { ILQR_BW_THREADS = 128 };
+template <typename T>
+__global__ void __launch_bounds__(ILQR_BW_THREADS) k_ilqr_backward2(Dev<T> d, const int* list, const int* count) {
+  if ((int)blockIdx.x >= *count) return;
+  const int b = list[blockIdx.x];
+  const int N = d.N;
+  const size_t K = d.K;
+  const size_t t0 = (size_t)b * N;
+  const int tid = threadIdx.x, nt = blockDim.x;
+  __shared__ T sAB[NX * NM], sVAB[NX * NM], sQ[NM * NM], sq[NM], sVxx[NX * NX], sVx[NX], sVn[NX * NX];
+  __shared__ T sQuu[NU * NU], sAug[NU * 2 * NU], sQi[NU * NU], skff[NU], sKg[NU * NX], sQk[NU], sQK[NU * NX], sdq[NDYN];
+  __shared__ int s_ok;
+  const T rho = d.rho[b];
+  {
+    const size_t t = t0 + N - 1;
+    for (int i = tid; i < NX; i += nt) sVx[i] = d.g[(size_t)i * K + t];
+    for (int e = tid; e < NX * NX; e += nt) sVxx[e] = d.Gh[(size_t)((e / NX) * NM + (e % NX)) * K + t];
+    if (tid == 0) s_ok = 1;
+  }
+  T dV1 = T(0), dV2 = T(0);
+  __syncthreads();
+  for (int k = N - 2; k >= 0; --k) {
+    const size_t t = t0 + k;
+    for (int i = tid; i < NDYN; i += nt) sdq[i] = d.dyn[(size_t)i * K + t];
+    __syncthreads();
+    // [A B] (build_AB, entry-parallel)
+    for (int e = tid; e < NX * NM; e += nt) {
+      const int r = e / NM, c = e % NM;
+      T v;
+      if (d.integrator == 0) {
+        if (r < NJ) v = ((c == r) ? T(1) : T(0)) + ((c == NJ + r) ? d.dt : T(0));
+        else v = d.dt * sdq[(r - NJ) * 3 * NJ + c] + ((c == r) ? T(1) : T(0));
+      } else {
+        const int a = (r < NJ) ? r : r - NJ;
+        const T dd = sdq[a * 3 * NJ + c];
+        if (r < NJ) v = d.dt * (((c == NJ + a) ? T(1) : T(0)) + d.dt * dd) + ((c == r) ? T(1) : T(0));
+        else v = d.dt * dd + ((c == r) ? T(1) : T(0));
+      }
+      sAB[e] = v;
+    }
+    __syncthreads();
+    for (int e = tid; e < NX * NM; e += nt) {            // VAB = Vxx [A B]
+      const int i = e / NM, c = e % NM;
+      T acc = T(0);
+      for (int r = 0; r < NX; ++r) acc += sVxx[i * NX + r] * sAB[r * NM + c];
+      sVAB[e] = acc;
+    }
+    __syncthreads();
+    for (int e = tid; e < NM * NM + NM; e += nt) {       // Q = H + [A B]^T VAB ; q = g + [A B]^T Vx
+      if (e < NM * NM) {
+        const int a = e / NM, c = e % NM;
+        T acc = d.Gh[(size_t)e * K + t];
+        for (int r = 0; r < NX; ++r) acc += sAB[r * NM + a] * sVAB[r * NM + c];
+        sQ[e] = acc;
+      } else {
+        const int a = e - NM * NM;
+        T acc = d.g[(size_t)a * K + t];
+        for (int r = 0; r < NX; ++r) acc += sAB[r * NM + a] * sVx[r];
+        sq[a] = acc;
+      }
+    }
+    __syncthreads();
+    for (int e = tid; e < NU * NU; e += nt) {
+      const int i = e / NU, c = e % NU;
+      const T v = sQ[(NX + i) * NM + NX + c] + ((i == c) ? rho : T(0));
+      sQuu[e] = v;
+      sAug[i * 2 * NU + c] = v;
+      sAug[i * 2 * NU + NU + c] = (i == c) ? T(1) : T(0);
+    }
+    __syncthreads();
+    // Gauss-Jordan on [Quu | I] without pivoting (SPD), row-parallel within warp 0; a non-positive pivot flags failure
+    if (tid < 32) {
+      for (int p = 0; p < NU; ++p) {
+        const T piv = sAug[p * 2 * NU + p];
+        if (!(piv > T(0))) { if (tid == 0) s_ok = 0; break; }
+        __syncwarp();
+        if (tid < 2 * NU) sAug[p * 2 * NU + tid] = sAug[p * 2 * NU + tid] / piv;
+        __syncwarp();
+        if (tid < NU && tid != p) {
+          const T fct = sAug[tid * 2 * NU + p];
+          for (int c = 0; c < 2 * NU; ++c) sAug[tid * 2 * NU + c] -= fct * sAug[p * 2 * NU + c];
+        }
+        __syncwarp();
+      }
+    }
+    __syncthreads();
+    if (!s_ok) break;
+    for (int e = tid; e < NU * NU; e += nt) sQi[e] = sAug[(e / NU) * 2 * NU + NU + (e % NU)];
+    __syncthreads();
+    for (int e = tid; e < NU + NU * NX; e += nt) {       // kff = -Qi Qu ; K = -Qi Qux
+      if (e < NU) {
+        T acc = T(0);
+        for (int c = 0; c < NU; ++c) acc += sQi[e * NU + c] * sq[NX + c];
+        skff[e] = -acc;
+      } else {
+        const int i = (e - NU) / NX, x = (e - NU) % NX;
+        T acc = T(0);
+        for (int c = 0; c < NU; ++c) acc += sQi[i * NU + c] * sQ[(NX + c) * NM + x];
+        sKg[i * NX + x] = -acc;
+      }
+    }
+    __syncthreads();
+    for (int e = tid; e < NU + NU * NX; e += nt) {       // Qk = Quu kff ; QK = Quu K
+      if (e < NU) {
+        T acc = T(0);
+        for (int c = 0; c < NU; ++c) acc += sQuu[e * NU + c] * skff[c];
+        sQk[e] = acc;
+      } else {
+        const int i = (e - NU) / NX, x = (e - NU) % NX;
+        T acc = T(0);
+        for (int c = 0; c < NU; ++c) acc += sQuu[i * NU + c] * sKg[c * NX + x];
+        sQK[i * NX + x] = acc;
+      }
+    }
+    __syncthreads();
+    if (tid == 0) {
+      T s1 = T(0), s2 = T(0);
+      for (int i = 0; i < NU; ++i) { s1 += skff[i] * sq[NX + i]; s2 += skff[i] * sQk[i]; }
+      dV1 += s1;
+      dV2 += T(0.5) * s2;
+    }
+    for (int e = tid; e < NX * NX + NX; e += nt) {       // Vx, Vxx (unsymmetrised)
+      if (e < NX * NX) {
+        const int x = e / NX, y = e % NX;
+        T a2 = sQ[x * NM + y];
+        for (int i = 0; i < NU; ++i) a2 += sKg[i * NX + x] * sQK[i * NX + y] + sKg[i * NX + x] * sQ[(NX + i) * NM + y] + sQ[(NX + i) * NM + x] * sKg[i * NX + y];
+        sVn[e] = a2;
+      } else {
+        const int x = e - NX * NX;
+        T acc = sq[x];
+        for (int i = 0; i < NU; ++i) acc += sKg[i * NX + x] * sQk[i] + sKg[i * NX + x] * sq[NX + i] + sQ[(NX + i) * NM + x] * skff[i];
+        sVx[x] = acc;
+      }
+    }
+    for (int e = tid; e < NU + NU * NX; e += nt) {       // gains to global (kff -> gam, K -> Sd)
+      if (e < NU) d.gam[(size_t)e * K + t] = skff[e];
+      else d.Sd[(size_t)(e - NU) * K + t] = sKg[e - NU];
+    }
+    __syncthreads();
+    for (int e = tid; e < NX * NX; e += nt) { const int x = e / NX, y = e % NX; sVxx[e] = T(0.5) * (sVn[x * NX + y] + sVn[y * NX + x]); }
+    __syncthreads();
+  }
+  if (tid == 0) {
+    d.D[b] = dV1;
+    d.ratio[b] = dV2;
+    d.err[b] = s_ok ? 0 : 1;
+    d.tot_qp[b] += 1;
+  }
+}
+
 template <typename T>
 __global__ void __launch_bounds__(32) k_ilqr_rollout0(Dev<T> d) {
   const int b = blockIdx.x * blockDim.x + threadIdx.x;

@@ -584,10 +584,15 @@ struct SolverT : SolverBase {
     int n = B;
     const long long cap = (long long)o->max_iter_soft * o->max_iter_SQP + 8;
     const size_t osmem = std::max((size_t)3 * d.N * sizeof(T), msmem);
+    // block-parallel Riccati pass for nx >= 8 (arm6: 114.8 -> 10.1 ms / 2048 instances); one thread per instance for tiny systems
+    // (cart-pole, nx = 4: 5.4 vs 9.8 ms).  B2T_ILQR_BW=1 / 2 forces a variant.
+    const char* bwenv = getenv("B2T_ILQR_BW");
+    const bool ilqr_bw_single = bwenv ? atoi(bwenv) == 1 : (NX < 8);
     for (long long iter = 0; n > 0 && iter < cap; ++iter) {
       launch_dynamics(d.act, d.n_act, n);
       { Scope sc(this, B2T_K_KKT); k_ilqr_cost<T><<<cdiv((size_t)n * d.N, 64), 64, 0, stream>>>(d, d.act, d.n_act); tick(B2T_K_KKT); }
-      { Scope sc(this, B2T_K_SCHUR); k_ilqr_backward<T><<<cdiv(n, 32), 32, 0, stream>>>(d, d.act, d.n_act); tick(B2T_K_SCHUR); }
+      if (ilqr_bw_single) { Scope sc(this, B2T_K_SCHUR); k_ilqr_backward<T><<<cdiv(n, 32), 32, 0, stream>>>(d, d.act, d.n_act); tick(B2T_K_SCHUR); }
+      else { Scope sc(this, B2T_K_SCHUR); k_ilqr_backward2<T><<<n, ILQR_BW_THREADS, 0, stream>>>(d, d.act, d.n_act); tick(B2T_K_SCHUR); }
       { Scope sc(this, B2T_K_TRIAL); k_ilqr_search<T><<<cdiv(n, 32), 32, 0, stream>>>(d, op); tick(B2T_K_TRIAL); }
       { Scope sc(this, B2T_K_CTRL); k_outer<T><<<n, mt, osmem, stream>>>(d, op, 1); tick(B2T_K_CTRL); }
       { Scope sc(this, B2T_K_CTRL); k_compact<T><<<1, 1024, 0, stream>>>(d, d_scratch); tick(B2T_K_CTRL); }
