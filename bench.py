@@ -248,9 +248,7 @@ def run_b200_arm(args):
     u0 = torch.zeros((B, 6, N - 1), dtype=torch.float64, device=dev)
     xg = torch.from_numpy(xg_np).to(dev)
     xo = torch.empty_like(x0); uo = torch.empty_like(u0)
-    pack_w = 12 * N + 6 * (N - 1)
-    packed = torch.empty((B, pack_w), dtype=torch.float64, device=dev)
-    gathered = torch.empty((world * B, pack_w), dtype=torch.float64, device=dev) if world > 1 else None
+    from trajoptmpcreference_b200 import dist as bdist      # sharding + gather helpers (covered by tests/test_dist_gloo.py)
 
     def step_device():
         if cons is not None:
@@ -259,10 +257,8 @@ def run_b200_arm(args):
         solver.set_trajectory(x0, u0)
         solver.solve(method, SOLVER_OPTS)
         solver.get_trajectory(xo, uo)
-        if world > 1:
-            packed[:, :12 * N] = xo.reshape(B, -1)
-            packed[:, 12 * N:] = uo.reshape(B, -1)
-            dist.all_gather_into_tensor(gathered, packed)
+        if world > 1:       # the only collective of the path: final gather of the packed (x, u) rows of every instance
+            step_device.gathered = bdist.all_gather_results(bdist.pack_results(xo, uo), B * world)
 
     # pinned host buffers for the end-to-end leg
     hx0 = torch.zeros((B, 12, N), dtype=torch.float64).pin_memory(); hu0 = torch.zeros((B, 6, N - 1), dtype=torch.float64).pin_memory()

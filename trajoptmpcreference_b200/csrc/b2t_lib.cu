@@ -180,6 +180,7 @@ struct SolverT : SolverBase {
     B2T_CUDA(cudaEventCreate(&ev0)); B2T_CUDA(cudaEventCreate(&ev1));
     // kernels that need > 48 KB of dynamic shared memory
     B2T_CUDA(cudaFuncSetAttribute(b2t::k_pcg<T>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+    B2T_CUDA(cudaFuncSetAttribute(b2t::k_linesearch<T>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
     B2T_CUDA(cudaFuncSetAttribute(b2t::k_schur_diag<T>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)((size_t)NJ * NM * SCHUR_THREADS * sizeof(T))));
     B2T_CUDA(cudaFuncSetAttribute(b2t::k_pcg2<T, PCG_RPT, 1, true, 256>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
     B2T_CUDA(cudaFuncSetAttribute(b2t::k_pcg2<T, PCG_RPT, 1, true, 512>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
