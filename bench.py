@@ -229,7 +229,8 @@ def run_b200_arm(args):
         raise SystemExit("bench.py needs a CUDA device (no CPU fallback)")
     torch.cuda.set_device(local)
     if world > 1:
-        os.environ["NCCL_DEBUG"] = os.environ.get("B2T_NCCL_DEBUG", "WARN")     # keep stdout to the single JSON line
+        if os.environ.get("NCCL_DEBUG", "").upper() in ("", "VERSION", "WARN"):      # keep stdout to the single JSON line:
+            os.environ["NCCL_DEBUG"] = "NONE"                                        # VERSION / WARN print "NCCL version ..." there
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
     B, N = args.batch, N_KNOTS
     xg_np = workload_goals(world, rank, B)
