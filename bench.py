@@ -352,7 +352,7 @@ def run_b200_arm(args):
         line = {"metric": METRIC, "value": value, "unit": "solves/s", "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3),
                 "ms_per_step": 1e3 * sec / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": args.dtype,
                 "data": "synthetic", "config": config_dict(args), "clocks": sampler.summary(),
-                "e2e": {"value": total_solves / sec_e2e, "unit": "solves/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h},
+                "e2e": {"value": total_solves / sec_e2e, "unit": "solves/s", "h2d_bytes_per_step": h2d * world, "d2h_bytes_per_step": d2h * world},
                 "gpu_launches": launches, "roofline": roof,
                 "iterations": {"qp_solves_per_instance": qp / B, "pcg_iters_per_instance": pcg / B, "ls_trials_per_instance": trials / B,
                                "exit_sqp_hist": np.bincount(r.exit_sqp, minlength=4).tolist(), "exit_soft_hist": np.bincount(r.exit_soft, minlength=4).tolist()},

@@ -114,7 +114,9 @@ typedef enum {
   /* per-knot cost terms at the current (x, u), evaluated on demand: TrajoptCost.value / gradient / hessian (TrajoptCost.py:49-83, 402-519) */
   B2T_ARR_COST_VALUE,   /* [N][1] */
   B2T_ARR_COST_GRAD,    /* [N][m]   (control part zero at the terminal knot) */
-  B2T_ARR_COST_HESS     /* [N][m*m] */
+  B2T_ARR_COST_HESS,    /* [N][m*m] */
+  B2T_ARR_COST_ERR,     /* [N][nx]  state error of the cost's state map (UrdfCost.delta_x, TrajoptCost.py:425-435) */
+  B2T_ARR_NU_TRACE      /* [128]    per instance: |r^T Pinv r| of PCG iteration 0..127 of the last b2t_stage_pcg (PCG.py:82,95) */
 } b2t_array;
 
 typedef struct b2t_solver b2t_solver;
@@ -171,6 +173,12 @@ int b2t_sqp_solve_host(b2t_solver* s, const double* x0, const double* u0, const 
 int b2t_stage_dynamics(b2t_solver* s);
 int b2t_stage_kkt(b2t_solver* s, double rho, int method);
 int b2t_stage_pcg(b2t_solver* s, int method, double tol, int max_iter, int* iters_out /* [batch] host */);
+/* standalone use of the PCG kernel (PCG(A, b, block_size = nx, Nblocks = N).solve(), PCG.py:5,214): upload a block-tridiagonal
+ * system, knot-major host doubles: Sd [batch][N][nx*nx] diagonal blocks, So [batch][N][nx*nx] sub-diagonal blocks S_{k,k-1}
+ * (block 0 ignored), gamma [batch][N][nx]; then b2t_stage_precond + b2t_stage_pcg, result via b2t_fetch(B2T_ARR_L). */
+int b2t_set_block_system(b2t_solver* s, const double* Sd, const double* So, const double* gamma);
+/* preconditioner blocks of the current S for `method` (PCG.compute_preconditioner, PCG.py:113-212) */
+int b2t_stage_precond(b2t_solver* s, int method);
 int b2t_stage_recover(b2t_solver* s);
 int b2t_stage_merit(b2t_solver* s, double alpha, double* J, double* c, double* D /* [batch] host each */);
 int b2t_fetch(b2t_solver* s, int which, double* out);

@@ -146,3 +146,33 @@ def test_urdf_cost_callbacks(oracle_models):
         assert abs(pc.value(x, None, 9) - vals[1]) < 1e-12 * max(1, abs(vals[1]))
         assert relerr(pc.gradient(x, None, 9), grads[1][:4]) < 1e-12
         assert relerr(pc.hessian(x, None, 9), hess[1][:4, :4]) < 1e-12
+
+
+@pytest.mark.parametrize("nb,N,kind", [(4, 10, "SS"), (12, 8, "BJ"), (6, 5, "J"), (12, 64, "SS")])
+def test_standalone_pcg_class(nb, N, kind):
+    """The reference's own PCG test idea (GBD-PCG-Python/test.py: PSD block system vs np.linalg.solve) through the drop-in PCG class,
+    plus the oracle's trace."""
+    rng = np.random.default_rng(nb * 100 + N)
+    # negative-definite block-tridiagonal matrix like the Schur complement: S = -(L L^T), L block lower-bidiagonal
+    L = np.zeros((nb * N, nb * N))
+    for k in range(N):
+        L[k * nb:(k + 1) * nb, k * nb:(k + 1) * nb] = rng.uniform(-1, 1, (nb, nb)) + 3 * np.eye(nb)
+        if k > 0:
+            L[k * nb:(k + 1) * nb, (k - 1) * nb:k * nb] = 0.5 * rng.uniform(-1, 1, (nb, nb))
+    S = -(L @ L.T)
+    b = rng.uniform(-1, 1, nb * N)
+    pcg = t.PCG(S, b, nb, N, options={"preconditioner_type": kind, "exit_tolerance": 1e-6, "max_iter": 100})
+    x, (trace, _) = pcg.solve()
+    Sd = np.stack([S[k * nb:(k + 1) * nb, k * nb:(k + 1) * nb] for k in range(N)])
+    So = np.stack([S[k * nb:(k + 1) * nb, (k - 1) * nb:k * nb] for k in range(1, N)])
+    Pd, Po = kkt.preconditioner(Sd, So, kind)
+    lo, tr_o = kkt.pcg(Sd, So, b.reshape(N, nb), Pd, Po)
+    assert abs(len(trace) - len(tr_o)) <= (1 if kind == "J" else 0)
+    k = min(len(trace), len(tr_o), 6)
+    assert np.allclose(trace[:k], tr_o[:k], rtol=1e-6)
+    exact = np.linalg.solve(S, b)
+    assert np.max(np.abs(x[:, 0] - exact)) < 5e-3 * max(1.0, np.max(np.abs(exact)))
+    # warm start (PCG.update_guess, PCG.py:33): starting at the exact solution needs no iteration to meet the tolerance
+    pcg.update_guess(exact); pcg.update_exit_tolerance(1e-10)
+    x2, (tr2, _) = pcg.solve()
+    assert np.max(np.abs(x2[:, 0] - exact)) < 1e-8 and len(tr2) <= 3

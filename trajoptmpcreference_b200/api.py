@@ -284,9 +284,9 @@ class UrdfCost(QuadraticCost):
         return H[:2 * self.n, :2 * self.n].copy() if u is None else H.copy()
 
     def delta_x(self, x):
-        """End-effector state error (TrajoptCost.py:425-435), recovered from the gradient: e = Q^-1 J_tot^-T grad is not needed by the
-        solver; provided for exampleHelpers-style reporting through value(): 0.5 e^T Q e."""
-        raise NotImplementedError("delta_x is internal to the kernels (urdf_cost_terms); use value()/gradient()")
+        """End-effector state error [ee_pos; J qd] - xg (TrajoptCost.py:425-435), evaluated by the cost kernel."""
+        s, k = self._knot(x, None, None)
+        return s.fetch("cost_err")[0, k].copy()
 
 
 # --------------------------------------------------------------------------------------------------- constraints
@@ -634,6 +634,15 @@ class BatchSolver:
         _lib.check(self.lib, self.lib.b2t_stage_pcg(self._h, _METHOD_CODE[method], float(tol), int(max_iter), _dptr(it)))
         return it
 
+    def set_block_system(self, Sd, So, gamma):
+        """Upload a block-tridiagonal system (batch, N, nx*nx) x2, (batch, N, nx) for the standalone PCG entry."""
+        a = _as_f64(Sd, (self.batch, self.N, self.nx * self.nx)); b = _as_f64(So, (self.batch, self.N, self.nx * self.nx))
+        c = _as_f64(gamma, (self.batch, self.N, self.nx))
+        _lib.check(self.lib, self.lib.b2t_set_block_system(self._h, _dptr(a), _dptr(b), _dptr(c)))
+
+    def stage_precond(self, method=SQPSolverMethods.PCG_SS):
+        _lib.check(self.lib, self.lib.b2t_stage_precond(self._h, _METHOD_CODE[method]))
+
     def stage_recover(self):
         _lib.check(self.lib, self.lib.b2t_stage_recover(self._h))
 
@@ -652,7 +661,12 @@ class BatchSolver:
         """Knot-major copy of an internal array: (batch, N, elems)."""
         E = {"x": self.nx, "u": self.nu, "xkp1": self.nx, "dqdd": self.n * 3 * self.n, "Ghat": self.m * self.m, "g": self.m,
              "Sd": self.nx * self.nx, "So": self.nx * self.nx, "Pd": self.nx * self.nx, "gamma": self.nx, "l": self.nx, "dz": self.m,
-             "xn": self.nx, "un": self.nu, "cost_value": 1, "cost_grad": self.m, "cost_hess": self.m * self.m}[name]
+             "xn": self.nx, "un": self.nu, "cost_value": 1, "cost_grad": self.m, "cost_hess": self.m * self.m, "cost_err": self.nx,
+             "nu_trace": None}[name]
+        if name == "nu_trace":
+            out = np.zeros((self.batch, 128))
+            _lib.check(self.lib, self.lib.b2t_fetch(self._h, _lib.ARR[name], _dptr(out)))
+            return out
         out = np.zeros((self.batch, self.N, E))
         _lib.check(self.lib, self.lib.b2t_fetch(self._h, _lib.ARR[name], _dptr(out)))
         return out
@@ -863,3 +877,105 @@ class TrajoptMPCReference:
         s.stage_dynamics()
         J, c, D = s.stage_merit(0.0)
         return float(J[0])
+
+
+# --------------------------------------------------------------------------------------------------- standalone PCG
+_PCG_ROBOT_BY_BLOCK = {2: "pend", 4: "arm2", 6: "arm3", 8: "arm4", 12: "arm6"}
+
+
+class PCG:
+    """GBD-PCG-Python's `PCG(A, b, block_size, Nblocks, guess=None, options={}).solve()` (PCG.py:5-214) on the GPU kernel.
+
+    A must be block-tridiagonal with `Nblocks` blocks of `block_size` (the structure of the Schur complement the solver builds);
+    the kernels are compiled per state dimension, so block_size must be one of 2, 4, 6, 8, 12 (the built-in robots).
+    Preconditioners 'J', 'BJ', 'SS' (PCG.py:113-212); `solve()` returns `(x, (trace, trace2))` like the reference, where trace holds
+    |r^T Pinv r| per iteration and trace2 (the reference's extra true-residual matvec per iteration, PCG.py:83,96) is left empty."""
+
+    def __init__(self, A, b, block_size, Nblocks, guess=None, options=None, overloading=False):
+        options = {} if options is None else options
+        if overloading:
+            raise ValueError("the operator-overloading tracer is not supported")
+        self.A = np.asarray(A, dtype=np.float64)
+        self.b = np.asarray(b, dtype=np.float64).reshape(-1)
+        self.block_size, self.Nblocks = int(block_size), int(Nblocks)
+        self.guess = None if guess is None else np.asarray(guess, dtype=np.float64).reshape(-1)
+        self.options = options
+        self.set_default_options(options)
+        if self.block_size not in _PCG_ROBOT_BY_BLOCK:
+            raise ValueError("block_size must be one of %r" % sorted(_PCG_ROBOT_BY_BLOCK))
+        n = self.block_size * self.Nblocks
+        if self.A.shape != (n, n) or self.b.shape != (n,):
+            raise ValueError("A must be (block_size*Nblocks)^2 and b of matching length")
+        self.Pinv = None
+
+    def set_default_options(self, options):
+        options.setdefault("exit_tolerance", 1e-6)
+        options.setdefault("max_iter", 100)
+        options.setdefault("DEBUG_MODE", False)
+        options.setdefault("RETURN_TRACE", False)
+        options.setdefault("preconditioner_type", "BJ")
+        self.validate_precon_type(options["preconditioner_type"])
+
+    def validate_precon_type(self, precon_type):
+        if precon_type not in ["J", "BJ", "SS"]:
+            raise ValueError("Invalid preconditioner options are [J : Jacobi, BJ: Block-Jacobi, SS: Symmetric Stair] ('0' is not offered on the GPU)")
+
+    def update_A(self, A):
+        self.A = np.asarray(A, dtype=np.float64)
+
+    def update_b(self, b):
+        self.b = np.asarray(b, dtype=np.float64).reshape(-1)
+
+    def update_guess(self, guess):
+        self.guess = np.asarray(guess, dtype=np.float64).reshape(-1)
+
+    def update_exit_tolerance(self, tol):
+        self.options["exit_tolerance"] = tol
+
+    def update_max_iter(self, max_iter):
+        self.options["max_iter"] = max_iter
+
+    def update_preconditioner_type(self, type):
+        self.validate_precon_type(type)
+        self.options["preconditioner_type"] = type
+
+    def _blocks(self):
+        nb, N = self.block_size, self.Nblocks
+        A = self.A
+        Sd = np.zeros((N, nb, nb)); So = np.zeros((N, nb, nb))
+        mask = np.zeros_like(A, dtype=bool)
+        for k in range(N):
+            sl = slice(k * nb, (k + 1) * nb)
+            Sd[k] = A[sl, sl]; mask[sl, sl] = True
+            if k > 0:
+                pl = slice((k - 1) * nb, k * nb)
+                So[k] = A[sl, pl]; mask[sl, pl] = True; mask[pl, sl] = True
+                if not np.allclose(A[pl, sl], A[sl, pl].T, rtol=1e-12, atol=1e-300):
+                    raise ValueError("A must be symmetric")
+        if np.any(A[~mask] != 0.0):
+            raise ValueError("A must be block-tridiagonal (GBD-PCG's Schur complement structure)")
+        return Sd, So
+
+    def solve(self):
+        nb, N = self.block_size, self.Nblocks
+        Sd, So = self._blocks()
+        b = self.b.copy()
+        if self.guess is not None and np.any(self.guess != 0):
+            b = b - self.A @ self.guess            # PCG from x0 == PCG from zero on the shifted system
+        plant = URDFPlant(options={"path_to_urdf": _PCG_ROBOT_BY_BLOCK[nb]})
+        n = plant.get_num_pos()
+        cost = QuadraticCost(np.eye(2 * n), np.eye(2 * n), np.eye(n), np.zeros(2 * n))
+        s = BatchSolver(plant, cost, None, N=max(N, 2), dt=0.1, batch=1)
+        if N < 2:
+            raise ValueError("Nblocks >= 2 required")
+        method = {"J": SQPSolverMethods.PCG_J, "BJ": SQPSolverMethods.PCG_BJ, "SS": SQPSolverMethods.PCG_SS}[self.options["preconditioner_type"]]
+        s.set_block_system(Sd.reshape(1, N, nb * nb), So.reshape(1, N, nb * nb), b.reshape(1, N, nb))
+        s.stage_precond(method)
+        it = s.stage_pcg(method, self.options["exit_tolerance"], self.options["max_iter"])
+        x = s.fetch("l")[0].reshape(-1)
+        if self.guess is not None:
+            x = x + self.guess
+        trace = s.fetch("nu_trace")[0, :int(it[0]) + 1].tolist()
+        self.Pinv = s.fetch("Pd")[0].reshape(N, nb, nb)
+        self.iterations = int(it[0])
+        return x.reshape(-1, 1), (trace, [])

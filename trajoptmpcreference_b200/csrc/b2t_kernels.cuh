@@ -17,6 +17,7 @@ namespace b2t {
 enum Phase { PH_SQP = 0, PH_OUTER = 1, PH_DONE = 2 };
 enum { TRACE_FIELDS = 12 };
 enum { MAX_LS_TRIALS = 32 };
+enum { NU_TRACE_LEN = 128 };
 
 template <typename T>
 struct Opts {
@@ -50,6 +51,7 @@ struct Dev {
   int *ls_list0, *ls_list1;
   int *restart_list, *n_restart;
   int *n_ls;          // [MAX_LS_TRIALS + 1]
+  T* nu_trace;        // optional [B][NU_TRACE_LEN]: |r^T Pinv r| of every PCG iteration (PCG.pcg's `trace`, PCG.py:82,95); null = off
   T* trace;           // [B][trace_cap][TRACE_FIELDS]
   int* trace_rows;
   int trace_cap;
@@ -626,6 +628,7 @@ __global__ void __launch_bounds__(1024) k_pcg(Dev<T> d, const int* list, const i
   T part = T(0);
   for (int m = 0, r = tid; r < R; r += nt, ++m) { pp[m] = rt[m]; part += rr[m] * rt[m]; }
   T nu = block_sum(part, red, tid, nt);
+  if (tid == 0 && d.nu_trace) d.nu_trace[(size_t)b * NU_TRACE_LEN] = fabs(nu);
   int iters = 0;
   for (int it = 0; it < max_iter; ++it) {
     for (int m = 0, r = tid; r < R; r += nt, ++m) p_s[r] = pp[m];
@@ -645,6 +648,7 @@ __global__ void __launch_bounds__(1024) k_pcg(Dev<T> d, const int* list, const i
     for (int m = 0, r = tid; r < R; r += nt, ++m) part += rr[m] * rt[m];
     const T nu_prime = block_sum(part, red, tid, nt);
     iters = it + 1;
+    if (tid == 0 && d.nu_trace && iters < NU_TRACE_LEN) d.nu_trace[(size_t)b * NU_TRACE_LEN + iters] = fabs(nu_prime);
     if (fabs(nu_prime) < tol) break;
     const T beta = nu_prime / nu;
     for (int m = 0, r = tid; r < R; r += nt, ++m) pp[m] = rt[m] + pp[m] * beta;
@@ -798,6 +802,7 @@ __global__ void __launch_bounds__(MAXT) k_pcg2(Dev<T> d, const int* list, const 
 #pragma unroll
   for (int k = 0; k < RPT; ++k) { pp[k] = rt[k]; part += rr[k] * rt[k]; }
   T nu = block_sum(lead ? part : T(0), red, tid, nt);   // its barriers also order the y reads above before the p store below
+  if (tid == 0 && d.nu_trace) d.nu_trace[(size_t)b * NU_TRACE_LEN] = fabs(nu);
   int iters = 0;
   for (int it = 0; it < max_iter; ++it) {
     store(A_s, pp);
@@ -828,6 +833,7 @@ __global__ void __launch_bounds__(MAXT) k_pcg2(Dev<T> d, const int* list, const 
     for (int k = 0; k < RPT; ++k) part += rr[k] * rt[k];
     const T nu_prime = block_sum(lead ? part : T(0), red, tid, nt);
     iters = it + 1;
+    if (tid == 0 && d.nu_trace && iters < NU_TRACE_LEN) d.nu_trace[(size_t)b * NU_TRACE_LEN + iters] = fabs(nu_prime);
     if (fabs(nu_prime) < tol) break;
     const T beta = nu_prime / nu;
 #pragma unroll
@@ -1014,6 +1020,7 @@ __global__ void __launch_bounds__(MAXT) k_pcg3(Dev<T> d, const int* list, const 
 #pragma unroll
   for (int r = 0; r < RPT; ++r) { pp[r] = rt[r]; part += rr[r] * rt[r]; }
   T nu = block_sum(part, red, tid, nt);
+  if (tid == 0 && d.nu_trace) d.nu_trace[(size_t)b * NU_TRACE_LEN] = fabs(nu);
   int iters = 0;
   for (int it = 0; it < max_iter; ++it) {
     publish(V, pp);
@@ -1047,6 +1054,7 @@ __global__ void __launch_bounds__(MAXT) k_pcg3(Dev<T> d, const int* list, const 
     for (int r = 0; r < RPT; ++r) part += rr[r] * rt[r];
     const T nu_prime = block_sum(part, red, tid, nt);
     iters = it + 1;
+    if (tid == 0 && d.nu_trace && iters < NU_TRACE_LEN) d.nu_trace[(size_t)b * NU_TRACE_LEN + iters] = fabs(nu_prime);
     if (fabs(nu_prime) < tol) break;
     const T beta = nu_prime / nu;
 #pragma unroll
@@ -1718,10 +1726,24 @@ __global__ void k_cost_eval(Dev<T> d, int what, double* out) {
   load_xu(d.x, d.u, d.K, gt, terminal, z, z + NX);
   for (int i = 0; i < NX; ++i) xg[i] = d.xg[(size_t)i * d.B + b];
   if (what == 0) { out[gt] = (double)cost_value(d.cost, z, z + NX, xg, k, terminal); return; }
+  if (what == 3) {      // state error of the cost's state map (UrdfCost.delta_x, TrajoptCost.py:425-435)
+    T e[NX], Jt[NX * NX]; bool hj;
+    cost_state(d.cost, z, xg, e, Jt, &hj);
+    for (int i = 0; i < NX; ++i) out[gt * NX + i] = (double)e[i];
+    return;
+  }
   T g[NM], H[NM * NM];
   cost_grad_hess<T, true>(d.cost, z, z + NX, xg, k, terminal, g, H);
   if (what == 1) { for (int i = 0; i < NM; ++i) out[gt * NM + i] = (double)g[i]; }
   else { for (int i = 0; i < NM * NM; ++i) out[gt * NM * NM + i] = (double)H[i]; }
+}
+// standalone PCG entry (PCG(A, b, block_size, Nblocks).solve()): upload of a block-tridiagonal system in knot-major doubles
+template <typename T>
+__global__ void k_set_block_system(Dev<T> d, const double* Sd, const double* So, const double* gam) {
+  const size_t gt = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (gt >= d.K) return;
+  for (int e = 0; e < NX * NX; ++e) { d.Sd[(size_t)e * d.K + gt] = (T)Sd[gt * NX * NX + e]; d.So[(size_t)e * d.K + gt] = (T)So[gt * NX * NX + e]; }
+  for (int i = 0; i < NX; ++i) d.gam[(size_t)i * d.K + gt] = (T)gam[gt * NX + i];
 }
 template <typename T>
 __global__ void k_fill(T* p, size_t n, T v) {

@@ -45,6 +45,8 @@ struct SolverBase {
   virtual int stage_kkt(double rho, int method) = 0;
   virtual int stage_pcg(int method, double tol, int max_iter, int* iters) = 0;
   virtual int stage_recover() = 0;
+  virtual int set_block_system(const double* Sd, const double* So, const double* gam) = 0;
+  virtual int stage_precond(int method) = 0;
   virtual int stage_merit(double alpha, double* J, double* c, double* D) = 0;
   virtual int fetch(int which, double* out) = 0;
   size_t ws_bytes = 0;
@@ -170,11 +172,13 @@ struct SolverT : SolverBase {
     B2T_ALLOC(d.phase, B); B2T_ALLOC(d.err, B); B2T_ALLOC(d.pcg_iters, B); B2T_ALLOC(d.tot_qp, B); B2T_ALLOC(d.tot_pcg, B); B2T_ALLOC(d.tot_trials, B);
     B2T_ALLOC(d.act, B); B2T_ALLOC(d.n_act, 1); B2T_ALLOC(d.ls_list0, B); B2T_ALLOC(d.ls_list1, B); B2T_ALLOC(d.restart_list, B); B2T_ALLOC(d.n_restart, 1);
     B2T_ALLOC(d.n_ls, MAX_LS_TRIALS + 1);
+    B2T_ALLOC(d.nu_trace, B * NU_TRACE_LEN);
     d.trace_cap = 104;
     B2T_ALLOC(d.trace, B * d.trace_cap * TRACE_FIELDS); B2T_ALLOC(d.trace_rows, B);
     B2T_ALLOC(d_scratch, B); B2T_ALLOC(d_status, B * 8); B2T_ALLOC(d_scalars, B * 4);
     B2T_ALLOC(stage_x, (size_t)B * NX * d.N); B2T_ALLOC(stage_u, (size_t)B * NU * (d.N - 1)); B2T_ALLOC(stage_g, (size_t)B * NX);
-    stage_out_bytes = std::max<size_t>({(size_t)NM * NM * K, (size_t)NDYN * K, (size_t)2 * NM * K, B * (size_t)d.trace_cap * TRACE_FIELDS}) * sizeof(double);
+    stage_out_bytes = std::max<size_t>({(size_t)NM * NM * K, (size_t)NDYN * K, (size_t)2 * NM * K, B * (size_t)d.trace_cap * TRACE_FIELDS,
+                                        (size_t)(2 * NX * NX + NX) * K}) * sizeof(double);
     { void* q; cudaError_t e = cudaMalloc(&q, stage_out_bytes); if (e != cudaSuccess) return fail(B2T_ERR_NOMEM, "cudaMalloc stage_out"); allocs.push_back(q); ws_bytes += stage_out_bytes; stage_out = (double*)q; }
     B2T_CUDA(cudaMallocHost((void**)&h_count, 64));
     B2T_CUDA(cudaEventCreate(&ev0)); B2T_CUDA(cudaEventCreate(&ev1));
@@ -656,6 +660,30 @@ struct SolverT : SolverBase {
     B2T_CUDA(cudaStreamSynchronize(stream));
     return 0;
   }
+  int set_block_system(const double* Sd, const double* So, const double* gam) override {
+    using namespace b2t;
+    if (!Sd || !So || !gam) return fail(B2T_ERR_INVALID, "Sd, So, gamma required");
+    B2T_CUDA(cudaSetDevice(device));
+    const size_t nb = d.K * NX * NX, nv = d.K * NX;
+    if ((2 * nb + nv) * sizeof(double) > stage_out_bytes) return fail(B2T_ERR_INVALID, "system too large for staging");
+    double* p0 = stage_out; double* p1 = p0 + nb; double* p2 = p1 + nb;
+    B2T_CUDA(cudaMemcpyAsync(p0, Sd, nb * sizeof(double), cudaMemcpyHostToDevice, stream));
+    B2T_CUDA(cudaMemcpyAsync(p1, So, nb * sizeof(double), cudaMemcpyHostToDevice, stream));
+    B2T_CUDA(cudaMemcpyAsync(p2, gam, nv * sizeof(double), cudaMemcpyHostToDevice, stream));
+    int r = all_list(); if (r) return r;
+    k_set_block_system<T><<<cdiv(d.K, 128), 128, 0, stream>>>(d, p0, p1, p2);
+    B2T_CUDA(cudaGetLastError());
+    B2T_CUDA(cudaStreamSynchronize(stream));
+    return 0;
+  }
+  int stage_precond(int method) override {
+    using namespace b2t;
+    B2T_CUDA(cudaSetDevice(device));
+    k_pinv<T><<<cdiv(d.K, 128), 128, 0, stream>>>(d, d.act, d.n_act, method == B2T_METHOD_PCG_J ? 1 : 0);
+    B2T_CUDA(cudaGetLastError());
+    B2T_CUDA(cudaStreamSynchronize(stream));
+    return 0;
+  }
   int stage_recover() override {
     B2T_CUDA(cudaSetDevice(device));
     launch_recover(d.act, d.n_act, d.B);
@@ -704,11 +732,19 @@ struct SolverT : SolverBase {
       case B2T_ARR_COST_VALUE: E = 1; break;
       case B2T_ARR_COST_GRAD: E = NM; break;
       case B2T_ARR_COST_HESS: E = NM * NM; break;
+      case B2T_ARR_COST_ERR: E = NX; break;
+      case B2T_ARR_NU_TRACE: {
+        std::vector<T> h((size_t)d.B * NU_TRACE_LEN);
+        B2T_CUDA(cudaStreamSynchronize(stream));
+        B2T_CUDA(cudaMemcpy(h.data(), d.nu_trace, h.size() * sizeof(T), cudaMemcpyDeviceToHost));
+        for (size_t i = 0; i < h.size(); ++i) out[i] = (double)h[i];
+        return 0;
+      }
       default: return fail(B2T_ERR_INVALID, "unknown array id");
     }
     const size_t n = K * E;
     if (n * sizeof(double) > stage_out_bytes) return fail(B2T_ERR_INVALID, "array too large for staging");
-    if (which >= B2T_ARR_COST_VALUE) k_cost_eval<T><<<cdiv(K, 64), 64, 0, stream>>>(d, which - B2T_ARR_COST_VALUE, stage_out);
+    if (which >= B2T_ARR_COST_VALUE && which <= B2T_ARR_COST_ERR) k_cost_eval<T><<<cdiv(K, 64), 64, 0, stream>>>(d, which - B2T_ARR_COST_VALUE, stage_out);
     else if (which == B2T_ARR_GHAT && d.diag_mode) k_fetch_ghat_diag<T><<<cdiv(K, 128), 128, 0, stream>>>(d, stage_out);
     else k_fetch_soa<T><<<cdiv(K, 128), 128, 0, stream>>>(src, K, E, stage_out);
     B2T_CUDA(cudaGetLastError());
@@ -837,6 +873,8 @@ int b2t_stage_dynamics(b2t_solver* s) { B2T_FWD(stage_dynamics()); }
 int b2t_stage_kkt(b2t_solver* s, double rho, int method) { B2T_FWD(stage_kkt(rho, method)); }
 int b2t_stage_pcg(b2t_solver* s, int method, double tol, int mi, int* it) { B2T_FWD(stage_pcg(method, tol, mi, it)); }
 int b2t_stage_recover(b2t_solver* s) { B2T_FWD(stage_recover()); }
+int b2t_set_block_system(b2t_solver* s, const double* a, const double* b, const double* c) { B2T_FWD(set_block_system(a, b, c)); }
+int b2t_stage_precond(b2t_solver* s, int method) { B2T_FWD(stage_precond(method)); }
 int b2t_stage_merit(b2t_solver* s, double a, double* J, double* c, double* D) { B2T_FWD(stage_merit(a, J, c, D)); }
 int b2t_fetch(b2t_solver* s, int which, double* out) { B2T_FWD(fetch(which, out)); }
 int b2t_measure_fma_peak(int device, int dtype, double* tflops) {
