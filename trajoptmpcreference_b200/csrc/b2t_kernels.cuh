@@ -336,7 +336,7 @@ __device__ __forceinline__ void load_Ab(const Dev<T>& d, size_t t, T* Ab) {
 // entry of S_jj / S_j,j-1 / gamma_j is written straight to global memory -- no per-thread local arrays.
 enum { SCHUR_THREADS = 64 };
 template <typename T>
-__global__ void __launch_bounds__(SCHUR_THREADS) k_schur_diag(Dev<T> d, const int* list, const int* count, int jacobi) {
+__global__ void __launch_bounds__(SCHUR_THREADS) k_schur_diag(Dev<T> d, const int* list, const int* count, int need_so) {
   extern __shared__ unsigned char smem_raw[];
   T* sAb = reinterpret_cast<T*>(smem_raw);            // [NJ*NM][SCHUR_THREADS]
   const int tx = threadIdx.x;
@@ -353,7 +353,6 @@ __global__ void __launch_bounds__(SCHUR_THREADS) k_schur_diag(Dev<T> d, const in
   T* gm_o = d.gam + (size_t)b * d.N;
   auto GH = [&](int e, size_t tt) -> T { return d.Gh[(size_t)e * K + tt]; };
   const T sj = GH(2 * NM, t);
-  (void)jacobi;
   if (j == 0) {
     static_for<0, NX>([&](auto ic) {
       constexpr int i = decltype(ic)::value;
@@ -440,8 +439,8 @@ __global__ void __launch_bounds__(SCHUR_THREADS) k_schur_diag(Dev<T> d, const in
       Sd_o[(size_t)((NJ + i) * NX + NJ + c) * K + j] = -((mic - sp * v[NJ + i] * v[NJ + c]) + gbb);
     });
   });
-  // S_{j,j-1} = AB[:, :nx] diag(d_x) - sp v h_x^T
-  static_for<0, NX>([&](auto cc) {
+  // S_{j,j-1} = AB[:, :nx] diag(d_x) - sp v h_x^T   (not needed by the matrix-free PCG kernels)
+  if (need_so) static_for<0, NX>([&](auto cc) {
     constexpr int c = decltype(cc)::value;
     const T dc = GH(c, tp), hc = GH(NM + c, tp);
     static_for<0, NJ>([&](auto ic) {
@@ -863,19 +862,20 @@ __global__ void __launch_bounds__(MAXT) k_pcg2(Dev<T> d, const int* list, const 
 // Same PCG recurrence and exit test as PCG.pcg (PCG.py:66-111); the products are algebraically identical to S p / O y
 // (verified against the explicit form: identical iteration counts, SURVEY.md 7.2 parity floor).
 // -----------------------------------------------------------------------------------------------------------------
-template <typename T, int MAXT>
-__global__ void __launch_bounds__(MAXT) k_pcg3(Dev<T> d, const int* list, const int* count, int stair, T tol, int max_iter) {
+template <typename T, int MAXT, bool PDS, int LPK>
+__global__ void __launch_bounds__(MAXT, PDS ? 2 : 1) k_pcg3(Dev<T> d, const int* list, const int* count, int stair, T tol, int max_iter) {
   if ((int)blockIdx.x >= *count) return;
-  // only launched when nx % 4 == 0 (the host falls back to k_pcg2 otherwise); RPT >= 1 keeps the definition well-formed
-  constexpr int RPT = (NX % 4 == 0) ? NX / 4 : 1;   // owned rows per lane
-  constexpr int MC = (NM + 3) / 4;            // Ab columns per lane
+  // LPK lanes per knot (2 or 4).  Only launched when nx % (2 LPK) == 0; the max() keeps the definition well-formed otherwise.
+  constexpr int RPT = (NX % LPK == 0) ? NX / LPK : 1;   // owned rows per lane; divides NJ
+  constexpr int MC = (NM + LPK - 1) / LPK;               // Ab columns per lane
+  using T2 = typename std::conditional<sizeof(T) == 8, double2, float2>::type;
   const int b = list[blockIdx.x];
   const int N = d.N;
   const size_t K = d.K;
   const int tid = threadIdx.x, nt = blockDim.x;
-  const bool live = tid < 4 * N;
-  const int k = live ? tid >> 2 : 0;          // knot
-  const int g = tid & 3;                      // lane within the knot group
+  const bool live = tid < LPK * N;
+  const int k = live ? tid / LPK : 0;         // knot
+  const int g = tid % LPK;                    // lane within the knot group
   const bool has_next = live && (k < N - 1);  // knot N-1 has no dynamics; its group owns block row 0
   const int jo = (k + 1 == N) ? 0 : k + 1;    // owned block row
   const int c0 = g * MC, i0 = g * RPT;
@@ -888,9 +888,16 @@ __global__ void __launch_bounds__(MAXT) k_pcg3(Dev<T> d, const int* list, const 
   T* W = V2 + (N + 1) * NX;                   // [N][NM]      w or q'
   T* Wq = W + N * NM;                         // [N][NM]      q
   T* red = Wq + N * NM;                       // 32
-  // ---- resident data
-  T ab[NJ][MC], dinv[MC], hh[MC], pd[RPT][NX];
+  // PDS: the preconditioner rows live in shared memory ([RPT][NX/2][MAXT] pairs, conflict-free 128-bit loads) instead of registers,
+  // so that TWO instances are resident per SM
+  T2* Pd_s = reinterpret_cast<T2*>(red + 32);
+  // ---- resident data (registers for all iterations)
+  T ab[NJ][MC], dinv[MC], hh[MC], pd[PDS ? 1 : RPT][PDS ? 2 : NX];
+  // per-column constants, computed once: validity, the E0^T coupling (which entry of z_q feeds column c, with which factor) and
+  // the self term ([p_k; 0])_c
   bool cval[MC];
+  T emul[MC], smul[MC];
+  int eidx[MC], sidx[MC];
 #pragma unroll
   for (int i = 0; i < MC; ++i) {
     const int c = c0 + i;
@@ -900,46 +907,60 @@ __global__ void __launch_bounds__(MAXT) k_pcg3(Dev<T> d, const int* list, const 
 #pragma unroll
     for (int a = 0; a < NJ; ++a)
       ab[a][i] = (cval[i] && has_next) ? d.dt * d.dyn[(size_t)(a * 3 * NJ + c) * K + tk] + ((c == NJ + a) ? T(1) : T(0)) : T(0);
+    emul[i] = (!has_next || !cval[i] || c >= NX) ? T(0) : (c < NJ ? T(1) : dte);
+    eidx[i] = (c < NJ) ? c : ((c < NX) ? c - NJ : 0);
+    smul[i] = (cval[i] && c < NX) ? T(1) : T(0);
+    sidx[i] = (c < NX) ? c : 0;
   }
   const T sS = live ? d.Gh[(size_t)(2 * NM) * K + tk] : T(0);
 #pragma unroll
   for (int r = 0; r < RPT; ++r)
 #pragma unroll
-    for (int c = 0; c < NX; ++c) pd[r][c] = live ? d.Pd[(size_t)((i0 + r) * NX + c) * K + tj] : T(0);
+    for (int c = 0; c < NX; c += 2) {
+      const T p0 = live ? d.Pd[(size_t)((i0 + r) * NX + c) * K + tj] : T(0);
+      const T p1 = live ? d.Pd[(size_t)((i0 + r) * NX + c + 1) * K + tj] : T(0);
+      if constexpr (PDS) { T2 v; v.x = p0; v.y = p1; Pd_s[(r * (NX / 2) + c / 2) * MAXT + tid] = v; }
+      else { pd[r][c] = p0; pd[r][c + 1] = p1; }
+    }
   for (int idx = tid; idx < 2 * (N + 1) * NX + 2 * N * NM; idx += nt) V[idx] = T(0);
   __syncthreads();
+  const bool top = i0 < NJ;                   // rows i0.. are q rows (top half of [A B]) for the first LPK/2 lanes, qd rows for the others
+  const bool odd = (i0 % NJ) != 0;            // row % NJ = (i0 % NJ) + r; with LPK = 4 that is RPT + r for the odd lanes, with LPK = 2 always r
+  const T topm = (top && has_next) ? T(1) : T(0);
+  const T hn = has_next ? T(1) : T(0);
+  const T livem = live ? T(1) : T(0);
+  const int ownV = jo * NX, ownW = jo * NM + i0, kV = k * NX, nV = (k + 1) * NX, kW = k * NM;
 
-  auto quad = [&](T v) -> T {                 // sum over the 4 lanes of the knot group (all lanes get it)
+  auto quad = [&](T v) -> T {                 // sum over the LPK lanes of the knot group (all lanes get it)
     v += __shfl_xor_sync(0xffffffffu, v, 1);
-    v += __shfl_xor_sync(0xffffffffu, v, 2);
+    if constexpr (LPK == 4) v += __shfl_xor_sync(0xffffffffu, v, 2);
     return v;
   };
   auto publish = [&](T* buf, const T* val) {  // owned rows of block jo
     if (live) {
 #pragma unroll
-      for (int r = 0; r < RPT; ++r) buf[jo * NX + i0 + r] = val[r];
+      for (int r = 0; r < RPT; ++r) buf[ownV + i0 + r] = val[r];
     }
   };
-  // t_c = (AB_k^T z)_c for my columns, z = the nx-vector stored in block k+1 of `buf` (zero block for k = N-1)
+  // tc_i = (AB_k^T z)_c for my columns, z = block k+1 of `buf` (the zero block for k = N-1)
   auto abt = [&](const T* buf, T* tc) {
-    T pi[NJ], zq[NJ];
-    const T* z = buf + (k + 1) * NX;
+    T pi[NJ];
 #pragma unroll
-    for (int a = 0; a < NJ; ++a) { zq[a] = z[a]; pi[a] = tau * zq[a] + z[NJ + a]; }
+    for (int a = 0; a < NJ; a += 2) {
+      const T2 zq = *reinterpret_cast<const T2*>(buf + nV + a);
+      const T2 zv = *reinterpret_cast<const T2*>(buf + nV + NJ + a);
+      pi[a] = tau * zq.x + zv.x;
+      if (a + 1 < NJ) pi[a + 1] = tau * zq.y + zv.y;
+    }
 #pragma unroll
     for (int i = 0; i < MC; ++i) {
-      const int c = c0 + i;
-      T acc = T(0);
+      T acc = emul[i] * buf[nV + eidx[i]];
 #pragma unroll
       for (int a = 0; a < NJ; ++a) acc += ab[a][i] * pi[a];
-      // E0^T z_q : identity on the q columns, dte on the qd columns (only where the knot has dynamics)
-      T e0 = T(0);
-#pragma unroll
-      for (int a = 0; a < NJ; ++a) { if (c == a) e0 = zq[a]; if (c == NJ + a) e0 = dte * zq[a]; }
-      tc[i] = has_next ? acc + e0 : T(0);
+      tc[i] = acc;
     }
   };
-  // out_r (owned rows of block jo) = AB_k zz + sign * Wn[jo][row], zz given by my columns (regs) and by smem copy `full` of knot k
+  // out_r (owned rows of block jo) = (AB_k zz)_row + sign * Wn[jo][row];  zz: my columns in zc (registers), all columns in `full`
   auto abmul = [&](const T* zc, const T* full, const T* Wn, T sign, T* out) {
     T pb[NJ];
 #pragma unroll
@@ -947,19 +968,17 @@ __global__ void __launch_bounds__(MAXT) k_pcg3(Dev<T> d, const int* list, const 
       T acc = T(0);
 #pragma unroll
       for (int i = 0; i < MC; ++i) acc += ab[a][i] * zc[i];
-      pb[a] = quad(acc);
+      pb[a] = acc;
     }
 #pragma unroll
-    for (int r = 0; r < RPT; ++r) {
-      const int row = i0 + r;
-      T val = T(0);
-      if (has_next) {
-        T bot = T(0);
+    for (int a = 0; a < NJ; ++a) pb[a] = quad(pb[a]);
 #pragma unroll
-        for (int a = 0; a < NJ; ++a) if ((row % NJ) == a) bot = pb[a];
-        val = (row < NJ) ? full[k * NM + row] + dte * full[k * NM + NJ + row] + tau * bot : bot;
-      }
-      out[r] = live ? val + sign * Wn[jo * NM + row] : T(0);
+    for (int r = 0; r < RPT; ++r) {
+      const T bot = odd ? pb[(RPT + r) % NJ] : pb[r % NJ];
+      // top rows: z_q + dte z_qd + tau (Ab z);  bottom rows: Ab z.  full[kW + row], full[kW + NJ + row] only matter for top rows
+      const T zq = full[kW + (top ? i0 + r : 0)], zd = full[kW + NJ + (top ? i0 + r : 0)];
+      const T val = topm * (zq + dte * zd + tau * bot) + (hn - topm) * bot;
+      out[r] = livem * (val + sign * Wn[ownW + r]);
     }
   };
   // out = Pd_jo * buf[jo]  (entries published by the lanes of this group: __syncwarp suffices)
@@ -969,9 +988,12 @@ __global__ void __launch_bounds__(MAXT) k_pcg3(Dev<T> d, const int* list, const 
     for (int r = 0; r < RPT; ++r) { o0[r] = T(0); o1[r] = T(0); }
 #pragma unroll
     for (int c = 0; c < NX; c += 2) {
-      const T v0 = buf[jo * NX + c], v1 = buf[jo * NX + c + 1];
+      const T2 v = *reinterpret_cast<const T2*>(buf + ownV + c);
 #pragma unroll
-      for (int r = 0; r < RPT; ++r) { o0[r] += pd[r][c] * v0; o1[r] += pd[r][c + 1] * v1; }
+      for (int r = 0; r < RPT; ++r) {
+        if constexpr (PDS) { const T2 m2 = Pd_s[(r * (NX / 2) + c / 2) * MAXT + tid]; o0[r] += m2.x * v.x; o1[r] += m2.y * v.y; }
+        else { o0[r] += pd[r][c] * v.x; o1[r] += pd[r][c + 1] * v.y; }
+      }
     }
 #pragma unroll
     for (int r = 0; r < RPT; ++r) out[r] = o0[r] + o1[r];
@@ -993,8 +1015,7 @@ __global__ void __launch_bounds__(MAXT) k_pcg3(Dev<T> d, const int* list, const 
     abt(V2, u2);
 #pragma unroll
     for (int i = 0; i < MC; ++i) {
-      const int c = c0 + i;
-      u1[i] = (cval[i] && c < NX) ? V2[k * NX + c] : T(0);
+      u1[i] = smul[i] * V2[kV + sidx[i]];
       h1 += hh[i] * u1[i];
       h2 += hh[i] * u2[i];
     }
@@ -1003,7 +1024,7 @@ __global__ void __launch_bounds__(MAXT) k_pcg3(Dev<T> d, const int* list, const 
     for (int i = 0; i < MC; ++i) {
       u1[i] = dinv[i] * u1[i] - sS * hh[i] * h1;
       u2[i] = dinv[i] * u2[i] - sS * hh[i] * h2;
-      if (cval[i]) { Wq[k * NM + c0 + i] = u1[i]; W[k * NM + c0 + i] = u2[i]; }
+      if (cval[i]) { Wq[kW + c0 + i] = u1[i]; W[kW + c0 + i] = u2[i]; }
     }
     __syncthreads();
     abmul(u1, Wq, W, T(1), tmp);
@@ -1029,15 +1050,14 @@ __global__ void __launch_bounds__(MAXT) k_pcg3(Dev<T> d, const int* list, const 
     abt(V, uc);
 #pragma unroll
     for (int i = 0; i < MC; ++i) {
-      const int c = c0 + i;
-      uc[i] = ((cval[i] && c < NX) ? V[k * NX + c] : T(0)) - uc[i];
+      uc[i] = smul[i] * V[kV + sidx[i]] - uc[i];
       hu += hh[i] * uc[i];
     }
     hu = quad(hu);
 #pragma unroll
     for (int i = 0; i < MC; ++i) {
       uc[i] = dinv[i] * uc[i] - sS * hh[i] * hu;
-      if (cval[i]) W[k * NM + c0 + i] = uc[i];
+      if (cval[i]) W[kW + c0 + i] = uc[i];
     }
     __syncthreads();
     abmul(uc, W, W, T(-1), ap);

@@ -190,9 +190,10 @@ struct SolverT : SolverBase {
     B2T_CUDA(cudaFuncSetAttribute(b2t::k_pcg2<T, PCG_RPT, 1, true, 512>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
     B2T_CUDA(cudaFuncSetAttribute(b2t::k_pcg2<T, PCG_RPT, 1, true, 1024>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
     if constexpr (b2t::NX % 4 == 0) {
-      B2T_CUDA(cudaFuncSetAttribute(b2t::k_pcg3<T, 256>, cudaFuncAttributeMaxDynamicSharedMemorySize, 160 * 1024));
-      B2T_CUDA(cudaFuncSetAttribute(b2t::k_pcg3<T, 512>, cudaFuncAttributeMaxDynamicSharedMemorySize, 160 * 1024));
-      B2T_CUDA(cudaFuncSetAttribute(b2t::k_pcg3<T, 1024>, cudaFuncAttributeMaxDynamicSharedMemorySize, 160 * 1024));
+      B2T_CUDA(cudaFuncSetAttribute(b2t::k_pcg3<T, 256, false, 4>, cudaFuncAttributeMaxDynamicSharedMemorySize, 160 * 1024));
+      B2T_CUDA(cudaFuncSetAttribute(b2t::k_pcg3<T, 512, false, 4>, cudaFuncAttributeMaxDynamicSharedMemorySize, 160 * 1024));
+      B2T_CUDA(cudaFuncSetAttribute(b2t::k_pcg3<T, 1024, false, 4>, cudaFuncAttributeMaxDynamicSharedMemorySize, 160 * 1024));
+      B2T_CUDA(cudaFuncSetAttribute(b2t::k_pcg3<T, 128, true, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, 112 * 1024));
     }
     if constexpr (PCG_CS_MAX == 2) {
       B2T_CUDA(cudaFuncSetAttribute(b2t::k_pcg2<T, PCG_RPT, 2, true, 256>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
@@ -390,13 +391,17 @@ struct SolverT : SolverBase {
     { Scope sc(this, B2T_K_FDGRAD); dim3 grid(cdiv(nthreads, 128), 2 * NJ); k_fd_grad<T><<<grid, 128, 0, stream>>>(d, list, count); tick(B2T_K_FDGRAD); }
     return 0;
   }
-  int launch_kkt(const int* list, const int* count, int bound, int method) {
+  int launch_kkt(const int* list, const int* count, int bound, int method, bool all_outputs = false) {
     using namespace b2t;
     const size_t nthreads = (size_t)bound * d.N;
     const int jac = method == B2T_METHOD_PCG_J ? 1 : 0;
     if (d.diag_mode) {
+      // the matrix-free PCG kernels never read the sub-diagonal blocks S_{k,k-1}: skip their stores (half of this kernel's traffic)
+      decide_pcg_variant();
+      const bool exact = method == B2T_METHOD_N || method == B2T_METHOD_S;
+      const int need_so = (all_outputs || exact || !(pcg_variant == 3 || pcg_variant == 4)) ? 1 : 0;
       { Scope sc(this, B2T_K_KKT); k_kkt_diag<T><<<cdiv(nthreads, 128), 128, 0, stream>>>(d, list, count); tick(B2T_K_KKT); }
-      { Scope sc(this, B2T_K_SCHUR); k_schur_diag<T><<<cdiv(nthreads, SCHUR_THREADS), SCHUR_THREADS, (size_t)NJ * NM * SCHUR_THREADS * sizeof(T), stream>>>(d, list, count, jac); tick(B2T_K_SCHUR); }
+      { Scope sc(this, B2T_K_SCHUR); k_schur_diag<T><<<cdiv(nthreads, SCHUR_THREADS), SCHUR_THREADS, (size_t)NJ * NM * SCHUR_THREADS * sizeof(T), stream>>>(d, list, count, need_so); tick(B2T_K_SCHUR); }
       if (method != B2T_METHOD_N && method != B2T_METHOD_S) {
         Scope sc(this, B2T_K_SCHUR); k_pinv<T><<<cdiv(nthreads, 128), 128, 0, stream>>>(d, list, count, jac); tick(B2T_K_SCHUR);
       }
@@ -435,17 +440,28 @@ struct SolverT : SolverBase {
     return v;
   }
   // 0: k_pcg (v1), 1: k_pcg2 with shared-memory diagonal blocks (default), 2: k_pcg2 streaming them from L1/L2,
-  // 3: k_pcg3 matrix-free (opt-in with B2T_PCG_VARIANT=3; measured slower than variant 1 on B200: 30.7 vs 23.8 ms / 2048 instances)
+  // 3: k_pcg3 matrix-free, register-resident (default for the structured path when 4 N <= 256), 4: k_pcg3 with two lanes per knot
+  // and the preconditioner rows in shared memory (two instances per SM; measured 24.4 ms)
   int pcg_variant = -1;
-  int launch_pcg(const int* list, const int* count, int bound, int method, T tol, int max_iter) {
-    using namespace b2t;
+  bool explicit_system = false;   // set by b2t_set_block_system: only S / Pinv blocks are valid -> the explicit kernels must run
+  void decide_pcg_variant() {
     if (pcg_variant < 0) {
       const char* e = getenv("B2T_PCG_VARIANT");
       if (e) pcg_variant = atoi(e);
+      else if (d.diag_mode && b2t::NX % 4 == 0 && 4 * d.N <= 256) pcg_variant = 3;     // measured: 21.9 ms vs 24.0 ms (variant 1) per 2048-instance step
       else if (pcg2_threads() > 1024) pcg_variant = 0;
       else pcg_variant = pcg2_smem(true) <= (size_t)220 * 1024 ? 1 : 2;
       if (pcg_variant == 3 && !(d.diag_mode && b2t::NX % 4 == 0 && 4 * d.N <= 1024)) pcg_variant = 1;
+      if (pcg_variant == 4 && !(d.diag_mode && b2t::NX % 4 == 0 && 2 * d.N <= 128)) pcg_variant = 1;
     }
+  }
+  int launch_pcg(const int* list, const int* count, int bound, int method, T tol, int max_iter) {
+    using namespace b2t;
+    decide_pcg_variant();
+    const int saved_variant = pcg_variant;
+    if (explicit_system && (pcg_variant == 3 || pcg_variant == 4))
+      pcg_variant = pcg2_threads() > 1024 ? 0 : (pcg2_smem(true) <= (size_t)220 * 1024 ? 1 : 2);
+    struct Restore { int& v; int s; ~Restore() { v = s; } } restore{pcg_variant, saved_variant};
     const int stair = method == B2T_METHOD_PCG_SS ? 1 : 0;
     Scope sc(this, B2T_K_PCG);
     if (method == B2T_METHOD_N || method == B2T_METHOD_S) {
@@ -454,13 +470,21 @@ struct SolverT : SolverBase {
       return 0;
     }
     const int nt = pcg2_threads();
-    if (pcg_variant == 3) {
+    if (pcg_variant == 3 || pcg_variant == 4) {
+      // 3: four lanes per knot, everything in registers, one instance per SM;  4: two lanes per knot, preconditioner rows in
+      // shared memory, two instances per SM
       if constexpr (b2t::NX % 4 == 0) {
-        const int nt3 = ((4 * d.N + 31) / 32) * 32;
-        const size_t sm3 = ((size_t)2 * (d.N + 1) * NX + (size_t)2 * d.N * NM + 32) * sizeof(T);
-        if (nt3 <= 256) k_pcg3<T, 256><<<bound, nt3, sm3, stream>>>(d, list, count, stair, tol, max_iter);
-        else if (nt3 <= 512) k_pcg3<T, 512><<<bound, nt3, sm3, stream>>>(d, list, count, stair, tol, max_iter);
-        else k_pcg3<T, 1024><<<bound, nt3, sm3, stream>>>(d, list, count, stair, tol, max_iter);
+        const size_t smv = ((size_t)2 * (d.N + 1) * NX + (size_t)2 * d.N * NM + 32) * sizeof(T);
+        if (pcg_variant == 4) {
+          const int nt4 = ((2 * d.N + 31) / 32) * 32;
+          const size_t smp = smv + (size_t)(NX / 2) * NX * 128 * sizeof(T);
+          k_pcg3<T, 128, true, 2><<<bound, nt4, smp, stream>>>(d, list, count, stair, tol, max_iter);
+        } else {
+          const int nt3 = ((4 * d.N + 31) / 32) * 32;
+          if (nt3 <= 256) k_pcg3<T, 256, false, 4><<<bound, nt3, smv, stream>>>(d, list, count, stair, tol, max_iter);
+          else if (nt3 <= 512) k_pcg3<T, 512, false, 4><<<bound, nt3, smv, stream>>>(d, list, count, stair, tol, max_iter);
+          else k_pcg3<T, 1024, false, 4><<<bound, nt3, smv, stream>>>(d, list, count, stair, tol, max_iter);
+        }
       }
       tick(B2T_K_PCG);
       return 0;
@@ -495,6 +519,7 @@ struct SolverT : SolverBase {
       return fail(B2T_ERR_INVALID, "method must be N, S, PCG-J, PCG-BJ or PCG-SS");
     if (o->max_iter_SQP + 1 > d.trace_cap) return fail(B2T_ERR_UNSUPPORTED, "max_iter_SQP_DDP > 103");
     B2T_CUDA(cudaSetDevice(device));
+    explicit_system = false;
     Opts<T> op = convert(o);
     int max_trials = 1;
     { double a = 1.0; while (a > o->alpha_min && max_trials < MAX_LS_TRIALS) { a *= o->alpha_factor; ++max_trials; } }
@@ -644,10 +669,11 @@ struct SolverT : SolverBase {
   int stage_kkt(double rho, int method) override {
     using namespace b2t;
     B2T_CUDA(cudaSetDevice(device));
+    explicit_system = false;
     int r = all_list(); if (r) return r;
     k_fill<T><<<cdiv(d.B, 128), 128, 0, stream>>>(d.rho, (size_t)d.B, (T)rho);
     launch_dynamics(d.act, d.n_act, d.B);
-    launch_kkt(d.act, d.n_act, d.B, method);
+    launch_kkt(d.act, d.n_act, d.B, method, true);
     B2T_CUDA(cudaGetLastError());
     B2T_CUDA(cudaStreamSynchronize(stream));
     return 0;
@@ -671,6 +697,7 @@ struct SolverT : SolverBase {
     B2T_CUDA(cudaMemcpyAsync(p1, So, nb * sizeof(double), cudaMemcpyHostToDevice, stream));
     B2T_CUDA(cudaMemcpyAsync(p2, gam, nv * sizeof(double), cudaMemcpyHostToDevice, stream));
     int r = all_list(); if (r) return r;
+    explicit_system = true;
     k_set_block_system<T><<<cdiv(d.K, 128), 128, 0, stream>>>(d, p0, p1, p2);
     B2T_CUDA(cudaGetLastError());
     B2T_CUDA(cudaStreamSynchronize(stream));
