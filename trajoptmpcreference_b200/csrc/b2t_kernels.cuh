@@ -862,12 +862,14 @@ __global__ void __launch_bounds__(MAXT) k_pcg2(Dev<T> d, const int* list, const 
 // Same PCG recurrence and exit test as PCG.pcg (PCG.py:66-111); the products are algebraically identical to S p / O y
 // (verified against the explicit form: identical iteration counts, SURVEY.md 7.2 parity floor).
 // -----------------------------------------------------------------------------------------------------------------
+constexpr int PCG3_NMS = (NM + 3) / 4 * 4;   // 18 -> 20 doubles: rows of consecutive knots start 4 double-banks apart
 template <typename T, int MAXT, bool PDS, int LPK>
 __global__ void __launch_bounds__(MAXT, PDS ? 2 : 1) k_pcg3(Dev<T> d, const int* list, const int* count, int stair, T tol, int max_iter) {
   if ((int)blockIdx.x >= *count) return;
   // LPK lanes per knot (2 or 4).  Only launched when nx % (2 LPK) == 0; the max() keeps the definition well-formed otherwise.
   constexpr int RPT = (NX % LPK == 0) ? NX / LPK : 1;   // owned rows per lane; divides NJ
   constexpr int MC = (NM + LPK - 1) / LPK;               // Ab columns per lane
+  constexpr int NMS = PCG3_NMS;                          // padded row stride of W / Wq: bank-conflict-free 64-bit accesses
   using T2 = typename std::conditional<sizeof(T) == 8, double2, float2>::type;
   const int b = list[blockIdx.x];
   const int N = d.N;
@@ -885,9 +887,9 @@ __global__ void __launch_bounds__(MAXT, PDS ? 2 : 1) k_pcg3(Dev<T> d, const int*
   extern __shared__ unsigned char smem_raw[];
   T* V = reinterpret_cast<T*>(smem_raw);      // [(N+1)][NX]  p / r / O y; block N stays zero
   T* V2 = V + (N + 1) * NX;                   // [(N+1)][NX]  y; block N stays zero
-  T* W = V2 + (N + 1) * NX;                   // [N][NM]      w or q'
-  T* Wq = W + N * NM;                         // [N][NM]      q
-  T* red = Wq + N * NM;                       // 32
+  T* W = V2 + (N + 1) * NX;                   // [N][NMS]     w or q'
+  T* Wq = W + N * NMS;                        // [N][NMS]     q
+  T* red = Wq + N * NMS;                      // 32
   // PDS: the preconditioner rows live in shared memory ([RPT][NX/2][MAXT] pairs, conflict-free 128-bit loads) instead of registers,
   // so that TWO instances are resident per SM
   T2* Pd_s = reinterpret_cast<T2*>(red + 32);
@@ -895,8 +897,8 @@ __global__ void __launch_bounds__(MAXT, PDS ? 2 : 1) k_pcg3(Dev<T> d, const int*
   T ab[NJ][MC], dinv[MC], hh[MC], pd[PDS ? 1 : RPT][PDS ? 2 : NX];
   // per-column constants, computed once: validity, the E0^T coupling (which entry of z_q feeds column c, with which factor) and
   // the self term ([p_k; 0])_c
-  bool cval[MC];
-  T emul[MC], smul[MC];
+  bool cval[MC], sval[MC];
+  T emul[MC];
   int eidx[MC], sidx[MC];
 #pragma unroll
   for (int i = 0; i < MC; ++i) {
@@ -909,7 +911,7 @@ __global__ void __launch_bounds__(MAXT, PDS ? 2 : 1) k_pcg3(Dev<T> d, const int*
       ab[a][i] = (cval[i] && has_next) ? d.dt * d.dyn[(size_t)(a * 3 * NJ + c) * K + tk] + ((c == NJ + a) ? T(1) : T(0)) : T(0);
     emul[i] = (!has_next || !cval[i] || c >= NX) ? T(0) : (c < NJ ? T(1) : dte);
     eidx[i] = (c < NJ) ? c : ((c < NX) ? c - NJ : 0);
-    smul[i] = (cval[i] && c < NX) ? T(1) : T(0);
+    sval[i] = cval[i] && c < NX;
     sidx[i] = (c < NX) ? c : 0;
   }
   const T sS = live ? d.Gh[(size_t)(2 * NM) * K + tk] : T(0);
@@ -922,14 +924,11 @@ __global__ void __launch_bounds__(MAXT, PDS ? 2 : 1) k_pcg3(Dev<T> d, const int*
       if constexpr (PDS) { T2 v; v.x = p0; v.y = p1; Pd_s[(r * (NX / 2) + c / 2) * MAXT + tid] = v; }
       else { pd[r][c] = p0; pd[r][c + 1] = p1; }
     }
-  for (int idx = tid; idx < 2 * (N + 1) * NX + 2 * N * NM; idx += nt) V[idx] = T(0);
+  for (int idx = tid; idx < 2 * (N + 1) * NX + 2 * N * NMS; idx += nt) V[idx] = T(0);
   __syncthreads();
   const bool top = i0 < NJ;                   // rows i0.. are q rows (top half of [A B]) for the first LPK/2 lanes, qd rows for the others
   const bool odd = (i0 % NJ) != 0;            // row % NJ = (i0 % NJ) + r; with LPK = 4 that is RPT + r for the odd lanes, with LPK = 2 always r
-  const T topm = (top && has_next) ? T(1) : T(0);
-  const T hn = has_next ? T(1) : T(0);
-  const T livem = live ? T(1) : T(0);
-  const int ownV = jo * NX, ownW = jo * NM + i0, kV = k * NX, nV = (k + 1) * NX, kW = k * NM;
+  const int ownV = jo * NX, ownW = jo * NMS + i0, kV = k * NX, nV = (k + 1) * NX, kW = k * NMS;
 
   auto quad = [&](T v) -> T {                 // sum over the LPK lanes of the knot group (all lanes get it)
     v += __shfl_xor_sync(0xffffffffu, v, 1);
@@ -970,15 +969,28 @@ __global__ void __launch_bounds__(MAXT, PDS ? 2 : 1) k_pcg3(Dev<T> d, const int*
       for (int i = 0; i < MC; ++i) acc += ab[a][i] * zc[i];
       pb[a] = acc;
     }
+    // the lanes of the group only need the RPT rows congruent to their own: with four lanes, exchange halves with the xor-1
+    // partner (reduce-scatter), then all-reduce over xor-2 -- same summation order as a plain butterfly, half the shuffles
+    T bot[RPT];
+    if constexpr (LPK == 4) {
 #pragma unroll
-    for (int a = 0; a < NJ; ++a) pb[a] = quad(pb[a]);
+      for (int r = 0; r < RPT; ++r) {
+        const T send = odd ? pb[r] : pb[RPT + r];
+        T keep = odd ? pb[RPT + r] : pb[r];
+        keep += __shfl_xor_sync(0xffffffffu, send, 1);
+        keep += __shfl_xor_sync(0xffffffffu, keep, 2);
+        bot[r] = keep;
+      }
+    } else {
+#pragma unroll
+      for (int r = 0; r < RPT; ++r) bot[r] = quad(pb[r % NJ]);
+    }
 #pragma unroll
     for (int r = 0; r < RPT; ++r) {
-      const T bot = odd ? pb[(RPT + r) % NJ] : pb[r % NJ];
       // top rows: z_q + dte z_qd + tau (Ab z);  bottom rows: Ab z.  full[kW + row], full[kW + NJ + row] only matter for top rows
       const T zq = full[kW + (top ? i0 + r : 0)], zd = full[kW + NJ + (top ? i0 + r : 0)];
-      const T val = topm * (zq + dte * zd + tau * bot) + (hn - topm) * bot;
-      out[r] = livem * (val + sign * Wn[ownW + r]);
+      const T val = top ? (zq + dte * zd + tau * bot[r]) : bot[r];
+      out[r] = has_next ? val + sign * Wn[ownW + r] : (live ? sign * Wn[ownW + r] : T(0));
     }
   };
   // out = Pd_jo * buf[jo]  (entries published by the lanes of this group: __syncwarp suffices)
@@ -1015,15 +1027,15 @@ __global__ void __launch_bounds__(MAXT, PDS ? 2 : 1) k_pcg3(Dev<T> d, const int*
     abt(V2, u2);
 #pragma unroll
     for (int i = 0; i < MC; ++i) {
-      u1[i] = smul[i] * V2[kV + sidx[i]];
+      u1[i] = sval[i] ? V2[kV + sidx[i]] : T(0);
       h1 += hh[i] * u1[i];
       h2 += hh[i] * u2[i];
     }
-    h1 = quad(h1); h2 = quad(h2);
+    h1 = sS * quad(h1); h2 = sS * quad(h2);
 #pragma unroll
     for (int i = 0; i < MC; ++i) {
-      u1[i] = dinv[i] * u1[i] - sS * hh[i] * h1;
-      u2[i] = dinv[i] * u2[i] - sS * hh[i] * h2;
+      u1[i] = dinv[i] * u1[i] - hh[i] * h1;
+      u2[i] = dinv[i] * u2[i] - hh[i] * h2;
       if (cval[i]) { Wq[kW + c0 + i] = u1[i]; W[kW + c0 + i] = u2[i]; }
     }
     __syncthreads();
@@ -1050,13 +1062,13 @@ __global__ void __launch_bounds__(MAXT, PDS ? 2 : 1) k_pcg3(Dev<T> d, const int*
     abt(V, uc);
 #pragma unroll
     for (int i = 0; i < MC; ++i) {
-      uc[i] = smul[i] * V[kV + sidx[i]] - uc[i];
+      uc[i] = (sval[i] ? V[kV + sidx[i]] : T(0)) - uc[i];
       hu += hh[i] * uc[i];
     }
-    hu = quad(hu);
+    hu = sS * quad(hu);
 #pragma unroll
     for (int i = 0; i < MC; ++i) {
-      uc[i] = dinv[i] * uc[i] - sS * hh[i] * hu;
+      uc[i] = dinv[i] * uc[i] - hh[i] * hu;
       if (cval[i]) W[kW + c0 + i] = uc[i];
     }
     __syncthreads();
