@@ -27,7 +27,7 @@
  *   b2t_fetch                the reference's saved_* lists (exampleHelpers.py:136-154), one array at a time
  *
  * Array layouts at the ABI are the reference's:  x is [batch][nx][N] (C order, i.e. numpy (nx, N) per
- * instance), u is [batch][nu][N-1], goals xg [batch][nx].  double precision at the boundary.
+ * instance), u is [batch][nu][N-1], goals xg [batch][nx] (B2T_COST_URDF_EE: (x, y, vx, vy) in the first 4 of the nx slots).  double precision at the boundary.
  */
 #ifndef B2T_H
 #define B2T_H
@@ -42,7 +42,7 @@ typedef enum {
   B2T_OK = 0,
   B2T_ERR_INVALID = -1,      /* bad argument (the reference print()s and exit()s) */
   B2T_ERR_CUDA = -2,         /* CUDA runtime error; see b2t_last_error */
-  B2T_ERR_UNSUPPORTED = -3,  /* e.g. UrdfCost on a robot with n != 2 (reference limitation, RBDReference.py:263) */
+  B2T_ERR_UNSUPPORTED = -3,  /* e.g. the end-effector cost on a 1-joint robot, integrator types 2-4 */
   B2T_ERR_NOMEM = -4
 } b2t_status;
 
@@ -64,7 +64,7 @@ typedef struct {
   double gravity;         /* options['gravity'], default -9.81 (TrajoptPlant.py:31) */
   int cost_kind;          /* b2t_cost_kind */
   int qf_start;           /* QF_start, -1 = None (TrajoptCost.py:40-47) */
-  const double* Q;        /* [nx*nx] row-major, host */
+  const double* Q;        /* [nx*nx] row-major, host; B2T_COST_URDF_EE: the 4 x 4 weights of (x, y, vx, vy) packed in the first 16 */
   const double* QF;       /* [nx*nx] */
   const double* R;        /* [nu*nu] */
   int limit_mode[3];      /* b2t_limit_mode per limit type */
@@ -116,6 +116,8 @@ typedef enum {
   B2T_ARR_COST_GRAD,    /* [N][m]   (control part zero at the terminal knot) */
   B2T_ARR_COST_HESS,    /* [N][m*m] */
   B2T_ARR_COST_ERR,     /* [N][nx]  state error of the cost's state map (UrdfCost.delta_x, TrajoptCost.py:425-435) */
+  B2T_ARR_KKT_HESS,     /* [N][m*m] G_k = cost Hessian + gck gck^T, without rho (TrajoptMPCReference.py:214-224) */
+  B2T_ARR_AB,           /* [N][nx*m] [A_k B_k] of the integrator, from the last dynamics pass (row N-1 zero) (:229-233) */
   B2T_ARR_NU_TRACE      /* [128]    per instance: |r^T Pinv r| of PCG iteration 0..127 of the last b2t_stage_pcg (PCG.py:82,95) */
 } b2t_array;
 
@@ -143,6 +145,15 @@ int b2t_set_multipliers(b2t_solver* s, const double* mu, const double* lam, cons
 int b2t_reset_multipliers(b2t_solver* s);
 
 int b2t_sqp_solve(b2t_solver* s, int method, const b2t_options* opts);
+/* Recording hook (replaces the reference's saved_* lists, TrajoptMPCReference.py:46-70, filled inside SQP when examples run with
+ * record=True, examples/exampleHelpers.py:85-154).  b2t_sqp_solve calls `hook(user, event, pass)` on the host between kernel
+ * launches, stream idle: B2T_HOOK_LINSYS after the linear system of an SQP iteration is solved (KKT blocks, Ghat, S, gamma,
+ * preconditioner, l, dz of every ACTIVE instance are valid and can be read with b2t_fetch; all blocks are written in this mode), and
+ * B2T_HOOK_STEP after its line search and exit logic (x, u, status updated).  A non-zero return aborts the solve with
+ * B2T_ERR_INVALID.  NULL removes the hook.  The hook must not call b2t_sqp_solve / b2t_stage_* on the same handle. */
+typedef int (*b2t_iteration_hook)(void* user, int event, int pass);
+enum { B2T_HOOK_LINSYS = 1, B2T_HOOK_STEP = 2 };
+int b2t_set_iteration_hook(b2t_solver* s, b2t_iteration_hook hook, void* user);
 /* iLQR / DDP on the same problem description (MPCSolverMethods.iLQR, TrajoptMPCReference.py:21-27; the reference ships no
  * implementation -- specification: oracle/ilqr.py).  x[:,0] is the start state, the state trajectory is re-rolled from u. */
 int b2t_ilqr_solve(b2t_solver* s, const b2t_options* opts);

@@ -71,22 +71,27 @@ class QuadraticCost:
 
 class UrdfCost(QuadraticCost):
     """Quadratic cost on the end-effector state (x, y, vx, vy); Gauss-Newton Hessian (hess_mode 0).
-    TrajoptCost.py:371-519.  n == 2 only, like the reference."""
+    TrajoptCost.py:371-519.  n == 2 restates the reference literally (including its dJdq, RBDReference.py:256-266) and is pinned;
+    n > 2 is the exact generalisation to an n-joint planar chain (UNPINNED; intent in
+    TrajoptCost_generalized.py:405-467): Q, QF are 4x4, xg = (x, y, vx, vy), J_tot is 4 x 2n."""
 
     def __init__(self, model, Q, QF, R, xg, QF_start=None):
         super().__init__(Q, QF, R, xg, QF_start)
         self.model = model
         self.n = model.n
-        assert self.n == 2
+        self.nx = 2 * self.n
+        assert self.n >= 2 and self.Q.shape == (4, 4)
 
     def state_error(self, X):
         """delta_x (:425-435): [ee_pos; J qd] - xg"""
         n = self.n
         pos = rbd.end_effector_positions(self.model, X[..., :n])
-        J = rbd.jacobian(self.model, X[..., :n])
+        J = rbd.jacobian(self.model, X[..., :n])[..., :2, :] if n == 2 else rbd.planar_jacobians(self.model, X[..., :n])[0]
         vel = np.matmul(J, X[..., n:, None])[..., 0]
         return np.concatenate([pos, vel], axis=-1) - self.xg
 
     def state_jacobian(self, X):
         n = self.n
-        return rbd.jacobian_tot_state(self.model, X[..., :n], X[..., n:])
+        if n == 2:
+            return rbd.jacobian_tot_state(self.model, X[..., :n], X[..., n:])
+        return rbd.jacobian_tot_state_general(self.model, X[..., :n], X[..., n:])

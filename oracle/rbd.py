@@ -69,6 +69,13 @@ class Model:
         f1, f2 = self.dbasis(j, np.asarray(t, dtype=np.float64))
         return f1[..., None, None] * self.Ha[j] + f2[..., None, None] * self.Hb[j]
 
+    def ddH(self, j, t):
+        """second derivative of the homogeneous transform (revolute: -(c Ha + s Hb); prismatic: 0)"""
+        t = np.asarray(t, dtype=np.float64)
+        if self.jtype[j] == "revolute":
+            return -np.cos(t)[..., None, None] * self.Ha[j] - np.sin(t)[..., None, None] * self.Hb[j]
+        return np.zeros(t.shape + (4, 4))
+
 
 def _mv(M, v):
     """(..,a,b) @ (..,b) -> (..,a)"""
@@ -303,6 +310,44 @@ def dJdq(model, q, offset=EE_OFFSET):
     out[..., 3, 0] = J[..., 0, 1]
     out[..., 3, 1] = J[..., 0, 1]
     return out
+
+
+def planar_jacobians(model, q, offset=EE_OFFSET):
+    """Exact first and second derivatives of the planar end-effector position for an n-joint chain (UNPINNED, SURVEY.md 8f-3:
+    the intent of RBDReference_generalized.py:425-459).  Returns J (..,2,n) = d(x,y)/dq and Hs (..,2,n,n) = d2(x,y)/dq_c dq_d."""
+    q = np.asarray(q, dtype=np.float64)
+    n = model.n
+    chain = _chain(model)
+    off = np.broadcast_to(offset, q.shape[:-1] + (4,))
+
+    def prod(orders):
+        T = np.broadcast_to(np.eye(4), q.shape[:-1] + (4, 4))
+        for j in chain:
+            o = orders.get(j, 0)
+            M = model.H(j, q[..., j]) if o == 0 else (model.dH(j, q[..., j]) if o == 1 else model.ddH(j, q[..., j]))
+            T = np.matmul(T, M)
+        return _mv(T, off)[..., :2]
+
+    J = np.zeros(q.shape[:-1] + (2, n))
+    Hs = np.zeros(q.shape[:-1] + (2, n, n))
+    for d in chain:
+        J[..., :, d] = prod({d: 1})
+        for c in chain:
+            if c > d:
+                continue
+            v = prod({d: 2}) if c == d else prod({c: 1, d: 1})
+            Hs[..., :, c, d] = v
+            Hs[..., :, d, c] = v
+    return J, Hs
+
+
+def jacobian_tot_state_general(model, q, qd, offset=EE_OFFSET):
+    """d(x,y,vx,vy)/d(q,qd) for an n-joint planar chain, exact:  [[J, 0], [d(J qd)/dq, J]]  -> (..,4,2n)."""
+    J, Hs = planar_jacobians(model, q, offset)
+    J2 = np.einsum("...rcd,...c->...rd", Hs, np.asarray(qd, dtype=np.float64))
+    top = np.concatenate([J, np.zeros_like(J)], axis=-1)
+    bot = np.concatenate([J2, J], axis=-1)
+    return np.concatenate([top, bot], axis=-2)
 
 
 def jacobian_tot_state(model, q, qd, offset=EE_OFFSET):

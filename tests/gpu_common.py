@@ -19,6 +19,7 @@ def make_pair(name, N, oracle_models, xg=None, limits=None, integrator=0, cost_k
         xg = np.array([-1.0, 1.5, 0, 0]) if cost_kind == "urdf" else (np.concatenate([np.linspace(0.5, -0.5, n), np.zeros(n)]) if name != "pend" else np.array([3.14159, 0.0]))
     plant = t.URDFPlant(integrator_type=integrator, options={"path_to_urdf": name})
     if cost_kind == "urdf":
+        Q, QF = np.eye(4), 100.0 * np.eye(4)       # weights of the end-effector state (x, y, vx, vy)
         pc = t.UrdfCost(plant, Q.copy(), QF.copy(), R.copy(), np.array(xg, dtype=float))
         oc = ocost.UrdfCost(m, Q, QF, R, xg)
     else:

@@ -44,27 +44,45 @@ def test_dynamics_math(name, integ, oracle_models):
     assert relerr(ABr[:, :, 2 * n:], D[name + "/B%d" % integ]) < 1e-13
 
 
-@pytest.mark.parametrize("name,kind", [("arm2", 1), ("arm2", 0), ("arm6", 0)])
+@pytest.mark.parametrize("name,kind", [("arm2", 1), ("arm2", 0), ("arm6", 0), ("arm3", 1), ("arm6", 1), ("cartpole", 1)])
 def test_cost_math(name, kind, oracle_models):
+    """kind 1 = end-effector cost: 4 x 4 weights on (x, y, vx, vy); n = 2 is the reference's literal arithmetic, n > 2 the exact
+    n-joint generalisation."""
     lib = hostemu.load(name)
-    m = oracle_models[name]
+    if name in oracle_models:
+        m = oracle_models[name]
+    else:       # not a reference model: extracted by this repository's own URDF reader
+        from oracle import rbd
+        from trajoptmpcreference_b200 import model as pmodel
+        m = rbd.Model(pmodel.extract_model(pmodel.builtin_urdf(name)))
     n = m.n; nx = 2 * n; nm = 3 * n
+    ne = 4 if kind == 1 else nx
     rng = np.random.default_rng(5)
-    A = rng.uniform(-1, 1, (nx, nx)); Q = A @ A.T + np.eye(nx)
-    A = rng.uniform(-1, 1, (nx, nx)); QF = 10 * (A @ A.T) + np.eye(nx)
+    A = rng.uniform(-1, 1, (ne, ne)); Q = A @ A.T + np.eye(ne)
+    A = rng.uniform(-1, 1, (ne, ne)); QF = 10 * (A @ A.T) + np.eye(ne)
     A = rng.uniform(-1, 1, (n, n)); R = A @ A.T + 0.1 * np.eye(n)
-    xg = rng.uniform(-1, 1, nx)
+    xg = rng.uniform(-1, 1, ne)
     N = 7
     X = rng.uniform(-1.5, 1.5, (N, nx)); U = rng.uniform(-1, 1, (N - 1, n))
     c = ocost.UrdfCost(m, Q, QF, R, xg, QF_start=4) if kind == 1 else ocost.QuadraticCost(Q, QF, R, xg, QF_start=4)
     Upad = np.zeros((N, n)); Upad[:N - 1] = U
     val = np.zeros(N); grad = np.zeros((N, nm)); hess = np.zeros((N, nm * nm))
     kidx = np.arange(N, dtype=np.int32); term = np.zeros(N, dtype=np.int32); term[-1] = 1
-    lib.he_cost(N, kind, 4, P(np.ascontiguousarray(Q)), P(np.ascontiguousarray(QF)), P(np.ascontiguousarray(R)), P(xg), P(X), P(Upad),
+
+    def pad(M, size):       # C-ABI layout: the packed ne x ne weights first, zeros after
+        out = np.zeros(size); out[:M.size] = M.reshape(-1); return out
+    lib.he_cost(N, kind, 4, P(pad(Q, nx * nx)), P(pad(QF, nx * nx)), P(np.ascontiguousarray(R)), P(pad(xg, nx)), P(X), P(Upad),
                 PI(kidx), PI(term), P(val), P(grad), P(hess))
     assert relerr(val, c.values(X, U)) < 1e-13
     assert relerr(grad, c.gradients(X, U)) < 1e-13
     assert relerr(hess.reshape(N, nm, nm), c.hessians(X, U)) < 1e-13
+    if kind == 1 and n > 2:     # unpinned: check the analytic gradient against central differences of the value
+        eps = 1e-6
+        for k in (0, N - 1):
+            for i in range(nx):
+                Xp = X.copy(); Xm = X.copy(); Xp[k, i] += eps; Xm[k, i] -= eps
+                fd = (c.values(Xp, U)[k] - c.values(Xm, U)[k]) / (2 * eps)
+                assert abs(fd - grad[k, i]) < 1e-6 * max(1.0, abs(fd))
 
 
 def test_soft_math():

@@ -18,7 +18,9 @@ LIMIT_NONE, LIMIT_QUADRATIC_PENALTY, LIMIT_AUGMENTED_LAGRANGIAN = 0, 1, 2
 STATUS_FIELDS, SCALAR_FIELDS, TRACE_FIELDS, KERNEL_FAMILIES = 8, 4, 12, 9
 KERNEL_FAMILY_NAMES = ["fd", "fd_grad", "kkt", "schur", "pcg", "recover", "trial_fd", "merit", "ctrl"]
 ARR = {"x": 0, "u": 1, "xkp1": 2, "dqdd": 3, "Ghat": 4, "g": 5, "Sd": 6, "So": 7, "Pd": 8, "gamma": 9, "l": 10, "dz": 11, "xn": 12, "un": 13,
-       "cost_value": 14, "cost_grad": 15, "cost_hess": 16, "cost_err": 17, "nu_trace": 18}
+       "cost_value": 14, "cost_grad": 15, "cost_hess": 16, "cost_err": 17, "kkt_hess": 18, "AB": 19, "nu_trace": 20}
+HOOK_LINSYS, HOOK_STEP = 1, 2
+ITERATION_HOOK = ctypes.CFUNCTYPE(c_int, c_void_p, c_int, c_int)
 
 
 class ProblemDesc(ctypes.Structure):
@@ -54,6 +56,7 @@ _SIGNATURES = {
     "b2t_set_multipliers": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p]),
     "b2t_reset_multipliers": (c_int, [c_void_p]),
     "b2t_sqp_solve": (c_int, [c_void_p, c_int, POINTER(Options)]),
+    "b2t_set_iteration_hook": (c_int, [c_void_p, ITERATION_HOOK, c_void_p]),
     "b2t_ilqr_solve": (c_int, [c_void_p, POINTER(Options)]),
     "b2t_mpc_shift": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p]),
     "b2t_get_trajectory": (c_int, [c_void_p, c_void_p, c_void_p, c_int]),

@@ -236,13 +236,17 @@ class QuadraticCost(TrajoptCost):
 
 class UrdfCost(QuadraticCost):
     """UrdfCost (TrajoptCost.py:371-519): quadratic cost on the planar end-effector state (x, y, vx, vy), Gauss-Newton
-    Hessian (hess_mode 0).  2-joint robots only, like the reference."""
+    Hessian (hess_mode 0).  Two joints: the reference's arithmetic, literally.  More than two joints (a planar
+    serial chain): the exact generalisation the reference only sketches (TrajoptCost_generalized.py:405-467):
+    Q, QF stay 4 x 4, xg = (x, y, vx, vy), J_tot = [[J, 0], [d(J qd)/dq, J]] is 4 x 2n."""
     _kind = _lib.COST_URDF_EE
 
     def __init__(self, plant, Q_in, QF_in, R_in, xg_in, QF_start=None, overloading=False):
         super().__init__(Q_in, QF_in, R_in, xg_in, QF_start)
-        if plant.get_num_pos() != 2:
-            raise ValueError("UrdfCost is defined for 2-joint robots only (RBDReference.py:263)")
+        if plant.get_num_pos() < 2:
+            raise ValueError("UrdfCost needs a planar chain of at least 2 joints")
+        if np.asarray(Q_in).shape != (4, 4) or np.asarray(QF_in).shape != (4, 4) or np.asarray(xg_in).size != 4:
+            raise ValueError("UrdfCost weighs the end-effector state (x, y, vx, vy): Q, QF must be 4 x 4 and xg of length 4")
         self.plant = plant
         self.n = plant.get_num_pos()
         self.offsets = [np.array([[0, 1, 0, 1]])]
@@ -286,7 +290,7 @@ class UrdfCost(QuadraticCost):
     def delta_x(self, x):
         """End-effector state error [ee_pos; J qd] - xg (TrajoptCost.py:425-435), evaluated by the cost kernel."""
         s, k = self._knot(x, None, None)
-        return s.fetch("cost_err")[0, k].copy()
+        return s.fetch("cost_err")[0, k, :4].copy()
 
 
 # --------------------------------------------------------------------------------------------------- constraints
@@ -449,7 +453,13 @@ class BatchSolver:
         d.cost_kind = cost._kind
         qs = cost.QF_start if qf_start_override is None else qf_start_override
         d.qf_start = -1 if qs is None else int(qs)
-        self._keep = [_as_f64(cost.Q, (self.nx, self.nx)), _as_f64(cost.QF, (self.nx, self.nx)), _as_f64(cost.R, (self.nu, self.nu))]
+        self.ne = 4 if cost._kind == _lib.COST_URDF_EE else self.nx      # size of the cost's error vector / of Q, QF, xg
+
+        def padded(M):      # the C ABI takes nx*nx doubles; an end-effector cost packs its 4 x 4 weights in the first 16
+            out = np.zeros(self.nx * self.nx)
+            out[:self.ne * self.ne] = _as_f64(M, (self.ne, self.ne)).reshape(-1)
+            return out
+        self._keep = [padded(cost.Q), padded(cost.QF), _as_f64(cost.R, (self.nu, self.nu))]
         d.Q, d.QF, d.R = [a.ctypes.data_as(ctypes.POINTER(ctypes.c_double)) for a in self._keep]
         lower = np.zeros(self.m); upper = np.zeros(self.m)
         self.has_limits = False
@@ -483,7 +493,7 @@ class BatchSolver:
                     os.environ.pop("B2T_DENSE_KKT", None)
                 else:
                     os.environ["B2T_DENSE_KKT"] = old
-        xg = np.broadcast_to(_as_f64(cost.xg).reshape(1, -1), (self.batch, self.nx))
+        xg = np.broadcast_to(_as_f64(cost.xg).reshape(1, -1), (self.batch, self.ne))
         self.set_goals(xg)
 
     def close(self):
@@ -518,7 +528,10 @@ class BatchSolver:
             assert xg.is_cuda and xg.is_contiguous() and tuple(xg.shape) == (self.batch, self.nx)
             _lib.check(self.lib, self.lib.b2t_set_goals(self._h, ctypes.c_void_p(xg.data_ptr()), 1))
             return
-        xg = _as_f64(xg, (self.batch, self.nx))
+        xg = _as_f64(xg, (self.batch, self.ne))
+        if self.ne != self.nx:      # end-effector goals (x, y, vx, vy) occupy the first 4 of the nx slots per instance
+            xg = np.concatenate([xg, np.zeros((self.batch, self.nx - self.ne))], axis=1)
+            xg = np.ascontiguousarray(xg)
         _lib.check(self.lib, self.lib.b2t_set_goals(self._h, _dptr(xg), 0))
         self._goal_keep = xg
 
@@ -559,7 +572,28 @@ class BatchSolver:
         if method not in _METHOD_CODE:
             raise ValueError("Invalid QP Solver options are: N, S, PCG-J, PCG-BJ, PCG-SS")
         o = self.make_options(options)
-        _lib.check(self.lib, self.lib.b2t_sqp_solve(self._h, _METHOD_CODE[method], ctypes.byref(o)))
+        code = self.lib.b2t_sqp_solve(self._h, _METHOD_CODE[method], ctypes.byref(o))
+        if getattr(self, "_hook_error", None) is not None:
+            exc, self._hook_error = self._hook_error, None
+            raise exc
+        _lib.check(self.lib, code)
+
+    def set_iteration_hook(self, fn):
+        """fn(event, pass) -> None, called on the host inside solve() after the linear solve (event _lib.HOOK_LINSYS) and after the step
+        (event _lib.HOOK_STEP) of every SQP iteration; `fetch`, `get_status`, `get_trajectory` may be called from it.  None removes it."""
+        if fn is None:
+            self._hook = _lib.ITERATION_HOOK(0)
+        else:
+            def tramp(_user, event, ipass):
+                try:
+                    fn(int(event), int(ipass))
+                    return 0
+                except BaseException as exc:       # cannot propagate through C: stop the solve and re-raise afterwards
+                    self._hook_error = exc
+                    return 1
+            self._hook = _lib.ITERATION_HOOK(tramp)
+        self._hook_error = None
+        _lib.check(self.lib, self.lib.b2t_set_iteration_hook(self._h, self._hook, None))
 
     def solve_ilqr(self, options=None):
         """iLQR on the trajectories / goals currently in the workspace (x[:,0] = start state, x re-rolled from u)."""
@@ -662,7 +696,7 @@ class BatchSolver:
         E = {"x": self.nx, "u": self.nu, "xkp1": self.nx, "dqdd": self.n * 3 * self.n, "Ghat": self.m * self.m, "g": self.m,
              "Sd": self.nx * self.nx, "So": self.nx * self.nx, "Pd": self.nx * self.nx, "gamma": self.nx, "l": self.nx, "dz": self.m,
              "xn": self.nx, "un": self.nu, "cost_value": 1, "cost_grad": self.m, "cost_hess": self.m * self.m, "cost_err": self.nx,
-             "nu_trace": None}[name]
+             "kkt_hess": self.m * self.m, "AB": self.nx * self.m, "nu_trace": None}[name]
         if name == "nu_trace":
             out = np.zeros((self.batch, 128))
             _lib.check(self.lib, self.lib.b2t_fetch(self._h, _lib.ARR[name], _dptr(out)))
@@ -745,8 +779,10 @@ class TrajoptMPCReference:
             self._solvers[key] = BatchSolver(self.plant, self.cost, self._constraints_or_none(), N, dt, batch, dtype, device)
         return self._solvers[key]
 
-    def SQP(self, x, u, N, dt, LINEAR_SYSTEM_SOLVER_METHOD=SQPSolverMethods.N, options=None, dtype="f64"):
-        """Same call and return value as the reference (:510, :760): (x, u, exit_sqp, exit_soft, outer_iter, sqp_iter)."""
+    def SQP(self, x, u, N, dt, LINEAR_SYSTEM_SOLVER_METHOD=SQPSolverMethods.N, options=None, dtype="f64", record=False):
+        """Same call and return value as the reference (:510, :760): (x, u, exit_sqp, exit_soft, outer_iter, sqp_iter).
+        record=True additionally fills the reference's `saved_*` lists (dense G, g, C, c, invG, S, gamma, Pinv, l, dxul, A_k, B_k, x, u
+        per SQP iteration) from the device through the iteration hook; see record.py."""
         options = {} if options is None else options
         self.set_default_options(options)
         if not isinstance(LINEAR_SYSTEM_SOLVER_METHOD, SQPSolverMethods):
@@ -761,7 +797,14 @@ class TrajoptMPCReference:
         if cons is not None:
             mu, lam, phi = cons.pack(N)
             s.set_multipliers(mu[None], lam[None], phi[None])
-        s.solve(LINEAR_SYSTEM_SOLVER_METHOD, options)
+        if record:
+            from .record import Recorder
+            s.set_iteration_hook(Recorder(self, s, LINEAR_SYSTEM_SOLVER_METHOD, x[:, 0], options))
+        try:
+            s.solve(LINEAR_SYSTEM_SOLVER_METHOD, options)
+        finally:
+            if record:
+                s.set_iteration_hook(None)
         r = s.result()
         if cons is not None:
             mu, lam, phi = s.get_multipliers()

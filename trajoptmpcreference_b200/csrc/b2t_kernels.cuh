@@ -1760,12 +1760,25 @@ __global__ void k_cost_eval(Dev<T> d, int what, double* out) {
   if (what == 0) { out[gt] = (double)cost_value(d.cost, z, z + NX, xg, k, terminal); return; }
   if (what == 3) {      // state error of the cost's state map (UrdfCost.delta_x, TrajoptCost.py:425-435)
     T e[NX], Jt[NX * NX]; bool hj;
-    cost_state(d.cost, z, xg, e, Jt, &hj);
-    for (int i = 0; i < NX; ++i) out[gt * NX + i] = (double)e[i];
+    const int ne = cost_state(d.cost, z, xg, e, Jt, &hj);
+    for (int i = 0; i < NX; ++i) out[gt * NX + i] = i < ne ? (double)e[i] : 0.0;
+    return;
+  }
+  if (what == 5) {      // [A_k B_k] of the integrator at (x_k, u_k) from the stored forward-dynamics gradient (row N-1 unused: zeros)
+    T dq[NDYN], AB[NX * NM];
+    for (int i = 0; i < NDYN; ++i) dq[i] = d.dyn[(size_t)i * d.K + gt];
+    build_AB(d.integrator, dq, d.dt, AB);
+    for (int i = 0; i < NX * NM; ++i) out[gt * NX * NM + i] = terminal ? 0.0 : (double)AB[i];
     return;
   }
   T g[NM], H[NM * NM];
   cost_grad_hess<T, true>(d.cost, z, z + NX, xg, k, terminal, g, H);
+  if (what == 4 && d.lim.any) {      // KKT Hessian block G_k = cost Hessian + gck gck^T  (TrajoptMPCReference.py:220-224), without rho
+    T gck[NM];
+    soft_grad(d.lim, z, d.mu + gt, d.lam + gt, d.K, terminal, gck);
+    for (int i = 0; i < NM; ++i)
+      for (int j = 0; j < NM; ++j) H[i * NM + j] += gck[i] * gck[j];
+  }
   if (what == 1) { for (int i = 0; i < NM; ++i) out[gt * NM + i] = (double)g[i]; }
   else { for (int i = 0; i < NM * NM; ++i) out[gt * NM * NM + i] = (double)H[i]; }
 }

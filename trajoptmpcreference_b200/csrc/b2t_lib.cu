@@ -49,6 +49,8 @@ struct SolverBase {
   virtual int stage_precond(int method) = 0;
   virtual int stage_merit(double alpha, double* J, double* c, double* D) = 0;
   virtual int fetch(int which, double* out) = 0;
+  b2t_iteration_hook hook = nullptr;
+  void* hook_user = nullptr;
   size_t ws_bytes = 0;
   cudaStream_t stream = 0;
   long long launches = 0;
@@ -109,8 +111,8 @@ struct SolverT : SolverBase {
     if (!p || p->batch < 1 || p->knots < 2) return fail(B2T_ERR_INVALID, "batch >= 1 and knots >= 2 required");
     if (p->integrator_type != 0 && p->integrator_type != 1)
       return fail(B2T_ERR_UNSUPPORTED, "integrator types 0 (euler) and 1 (semi-implicit euler) only");
-    if (p->cost_kind == B2T_COST_URDF_EE && NJ != 2)
-      return fail(B2T_ERR_UNSUPPORTED, "UrdfCost needs a 2-joint robot (reference limitation, RBDReference.py:263)");
+    if (p->cost_kind == B2T_COST_URDF_EE && NJ < 2)
+      return fail(B2T_ERR_UNSUPPORTED, "the end-effector cost needs a planar chain of at least 2 joints");
     if (p->cost_kind != B2T_COST_QUADRATIC && p->cost_kind != B2T_COST_URDF_EE) return fail(B2T_ERR_INVALID, "cost_kind");
     if (!p->Q || !p->QF || !p->R) return fail(B2T_ERR_INVALID, "Q, QF, R required");
     if ((size_t)p->knots * NX > (size_t)PCG_MAX_RPT * 1024) return fail(B2T_ERR_UNSUPPORTED, "knots * nx too large for the PCG block");
@@ -541,9 +543,13 @@ struct SolverT : SolverBase {
     const size_t osmem = std::max((size_t)3 * d.N * sizeof(T), msmem);
     for (long long iter = 0; n > 0 && iter < cap; ++iter) {
       launch_dynamics(d.act, d.n_act, n);
-      launch_kkt(d.act, d.n_act, n, method);
+      launch_kkt(d.act, d.n_act, n, method, hook != nullptr);
       launch_pcg(d.act, d.n_act, n, method, op.tol_lin, op.max_iter_lin);
       launch_recover(d.act, d.n_act, n);
+      if (hook) {
+        B2T_CUDA(cudaStreamSynchronize(stream));
+        if (hook(hook_user, B2T_HOOK_LINSYS, (int)iter)) return fail(B2T_ERR_INVALID, "iteration hook asked to stop");
+      }
       if (!legacy_ls) {
         { Scope sc(this, B2T_K_TRIAL); k_linesearch<T><<<n, lst, lsmem, stream>>>(d, op); tick(B2T_K_TRIAL); }
         { Scope sc(this, B2T_K_CTRL); k_outer<T><<<n, mt, osmem, stream>>>(d, op, 1); tick(B2T_K_CTRL); }
@@ -563,6 +569,7 @@ struct SolverT : SolverBase {
       B2T_CUDA(cudaMemcpyAsync(h_count, d.n_act, sizeof(int), cudaMemcpyDeviceToHost, stream));
       B2T_CUDA(cudaStreamSynchronize(stream));
       n = h_count[0];
+      if (hook && hook(hook_user, B2T_HOOK_STEP, (int)iter)) return fail(B2T_ERR_INVALID, "iteration hook asked to stop");
     }
     B2T_CUDA(cudaEventRecord(ev1, stream));
     B2T_CUDA(cudaEventSynchronize(ev1));
@@ -760,6 +767,8 @@ struct SolverT : SolverBase {
       case B2T_ARR_COST_GRAD: E = NM; break;
       case B2T_ARR_COST_HESS: E = NM * NM; break;
       case B2T_ARR_COST_ERR: E = NX; break;
+      case B2T_ARR_KKT_HESS: E = NM * NM; break;
+      case B2T_ARR_AB: E = NX * NM; break;
       case B2T_ARR_NU_TRACE: {
         std::vector<T> h((size_t)d.B * NU_TRACE_LEN);
         B2T_CUDA(cudaStreamSynchronize(stream));
@@ -771,7 +780,7 @@ struct SolverT : SolverBase {
     }
     const size_t n = K * E;
     if (n * sizeof(double) > stage_out_bytes) return fail(B2T_ERR_INVALID, "array too large for staging");
-    if (which >= B2T_ARR_COST_VALUE && which <= B2T_ARR_COST_ERR) k_cost_eval<T><<<cdiv(K, 64), 64, 0, stream>>>(d, which - B2T_ARR_COST_VALUE, stage_out);
+    if (which >= B2T_ARR_COST_VALUE && which <= B2T_ARR_AB) k_cost_eval<T><<<cdiv(K, 64), 64, 0, stream>>>(d, which - B2T_ARR_COST_VALUE, stage_out);
     else if (which == B2T_ARR_GHAT && d.diag_mode) k_fetch_ghat_diag<T><<<cdiv(K, 128), 128, 0, stream>>>(d, stage_out);
     else k_fetch_soa<T><<<cdiv(K, 128), 128, 0, stream>>>(src, K, E, stage_out);
     B2T_CUDA(cudaGetLastError());
@@ -875,6 +884,11 @@ int b2t_set_initial_state(b2t_solver* s, const double* xs) { B2T_FWD(set_initial
 int b2t_set_multipliers(b2t_solver* s, const double* mu, const double* lam, const double* phi) { B2T_FWD(set_multipliers(mu, lam, phi)); }
 int b2t_reset_multipliers(b2t_solver* s) { B2T_FWD(reset_multipliers()); }
 int b2t_sqp_solve(b2t_solver* s, int method, const b2t_options* o) { B2T_FWD(solve(method, o)); }
+int b2t_set_iteration_hook(b2t_solver* s, b2t_iteration_hook hook, void* user) {
+  if (!s) return fail(B2T_ERR_INVALID, "null solver");
+  s->impl->hook = hook; s->impl->hook_user = user;
+  return 0;
+}
 int b2t_ilqr_solve(b2t_solver* s, const b2t_options* o) { B2T_FWD(solve_ilqr(o)); }
 int b2t_mpc_shift(b2t_solver* s, const double* xn, double* x0, double* u0, double* xno) { B2T_FWD(mpc_shift(xn, x0, u0, xno)); }
 int b2t_get_trajectory(b2t_solver* s, double* x, double* u, int od) { B2T_FWD(get_trajectory(x, u, od)); }
