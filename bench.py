@@ -185,11 +185,11 @@ def run_reference_arm(args):
 def ncu_traffic(family, batch, launches_per_step, qp_per_instance):
     """DRAM bytes per launch of the dominant kernel from the committed `ncu --set full` capture (profiles/): the capture gives
     dram__bytes_read.sum + dram__bytes_write.sum for ONE launch over `launch__grid_size` instances; scaled to the average number
-    of instances per launch of this run (the per-instance traffic of k_pcg2 does not depend on the batch: every instance's
-    S, Pinv and gamma blocks are read once, l is written once)."""
+    of instances per launch of this run (the per-instance traffic of k_pcg3 does not depend on the batch: every instance's
+    dynamics Jacobians, Ghat factors, preconditioner blocks and gamma are read once, l is written once)."""
     if family != "pcg":
         return None, "no ncu capture for this kernel family"
-    path = os.path.join(ROOT, "profiles", "r01_v2_ncu_full_k_pcg2.csv")
+    path = os.path.join(ROOT, "profiles", "r01_v3_ncu_full_k_pcg3.csv")
     try:
         vals = {}
         with open(path) as f:
@@ -200,7 +200,7 @@ def ncu_traffic(family, batch, launches_per_step, qp_per_instance):
         grid = float(vals["launch__grid_size"])
         per_inst = (float(vals["dram__bytes_read.sum"]) + float(vals["dram__bytes_write.sum"])) * 1e6 / grid
         inst_per_launch = batch * qp_per_instance / max(launches_per_step, 1)
-        return per_inst * inst_per_launch, "profiles/r01_v2_ncu_full_k_pcg2.csv: %.0f bytes per instance x %.0f instances per launch (avg)" % (per_inst, inst_per_launch)
+        return per_inst * inst_per_launch, "profiles/r01_v3_ncu_full_k_pcg3.csv: %.0f bytes per instance x %.0f instances per launch (avg)" % (per_inst, inst_per_launch)
     except Exception as e:      # noqa: BLE001
         return None, "ncu capture unreadable: %s" % e
 
