@@ -889,10 +889,10 @@ __global__ void __launch_bounds__(MAXT, PDS ? 2 : 1) k_pcg3(Dev<T> d, const int*
   T* V2 = V + (N + 1) * NX;                   // [(N+1)][NX]  y; block N stays zero
   T* W = V2 + (N + 1) * NX;                   // [N][NMS]     w or q'
   T* Wq = W + N * NMS;                        // [N][NMS]     q
-  T* red = Wq + N * NMS;                      // 32
+  T* red = Wq + N * NMS;                      // 2 x 32: double-buffered warp partial sums (zero beyond the launched warps)
   // PDS: the preconditioner rows live in shared memory ([RPT][NX/2][MAXT] pairs, conflict-free 128-bit loads) instead of registers,
   // so that TWO instances are resident per SM
-  T2* Pd_s = reinterpret_cast<T2*>(red + 32);
+  T2* Pd_s = reinterpret_cast<T2*>(red + 64);
   // ---- resident data (registers for all iterations)
   T ab[NJ][MC], dinv[MC], hh[MC], pd[PDS ? 1 : RPT][PDS ? 2 : NX];
   // per-column constants, computed once: validity, the E0^T coupling (which entry of z_q feeds column c, with which factor) and
@@ -915,6 +915,7 @@ __global__ void __launch_bounds__(MAXT, PDS ? 2 : 1) k_pcg3(Dev<T> d, const int*
     sidx[i] = (c < NX) ? c : 0;
   }
   const T sS = live ? d.Gh[(size_t)(2 * NM) * K + tk] : T(0);
+  const bool rank1 = d.lim.any != 0;          // without soft limits gck = 0: Ghat is diagonal, s = 0 (k_kkt_diag) and the h-reductions vanish
 #pragma unroll
   for (int r = 0; r < RPT; ++r)
 #pragma unroll
@@ -924,7 +925,7 @@ __global__ void __launch_bounds__(MAXT, PDS ? 2 : 1) k_pcg3(Dev<T> d, const int*
       if constexpr (PDS) { T2 v; v.x = p0; v.y = p1; Pd_s[(r * (NX / 2) + c / 2) * MAXT + tid] = v; }
       else { pd[r][c] = p0; pd[r][c + 1] = p1; }
     }
-  for (int idx = tid; idx < 2 * (N + 1) * NX + 2 * N * NMS; idx += nt) V[idx] = T(0);
+  for (int idx = tid; idx < 2 * (N + 1) * NX + 2 * N * NMS + 64; idx += nt) V[idx] = T(0);
   __syncthreads();
   const bool top = i0 < NJ;                   // rows i0.. are q rows (top half of [A B]) for the first LPK/2 lanes, qd rows for the others
   const bool odd = (i0 % NJ) != 0;            // row % NJ = (i0 % NJ) + r; with LPK = 4 that is RPT + r for the odd lanes, with LPK = 2 always r
@@ -934,6 +935,26 @@ __global__ void __launch_bounds__(MAXT, PDS ? 2 : 1) k_pcg3(Dev<T> d, const int*
     v += __shfl_xor_sync(0xffffffffu, v, 1);
     if constexpr (LPK == 4) v += __shfl_xor_sync(0xffffffffu, v, 2);
     return v;
+  };
+  // deterministic block sum: warp butterfly, one barrier, pairwise tree over the warp partials; `red` alternates between two buffers
+  // (the barrier of the next reduction orders the reads of this one before the buffer is written again)
+  int red_sel = 0;
+  auto bsum = [&](T v) -> T {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+    T* rb = red + 32 * red_sel;
+    red_sel ^= 1;
+    if ((tid & 31) == 0) rb[tid >> 5] = v;
+    __syncthreads();
+    constexpr int NW = MAXT / 32;
+    T t[NW];
+#pragma unroll
+    for (int i = 0; i < NW; i += 2) { const T2 p2 = *reinterpret_cast<const T2*>(rb + i); t[i] = p2.x; t[i + 1] = p2.y; }
+#pragma unroll
+    for (int st = 1; st < NW; st *= 2)
+#pragma unroll
+      for (int i = 0; i + st < NW; i += 2 * st) t[i] += t[i + st];
+    return t[0];
   };
   auto publish = [&](T* buf, const T* val) {  // owned rows of block jo
     if (live) {
@@ -952,11 +973,14 @@ __global__ void __launch_bounds__(MAXT, PDS ? 2 : 1) k_pcg3(Dev<T> d, const int*
       if (a + 1 < NJ) pi[a + 1] = tau * zq.y + zv.y;
     }
 #pragma unroll
-    for (int i = 0; i < MC; ++i) {
-      T acc = emul[i] * buf[nV + eidx[i]];
+    for (int i = 0; i < MC; ++i) {      // two accumulators per column: half the dependent-FMA depth
+      T acc0 = emul[i] * buf[nV + eidx[i]], acc1 = T(0);
 #pragma unroll
-      for (int a = 0; a < NJ; ++a) acc += ab[a][i] * pi[a];
-      tc[i] = acc;
+      for (int a = 0; a < NJ; a += 2) {
+        acc0 += ab[a][i] * pi[a];
+        if (a + 1 < NJ) acc1 += ab[a + 1][i] * pi[a + 1];
+      }
+      tc[i] = acc0 + acc1;
     }
   };
   // out_r (owned rows of block jo) = (AB_k zz)_row + sign * Wn[jo][row];  zz: my columns in zc (registers), all columns in `full`
@@ -995,7 +1019,7 @@ __global__ void __launch_bounds__(MAXT, PDS ? 2 : 1) k_pcg3(Dev<T> d, const int*
   };
   // out = Pd_jo * buf[jo]  (entries published by the lanes of this group: __syncwarp suffices)
   auto pd_mul = [&](const T* buf, T* out) {
-    T o0[RPT], o1[RPT];
+    T o0[RPT], o1[RPT];                       // two accumulators per row (four were measured 2 % slower)
 #pragma unroll
     for (int r = 0; r < RPT; ++r) { o0[r] = T(0); o1[r] = T(0); }
 #pragma unroll
@@ -1031,7 +1055,7 @@ __global__ void __launch_bounds__(MAXT, PDS ? 2 : 1) k_pcg3(Dev<T> d, const int*
       h1 += hh[i] * u1[i];
       h2 += hh[i] * u2[i];
     }
-    h1 = sS * quad(h1); h2 = sS * quad(h2);
+    if (rank1) { h1 = sS * quad(h1); h2 = sS * quad(h2); } else { h1 = T(0); h2 = T(0); }
 #pragma unroll
     for (int i = 0; i < MC; ++i) {
       u1[i] = dinv[i] * u1[i] - hh[i] * h1;
@@ -1052,10 +1076,11 @@ __global__ void __launch_bounds__(MAXT, PDS ? 2 : 1) k_pcg3(Dev<T> d, const int*
   T part = T(0);
 #pragma unroll
   for (int r = 0; r < RPT; ++r) { pp[r] = rt[r]; part += rr[r] * rt[r]; }
-  T nu = block_sum(part, red, tid, nt);
+  T nu = bsum(part);
   if (tid == 0 && d.nu_trace) d.nu_trace[(size_t)b * NU_TRACE_LEN] = fabs(nu);
   int iters = 0;
   for (int it = 0; it < max_iter; ++it) {
+    const T inv_nu = T(1) / nu;               // off the critical path: beta = nu' / nu needs it only at the end of the iteration
     publish(V, pp);
     __syncthreads();
     T uc[MC], hu = T(0), ap[RPT];
@@ -1065,7 +1090,7 @@ __global__ void __launch_bounds__(MAXT, PDS ? 2 : 1) k_pcg3(Dev<T> d, const int*
       uc[i] = (sval[i] ? V[kV + sidx[i]] : T(0)) - uc[i];
       hu += hh[i] * uc[i];
     }
-    hu = sS * quad(hu);
+    hu = rank1 ? sS * quad(hu) : T(0);
 #pragma unroll
     for (int i = 0; i < MC; ++i) {
       uc[i] = dinv[i] * uc[i] - hh[i] * hu;
@@ -1076,7 +1101,7 @@ __global__ void __launch_bounds__(MAXT, PDS ? 2 : 1) k_pcg3(Dev<T> d, const int*
     part = T(0);
 #pragma unroll
     for (int r = 0; r < RPT; ++r) part += pp[r] * ap[r];
-    const T pAp = block_sum(part, red, tid, nt);
+    const T pAp = bsum(part);
     const T alpha = nu / pAp;
 #pragma unroll
     for (int r = 0; r < RPT; ++r) { rr[r] -= ap[r] * alpha; xx[r] += pp[r] * alpha; }
@@ -1084,11 +1109,11 @@ __global__ void __launch_bounds__(MAXT, PDS ? 2 : 1) k_pcg3(Dev<T> d, const int*
     part = T(0);
 #pragma unroll
     for (int r = 0; r < RPT; ++r) part += rr[r] * rt[r];
-    const T nu_prime = block_sum(part, red, tid, nt);
+    const T nu_prime = bsum(part);
     iters = it + 1;
     if (tid == 0 && d.nu_trace && iters < NU_TRACE_LEN) d.nu_trace[(size_t)b * NU_TRACE_LEN + iters] = fabs(nu_prime);
     if (fabs(nu_prime) < tol) break;
-    const T beta = nu_prime / nu;
+    const T beta = nu_prime * inv_nu;
 #pragma unroll
     for (int r = 0; r < RPT; ++r) pp[r] = rt[r] + pp[r] * beta;
     nu = nu_prime;

@@ -476,7 +476,7 @@ struct SolverT : SolverBase {
       // 3: four lanes per knot, everything in registers, one instance per SM;  4: two lanes per knot, preconditioner rows in
       // shared memory, two instances per SM
       if constexpr (b2t::NX % 4 == 0) {
-        const size_t smv = ((size_t)2 * (d.N + 1) * NX + (size_t)2 * d.N * PCG3_NMS + 32) * sizeof(T);
+        const size_t smv = ((size_t)2 * (d.N + 1) * NX + (size_t)2 * d.N * PCG3_NMS + 64) * sizeof(T);
         if (pcg_variant == 4) {
           const int nt4 = ((2 * d.N + 31) / 32) * 32;
           const size_t smp = smv + (size_t)(NX / 2) * NX * 128 * sizeof(T);
