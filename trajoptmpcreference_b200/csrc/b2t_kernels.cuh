@@ -1446,31 +1446,34 @@ __global__ void __launch_bounds__(128) k_linesearch(Dev<T> d, Opts<T> o) {
       for (int i = 0; i < NX; ++i) { z[i] = z[i] - alpha * dzk[i]; d.xn[(size_t)i * K + t] = z[i]; xg[i] = d.xg[(size_t)i * d.B + b]; }
       if (!terminal)
         for (int i = 0; i < NU; ++i) { z[NX + i] = z[NX + i] - alpha * dzk[NX + i]; d.un[(size_t)i * K + t] = z[NX + i]; }
-      if (!terminal) {
-        T qdd[NJ], Minv[NJ * NJ], v[NJ][6], a[NJ][6], f[NJ][6], xnext[NX];
-        forward_dynamics<T, false>(z, z + NJ, z + NX, d.gravity, qdd, Minv, v, a, f);
-        integrate(d.integrator, z, qdd, d.dt, xnext);
-        for (int i = 0; i < NX; ++i) s_xn[k * NX + i] = xnext[i];
-      }
-      s_cost[k] = cost_value(d.cost, z, z + NX, xg, k, terminal);
-      s_soft[k] = d.lim.any ? soft_value(d.lim, z, d.mu + t, d.lam + t, K, terminal) : T(0);
-      T g[NM];
-      cost_grad_hess<T, false>(d.cost, z, z + NX, xg, k, terminal, g, (T*)nullptr);
       const int M = terminal ? NX : NM;
-      T acc = T(0);
-      for (int i = 0; i < M; ++i) acc += g[i] * dzk[i];
-      s_D[k] = acc;
-      T accs = T(0);
-      if (d.lim.any) {
-        T gck[NM];
-        soft_grad(d.lim, z, d.mu + t, d.lam + t, K, terminal, gck);
-        for (int i = 0; i < M; ++i) accs += gck[i] * dzk[i];
+      if (d.diag_mode) {        // diagonal weights: value and g . dz in one pass (bit-identical to the general functions)
+        T cv, cd;
+        cost_value_dir_diag(d.cost, z, z + NX, xg, k, terminal, dzk, &cv, &cd);
+        s_cost[k] = cv; s_D[k] = cd;
+      } else {
+        s_cost[k] = cost_value(d.cost, z, z + NX, xg, k, terminal);
+        T g[NM];
+        cost_grad_hess<T, false>(d.cost, z, z + NX, xg, k, terminal, g, (T*)nullptr);
+        T acc = T(0);
+        for (int i = 0; i < M; ++i) acc += g[i] * dzk[i];
+        s_D[k] = acc;
       }
+      T sv = T(0), accs = T(0);
+      if (d.lim.any) soft_value_dir(d.lim, z, d.mu + t, d.lam + t, K, terminal, dzk, &sv, &accs);
+      s_soft[k] = sv;
       s_Ds[k] = accs;
       if (k == 0) {
         T cc = T(0);
         for (int i = 0; i < NX; ++i) cc += fabs(z[i] - d.xs[(size_t)i * d.B + b]);
         s_c[0] = cc;
+      }
+      // dynamics last: dz, xg and the multipliers are dead by now, which keeps the recursion's temporaries in registers
+      if (!terminal) {
+        T qdd[NJ], Minv[NJ * NJ], v[NJ][6], a[NJ][6], f[NJ][6], xnext[NX];
+        forward_dynamics<T, false>(z, z + NJ, z + NX, d.gravity, qdd, Minv, v, a, f);
+        integrate(d.integrator, z, qdd, d.dt, xnext);
+        for (int i = 0; i < NX; ++i) s_xn[k * NX + i] = xnext[i];
       }
     }
     __syncthreads();
@@ -1483,12 +1486,19 @@ __global__ void __launch_bounds__(128) k_linesearch(Dev<T> d, Opts<T> o) {
     }
     __syncthreads();
     if (threadIdx.x == 0) {
+      // J (costs, then penalties), c and D each summed in the reference's sequential order; the three dependent chains are
+      // interleaved in one loop so that their add latencies overlap
       T Jn = T(0), cn = T(0), D = T(0);
-      for (int k = 0; k < N; ++k) Jn += s_cost[k];
-      if (d.lim.any)
+      const bool lim_any = d.lim.any != 0;
+      for (int k = 0; k < N; ++k) {
+        Jn += s_cost[k];
+        cn += s_c[k];
+        D += s_D[k];
+        if (lim_any) D += s_Ds[k];
+      }
+      if (lim_any) {
         for (int k = 0; k < N; ++k) Jn += s_soft[k];
-      for (int k = 0; k < N; ++k) cn += s_c[k];
-      for (int k = 0; k < N; ++k) { D += s_D[k]; if (d.lim.any) D += s_Ds[k]; }
+      }
       const T mu = o.merit_mu;
       const T merit_new = Jn + mu * cn;
       const T delta_J = d.J[b] - Jn;
