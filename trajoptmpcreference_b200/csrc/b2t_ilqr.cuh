@@ -421,4 +421,115 @@ __global__ void __launch_bounds__(32) k_ilqr_search(Dev<T> d, Opts<T> o) {
   d.alpha[b] = alpha;
 }
 
+// -----------------------------------------------------------------------------------------------------------------
+// k_ilqr_search2: the same line search with every step length tried AT ONCE.  ILQR_LPI lanes per instance, lane i rolls the closed
+// loop out with alpha_i = alpha_factor^i (computed by the same repeated multiplication as the sequential loop); the accepted trial is
+// the lowest accepted index -- exactly the trial the sequential loop of k_ilqr_search stops at -- and the counters advance by that
+// index + 1, so results, iteration and trial counts are identical; only the latency drops from (trials) to one rollout.
+// Trial trajectories and per-knot penalty values go to `scratch` [(NM + 1)][K][ILQR_LPI] (lanes of an instance are contiguous: one
+// 128-byte line per element); the winner's trajectory is copied to x, u by all lanes of the instance.
+// -----------------------------------------------------------------------------------------------------------------
+enum { ILQR_LPI = 16 };
+
+template <typename T>
+__global__ void __launch_bounds__(64) k_ilqr_search2(Dev<T> d, Opts<T> o, T* scratch, int max_trials) {
+  const int gl = blockIdx.x * blockDim.x + threadIdx.x;
+  const int slot = gl / ILQR_LPI, lane = gl % ILQR_LPI;
+  const bool slot_ok = slot < *d.n_act;
+  const int b = slot_ok ? d.act[slot] : 0;
+  const int N = d.N;
+  const size_t K = d.K;
+  const size_t t0 = (size_t)b * N;
+  const bool error0 = d.err[b] != 0;
+  const bool active = slot_ok && !error0 && lane < max_trials;
+  T alpha = T(1);
+  for (int i = 0; i < lane; ++i) alpha *= o.alpha_factor;
+  const T dV1 = d.D[b], dV2 = d.ratio[b];
+  auto SC = [&](int e, size_t t) -> T& { return scratch[((size_t)e * K + t) * ILQR_LPI + lane]; };
+  T delta_J = T(0), ratio = T(0), Jn = T(0);
+  bool accept = false;
+  if (active) {
+    T xg[NX];
+    for (int i = 0; i < NX; ++i) xg[i] = d.xg[(size_t)i * d.B + b];
+    T z[NM], Jc = T(0);
+    for (int i = 0; i < NX; ++i) z[i] = d.x[(size_t)i * K + t0];            // x_0 is fixed
+    for (int k = 0; k < N; ++k) {
+      const size_t t = t0 + k;
+      const bool terminal = (k == N - 1);
+      for (int i = 0; i < NX; ++i) SC(i, t) = z[i];
+      if (!terminal) {
+        for (int i = 0; i < NU; ++i) {
+          T acc = d.u[(size_t)i * K + t] + alpha * d.gam[(size_t)i * K + t];
+          for (int x = 0; x < NX; ++x) acc += d.Sd[(size_t)(i * NX + x) * K + t] * (z[x] - d.x[(size_t)x * K + t]);
+          z[NX + i] = acc;
+          SC(NX + i, t) = acc;
+        }
+      } else {
+        for (int i = 0; i < NU; ++i) z[NX + i] = T(0);
+      }
+      Jc += cost_value(d.cost, z, z + NX, xg, k, terminal);
+      if (d.lim.any) SC(NM, t) = soft_value(d.lim, z, d.mu + t, d.lam + t, K, terminal);
+      if (!terminal) {
+        T qdd[NJ], Minv[NJ * NJ], v[NJ][6], a[NJ][6], f[NJ][6], xn[NX];
+        forward_dynamics<T, false>(z, z + NJ, z + NX, d.gravity, qdd, Minv, v, a, f);
+        integrate(d.integrator, z, qdd, d.dt, xn);
+        for (int i = 0; i < NX; ++i) z[i] = xn[i];
+      }
+    }
+    Jn = Jc;
+    if (d.lim.any)
+      for (int k = 0; k < N; ++k) Jn += SC(NM, t0 + k);                      // costs first, then the penalties knot by knot (totalCost :296-310)
+    delta_J = d.J[b] - Jn;
+    const T expected = -(alpha * dV1 + alpha * alpha * dV2);
+    ratio = delta_J / expected;
+    const bool finite = (Jn == Jn) && (fabs(Jn) < T(1e300));
+    accept = expected > T(0) && finite && ratio >= o.er_min && ratio <= o.er_max;
+  }
+  const unsigned grp_shift = (threadIdx.x & 31) / ILQR_LPI * ILQR_LPI;
+  const unsigned votes = (__ballot_sync(0xffffffffu, accept) >> grp_shift) & ((1u << ILQR_LPI) - 1u);
+  __syncwarp();                       // the winner's scratch stores are ordered before the other lanes' loads below
+  if (!slot_ok) return;
+  const int win = votes ? __ffs((int)votes) - 1 : -1;
+  const int last = error0 ? -1 : (win >= 0 ? win : max_trials - 1);           // the trial the sequential loop ends on
+  if (win >= 0) {
+    for (int idx = lane; idx < N * NM; idx += ILQR_LPI) {
+      const int e = idx / N, k = idx % N;
+      if (e >= NX && k == N - 1) continue;
+      const T val = scratch[((size_t)e * K + t0 + k) * ILQR_LPI + win];
+      if (e < NX) d.x[(size_t)e * K + t0 + k] = val; else d.u[(size_t)(e - NX) * K + t0 + k] = val;
+    }
+  }
+  if (lane != (last < 0 ? 0 : last)) return;
+  bool error = error0;
+  if (!error0) {
+    d.tot_trials[b] += last + 1;
+    if (win >= 0) {
+      d.J[b] = Jn;
+      d.merit[b] = Jn;
+      const T drho = fmin(d.drho[b] / o.rho_factor, T(1) / o.rho_factor);
+      d.drho[b] = drho; d.rho[b] = fmax(d.rho[b] * drho, o.rho_min);
+      trace_row(d, b, last, alpha, dV1, ratio, 0, 1);
+    } else {
+      error = true;
+      trace_row(d, b, last, alpha, dV1, ratio, 0, 0);
+    }
+  }
+  // check_for_exit_or_error (TrajoptMPCReference.py:463-481)
+  bool exit_flag = false;
+  if (error) {
+    const T drho = fmax(d.drho[b] * o.rho_factor, o.rho_factor);
+    const T rho = fmax(d.rho[b] * drho, o.rho_min);
+    d.drho[b] = drho; d.rho[b] = rho;
+    if (rho > o.rho_max) { d.exit_sqp[b] = 2; exit_flag = true; }
+  } else if (delta_J < o.tol_sqp) {
+    d.exit_sqp[b] = 1; exit_flag = true;
+  }
+  if (d.sqp_iter[b] == o.max_iter_sqp - 1) { d.exit_sqp[b] = 3; exit_flag = true; }
+  else d.sqp_iter[b] += 1;
+  if (exit_flag) d.phase[b] = PH_OUTER;
+  d.deltaJ[b] = delta_J;
+  d.ls_iter[b] = last < 0 ? 0 : last;
+  d.alpha[b] = last < 0 ? T(1) : alpha;
+}
+
 }  // namespace b2t

@@ -67,6 +67,7 @@ struct SolverT : SolverBase {
   std::vector<void*> allocs;
   double* stage_x = nullptr; double* stage_u = nullptr; double* stage_g = nullptr; double* stage_out = nullptr;
   size_t stage_out_bytes = 0;
+  T* ilqr_scratch = nullptr; T* ilqr_scratch_owned = nullptr;      // trial trajectories of the parallel iLQR line search
   int* h_count = nullptr;        // pinned
   int* d_status = nullptr; double* d_scalars = nullptr;
   int* d_scratch = nullptr;
@@ -623,6 +624,19 @@ struct SolverT : SolverBase {
     const size_t osmem = std::max((size_t)3 * d.N * sizeof(T), msmem);
     // block-parallel Riccati pass for nx >= 8 (arm6: 114.8 -> 10.1 ms / 2048 instances); one thread per instance for tiny systems
     // (cart-pole, nx = 4: 5.4 vs 9.8 ms).  B2T_ILQR_BW=1 / 2 forces a variant.
+    // line search: all step lengths at once, ILQR_LPI lanes per instance (B2T_ILQR_SEARCH=1 selects the sequential kernel);
+    // its trial buffer is allocated on first use
+    int max_trials = 1;
+    { double a = 1.0; while (a > o->alpha_min && max_trials < MAX_LS_TRIALS) { a *= o->alpha_factor; ++max_trials; } }
+    {
+      const char* se = getenv("B2T_ILQR_SEARCH");
+      const bool sequential = (se && atoi(se) == 1) || max_trials > ILQR_LPI;
+      if (sequential) ilqr_scratch = nullptr;
+      else if (!ilqr_scratch_owned) {
+        B2T_ALLOC(ilqr_scratch_owned, (size_t)(NM + 1) * d.K * ILQR_LPI);
+        ilqr_scratch = ilqr_scratch_owned;
+      } else ilqr_scratch = ilqr_scratch_owned;
+    }
     const char* bwenv = getenv("B2T_ILQR_BW");
     const bool ilqr_bw_single = bwenv ? atoi(bwenv) == 1 : (NX < 8);
     for (long long iter = 0; n > 0 && iter < cap; ++iter) {
@@ -630,7 +644,8 @@ struct SolverT : SolverBase {
       { Scope sc(this, B2T_K_KKT); k_ilqr_cost<T><<<cdiv((size_t)n * d.N, 64), 64, 0, stream>>>(d, d.act, d.n_act); tick(B2T_K_KKT); }
       if (ilqr_bw_single) { Scope sc(this, B2T_K_SCHUR); k_ilqr_backward<T><<<cdiv(n, 32), 32, 0, stream>>>(d, d.act, d.n_act); tick(B2T_K_SCHUR); }
       else { Scope sc(this, B2T_K_SCHUR); k_ilqr_backward2<T><<<n, ILQR_BW_THREADS, 0, stream>>>(d, d.act, d.n_act); tick(B2T_K_SCHUR); }
-      { Scope sc(this, B2T_K_TRIAL); k_ilqr_search<T><<<cdiv(n, 32), 32, 0, stream>>>(d, op); tick(B2T_K_TRIAL); }
+      if (ilqr_scratch) { Scope sc(this, B2T_K_TRIAL); k_ilqr_search2<T><<<cdiv((size_t)n * ILQR_LPI, 64), 64, 0, stream>>>(d, op, ilqr_scratch, max_trials); tick(B2T_K_TRIAL); }
+      else { Scope sc(this, B2T_K_TRIAL); k_ilqr_search<T><<<cdiv(n, 32), 32, 0, stream>>>(d, op); tick(B2T_K_TRIAL); }
       { Scope sc(this, B2T_K_CTRL); k_outer<T><<<n, mt, osmem, stream>>>(d, op, 1); tick(B2T_K_CTRL); }
       { Scope sc(this, B2T_K_CTRL); k_compact<T><<<1, 1024, 0, stream>>>(d, d_scratch); tick(B2T_K_CTRL); }
       B2T_CUDA(cudaMemcpyAsync(h_count, d.n_act, sizeof(int), cudaMemcpyDeviceToHost, stream));
