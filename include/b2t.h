@@ -173,7 +173,8 @@ int b2t_get_multipliers(b2t_solver* s, double* mu, double* lam, double* phi);
 int b2t_get_launch_stats(b2t_solver* s, long long* launches, double* device_seconds);
 /* CUDA-event time of each kernel family accumulated over the last solve: [B2T_KERNEL_FAMILIES] seconds and launch counts */
 enum { B2T_K_FD = 0, B2T_K_FDGRAD, B2T_K_KKT, B2T_K_SCHUR, B2T_K_PCG, B2T_K_RECOVER, B2T_K_TRIAL, B2T_K_MERIT, B2T_K_CTRL, B2T_KERNEL_FAMILIES };
-int b2t_set_profiling(b2t_solver* s, int enabled);
+/* mode 0: no events; 1: every launch bracketed by CUDA events on the solver's stream; 2 + f: only the launches of family f */
+int b2t_set_profiling(b2t_solver* s, int mode);
 int b2t_get_kernel_times(b2t_solver* s, double* seconds, long long* launches);
 
 /* host -> device, solve, device -> host in one call (pinned staging inside the handle) */

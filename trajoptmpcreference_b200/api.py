@@ -642,8 +642,11 @@ class BatchSolver:
         _lib.check(self.lib, self.lib.b2t_get_launch_stats(self._h, ctypes.byref(n), ctypes.byref(s)))
         return int(n.value), float(s.value)
 
-    def set_profiling(self, enabled):
-        _lib.check(self.lib, self.lib.b2t_set_profiling(self._h, int(bool(enabled))))
+    def set_profiling(self, enabled, family=None):
+        """CUDA-event timing of the kernel families of the next solves: all of them, or only `family` (a name of
+        _lib.KERNEL_FAMILY_NAMES; two event records per launch cost ~2 % of a step when every family is timed)."""
+        mode = 0 if not enabled else (1 if family is None else 2 + _lib.KERNEL_FAMILY_NAMES.index(family))
+        _lib.check(self.lib, self.lib.b2t_set_profiling(self._h, mode))
 
     def kernel_times(self):
         sec = (ctypes.c_double * _lib.KERNEL_FAMILIES)(); cnt = (ctypes.c_longlong * _lib.KERNEL_FAMILIES)()

@@ -56,6 +56,7 @@ struct SolverBase {
   long long launches = 0;
   double device_seconds = 0;
   bool profiling = false;
+  unsigned profile_mask = 0;       // bit f set: launches of kernel family f are bracketed by CUDA events
   double fam_seconds[B2T_KERNEL_FAMILIES] = {0};
   long long fam_launches[B2T_KERNEL_FAMILIES] = {0};
 };
@@ -219,9 +220,9 @@ struct SolverT : SolverBase {
   struct Scope {
     SolverT* s; int fam; cudaEvent_t a = nullptr, b = nullptr;
     Scope(SolverT* s_, int fam_) : s(s_), fam(fam_) {
-      if (s->profiling) { a = s->next_event(); b = s->next_event(); s->ev_family.push_back(fam); cudaEventRecord(a, s->stream); }
+      if ((s->profile_mask >> fam) & 1u) { a = s->next_event(); b = s->next_event(); s->ev_family.push_back(fam); cudaEventRecord(a, s->stream); }
     }
-    ~Scope() { if (s->profiling) cudaEventRecord(b, s->stream); }
+    ~Scope() { if (b) cudaEventRecord(b, s->stream); }
   };
   cudaEvent_t next_event() {
     if (ev_used == ev_pool.size()) { cudaEvent_t e; cudaEventCreate(&e); ev_pool.push_back(e); }
@@ -917,7 +918,13 @@ int b2t_get_launch_stats(b2t_solver* s, long long* l, double* sec) {
   if (sec) *sec = s->impl->device_seconds;
   return 0;
 }
-int b2t_set_profiling(b2t_solver* s, int en) { if (!s) return fail(B2T_ERR_INVALID, "null solver"); s->impl->profiling = en != 0; return 0; }
+int b2t_set_profiling(b2t_solver* s, int mode) {
+  if (!s) return fail(B2T_ERR_INVALID, "null solver");
+  if (mode < 0 || mode >= 2 + B2T_KERNEL_FAMILIES) return fail(B2T_ERR_INVALID, "profiling mode");
+  s->impl->profiling = mode != 0;
+  s->impl->profile_mask = mode == 0 ? 0u : (mode == 1 ? (1u << B2T_KERNEL_FAMILIES) - 1u : 1u << (mode - 2));
+  return 0;
+}
 int b2t_get_kernel_times(b2t_solver* s, double* sec, long long* l) {
   if (!s) return fail(B2T_ERR_INVALID, "null solver");
   for (int i = 0; i < B2T_KERNEL_FAMILIES; ++i) { if (sec) sec[i] = s->impl->fam_seconds[i]; if (l) l[i] = s->impl->fam_launches[i]; }
