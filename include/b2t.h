@@ -118,6 +118,8 @@ typedef enum {
   B2T_ARR_COST_ERR,     /* [N][nx]  state error of the cost's state map (UrdfCost.delta_x, TrajoptCost.py:425-435) */
   B2T_ARR_KKT_HESS,     /* [N][m*m] G_k = cost Hessian + gck gck^T, without rho (TrajoptMPCReference.py:214-224) */
   B2T_ARR_AB,           /* [N][nx*m] [A_k B_k] of the integrator, from the last dynamics pass (row N-1 zero) (:229-233) */
+  B2T_ARR_SOFT_VALUE,   /* [N][1]   value_soft_constraints at (x_k, u_k) with the current multipliers (TrajoptConstraint.py:295-308) */
+  B2T_ARR_SOFT_GRAD,    /* [N][m]   summed penalty gradient gck (jacobian_soft_constraints, :310-340; element-wise restatement) */
   B2T_ARR_NU_TRACE      /* [128]    per instance: |r^T Pinv r| of PCG iteration 0..127 of the last b2t_stage_pcg (PCG.py:82,95) */
 } b2t_array;
 

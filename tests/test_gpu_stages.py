@@ -176,3 +176,26 @@ def test_standalone_pcg_class(nb, N, kind):
     pcg.update_guess(exact); pcg.update_exit_tolerance(1e-10)
     x2, (tr2, _) = pcg.solve()
     assert np.max(np.abs(x2[:, 0] - exact)) < 1e-8 and len(tr2) <= 3
+
+
+def test_soft_constraint_callbacks(oracle_models):
+    """TrajoptConstraint.value_soft_constraints / jacobian_soft_constraints (TrajoptConstraint.py:295-340) through the constraint kernels,
+    with non-trivial multipliers, against the oracle's element-wise restatement."""
+    N = 6
+    limits = {"torque": ([0.4], [-0.4], "AUGMENTED_LAGRANGIAN"), "joint": ([0.45], [-0.45], "QUADRATIC_PENALTY"),
+              "velocity": ([0.3, 0.5, 0.7], [-0.3, -0.5, -0.7], "AUGMENTED_LAGRANGIAN")}
+    (plant, pc, pcons), (m, oc, ocn) = make_pair("arm3", N, oracle_models, limits=limits)
+    n = m.n
+    rng = np.random.default_rng(3)
+    for p_lim, o_lim in ((pcons.joint_limits, ocn.limits["joint"]), (pcons.velocity_limits, ocn.limits["velocity"]), (pcons.torque_limits, ocn.limits["torque"])):
+        mu = rng.uniform(0.5, 2.0, p_lim.quadratic_penalty_mu.shape); lam = rng.uniform(-0.05, 0.05, mu.shape)
+        p_lim.quadratic_penalty_mu[:] = mu; p_lim.augmented_lagrangian_lambda[:] = lam
+        o_lim.mu[:] = mu; o_lim.lam[:] = lam
+    solver = t.TrajoptMPCReference(plant, pc, pcons)           # binds the constraint object to the plant's library
+    X = rng.uniform(-0.8, 0.8, (N, 2 * n)); U = rng.uniform(-0.8, 0.8, (N - 1, n))
+    vals = ocn.values(X, U); grads = ocn.gradients(X, U)
+    for k in (0, 2, N - 1):
+        uk = U[k] if k < N - 1 else None
+        assert abs(pcons.value_soft_constraints(X[k], uk, k) - vals[k]) < 1e-13 * max(1.0, abs(vals[k]))
+        g = pcons.jacobian_soft_constraints(X[k], uk, k)
+        assert g.shape == (3 * n, 1) and np.allclose(g[:, 0], grads[k], rtol=1e-13, atol=1e-14)

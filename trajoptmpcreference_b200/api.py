@@ -393,6 +393,43 @@ class TrajoptConstraint:
             if lim is not None:
                 lim.shift_soft_constraint_constants(shift_steps)
 
+    # ---- per-knot callbacks (TrajoptConstraint.py:295-340), evaluated by the constraint kernels with this object's multipliers
+    def bind_plant(self, plant):
+        """The callbacks run on the robot's CUDA library: tell the constraint object which plant it belongs to (TrajoptMPCReference
+        does this for the objects it is given)."""
+        self._plant = plant
+        return self
+
+    def _knot(self, xk, uk, timestep):
+        plant = getattr(self, "_plant", None)
+        if plant is None:
+            raise ValueError("call bind_plant(plant) first (or pass the object to TrajoptMPCReference): the constraint callbacks run on the GPU")
+        N = self.num_timesteps
+        if timestep is None:
+            timestep = N - 1
+        cache = self.__dict__.setdefault("_probe", {})
+        if "s" not in cache:
+            n = self.nq
+            cache["s"] = BatchSolver(plant, QuadraticCost(np.eye(2 * n), np.eye(2 * n), np.eye(n), np.zeros(2 * n)), self, N=N, dt=0.1, batch=1)
+        s = cache["s"]
+        mu, lam, phi = self.pack(N)
+        s.set_multipliers(mu[None], lam[None], phi[None])
+        X = np.zeros((1, 2 * self.nq, N)); U = np.zeros((1, self.nu, N - 1))
+        X[0, :, timestep] = np.asarray(xk, dtype=np.float64).reshape(-1)
+        if uk is not None and timestep < N - 1:
+            U[0, :, timestep] = np.asarray(uk, dtype=np.float64).reshape(-1)
+        s.set_trajectory(X, U)
+        return s, timestep
+
+    def value_soft_constraints(self, xk, uk=None, timestep=None):
+        s, k = self._knot(xk, uk, timestep)
+        return float(s.fetch("soft_value")[0, k, 0])
+
+    def jacobian_soft_constraints(self, xk, uk=None, timestep=None):
+        """Summed penalty gradient gck as an (m, 1) column (what SQP adds to g_k, TrajoptMPCReference.py:220-224)."""
+        s, k = self._knot(xk, uk, timestep)
+        return s.fetch("soft_grad")[0, k].reshape(-1, 1).copy()
+
     # ---- device layout helpers: [2m][N] per instance, lower coordinate i -> row i, upper -> row m + i
     def pack(self, N):
         m = self.nq + self.nv + self.nu
@@ -699,7 +736,7 @@ class BatchSolver:
         E = {"x": self.nx, "u": self.nu, "xkp1": self.nx, "dqdd": self.n * 3 * self.n, "Ghat": self.m * self.m, "g": self.m,
              "Sd": self.nx * self.nx, "So": self.nx * self.nx, "Pd": self.nx * self.nx, "gamma": self.nx, "l": self.nx, "dz": self.m,
              "xn": self.nx, "un": self.nu, "cost_value": 1, "cost_grad": self.m, "cost_hess": self.m * self.m, "cost_err": self.nx,
-             "kkt_hess": self.m * self.m, "AB": self.nx * self.m, "nu_trace": None}[name]
+             "kkt_hess": self.m * self.m, "AB": self.nx * self.m, "soft_value": 1, "soft_grad": self.m, "nu_trace": None}[name]
         if name == "nu_trace":
             out = np.zeros((self.batch, 128))
             _lib.check(self.lib, self.lib.b2t_fetch(self._h, _lib.ARR[name], _dptr(out)))
@@ -724,6 +761,8 @@ class TrajoptMPCReference:
         elif not isinstance(constraintObj, TrajoptConstraint):
             raise ValueError("If passing in additional constraints must pass in a TrajoptConstraint object to TrajoptMPCReference.")
         self.plant, self.cost, self.other_constraints = plantObj, costObj, constraintObj
+        if isinstance(plantObj, URDFPlant):
+            constraintObj.bind_plant(plantObj)
         self.trace = []
         self.exit_soft = 0
         self.exit_sqp = 0
@@ -745,6 +784,8 @@ class TrajoptMPCReference:
     def update_constraints(self, constraintObj):
         assert isinstance(constraintObj, TrajoptConstraint), "Must pass in a TrajoptConstraint object to update_constraints in TrajoptMPCReference."
         self.other_constraints = constraintObj
+        if isinstance(self.plant, URDFPlant):
+            constraintObj.bind_plant(self.plant)
         self._solvers.clear()
 
     def set_default_options(self, options: dict):

@@ -1799,6 +1799,18 @@ __global__ void k_cost_eval(Dev<T> d, int what, double* out) {
     for (int i = 0; i < NX; ++i) out[gt * NX + i] = i < ne ? (double)e[i] : 0.0;
     return;
   }
+  if (what == 6 || what == 7) {      // soft box limits at (x_k, u_k) with the current multipliers: value, resp. summed gradient gck (NM)
+    T gck[NM];
+    for (int i = 0; i < NM; ++i) gck[i] = T(0);
+    T val = T(0);
+    if (d.lim.any) {
+      val = soft_value(d.lim, z, d.mu + gt, d.lam + gt, d.K, terminal);
+      soft_grad(d.lim, z, d.mu + gt, d.lam + gt, d.K, terminal, gck);
+    }
+    if (what == 6) out[gt] = (double)val;
+    else for (int i = 0; i < NM; ++i) out[gt * NM + i] = (double)gck[i];
+    return;
+  }
   if (what == 5) {      // [A_k B_k] of the integrator at (x_k, u_k) from the stored forward-dynamics gradient (row N-1 unused: zeros)
     T dq[NDYN], AB[NX * NM];
     for (int i = 0; i < NDYN; ++i) dq[i] = d.dyn[(size_t)i * d.K + gt];
