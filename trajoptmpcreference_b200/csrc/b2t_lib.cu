@@ -540,6 +540,7 @@ struct SolverT : SolverBase {
     int n = B;
     const long long cap = (long long)o->max_iter_soft * o->max_iter_SQP + 8;
     const bool legacy_ls = getenv("B2T_LEGACY_LS") && atoi(getenv("B2T_LEGACY_LS")) != 0;
+    const bool trace_active = getenv("B2T_TRACE_ACTIVE") != nullptr;      // debugging: active-instance count after every SQP pass on stderr
     const size_t lsmem = (size_t)(5 + NX) * d.N * sizeof(T);
     const int lst = std::min(128, ((d.N + 31) / 32) * 32);
     const size_t osmem = std::max((size_t)3 * d.N * sizeof(T), msmem);
@@ -571,6 +572,7 @@ struct SolverT : SolverBase {
       B2T_CUDA(cudaMemcpyAsync(h_count, d.n_act, sizeof(int), cudaMemcpyDeviceToHost, stream));
       B2T_CUDA(cudaStreamSynchronize(stream));
       n = h_count[0];
+      if (trace_active) fprintf(stderr, "%d ", n);
       if (hook && hook(hook_user, B2T_HOOK_STEP, (int)iter)) return fail(B2T_ERR_INVALID, "iteration hook asked to stop");
     }
     B2T_CUDA(cudaEventRecord(ev1, stream));
