@@ -199,3 +199,30 @@ def test_soft_constraint_callbacks(oracle_models):
         assert abs(pcons.value_soft_constraints(X[k], uk, k) - vals[k]) < 1e-13 * max(1.0, abs(vals[k]))
         g = pcons.jacobian_soft_constraints(X[k], uk, k)
         assert g.shape == (3 * n, 1) and np.allclose(g[:, 0], grads[k], rtol=1e-13, atol=1e-14)
+
+
+@pytest.mark.parametrize("name,N", [("arm6", 3), ("arm6", 7), ("arm6", 33), ("arm6", 64), ("arm6", 96), ("arm6", 130), ("arm2", 5), ("arm2", 200),
+                                    ("arm3", 9), ("arm3", 150)])
+def test_pcg_variants_over_horizon_lengths(name, N, oracle_models):
+    """Every horizon length selects a PCG kernel (matrix-free k_pcg3 up to 64 knots when nx % 4 == 0, explicit k_pcg2 / k_pcg beyond or
+    for other nx): the CONVERGED PCG solution must equal the exact block-tridiagonal solve (method S) of the same system, ragged sizes
+    included; the two paths share nothing but the KKT blocks."""
+    (plant, pc, _), (m, _, _) = make_pair(name, N, oracle_models, cost_kind="quadratic")
+    n = m.n
+    B = 3
+    rng = np.random.default_rng(N)
+    s = t.BatchSolver(plant, pc, None, N=N, dt=0.1, batch=B)
+    s.set_goals(np.tile(np.concatenate([np.linspace(0.5, -0.5, n), np.zeros(n)]), (B, 1)))
+    x = rng.uniform(-0.3, 0.3, (B, 2 * n, N)); u = rng.uniform(-0.3, 0.3, (B, n, N - 1))
+    s.set_trajectory(x, u)
+    s.set_initial_state(x[:, :, 0] + 0.01)
+    s.stage_dynamics()
+    s.stage_kkt(1e-3, t.SQPSolverMethods.PCG_SS)
+    it = s.stage_pcg(t.SQPSolverMethods.PCG_SS, tol=1e-24, max_iter=4000)
+    l_pcg = s.fetch("l")
+    s.stage_kkt(1e-3, t.SQPSolverMethods.S)
+    s.stage_pcg(t.SQPSolverMethods.S)
+    l_s = s.fetch("l")
+    assert np.all(it < 4000)
+    assert np.max(np.abs(l_pcg - l_s)) < 1e-6 * np.max(np.abs(l_s))
+    s.close()
