@@ -110,14 +110,15 @@ __global__ void __launch_bounds__(128) k_fd(Dev<T> d, const int* list, const int
 // -----------------------------------------------------------------------------------------------------------------
 template <typename T>
 __global__ void __launch_bounds__(128) k_fd_grad(Dev<T> d, const int* list, const int* count) {
-  const size_t per_col = (size_t)gridDim.x * blockDim.x;
-  (void)per_col;
-  const size_t gt = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  // 1-D grid, the column index fastest: the 2 NJ blocks that differentiate the SAME 128 knots are scheduled together, so v, a, f, Minv
+  // are read from DRAM once and served from L2 to the other columns (with the column as grid.y every column pass streamed the whole
+  // input again: 996 MB instead of 158 MB of DRAM reads per launch at 116 k knots)
+  const int colid = (int)(blockIdx.x % (2 * NJ));   // 0 .. 2*NJ-1
+  const size_t gt = (size_t)(blockIdx.x / (2 * NJ)) * blockDim.x + threadIdx.x;
   const int slot = (int)(gt / d.N);
   if (slot >= *count) return;
   const int k = (int)(gt % d.N);
   if (k == d.N - 1) return;
-  const int colid = blockIdx.y;                 // 0 .. 2*NJ-1
   const bool is_qd = colid >= NJ;
   const int col = is_qd ? colid - NJ : colid;
   const int b = list[slot];

@@ -392,7 +392,7 @@ struct SolverT : SolverBase {
     using namespace b2t;
     const size_t nthreads = (size_t)bound * d.N;
     { Scope sc(this, B2T_K_FD); k_fd<T, false><<<cdiv(nthreads, 128), 128, 0, stream>>>(d, list, count); tick(B2T_K_FD); }
-    { Scope sc(this, B2T_K_FDGRAD); dim3 grid(cdiv(nthreads, 128), 2 * NJ); k_fd_grad<T><<<grid, 128, 0, stream>>>(d, list, count); tick(B2T_K_FDGRAD); }
+    { Scope sc(this, B2T_K_FDGRAD); k_fd_grad<T><<<(unsigned)(cdiv(nthreads, 128) * 2 * NJ), 128, 0, stream>>>(d, list, count); tick(B2T_K_FDGRAD); }
     return 0;
   }
   int launch_kkt(const int* list, const int* count, int bound, int method, bool all_outputs = false) {
