@@ -50,6 +50,7 @@ struct Dev {
   int *act, *n_act;
   int *ls_list0, *ls_list1;
   int *restart_list, *n_restart;
+  int *dyn_ok;        // [B] 1: dynamics, gradient and x+ of the current (x, u) are still valid (the last line search failed: x, u unchanged)
   int *n_ls;          // [MAX_LS_TRIALS + 1]
   T* nu_trace;        // optional [B][NU_TRACE_LEN]: |r^T Pinv r| of every PCG iteration (PCG.pcg's `trace`, PCG.py:82,95); null = off
   T* trace;           // [B][trace_cap][TRACE_FIELDS]
@@ -75,6 +76,7 @@ __global__ void __launch_bounds__(128) k_fd(Dev<T> d, const int* list, const int
   if (slot >= *count) return;
   const int k = (int)(gt % d.N);
   const int b = list[slot];
+  if constexpr (!TRIAL) { if (d.dyn_ok[b]) return; }      // unchanged iterate (failed line search): nothing to recompute
   const size_t t = (size_t)b * d.N + k;
   const size_t K = d.K;
   const bool terminal = (k == d.N - 1);
@@ -122,6 +124,7 @@ __global__ void __launch_bounds__(128) k_fd_grad(Dev<T> d, const int* list, cons
   const bool is_qd = colid >= NJ;
   const int col = is_qd ? colid - NJ : colid;
   const int b = list[slot];
+  if (d.dyn_ok[b]) return;
   const size_t t = (size_t)b * d.N + k;
   const size_t K = d.K;
   T q[NJ], qd[NJ], Minv[NJ * NJ], v[NJ][6], a[NJ][6], f[NJ][6];
@@ -1551,6 +1554,7 @@ __global__ void __launch_bounds__(128) k_linesearch(Dev<T> d, Opts<T> o) {
         if (exit_flag) d.phase[b] = PH_OUTER;
         d.ls_iter[b] = ls;
         d.alpha[b] = alpha;
+        d.dyn_ok[b] = (st == 2) ? 1 : 0;      // a failed search leaves x, u (hence A, B, x+) untouched; only rho changes
       }
       return;
     }
@@ -1876,6 +1880,7 @@ __global__ void k_init_state(Dev<T> d) {
   if (b == 0) *d.n_act = d.B;
   if (b >= d.B) return;
   d.act[b] = b;
+  d.dyn_ok[b] = 0;
   d.outer_iter[b] = 0; d.sqp_iter[b] = 0; d.exit_sqp[b] = 0; d.exit_soft[b] = 0; d.phase[b] = PH_SQP; d.err[b] = 0;
   d.pcg_iters[b] = 0; d.tot_qp[b] = 0; d.tot_pcg[b] = 0; d.tot_trials[b] = 0; d.trace_rows[b] = 0; d.ls_iter[b] = 0;
   d.alpha[b] = T(1); d.deltaJ[b] = T(0); d.c[b] = T(0); d.J[b] = T(0); d.merit[b] = T(0); d.rho[b] = T(0); d.drho[b] = T(1);

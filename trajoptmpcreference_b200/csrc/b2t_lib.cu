@@ -173,7 +173,7 @@ struct SolverT : SolverBase {
     B2T_ALLOC(d.rho, B); B2T_ALLOC(d.drho, B); B2T_ALLOC(d.J, B); B2T_ALLOC(d.c, B); B2T_ALLOC(d.merit, B); B2T_ALLOC(d.alpha, B);
     B2T_ALLOC(d.deltaJ, B); B2T_ALLOC(d.D, B); B2T_ALLOC(d.ratio, B);
     B2T_ALLOC(d.ls_iter, B); B2T_ALLOC(d.sqp_iter, B); B2T_ALLOC(d.outer_iter, B); B2T_ALLOC(d.exit_sqp, B); B2T_ALLOC(d.exit_soft, B);
-    B2T_ALLOC(d.phase, B); B2T_ALLOC(d.err, B); B2T_ALLOC(d.pcg_iters, B); B2T_ALLOC(d.tot_qp, B); B2T_ALLOC(d.tot_pcg, B); B2T_ALLOC(d.tot_trials, B);
+    B2T_ALLOC(d.phase, B); B2T_ALLOC(d.dyn_ok, B); B2T_ALLOC(d.err, B); B2T_ALLOC(d.pcg_iters, B); B2T_ALLOC(d.tot_qp, B); B2T_ALLOC(d.tot_pcg, B); B2T_ALLOC(d.tot_trials, B);
     B2T_ALLOC(d.act, B); B2T_ALLOC(d.n_act, 1); B2T_ALLOC(d.ls_list0, B); B2T_ALLOC(d.ls_list1, B); B2T_ALLOC(d.restart_list, B); B2T_ALLOC(d.n_restart, 1);
     B2T_ALLOC(d.n_ls, MAX_LS_TRIALS + 1);
     B2T_ALLOC(d.nu_trace, B * NU_TRACE_LEN);
@@ -686,6 +686,7 @@ struct SolverT : SolverBase {
   int stage_dynamics() override {
     B2T_CUDA(cudaSetDevice(device));
     int r = all_list(); if (r) return r;
+    B2T_CUDA(cudaMemsetAsync(d.dyn_ok, 0, (size_t)d.B * sizeof(int), stream));
     launch_dynamics(d.act, d.n_act, d.B);
     B2T_CUDA(cudaGetLastError());
     B2T_CUDA(cudaStreamSynchronize(stream));
