@@ -189,7 +189,7 @@ def ncu_traffic(family, batch, launches_per_step, qp_per_instance):
     dynamics Jacobians, Ghat factors, preconditioner blocks and gamma are read once, l is written once)."""
     if family != "pcg":
         return None, "no ncu capture for this kernel family"
-    path = os.path.join(ROOT, "profiles", "r01_v4_ncu_full_k_pcg3.csv")
+    path = os.path.join(ROOT, "profiles", "r01_v6_ncu_full_k_pcg3.csv")
     try:
         vals = {}
         with open(path) as f:
@@ -200,7 +200,7 @@ def ncu_traffic(family, batch, launches_per_step, qp_per_instance):
         grid = float(vals["launch__grid_size"])
         per_inst = (float(vals["dram__bytes_read.sum"]) + float(vals["dram__bytes_write.sum"])) * 1e6 / grid
         inst_per_launch = batch * qp_per_instance / max(launches_per_step, 1)
-        return per_inst * inst_per_launch, "profiles/r01_v4_ncu_full_k_pcg3.csv: %.0f bytes per instance x %.0f instances per launch (avg)" % (per_inst, inst_per_launch)
+        return per_inst * inst_per_launch, "profiles/r01_v6_ncu_full_k_pcg3.csv: %.0f bytes per instance x %.0f instances per launch (avg)" % (per_inst, inst_per_launch)
     except Exception as e:      # noqa: BLE001
         return None, "ncu capture unreadable: %s" % e
 
