@@ -457,6 +457,143 @@ __global__ void __launch_bounds__(SCHUR_THREADS) k_schur_diag(Dev<T> d, const in
   });
 }
 
+// k_schur_rows: the same block row, NJ threads per knot -- thread (i, knot) owns row i of Ab in registers and produces rows i and
+// NJ+i of S_jj / S_j,j-1 / gamma_j (the body of k_schur_diag's outer loop over i).  k_schur_diag runs one 1700-FMA chain per thread at
+// 8 warps per SM (255 registers, 55 KB of shared memory per 64 knots) and is pure latency (ncu: FP64 pipe 4 %, long-scoreboard stall
+// 18.8 cycles per issue); here the chain is NJ times shorter, the thread needs ~1/4 of the registers, and the per-knot vectors
+// (dinv, h, Ghat g of knot j-1, h of knot j) are staged once per knot instead of being re-read by every use.  Thread layout
+// tx = i * SCHUR_KB + knot, so a warp is 32 consecutive knots of one row index: global accesses stay coalesced and the per-knot
+// shared-memory records (odd stride) are conflict-free.  Every sum keeps k_schur_diag's operand order: bit-identical outputs.
+enum { SCHUR_KB = 32 };
+constexpr int SCHUR_REC = (NJ * NM + 3 * NM + NX + NJ * NJ + NX) | 1;   // Ab, dinv/h/Gg of knot j-1, h_x of knot j, F, v
+template <typename T>
+__global__ void __launch_bounds__(SCHUR_KB * NJ, 3) k_schur_rows(Dev<T> d, const int* list, const int* count, int need_so) {
+  extern __shared__ unsigned char smem_raw[];
+  const int i = threadIdx.x / SCHUR_KB, jj = threadIdx.x % SCHUR_KB;
+  T* rec = reinterpret_cast<T*>(smem_raw) + (size_t)jj * SCHUR_REC;
+  T* sAb = rec;                         // [NJ][NM]
+  T* sD = sAb + NJ * NM;                // dinv of knot j-1
+  T* sH = sD + NM;                      // h of knot j-1
+  T* sG = sH + NM;                      // Ghat g of knot j-1
+  T* sHx = sG + NM;                     // h[:nx] of knot j
+  T* sF = sHx + NX;                     // [NJ][NJ]
+  T* sv = sF + NJ * NJ;                 // [NX]
+  const size_t gt = (size_t)blockIdx.x * SCHUR_KB + jj;
+  const int slot = (int)(gt / d.N);
+  const bool act = slot < *count;
+  const int j = (int)(gt % d.N);
+  const int b = act ? list[slot] : 0;
+  const size_t t = (size_t)b * d.N + j;
+  const size_t K = d.K;
+  T* Sd_o = d.Sd + (size_t)b * d.N;
+  T* So_o = d.So + (size_t)b * d.N;
+  T* gm_o = d.gam + (size_t)b * d.N;
+  auto GH = [&](int e, size_t tt) -> T { return d.Gh[(size_t)e * K + tt]; };
+  const bool first = (j == 0);
+  const bool work = act && !first;
+  const size_t tp = work ? t - 1 : t;
+  const T dte = d.integrator == 0 ? d.dt : T(0);
+  const T tau = d.integrator == 0 ? T(0) : d.dt;
+  T row[NM];
+  if (act) {
+    for (int e = i; e < NX; e += NJ) sHx[e] = GH(NM + e, t);
+    if (work) {
+      for (int e = i; e < NM; e += NJ) { sD[e] = GH(e, tp); sH[e] = GH(NM + e, tp); sG[e] = d.Gg[(size_t)e * K + tp]; }
+      static_for<0, NM>([&](auto cc) {
+        constexpr int c = decltype(cc)::value;
+        row[c] = d.dt * d.dyn[(size_t)(i * 3 * NJ + c) * K + tp] + ((c == NJ + i) ? T(1) : T(0));
+        sAb[i * NM + c] = row[c];
+      });
+    }
+  }
+  __syncthreads();
+  const T sj = act ? GH(2 * NM, t) : T(0);
+  const T sp = work ? GH(2 * NM, tp) : T(0);
+  T Mi[NJ], Fi[NJ], vbi = T(0), wbi = T(0);
+  static_for<0, NJ>([&](auto cc) { constexpr int c = decltype(cc)::value; Mi[c] = T(0); Fi[c] = T(0); });
+  T vi = T(0), vni = T(0);
+  if (work) {
+    static_for<0, NM>([&](auto rc) {
+      constexpr int r = decltype(rc)::value;
+      const T dr = sD[r], hr = sH[r], gr = sG[r];
+      const T own = row[r];
+      vbi += own * hr;
+      wbi += own * gr;
+      const T cdi = own * dr;
+      static_for<0, NJ>([&](auto cc) {
+        constexpr int c = decltype(cc)::value;
+        const T oc = sAb[c * NM + r];
+        // entry (i, c) of the symmetric M: k_schur_diag accumulates (col[a] d_r) col[c] for a >= c
+        const bool up = c > i;
+        const T hi = up ? oc * dr : cdi, lo = up ? own : oc;
+        Mi[c] += hi * lo;
+      });
+      if constexpr (r < NJ) Fi[r] += cdi;
+      else if constexpr (r < NX) Fi[r - NJ] += dte * cdi;
+    });
+    // gamma_j = c_j + AB (Ghat g)_{j-1} - (Ghat g)_j[:nx]
+    {
+      const T wt = sG[i] + dte * sG[NJ + i] + tau * wbi;
+      const T ckt = d.x[(size_t)i * K + t] - d.xkp1[(size_t)i * K + tp];
+      gm_o[(size_t)i * K + j] = (ckt + wt) - d.Gg[(size_t)i * K + t];
+      const T ckb = d.x[(size_t)(NJ + i) * K + t] - d.xkp1[(size_t)(NJ + i) * K + tp];
+      gm_o[(size_t)(NJ + i) * K + j] = (ckb + wbi) - d.Gg[(size_t)(NJ + i) * K + t];
+    }
+    vi = sH[i] + dte * sH[NJ + i] + tau * vbi;
+    vni = vbi;
+    sv[i] = vi; sv[NJ + i] = vni;
+    static_for<0, NJ>([&](auto cc) { constexpr int c = decltype(cc)::value; sF[i * NJ + c] = Fi[c]; });
+  }
+  __syncthreads();
+  if (!act) return;
+  if (first) {
+    // S_00 = -Ghat_0[:nx,:nx], gamma_0 = (x_0 - xs) - (Ghat g)_0[:nx]; rows i and NJ+i
+    for (int h = 0; h < 2; ++h) {
+      const int ri = h * NJ + i;
+      const T hi = sHx[ri], di = GH(ri, t);
+      static_for<0, NX>([&](auto cc) {
+        constexpr int c = decltype(cc)::value;
+        const T val = -(((ri == c) ? di : T(0)) - sj * hi * sHx[c]);
+        Sd_o[(size_t)(ri * NX + c) * K + j] = val;
+        So_o[(size_t)(ri * NX + c) * K + j] = T(0);
+      });
+      gm_o[(size_t)ri * K + j] = (d.x[(size_t)ri * K + t] - d.xs[(size_t)ri * d.B + b]) - d.Gg[(size_t)ri * K + t];
+    }
+    return;
+  }
+  // S_jj = -(AB D AB^T - sp v v^T + Ghat_j[:nx,:nx])
+  {
+    const T Zi = sD[i] + dte * dte * sD[NJ + i];
+    const T hxi = sHx[i], hxni = sHx[NJ + i];
+    const T gdi = GH(i, t), gdni = GH(NJ + i, t);
+    static_for<0, NJ>([&](auto cc) {
+      constexpr int c = decltype(cc)::value;
+      const T hxc = sHx[c], hxnc = sHx[NJ + c];
+      const T mic = Mi[c];
+      const T Fci = sF[c * NJ + i], Fic = Fi[c];
+      const T vc = sv[c], vnc = sv[NJ + c];
+      const T tt = ((i == c) ? Zi : T(0)) + tau * (Fci + Fic) + tau * tau * mic;
+      const T tb = Fci + tau * mic;                               // (top i, bottom c)
+      const T gtt = ((i == c) ? gdi : T(0)) - sj * hxi * hxc;
+      const T gtb = -sj * hxi * hxnc;
+      const T gbb = ((i == c) ? gdni : T(0)) - sj * hxni * hxnc;
+      Sd_o[(size_t)(i * NX + c) * K + j] = -((tt - sp * vi * vc) + gtt);
+      Sd_o[(size_t)(i * NX + NJ + c) * K + j] = -((tb - sp * vi * vnc) + gtb);
+      Sd_o[(size_t)((NJ + c) * NX + i) * K + j] = -((tb - sp * vnc * vi) + gtb);
+      Sd_o[(size_t)((NJ + i) * NX + NJ + c) * K + j] = -((mic - sp * vni * vnc) + gbb);
+    });
+  }
+  // S_{j,j-1} = AB[:, :nx] diag(d_x) - sp v h_x^T   (not needed by the matrix-free PCG kernels)
+  if (need_so) static_for<0, NX>([&](auto cc) {
+    constexpr int c = decltype(cc)::value;
+    const T dc = sD[c], hc = sH[c];
+    const T ab = row[c];
+    const T e0 = ((c == i) ? T(1) : T(0)) + ((c == NJ + i) ? dte : T(0));
+    So_o[(size_t)(i * NX + c) * K + j] = (e0 + tau * ab) * dc - sp * vi * hc;
+    So_o[(size_t)((NJ + i) * NX + c) * K + j] = ab * dc - sp * vni * hc;
+  });
+}
+
 // Pd_j = S_jj^-1 (block Jacobi / symmetric stair) or diag(S_jj)^-1 (Jacobi) -- PCG.compute_preconditioner (PCG.py:166-212).
 // One thread per block row; -S_jj (SPD) is inverted in packed storage with a fully unrolled Cholesky, all in registers.
 template <typename T>

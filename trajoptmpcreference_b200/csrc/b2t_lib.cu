@@ -70,6 +70,7 @@ struct SolverT : SolverBase {
   size_t stage_out_bytes = 0;
   T* ilqr_scratch = nullptr; T* ilqr_scratch_owned = nullptr;      // trial trajectories of the parallel iLQR line search
   int* h_count = nullptr;        // pinned
+  bool schur_v1 = false;
   int* d_status = nullptr; double* d_scalars = nullptr;
   int* d_scratch = nullptr;
   cudaEvent_t ev0 = nullptr, ev1 = nullptr;
@@ -190,6 +191,8 @@ struct SolverT : SolverBase {
     B2T_CUDA(cudaFuncSetAttribute(b2t::k_pcg<T>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
     B2T_CUDA(cudaFuncSetAttribute(b2t::k_linesearch<T>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
     B2T_CUDA(cudaFuncSetAttribute(b2t::k_schur_diag<T>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)((size_t)NJ * NM * SCHUR_THREADS * sizeof(T))));
+    B2T_CUDA(cudaFuncSetAttribute(b2t::k_schur_rows<T>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)((size_t)SCHUR_REC * SCHUR_KB * sizeof(T))));
+    { const char* e = getenv("B2T_SCHUR_V1"); schur_v1 = e && atoi(e) != 0; }     // A/B switch: the one-thread-per-block-row kernel
     B2T_CUDA(cudaFuncSetAttribute(b2t::k_pcg2<T, PCG_RPT, 1, true, 256>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
     B2T_CUDA(cudaFuncSetAttribute(b2t::k_pcg2<T, PCG_RPT, 1, true, 512>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
     B2T_CUDA(cudaFuncSetAttribute(b2t::k_pcg2<T, PCG_RPT, 1, true, 1024>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
@@ -405,7 +408,8 @@ struct SolverT : SolverBase {
       const bool exact = method == B2T_METHOD_N || method == B2T_METHOD_S;
       const int need_so = (all_outputs || exact || !(pcg_variant == 3 || pcg_variant == 4)) ? 1 : 0;
       { Scope sc(this, B2T_K_KKT); k_kkt_diag<T><<<cdiv(nthreads, 128), 128, 0, stream>>>(d, list, count); tick(B2T_K_KKT); }
-      { Scope sc(this, B2T_K_SCHUR); k_schur_diag<T><<<cdiv(nthreads, SCHUR_THREADS), SCHUR_THREADS, (size_t)NJ * NM * SCHUR_THREADS * sizeof(T), stream>>>(d, list, count, need_so); tick(B2T_K_SCHUR); }
+      if (schur_v1) { Scope sc(this, B2T_K_SCHUR); k_schur_diag<T><<<cdiv(nthreads, SCHUR_THREADS), SCHUR_THREADS, (size_t)NJ * NM * SCHUR_THREADS * sizeof(T), stream>>>(d, list, count, need_so); tick(B2T_K_SCHUR); }
+      else { Scope sc(this, B2T_K_SCHUR); k_schur_rows<T><<<cdiv(nthreads, SCHUR_KB), SCHUR_KB * NJ, (size_t)SCHUR_REC * SCHUR_KB * sizeof(T), stream>>>(d, list, count, need_so); tick(B2T_K_SCHUR); }
       if (method != B2T_METHOD_N && method != B2T_METHOD_S) {
         Scope sc(this, B2T_K_SCHUR); k_pinv<T><<<cdiv(nthreads, 128), 128, 0, stream>>>(d, list, count, jac); tick(B2T_K_SCHUR);
       }
