@@ -1056,7 +1056,12 @@ __global__ void __launch_bounds__(MAXT, PDS ? 2 : 1) k_pcg3(Dev<T> d, const int*
     sidx[i] = (c < NX) ? c : 0;
   }
   const T sS = live ? d.Gh[(size_t)(2 * NM) * K + tk] : T(0);
-  const bool rank1 = d.lim.any != 0;          // without soft limits gck = 0: Ghat is diagonal, s = 0 (k_kkt_diag) and the h-reductions vanish
+  // without soft limits gck = 0: Ghat is diagonal (k_kkt_diag) and the h-reductions vanish.  With limits the same holds for every knot
+  // without a violated bound (h_k = 0, so h^T u = 0 exactly): a warp whose 8 knots all have h = 0 skips the shuffles -- same values
+  bool hnz = false;
+#pragma unroll
+  for (int i = 0; i < MC; ++i) hnz = hnz || (hh[i] != T(0));
+  const bool rank1 = d.lim.any != 0 && __any_sync(0xffffffffu, hnz);
 #pragma unroll
   for (int r = 0; r < RPT; ++r)
 #pragma unroll
@@ -1566,7 +1571,10 @@ __global__ void k_merit(Dev<T> d, const int* list, const int* count, int* next_l
 // smem: (5 + NX) * N scalars.
 // -----------------------------------------------------------------------------------------------------------------
 template <typename T>
-__global__ void __launch_bounds__(128) k_linesearch(Dev<T> d, Opts<T> o) {
+__device__ __forceinline__ void outer_update(const Dev<T>& d, const Opts<T>& o, int b, T* sm, int fused_restart);   // defined below
+
+template <typename T>
+__global__ void __launch_bounds__(128) k_linesearch(Dev<T> d, Opts<T> o, int fuse_outer) {
   if ((int)blockIdx.x >= *d.n_act) return;
   const int b = d.act[blockIdx.x];
   const int N = d.N;
@@ -1575,6 +1583,7 @@ __global__ void __launch_bounds__(128) k_linesearch(Dev<T> d, Opts<T> o) {
   T* sm = reinterpret_cast<T*>(smem_raw);
   T* s_cost = sm; T* s_soft = sm + N; T* s_c = sm + 2 * N; T* s_D = sm + 3 * N; T* s_Ds = sm + 4 * N; T* s_xn = sm + 5 * N;   // [N][NX]
   __shared__ int s_state;     // 0: accepted, 1: try a smaller alpha, 2: failed
+  __shared__ int s_exit;      // the SQP loop of this instance exited
   T alpha = T(1);
   int ls = 0;
   for (;;) {
@@ -1692,7 +1701,12 @@ __global__ void __launch_bounds__(128) k_linesearch(Dev<T> d, Opts<T> o) {
         d.ls_iter[b] = ls;
         d.alpha[b] = alpha;
         d.dyn_ok[b] = (st == 2) ? 1 : 0;      // a failed search leaves x, u (hence A, B, x+) untouched; only rho changes
+        s_exit = exit_flag ? 1 : 0;
       }
+      __syncthreads();
+      // the SQP loop of this instance exited: soft-constraint check / update and the restart of the next outer iteration right here
+      // (what a separate k_outer launch over all active instances did for the few that exit in a pass)
+      if (fuse_outer && s_exit) outer_update(d, o, b, sm, 1);
       return;
     }
     alpha *= o.alpha_factor;
@@ -1741,13 +1755,9 @@ __global__ void k_sqp_ctrl(Dev<T> d, Opts<T> o) {
 // Instances that continue re-enter the SQP loop through k_outer_begin (the host relaunches it on the `restart` list).
 // -----------------------------------------------------------------------------------------------------------------
 template <typename T>
-__global__ void k_outer(Dev<T> d, Opts<T> o, int fused_restart) {
+__device__ __forceinline__ void outer_update(const Dev<T>& d, const Opts<T>& o, int b, T* sm, int fused_restart) {
   int* restart_list = d.restart_list;
   int* restart_count = d.n_restart;
-  const int n = *d.n_act;
-  if ((int)blockIdx.x >= n) return;
-  const int b = d.act[blockIdx.x];
-  if (d.phase[b] != PH_OUTER) return;
   const int N = d.N;
   const size_t K = d.K;
   __shared__ T s_max[3];
@@ -1757,9 +1767,7 @@ __global__ void k_outer(Dev<T> d, Opts<T> o, int fused_restart) {
   __syncthreads();
   T max_c = T(0);
   if (d.lim.any) {
-    // per limit type: max over knots of | min over the type's 2*cs values |
-    extern __shared__ unsigned char smem_raw[];
-    T* sm = reinterpret_cast<T*>(smem_raw);     // [3][N]
+    // per limit type: max over knots of | min over the type's 2*cs values |;  sm: [3][N]
     for (int k = threadIdx.x; k < N; k += blockDim.x) {
       const size_t t = (size_t)b * N + k;
       const bool terminal = (k == N - 1);
@@ -1842,10 +1850,8 @@ __global__ void k_outer(Dev<T> d, Opts<T> o, int fused_restart) {
   __threadfence_block();
   __syncthreads();
   {
-    extern __shared__ unsigned char smem_raw2[];
-    T* sm2 = reinterpret_cast<T*>(smem_raw2);
     __shared__ T Jb, cb, Db;
-    merit_terms<T, false, false, false>(d, b, sm2, &Jb, &cb, &Db);
+    merit_terms<T, false, false, false>(d, b, sm, &Jb, &cb, &Db);
     if (threadIdx.x == 0) {
       d.J[b] = Jb;
       d.rho[b] = o.rho_init;
@@ -1857,6 +1863,16 @@ __global__ void k_outer(Dev<T> d, Opts<T> o, int fused_restart) {
       trace_row(d, b, 0, T(1), T(0), T(0), 0, 0);
     }
   }
+}
+
+// standalone launch of outer_update (legacy line-search path); smem: max(3, 5) * N scalars
+template <typename T>
+__global__ void k_outer(Dev<T> d, Opts<T> o, int fused_restart) {
+  if ((int)blockIdx.x >= *d.n_act) return;
+  const int b = d.act[blockIdx.x];
+  if (d.phase[b] != PH_OUTER) return;
+  extern __shared__ unsigned char smem_raw[];
+  outer_update(d, o, b, reinterpret_cast<T*>(smem_raw), fused_restart);
 }
 
 // rebuild the active list (order-preserving, single block of 1024 threads: per-thread chunk counts + block scan)

@@ -558,8 +558,8 @@ struct SolverT : SolverBase {
         if (hook(hook_user, B2T_HOOK_LINSYS, (int)iter)) return fail(B2T_ERR_INVALID, "iteration hook asked to stop");
       }
       if (!legacy_ls) {
-        { Scope sc(this, B2T_K_TRIAL); k_linesearch<T><<<n, lst, lsmem, stream>>>(d, op); tick(B2T_K_TRIAL); }
-        { Scope sc(this, B2T_K_CTRL); k_outer<T><<<n, mt, osmem, stream>>>(d, op, 1); tick(B2T_K_CTRL); }
+        // k_linesearch also runs the outer (soft-constraint) update of the instances whose SQP loop exits in this pass
+        { Scope sc(this, B2T_K_TRIAL); k_linesearch<T><<<n, lst, lsmem, stream>>>(d, op, 1); tick(B2T_K_TRIAL); }
       } else {
         { Scope sc(this, B2T_K_CTRL); k_iter_begin<T><<<cdiv(n, 128), 128, 0, stream>>>(d); tick(B2T_K_CTRL); }
         for (int t = 0; t < max_trials; ++t) {
