@@ -628,16 +628,11 @@ __global__ void __launch_bounds__(128) k_pinv(Dev<T> d, const int* list, const i
   });
 }
 
+// dz_k = Ghat_k (g_k - [l_k; 0] + AB_k^T l_{k+1}) of one knot (structured path)
 template <typename T>
-__global__ void __launch_bounds__(128) k_recover_diag(Dev<T> d, const int* list, const int* count) {
-  const size_t gt = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
-  const int slot = (int)(gt / d.N);
-  if (slot >= *count) return;
-  const int k = (int)(gt % d.N);
-  const int b = list[slot];
+__device__ __forceinline__ void recover_diag_knot(const Dev<T>& d, int b, int k) {
   const size_t t = (size_t)b * d.N + k;
   const size_t K = d.K;
-  (void)0;
   const bool terminal = (k == d.N - 1);
   T rhs[NM];
   for (int i = 0; i < NM; ++i) rhs[i] = d.g[(size_t)i * K + t];
@@ -662,6 +657,14 @@ __global__ void __launch_bounds__(128) k_recover_diag(Dev<T> d, const int* list,
   for (int i = 0; i < NM; ++i) { dinv[i] = d.Gh[(size_t)i * K + t]; h[i] = d.Gh[(size_t)(NM + i) * K + t]; hr += h[i] * rhs[i]; }
   const T sS = d.Gh[(size_t)(2 * NM) * K + t];
   for (int i = 0; i < NM; ++i) d.dz[(size_t)i * K + t] = dinv[i] * rhs[i] - sS * h[i] * hr;
+}
+
+template <typename T>
+__global__ void __launch_bounds__(128) k_recover_diag(Dev<T> d, const int* list, const int* count) {
+  const size_t gt = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  const int slot = (int)(gt / d.N);
+  if (slot >= *count) return;
+  recover_diag_knot(d, list[slot], (int)(gt % d.N));
 }
 
 // dense reconstruction of Ghat from its structured form (B2T_ARR_GHAT in diag_mode)
@@ -1574,11 +1577,15 @@ template <typename T>
 __device__ __forceinline__ void outer_update(const Dev<T>& d, const Opts<T>& o, int b, T* sm, int fused_restart);   // defined below
 
 template <typename T>
-__global__ void __launch_bounds__(128) k_linesearch(Dev<T> d, Opts<T> o, int fuse_outer) {
+__global__ void __launch_bounds__(128) k_linesearch(Dev<T> d, Opts<T> o, int fuse_outer, int fuse_recover) {
   if ((int)blockIdx.x >= *d.n_act) return;
   const int b = d.act[blockIdx.x];
   const int N = d.N;
   const size_t K = d.K;
+  // the step dz_k of the structured path is computed here (what k_recover_diag does in its own launch): each thread produces
+  // the knots it evaluates below, so no barrier is needed
+  if (fuse_recover)
+    for (int k = threadIdx.x; k < N; k += blockDim.x) recover_diag_knot(d, b, k);
   extern __shared__ unsigned char smem_raw[];
   T* sm = reinterpret_cast<T*>(smem_raw);
   T* s_cost = sm; T* s_soft = sm + N; T* s_c = sm + 2 * N; T* s_D = sm + 3 * N; T* s_Ds = sm + 4 * N; T* s_xn = sm + 5 * N;   // [N][NX]

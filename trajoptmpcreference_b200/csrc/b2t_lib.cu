@@ -552,14 +552,16 @@ struct SolverT : SolverBase {
       launch_dynamics(d.act, d.n_act, n);
       launch_kkt(d.act, d.n_act, n, method, hook != nullptr);
       launch_pcg(d.act, d.n_act, n, method, op.tol_lin, op.max_iter_lin);
-      launch_recover(d.act, d.n_act, n);
+      // structured path: the step recovery runs inside k_linesearch (unless a hook wants to see dz before the search)
+      const int fuse_recover = (d.diag_mode && !legacy_ls && !hook) ? 1 : 0;
+      if (!fuse_recover) launch_recover(d.act, d.n_act, n);
       if (hook) {
         B2T_CUDA(cudaStreamSynchronize(stream));
         if (hook(hook_user, B2T_HOOK_LINSYS, (int)iter)) return fail(B2T_ERR_INVALID, "iteration hook asked to stop");
       }
       if (!legacy_ls) {
         // k_linesearch also runs the outer (soft-constraint) update of the instances whose SQP loop exits in this pass
-        { Scope sc(this, B2T_K_TRIAL); k_linesearch<T><<<n, lst, lsmem, stream>>>(d, op, 1); tick(B2T_K_TRIAL); }
+        { Scope sc(this, B2T_K_TRIAL); k_linesearch<T><<<n, lst, lsmem, stream>>>(d, op, 1, fuse_recover); tick(B2T_K_TRIAL); }
       } else {
         { Scope sc(this, B2T_K_CTRL); k_iter_begin<T><<<cdiv(n, 128), 128, 0, stream>>>(d); tick(B2T_K_CTRL); }
         for (int t = 0; t < max_trials; ++t) {
