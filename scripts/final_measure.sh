@@ -2,6 +2,8 @@
 # One gpurun call that produces the artefacts summarised under profiles/ for a version tag:
 #   gpurun --timeout 1500 -- 'bash scripts/final_measure.sh r01_v7'
 # bench lines are taken WITHOUT a profiler; the ncu passes come after and their printed numbers are never bench values.
+# The .ncu-rep files exceed gpurun's 64 MiB return limit: their raw pages (and the SASS page of the dominant kernel) are exported
+# here and the reports deleted; scripts/profile_summary.py reads the exported CSVs.
 TAG=${1:-r01_vX}
 O=gpurun_out
 mkdir -p $O
@@ -10,8 +12,13 @@ timeout 600 python bench.py > $O/${TAG}_bench_default.json 2> $O/${TAG}_bench_de
 timeout 300 python bench.py --limits 0 --no-cpu-baseline > $O/${TAG}_bench_nolimits.json 2> /dev/null
 timeout 600 ncu --metrics gpu__time_duration.sum --clock-control none -c 600 --csv --log-file $O/${TAG}_ncu_launches.csv \
   python bench.py --batch 2048 --steps 1 --warmup 1 --no-cpu-baseline > $O/${TAG}_ncu_launches.log 2>&1
-timeout 600 ncu --set full --clock-control none --import-source on -k regex:k_pcg3 -s 30 -c 1 -f -o $O/${TAG}_pcg3 \
+timeout 600 ncu --set full --clock-control none --import-source on -k regex:k_pcg3 -s 30 -c 1 -f -o /tmp/${TAG}_pcg3 \
   python bench.py --batch 2048 --steps 1 --warmup 1 --no-cpu-baseline > $O/${TAG}_ncu_pcg3.log 2>&1
-timeout 600 ncu --set full --clock-control none --import-source on -k 'regex:k_schur_rows|k_pinv|k_linesearch|k_kkt_diag|k_fd' -s 40 -c 5 -f -o $O/${TAG}_others \
+ncu -i /tmp/${TAG}_pcg3.ncu-rep --page raw --csv > $O/${TAG}_pcg3_raw.csv
+ncu -i /tmp/${TAG}_pcg3.ncu-rep --page source --csv --print-source sass | cut -d, -f1-12,33-50 > $O/${TAG}_pcg3_sass.csv
+timeout 600 ncu --set full --clock-control none --import-source on -k 'regex:k_schur_rows|k_pinv|k_linesearch|k_kkt_diag|k_fd' -s 40 -c 5 -f -o /tmp/${TAG}_others \
   python bench.py --batch 2048 --steps 1 --warmup 1 --no-cpu-baseline > $O/${TAG}_ncu_others.log 2>&1
+ncu -i /tmp/${TAG}_others.ncu-rep --page raw --csv > $O/${TAG}_others_raw.csv
+ncu -i /tmp/${TAG}_others.ncu-rep --page source --csv --print-source sass -k regex:k_linesearch | cut -d, -f1-12,33-50 > $O/${TAG}_linesearch_sass.csv
+ls -la /tmp/*.ncu-rep $O | tail -20
 tail -c 600 $O/${TAG}_bench_default.json

@@ -41,16 +41,23 @@ def launch_summary(tag, path):
 
 
 def full_summary(tag, rep, kernel):
-    raw = subprocess.run(['ncu', '-i', rep, '--page', 'raw', '--csv'], capture_output=True, text=True).stdout
-    rows = list(csv.reader(raw.splitlines()))
-    hdr, units, r = rows[0], rows[1], rows[2]
+    """rep: a .ncu-rep (read with ncu) or the raw page already exported on the GPU box (`ncu -i x.ncu-rep --page raw --csv > x_raw.csv`;
+    the reports themselves exceed gpurun's 64 MiB return limit).  One column per captured launch."""
+    if rep.endswith('.csv'):
+        raw = open(rep).read()
+    else:
+        raw = subprocess.run(['ncu', '-i', rep, '--page', 'raw', '--csv'], capture_output=True, text=True).stdout
+    rows = [r for r in csv.reader(l for l in raw.splitlines() if not l.startswith('==')) if r]
+    hdr, units, launches = rows[0], rows[1], rows[2:]
     keys = KEEP + [h for h in hdr if 'issue_stalled' in h and h.endswith('per_issue_active.ratio')]
     out = os.path.join(ROOT, 'profiles', '%s_ncu_full_%s.csv' % (tag, kernel))
+    ik = hdr.index('Kernel Name')
     with open(out, 'w') as f:
-        f.write('# ncu --set full --clock-control none, first captured launch of %s in %s\n' % (kernel, os.path.basename(rep)))
+        f.write('# ncu --set full --clock-control none, captured launches of %s in %s\n' % (kernel, os.path.basename(rep)))
+        f.write('metric,unit,%s\n' % ','.join(re.sub(r'<.*', '', r[ik]).replace('void b2t::', '') for r in launches))
         for k in keys:
             if k in hdr:
-                f.write('%s,%s,%s\n' % (k, r[hdr.index(k)], units[hdr.index(k)]))
+                f.write('%s,%s,%s\n' % (k, units[hdr.index(k)], ','.join(r[hdr.index(k)].replace(',', '') for r in launches)))
     return out
 
 

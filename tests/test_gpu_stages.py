@@ -50,7 +50,7 @@ def _kkt_case(tag, oracle_models):
                                        ("pend_al", False), ("pend_al", True)])
 @pytest.mark.parametrize("batch", [1, 3])
 def test_kkt_schur_pcg_recover_merit(tag, dense_kkt, batch, oracle_models):
-    """dense_kkt=False: structured kernels when the cost is diagonal (k_kkt_diag / k_schur_diag / k_recover_diag);
+    """dense_kkt=False: structured kernels when the cost is diagonal (k_kkt_diag / k_schur_rows / k_recover_diag);
     dense_kkt=True: general dense-G_k kernels (always used for UrdfCost)."""
     K, plant, pc, pcons, m, oc, ocn, x, u, xs, N = _kkt_case(tag, oracle_models)
     n = m.n; nx = 2 * n; mm = 3 * n

@@ -70,6 +70,8 @@ struct SolverT : SolverBase {
   size_t stage_out_bytes = 0;
   T* ilqr_scratch = nullptr; T* ilqr_scratch_owned = nullptr;      // trial trajectories of the parallel iLQR line search
   int* h_count = nullptr;        // pinned
+  enum { COUNT_RING = 4 };
+  cudaEvent_t ev_count[COUNT_RING] = {nullptr, nullptr, nullptr, nullptr};
   bool schur_v1 = false;
   int* d_status = nullptr; double* d_scalars = nullptr;
   int* d_scratch = nullptr;
@@ -83,6 +85,7 @@ struct SolverT : SolverBase {
     if (h_count) cudaFreeHost(h_count);
     if (ev0) cudaEventDestroy(ev0);
     if (ev1) cudaEventDestroy(ev1);
+    for (auto e : ev_count) if (e) cudaEventDestroy(e);
     for (auto e : ev_pool) cudaEventDestroy(e);
   }
 
@@ -187,6 +190,7 @@ struct SolverT : SolverBase {
     { void* q; cudaError_t e = cudaMalloc(&q, stage_out_bytes); if (e != cudaSuccess) return fail(B2T_ERR_NOMEM, "cudaMalloc stage_out"); allocs.push_back(q); ws_bytes += stage_out_bytes; stage_out = (double*)q; }
     B2T_CUDA(cudaMallocHost((void**)&h_count, 64));
     B2T_CUDA(cudaEventCreate(&ev0)); B2T_CUDA(cudaEventCreate(&ev1));
+    for (int i = 0; i < COUNT_RING; ++i) B2T_CUDA(cudaEventCreateWithFlags(&ev_count[i], cudaEventDisableTiming));
     // kernels that need > 48 KB of dynamic shared memory
     B2T_CUDA(cudaFuncSetAttribute(b2t::k_pcg<T>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
     B2T_CUDA(cudaFuncSetAttribute(b2t::k_linesearch<T>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
@@ -545,6 +549,7 @@ struct SolverT : SolverBase {
     const long long cap = (long long)o->max_iter_soft * o->max_iter_SQP + 8;
     const bool legacy_ls = getenv("B2T_LEGACY_LS") && atoi(getenv("B2T_LEGACY_LS")) != 0;
     const bool trace_active = getenv("B2T_TRACE_ACTIVE") != nullptr;      // debugging: active-instance count after every SQP pass on stderr
+    const bool lagged = !hook && !trace_active && !(getenv("B2T_SYNC_PASSES") && atoi(getenv("B2T_SYNC_PASSES")) != 0);
     const size_t lsmem = (size_t)(5 + NX) * d.N * sizeof(T);
     const int lst = std::min(128, ((d.N + 31) / 32) * 32);
     const size_t osmem = std::max((size_t)3 * d.N * sizeof(T), msmem);
@@ -575,6 +580,20 @@ struct SolverT : SolverBase {
         { Scope sc(this, B2T_K_MERIT); k_outer_begin<T><<<n, mt, msmem, stream>>>(d, d.restart_list, d.n_restart, op, 0); tick(B2T_K_MERIT); }
       }
       { Scope sc(this, B2T_K_CTRL); k_compact<T><<<1, 1024, 0, stream>>>(d, d_scratch); tick(B2T_K_CTRL); }
+      if (lagged) {
+        // no host round trip between passes: the count of pass i is copied asynchronously and read one pass later.  The active count
+        // never grows, so the count of pass i-1 is a valid grid bound for pass i+1 (every kernel checks the device-side count), and
+        // the pass launched after the last instance finished finds an empty list.
+        const int slot = (int)(iter % COUNT_RING);
+        B2T_CUDA(cudaMemcpyAsync(h_count + slot, d.n_act, sizeof(int), cudaMemcpyDeviceToHost, stream));
+        B2T_CUDA(cudaEventRecord(ev_count[slot], stream));
+        if (iter >= 1) {
+          const int prev = (int)((iter - 1) % COUNT_RING);
+          B2T_CUDA(cudaEventSynchronize(ev_count[prev]));
+          n = h_count[prev];
+        }
+        continue;
+      }
       B2T_CUDA(cudaMemcpyAsync(h_count, d.n_act, sizeof(int), cudaMemcpyDeviceToHost, stream));
       B2T_CUDA(cudaStreamSynchronize(stream));
       n = h_count[0];
