@@ -15,10 +15,10 @@ timeout 600 ncu --metrics gpu__time_duration.sum --clock-control none -c 600 --c
 timeout 600 ncu --set full --clock-control none --import-source on -k regex:k_pcg3 -s 30 -c 1 -f -o /tmp/${TAG}_pcg3 \
   python bench.py --batch 2048 --steps 1 --warmup 1 --no-cpu-baseline > $O/${TAG}_ncu_pcg3.log 2>&1
 ncu -i /tmp/${TAG}_pcg3.ncu-rep --page raw --csv > $O/${TAG}_pcg3_raw.csv
-ncu -i /tmp/${TAG}_pcg3.ncu-rep --page source --csv --print-source sass | cut -d, -f1-12,33-50 > $O/${TAG}_pcg3_sass.csv
+ncu -i /tmp/${TAG}_pcg3.ncu-rep --page source --csv --print-source sass | gzip > $O/${TAG}_pcg3_sass.csv.gz
 timeout 600 ncu --set full --clock-control none --import-source on -k 'regex:k_schur_rows|k_pinv|k_linesearch|k_kkt_diag|k_fd' -s 40 -c 5 -f -o /tmp/${TAG}_others \
   python bench.py --batch 2048 --steps 1 --warmup 1 --no-cpu-baseline > $O/${TAG}_ncu_others.log 2>&1
 ncu -i /tmp/${TAG}_others.ncu-rep --page raw --csv > $O/${TAG}_others_raw.csv
-ncu -i /tmp/${TAG}_others.ncu-rep --page source --csv --print-source sass -k regex:k_linesearch | cut -d, -f1-12,33-50 > $O/${TAG}_linesearch_sass.csv
+ncu -i /tmp/${TAG}_others.ncu-rep --page source --csv --print-source sass -k regex:k_linesearch | gzip > $O/${TAG}_linesearch_sass.csv.gz
 ls -la /tmp/*.ncu-rep $O | tail -20
 tail -c 600 $O/${TAG}_bench_default.json
