@@ -189,18 +189,19 @@ def ncu_traffic(family, batch, launches_per_step, qp_per_instance):
     dynamics Jacobians, Ghat factors, preconditioner blocks and gamma are read once, l is written once)."""
     if family != "pcg":
         return None, "no ncu capture for this kernel family"
-    path = os.path.join(ROOT, "profiles", "r01_v6_ncu_full_k_pcg3.csv")
+    name = "r01_v7_ncu_full_k_pcg3.csv"
+    path = os.path.join(ROOT, "profiles", name)
     try:
         vals = {}
         with open(path) as f:
             for line in f:
-                parts = line.strip().split(",")
-                if len(parts) >= 2:
-                    vals[parts[0]] = parts[1]
+                parts = line.strip().split(",")       # metric,unit,value (scripts/profile_summary.py)
+                if len(parts) >= 3:
+                    vals[parts[0]] = parts[2]
         grid = float(vals["launch__grid_size"])
         per_inst = (float(vals["dram__bytes_read.sum"]) + float(vals["dram__bytes_write.sum"])) * 1e6 / grid
         inst_per_launch = batch * qp_per_instance / max(launches_per_step, 1)
-        return per_inst * inst_per_launch, "profiles/r01_v6_ncu_full_k_pcg3.csv: %.0f bytes per instance x %.0f instances per launch (avg)" % (per_inst, inst_per_launch)
+        return per_inst * inst_per_launch, "profiles/%s: %.0f bytes per instance x %.0f instances per launch (avg)" % (name, per_inst, inst_per_launch)
     except Exception as e:      # noqa: BLE001
         return None, "ncu capture unreadable: %s" % e
 

@@ -457,7 +457,7 @@ __global__ void __launch_bounds__(SCHUR_THREADS) k_schur_diag(Dev<T> d, const in
   });
 }
 
-// k_schur_rows: the same block row, NJ threads per knot -- thread (i, knot) owns row i of Ab in registers and produces rows i and
+// k_schur_rows: the same block row, NJ threads per knot -- thread (i, knot) stages row i of Ab and produces rows i and
 // NJ+i of S_jj / S_j,j-1 / gamma_j (the body of k_schur_diag's outer loop over i).  k_schur_diag runs one 1700-FMA chain per thread at
 // 8 warps per SM (255 registers, 55 KB of shared memory per 64 knots) and is pure latency (ncu: FP64 pipe 4 %, long-scoreboard stall
 // 18.8 cycles per issue); here the chain is NJ times shorter, the thread needs ~1/4 of the registers, and the per-knot vectors
@@ -466,8 +466,8 @@ __global__ void __launch_bounds__(SCHUR_THREADS) k_schur_diag(Dev<T> d, const in
 // shared-memory records (odd stride) are conflict-free.  Every sum keeps k_schur_diag's operand order: bit-identical outputs.
 enum { SCHUR_KB = 32 };
 constexpr int SCHUR_REC = (NJ * NM + 3 * NM + NX + NJ * NJ + NX) | 1;   // Ab, dinv/h/Gg of knot j-1, h_x of knot j, F, v
-template <typename T>
-__global__ void __launch_bounds__(SCHUR_KB * NJ, 3) k_schur_rows(Dev<T> d, const int* list, const int* count, int need_so) {
+template <typename T, int MINB>      // MINB: CTAs per SM the register allocation aims for (3: 96 registers, spills to L2; 2: 168, none -- measured 22.9 vs 31.5 ms)
+__global__ void __launch_bounds__(SCHUR_KB * NJ, MINB) k_schur_rows(Dev<T> d, const int* list, const int* count, int need_so) {
   extern __shared__ unsigned char smem_raw[];
   const int i = threadIdx.x / SCHUR_KB, jj = threadIdx.x % SCHUR_KB;
   T* rec = reinterpret_cast<T*>(smem_raw) + (size_t)jj * SCHUR_REC;
@@ -494,15 +494,13 @@ __global__ void __launch_bounds__(SCHUR_KB * NJ, 3) k_schur_rows(Dev<T> d, const
   const size_t tp = work ? t - 1 : t;
   const T dte = d.integrator == 0 ? d.dt : T(0);
   const T tau = d.integrator == 0 ? T(0) : d.dt;
-  T row[NM];
   if (act) {
     for (int e = i; e < NX; e += NJ) sHx[e] = GH(NM + e, t);
     if (work) {
       for (int e = i; e < NM; e += NJ) { sD[e] = GH(e, tp); sH[e] = GH(NM + e, tp); sG[e] = d.Gg[(size_t)e * K + tp]; }
       static_for<0, NM>([&](auto cc) {
         constexpr int c = decltype(cc)::value;
-        row[c] = d.dt * d.dyn[(size_t)(i * 3 * NJ + c) * K + tp] + ((c == NJ + i) ? T(1) : T(0));
-        sAb[i * NM + c] = row[c];
+        sAb[i * NM + c] = d.dt * d.dyn[(size_t)(i * 3 * NJ + c) * K + tp] + ((c == NJ + i) ? T(1) : T(0));
       });
     }
   }
@@ -516,7 +514,7 @@ __global__ void __launch_bounds__(SCHUR_KB * NJ, 3) k_schur_rows(Dev<T> d, const
     static_for<0, NM>([&](auto rc) {
       constexpr int r = decltype(rc)::value;
       const T dr = sD[r], hr = sH[r], gr = sG[r];
-      const T own = row[r];
+      const T own = sAb[i * NM + r];      // own row re-read from the record instead of a private register copy
       vbi += own * hr;
       wbi += own * gr;
       const T cdi = own * dr;
@@ -587,7 +585,7 @@ __global__ void __launch_bounds__(SCHUR_KB * NJ, 3) k_schur_rows(Dev<T> d, const
   if (need_so) static_for<0, NX>([&](auto cc) {
     constexpr int c = decltype(cc)::value;
     const T dc = sD[c], hc = sH[c];
-    const T ab = row[c];
+    const T ab = sAb[i * NM + c];
     const T e0 = ((c == i) ? T(1) : T(0)) + ((c == NJ + i) ? dte : T(0));
     So_o[(size_t)(i * NX + c) * K + j] = (e0 + tau * ab) * dc - sp * vi * hc;
     So_o[(size_t)((NJ + i) * NX + c) * K + j] = ab * dc - sp * vni * hc;
@@ -1582,12 +1580,12 @@ __global__ void __launch_bounds__(128) k_linesearch(Dev<T> d, Opts<T> o, int fus
   const int b = d.act[blockIdx.x];
   const int N = d.N;
   const size_t K = d.K;
+  extern __shared__ unsigned char smem_raw[];
+  T* sm = reinterpret_cast<T*>(smem_raw);
   // the step dz_k of the structured path is computed here (what k_recover_diag does in its own launch): each thread produces
   // the knots it evaluates below, so no barrier is needed
   if (fuse_recover)
     for (int k = threadIdx.x; k < N; k += blockDim.x) recover_diag_knot(d, b, k);
-  extern __shared__ unsigned char smem_raw[];
-  T* sm = reinterpret_cast<T*>(smem_raw);
   T* s_cost = sm; T* s_soft = sm + N; T* s_c = sm + 2 * N; T* s_D = sm + 3 * N; T* s_Ds = sm + 4 * N; T* s_xn = sm + 5 * N;   // [N][NX]
   __shared__ int s_state;     // 0: accepted, 1: try a smaller alpha, 2: failed
   __shared__ int s_exit;      // the SQP loop of this instance exited

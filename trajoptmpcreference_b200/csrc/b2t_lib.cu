@@ -73,6 +73,7 @@ struct SolverT : SolverBase {
   enum { COUNT_RING = 4 };
   cudaEvent_t ev_count[COUNT_RING] = {nullptr, nullptr, nullptr, nullptr};
   bool schur_v1 = false;
+  int schur_minb = 2;
   int* d_status = nullptr; double* d_scalars = nullptr;
   int* d_scratch = nullptr;
   cudaEvent_t ev0 = nullptr, ev1 = nullptr;
@@ -195,7 +196,9 @@ struct SolverT : SolverBase {
     B2T_CUDA(cudaFuncSetAttribute(b2t::k_pcg<T>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
     B2T_CUDA(cudaFuncSetAttribute(b2t::k_linesearch<T>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
     B2T_CUDA(cudaFuncSetAttribute(b2t::k_schur_diag<T>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)((size_t)NJ * NM * SCHUR_THREADS * sizeof(T))));
-    B2T_CUDA(cudaFuncSetAttribute(b2t::k_schur_rows<T>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)((size_t)SCHUR_REC * SCHUR_KB * sizeof(T))));
+    B2T_CUDA(cudaFuncSetAttribute(b2t::k_schur_rows<T, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)((size_t)SCHUR_REC * SCHUR_KB * sizeof(T))));
+    B2T_CUDA(cudaFuncSetAttribute(b2t::k_schur_rows<T, 3>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)((size_t)SCHUR_REC * SCHUR_KB * sizeof(T))));
+    { const char* e = getenv("B2T_SCHUR_MINB"); schur_minb = (e && atoi(e) == 3) ? 3 : 2; }
     { const char* e = getenv("B2T_SCHUR_V1"); schur_v1 = e && atoi(e) != 0; }     // A/B switch: the one-thread-per-block-row kernel
     B2T_CUDA(cudaFuncSetAttribute(b2t::k_pcg2<T, PCG_RPT, 1, true, 256>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
     B2T_CUDA(cudaFuncSetAttribute(b2t::k_pcg2<T, PCG_RPT, 1, true, 512>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
@@ -413,7 +416,13 @@ struct SolverT : SolverBase {
       const int need_so = (all_outputs || exact || !(pcg_variant == 3 || pcg_variant == 4)) ? 1 : 0;
       { Scope sc(this, B2T_K_KKT); k_kkt_diag<T><<<cdiv(nthreads, 128), 128, 0, stream>>>(d, list, count); tick(B2T_K_KKT); }
       if (schur_v1) { Scope sc(this, B2T_K_SCHUR); k_schur_diag<T><<<cdiv(nthreads, SCHUR_THREADS), SCHUR_THREADS, (size_t)NJ * NM * SCHUR_THREADS * sizeof(T), stream>>>(d, list, count, need_so); tick(B2T_K_SCHUR); }
-      else { Scope sc(this, B2T_K_SCHUR); k_schur_rows<T><<<cdiv(nthreads, SCHUR_KB), SCHUR_KB * NJ, (size_t)SCHUR_REC * SCHUR_KB * sizeof(T), stream>>>(d, list, count, need_so); tick(B2T_K_SCHUR); }
+      else {
+        Scope sc(this, B2T_K_SCHUR);
+        const size_t sm = (size_t)SCHUR_REC * SCHUR_KB * sizeof(T);
+        if (schur_minb == 3) k_schur_rows<T, 3><<<cdiv(nthreads, SCHUR_KB), SCHUR_KB * NJ, sm, stream>>>(d, list, count, need_so);
+        else k_schur_rows<T, 2><<<cdiv(nthreads, SCHUR_KB), SCHUR_KB * NJ, sm, stream>>>(d, list, count, need_so);
+        tick(B2T_K_SCHUR);
+      }
       if (method != B2T_METHOD_N && method != B2T_METHOD_S) {
         Scope sc(this, B2T_K_SCHUR); k_pinv<T><<<cdiv(nthreads, 128), 128, 0, stream>>>(d, list, count, jac); tick(B2T_K_SCHUR);
       }
