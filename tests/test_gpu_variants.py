@@ -1,0 +1,86 @@
+"""-m gpu: kernel variants that claim bit-identical results must produce them.
+
+k_schur_rows (n threads per block row; 2- and 3-CTA register allocations) against k_schur_diag (one thread per block row,
+B2T_SCHUR_V1=1), and the asynchronous active-count read-back against the blocking one (B2T_SYNC_PASSES=1) on complete solves.
+The switches are read when a solver is created / a solve starts, so each variant gets its own BatchSolver."""
+import os
+
+import numpy as np
+import pytest
+
+import trajoptmpcreference_b200 as t
+from gpu_common import make_pair
+
+pytestmark = pytest.mark.gpu
+
+
+class _env:
+    def __init__(self, **kv):
+        self.kv = kv
+
+    def __enter__(self):
+        self.old = {k: os.environ.get(k) for k in self.kv}
+        for k, v in self.kv.items():
+            if v is None:
+                os.environ.pop(k, None)
+            else:
+                os.environ[k] = v
+
+    def __exit__(self, *a):
+        for k, v in self.old.items():
+            if v is None:
+                os.environ.pop(k, None)
+            else:
+                os.environ[k] = v
+
+
+def _problem(name, N, batch, oracle_models, seed):
+    m = oracle_models[name]
+    n = m.n
+    rng = np.random.default_rng(seed)
+    xg = np.concatenate([rng.uniform(-0.5, 0.5, n), np.zeros(n)])
+    limits = {"torque": ([1.0] * n, [-1.0] * n, "QUADRATIC_PENALTY"), "joint": ([0.45] * n, [-0.45] * n, "QUADRATIC_PENALTY")}
+    (plant, pc, pcons), _ = make_pair(name, N, oracle_models, xg=xg, limits=limits)
+    x = 0.3 * rng.standard_normal((batch, 2 * n, N))
+    u = 0.5 * rng.standard_normal((batch, n, N - 1))
+    return plant, pc, pcons, x, u
+
+
+@pytest.mark.parametrize("name,N", [("arm6", 64), ("arm6", 9), ("arm2", 33), ("pend", 5)])
+@pytest.mark.parametrize("rho", [1e-3, 4.0])
+def test_schur_variants_bit_identical(name, N, rho, oracle_models):
+    batch = 3
+    out = {}
+    for tag, env in (("rows2", dict(B2T_SCHUR_V1=None, B2T_SCHUR_MINB=None)), ("rows3", dict(B2T_SCHUR_V1=None, B2T_SCHUR_MINB="3")),
+                     ("diag", dict(B2T_SCHUR_V1="1", B2T_SCHUR_MINB=None))):
+        with _env(**env):
+            plant, pc, pcons, x, u = _problem(name, N, batch, oracle_models, seed=N)      # fresh objects: constraints carry state
+            s = t.BatchSolver(plant, pc, pcons, N=N, dt=0.1, batch=batch)
+            s.set_trajectory(x, u)
+            s.set_initial_state(x[:, :, 0] + 0.01)
+            s.stage_dynamics()
+            s.stage_kkt(rho, t.SQPSolverMethods.S)        # exact method: the sub-diagonal blocks are written too
+            out[tag] = [s.fetch(k).copy() for k in ("Sd", "So", "gamma")]
+            del s
+    for tag in ("rows3", "diag"):
+        for a, b, k in zip(out["rows2"], out[tag], ("Sd", "So", "gamma")):
+            assert np.array_equal(a, b), (tag, k, float(np.max(np.abs(a - b))))
+
+
+def test_lagged_count_readback_identical(oracle_models):
+    """complete solves: the pass loop that reads the active count one pass late returns exactly what the blocking loop returns"""
+    N, batch = 16, 37
+    res = {}
+    for tag, env in (("lagged", dict(B2T_SYNC_PASSES=None)), ("sync", dict(B2T_SYNC_PASSES="1"))):
+        with _env(**env):
+            plant, pc, pcons, x, u = _problem("arm6", N, batch, oracle_models, seed=5)
+            s = t.BatchSolver(plant, pc, pcons, N=N, dt=0.1, batch=batch)
+            s.set_trajectory(np.zeros_like(x), np.zeros_like(u))
+            s.set_initial_state(np.zeros((batch, x.shape[1])))
+            s.set_goals(np.concatenate([np.random.default_rng(9).uniform(-0.5, 0.5, (batch, 6)), np.zeros((batch, 6))], axis=1))
+            s.solve(t.SQPSolverMethods.PCG_SS, options={"expected_reduction_min_SQP_DDP": -100})
+            res[tag] = s.result()
+            del s
+    a, b = res["lagged"], res["sync"]
+    assert np.array_equal(a.x, b.x) and np.array_equal(a.u, b.u)
+    assert np.array_equal(a.sqp_iter, b.sqp_iter) and np.array_equal(a.exit_sqp, b.exit_sqp) and np.array_equal(a.exit_soft, b.exit_soft)
