@@ -189,7 +189,7 @@ def ncu_traffic(family, batch, launches_per_step, qp_per_instance):
     dynamics Jacobians, Ghat factors, preconditioner blocks and gamma are read once, l is written once)."""
     if family != "pcg":
         return None, "no ncu capture for this kernel family"
-    name = "r01_v7_ncu_full_k_pcg3.csv"
+    name = "r01_v8_ncu_full_k_pcg3.csv"
     path = os.path.join(ROOT, "profiles", name)
     try:
         vals = {}
