@@ -22,6 +22,13 @@ import sys
 import threading
 import time
 
+# CPU arms (--impl reference, --cpu-worker): one BLAS / OpenMP thread per process, exported BEFORE numpy is imported (a pin set
+# after the import does not reach the already-initialised thread pools); parallelism comes from processes, the reference's own
+# pattern (examples/test_multiple.py:123-128)
+if "--cpu-worker" in sys.argv or ("--impl" in sys.argv and sys.argv[sys.argv.index("--impl") + 1:][:1] == ["reference"]) or "--impl=reference" in sys.argv:
+    for _v in ("OMP_NUM_THREADS", "OPENBLAS_NUM_THREADS", "MKL_NUM_THREADS", "NUMEXPR_NUM_THREADS"):
+        os.environ[_v] = "1"
+
 import numpy as np
 
 ROOT = os.path.dirname(os.path.abspath(__file__))
@@ -41,9 +48,10 @@ def goals(total, seed):
     return xg
 
 
-def workload_goals(world, rank, batch):
-    """C4 (1 GPU, default_rng(1)) / C5 (N GPUs: default_rng(2), contiguous shards)."""
-    if world == 1:
+def workload_goals(world, rank, batch, c5=False):
+    """C4 (1 GPU, default_rng(1)) / C5 (N GPUs: default_rng(2), contiguous shards of `batch`).  c5=True at world 1 gives shard 0 of
+    the C5 stream, so that a scaling series N = 1, 2, 4, 8 run with --workload c5 compares the same kind of shard at every N."""
+    if world == 1 and not c5:
         return goals(batch, 1)
     return goals(batch * world, 2)[rank * batch:(rank + 1) * batch]
 
@@ -111,7 +119,13 @@ class ClockSampler(threading.Thread):
                 "reasons": reasons, "samples": len(self.rows)}
 
 
-# ------------------------------------------------------------------------------------------------ CPU arms (oracle port)
+# ------------------------------------------------------------------------------------------------ CPU arms
+# Two CPU implementations are timed on the box's host cores (never on the product path):
+#   "port"      oracle/sqp.py, the numpy restatement (block-structured, no sympy): runs the FULL workload incl. the multi-coordinate
+#               box limits, on which the reference itself crashes;
+#   "reference" the UNMODIFIED reference staged in oracle/_ref by oracle/build_ref.py, imported through tests/ref/refshim.py
+#               (stock, or with the bit-identical lambdify memoisation of SURVEY.md 0.10): runs the reference-pinned variant
+#               (same robot / horizon / cost / goals, no box limits).
 def _oracle_problem(use_limits):
     from oracle import rbd, cost as ocost, constraint as ocons
     with open(os.path.join(ROOT, "tests", "golden", "models.json")) as f:
@@ -125,72 +139,174 @@ def _oracle_problem(use_limits):
     return model, c, cons
 
 
-def _oracle_solve(args):
+def _oracle_solve_full(args):
     xg, use_limits = args
-    os.environ.setdefault("OMP_NUM_THREADS", "1")
     from oracle import sqp
     model, c, cons = _oracle_problem(use_limits)
     c.xg = np.asarray(xg)
     r = sqp.sqp(model, c, cons, np.zeros((12, N_KNOTS)), np.zeros((6, N_KNOTS - 1)), N_KNOTS, DT, "PCG-SS", dict(SOLVER_OPTS))
-    return r["J"], len(r["pcg_iters"]), sum(r["pcg_iters"]), sum(r["ls_trials"])
+    return dict(J=r["J"], counts=[r["exit_sqp"], r["exit_soft"], r["outer_iter"], r["sqp_iter"], len(r["pcg_iters"]), sum(r["pcg_iters"]), sum(r["ls_trials"])],
+                x=r["x"], u=r["u"])
 
 
-def cpu_baseline_port(xg, use_limits, budget_s=20.0, max_instances=8):
-    """Oracle port, 1 process, sequential over the first instances of the workload until ~budget_s of CPU work."""
-    t0 = time.perf_counter()
+def _oracle_solve(args):
+    r = _oracle_solve_full(args)
+    return r["J"], r["counts"][4], r["counts"][5], r["counts"][6]
+
+
+_REF_NS = {}
+
+
+def _reference_solve(args):
+    """One SQP solve of the staged, unmodified reference (no box limits).  args = (xg, memoise)."""
+    xg, memoise = args
+    key = bool(memoise)
+    if key not in _REF_NS:
+        os.environ["B2T_REFERENCE"] = os.path.join(ROOT, "oracle", "_ref")
+        sys.path.insert(0, os.path.join(ROOT, "tests", "ref"))
+        import refshim
+        _REF_NS[key] = refshim.load(memoise=key)
+    R = _REF_NS[key]
+    import io
+    import contextlib
+    urdf = os.path.join(ROOT, "trajoptmpcreference_b200", "urdf", "arm6.urdf")
+    plant = R.URDFPlant(integrator_type=0, options={"path_to_urdf": urdf, "overloading": False, "gravity": -9.81})
+    cost = R.QC(np.eye(12), 100.0 * np.eye(12), 0.1 * np.eye(6), np.asarray(xg, dtype=float))
+    solver = R.TrajoptMPCReference(plant, cost)
+    o = dict(SOLVER_OPTS); o["overloading"] = False
+    with contextlib.redirect_stdout(io.StringIO()):
+        x, u, e1, e2, outer, it = solver.SQP(np.zeros((12, N_KNOTS)), np.zeros((6, N_KNOTS - 1)), N_KNOTS, DT, R.SQPSolverMethods.PCG_SS, options=o)
+        J = float(solver.totalCost(x, u, N_KNOTS))
+    return dict(J=J, counts=[int(e1), int(e2), int(outer), int(it)], x=np.array(x), u=np.array(u))
+
+
+def reference_staged():
+    return os.path.isfile(os.path.join(ROOT, "oracle", "_ref", "TrajoptMPCReference.py"))
+
+
+def pool_throughput(fn, tasks, warm, cores):
+    """Throughput of a persistent process pool over a continuous stream of tasks (no per-step barrier: a step is a group of
+    consecutive completions).  The first `warm` completions are warm-up; returns (seconds for the rest, their count)."""
+    import multiprocessing as mp
+    t_start = None
     done = 0
-    for b in range(min(max_instances, len(xg))):
-        _oracle_solve((xg[b], use_limits))
-        done += 1
-        if time.perf_counter() - t0 > budget_s:
-            break
-    el = time.perf_counter() - t0
-    return {"value": done / el, "unit": "solves/s", "cores": 1, "kind": "port",
-            "sample": "first %d instances of the workload, sequential, numpy oracle (oracle/sqp.py), %.1f s" % (done, el)}
+    with mp.get_context("fork").Pool(cores) as pool:
+        if warm == 0:
+            t_start = time.perf_counter()
+        for _ in pool.imap_unordered(fn, tasks, chunksize=1):
+            done += 1
+            if done == warm:
+                t_start = time.perf_counter()
+        t_end = time.perf_counter()
+    return t_end - t_start, len(tasks) - warm
+
+
+def cpu_worker(args):
+    """`bench.py --cpu-worker MODE`: the cpu_baseline legs of the GPU arm, run as a child process so that the thread pins above
+    apply before numpy loads.  Writes one JSON line to stdout (and arrays to --out)."""
+    xg = workload_goals(1, 0, args.batch, c5=args.workload == "c5")
+    if args.cpu_worker == "port-seq":
+        t0 = time.perf_counter()
+        res = []
+        for b in range(min(args.max_instances, len(xg))):
+            res.append(_oracle_solve_full((xg[b], bool(args.limits))))
+            if time.perf_counter() - t0 > args.budget:
+                break
+        el = time.perf_counter() - t0
+        if args.out:
+            np.savez(args.out, J=np.array([r["J"] for r in res]), counts=np.array([r["counts"] for r in res]),
+                     x=np.stack([r["x"] for r in res]), u=np.stack([r["u"] for r in res]))
+        print(json.dumps({"value": len(res) / el, "unit": "solves/s", "cores": 1, "kind": "port",
+                          "sample": "first %d instances of the workload, sequential, numpy oracle (oracle/sqp.py), 1 BLAS thread, %.1f s" % (len(res), el)}))
+    elif args.cpu_worker == "ref-anchor":
+        # the reference-pinned variant (no limits) with the unmodified reference: memoised lambdify (bit-identical), optionally stock
+        out = {}
+        k = 0
+        t0 = time.perf_counter()
+        while k < min(args.max_instances, len(xg)) and time.perf_counter() - t0 < args.budget:
+            _reference_solve((xg[k], True)); k += 1
+        out["memoised"] = {"value": k / (time.perf_counter() - t0), "unit": "solves/s", "cores": 1, "kind": "reference",
+                           "sample": "first %d instances, no box limits, unmodified reference (oracle/_ref) with memoised sympy lambdify" % k}
+        if args.stock:
+            t0 = time.perf_counter()
+            _reference_solve((xg[0], False))
+            out["stock"] = {"value": 1.0 / (time.perf_counter() - t0), "unit": "solves/s", "cores": 1, "kind": "reference",
+                            "sample": "instance 0, no box limits, unmodified reference (oracle/_ref), stock (sympy lambdify per joint lookup)"}
+        print(json.dumps(out))
+
+
+def run_cpu_worker(mode, args, extra):
+    cmd = [sys.executable, os.path.abspath(__file__), "--cpu-worker", mode, "--batch", str(args.batch), "--limits", str(args.limits),
+           "--workload", args.workload] + extra
+    res = subprocess.run(cmd, capture_output=True, text=True)
+    if res.returncode != 0:
+        return {"error": (res.stderr or res.stdout)[-400:]}
+    return json.loads(res.stdout.strip().splitlines()[-1])
 
 
 def run_reference_arm(args):
-    """--impl reference: the reference's algorithm on all host cores (multiprocessing.Pool over instances, the reference's own
-    fan-out pattern, examples/test_multiple.py:127).  Rank 0 only."""
+    """--impl reference: the reference's algorithm on ALL host cores, timed as throughput of a persistent multiprocessing pool over a
+    continuous stream of instances (the reference's own fan-out pattern, examples/test_multiple.py:123-128; no per-step barrier, so
+    the figure is not the slowest instance of a small group).  The workload with box limits can only be run by the oracle port (the
+    reference crashes on multi-coordinate limits) -> kind "port"; `reference_anchor` adds the unmodified reference
+    (oracle/_ref) on the no-limits variant of the same instances.  Rank 0 only."""
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
-    import multiprocessing as mp
     cores = os.cpu_count() or 1
-    xg = workload_goals(args.gpus, 0, args.batch)
-    S = min(len(xg), cores)
-    sample = [(xg[b], bool(args.limits)) for b in range(S)]
-    ctx = mp.get_context("fork")
-    times = []
-    with ctx.Pool(cores) as pool:
-        for step in range(args.warmup + args.steps):
-            t0 = time.perf_counter()
-            pool.map(_oracle_solve, sample, chunksize=1)
-            el = time.perf_counter() - t0
-            if step >= args.warmup:
-                times.append(el)
-    total = sum(times)
-    value = S * args.steps / total
-    line = {"metric": METRIC, "value": value, "unit": "solves/s", "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
-            "ms_per_step": 1e3 * total / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64",
-            "data": "synthetic", "impl": "reference",
-            "config": config_dict(args, note="CPU arm: each step solves the first %d instances of the workload" % S),
-            "cpu_baseline": {"value": value, "unit": "solves/s", "cores": cores, "kind": "port",
-                             "sample": "first %d instances per step, multiprocessing.Pool(%d), numpy oracle (oracle/sqp.py)" % (S, cores)},
+    xg = workload_goals(args.gpus, 0, args.batch, c5=args.workload == "c5")
+    steps, warm_steps = args.steps, args.warmup
+    # instances per step: bounded so that the whole run ends within a few minutes (~1.5-2.5 s per instance and core)
+    per_step = int(max(cores, min(8 * cores, (150.0 * cores / 2.5) // max(1, steps + warm_steps))))
+    total = per_step * (steps + warm_steps)
+    tasks = [(xg[i % len(xg)], bool(args.limits)) for i in range(total)]
+    sec, cnt = pool_throughput(_oracle_solve, tasks, per_step * warm_steps, cores)
+    value = cnt / sec
+    sample = "continuous stream of %d instances per step (first instances of the workload, %d steps + %d warm-up), persistent " \
+             "multiprocessing.Pool(%d), 1 BLAS thread per process, numpy oracle (oracle/sqp.py)" % (per_step, steps, warm_steps, cores)
+    line = {"metric": METRIC, "value": value, "unit": "solves/s", "n_gpus": args.gpus, "steps": steps, "warmup": warm_steps,
+            "ms_per_step": 1e3 * sec / steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64",
+            "data": "synthetic", "impl": "reference", "config": config_dict(args),
+            "cpu_baseline": {"value": value, "unit": "solves/s", "cores": cores, "kind": "port", "sample": sample},
             "e2e": {"value": value, "unit": "solves/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
-            "gpu_launches": 0}
+            "gpu_launches": 0, "instances_per_step": per_step}
+    if reference_staged() and not args.no_ref_anchor:
+        # unmodified reference, no-limits variant: memoised x all cores (pool), memoised x 1, and (--stock) the stock reference
+        n_ref = 2 * cores
+        tasks = [(xg[i % len(xg)], True) for i in range(n_ref + cores)]
+        try:
+            sec_r, cnt_r = pool_throughput(_reference_solve, tasks, cores, cores)
+            anchor = {"memoised_pool": {"value": cnt_r / sec_r, "unit": "solves/s", "cores": cores, "kind": "reference",
+                                        "sample": "%d instances (no box limits), unmodified reference from oracle/_ref, memoised lambdify, Pool(%d)" % (cnt_r, cores)}}
+            anchor.update(run_cpu_worker("ref-anchor", args, ["--budget", "12", "--max-instances", "3"] + (["--stock"] if args.stock else [])))
+            sec_p, cnt_p = pool_throughput(_oracle_solve, [(xg[i % len(xg)], False) for i in range(9 * cores)], cores, cores)
+            anchor["port_pool_nolimits"] = {"value": cnt_p / sec_p, "unit": "solves/s", "cores": cores, "kind": "port",
+                                            "sample": "%d instances (no box limits), numpy oracle, Pool(%d)" % (cnt_p, cores)}
+            line["reference_anchor"] = anchor
+        except Exception as e:      # noqa: BLE001
+            line["reference_anchor"] = {"error": repr(e)[:300]}
     print(json.dumps(line))
 
 
-def ncu_traffic(family, batch, launches_per_step, qp_per_instance):
-    """DRAM bytes per launch of the dominant kernel from the committed `ncu --set full` capture (profiles/): the capture gives
-    dram__bytes_read.sum + dram__bytes_write.sum for ONE launch over `launch__grid_size` instances; scaled to the average number
-    of instances per launch of this run (the per-instance traffic of k_pcg3 does not depend on the batch: every instance's
-    dynamics Jacobians, Ghat factors, preconditioner blocks and gamma are read once, l is written once)."""
+def ncu_traffic(family, batch, launches_per_step, qp_per_instance, kernel_name=None):
+    """DRAM bytes per launch of the dominant kernel from the NEWEST committed `ncu --set full` capture of that kernel under
+    profiles/ (files named r<round>_v<n>_ncu_full_<kernel>.csv; the line names the file, so a stale capture is visible): the capture
+    gives dram__bytes_read.sum + dram__bytes_write.sum for ONE launch over `launch__grid_size` instances; scaled to the average
+    number of instances per launch of this run (per-instance traffic of the PCG kernels does not depend on the batch: every
+    instance's dynamics Jacobians, Ghat factors, preconditioner blocks and gamma are read once, l is written once)."""
     if family != "pcg":
         return None, "no ncu capture for this kernel family"
-    name = "r01_v8_ncu_full_k_pcg3.csv"
-    path = os.path.join(ROOT, "profiles", name)
+    import glob
+    import re
+    cands = []
+    for path in glob.glob(os.path.join(ROOT, "profiles", "r*_v*_ncu_full_k_pcg*.csv")):
+        m = re.match(r"r(\d+)_v(\d+)_ncu_full_(k_pcg\w*)\.csv", os.path.basename(path))
+        if m and (kernel_name is None or m.group(3) == kernel_name):
+            cands.append(((int(m.group(1)), int(m.group(2))), path))
+    if not cands:
+        return None, "no ncu capture of %s under profiles/" % (kernel_name or "the PCG kernel")
+    path = max(cands)[1]
+    name = os.path.basename(path)
     try:
         vals = {}
         with open(path) as f:
@@ -206,15 +322,14 @@ def ncu_traffic(family, batch, launches_per_step, qp_per_instance):
         return None, "ncu capture unreadable: %s" % e
 
 
-def config_dict(args, note=None):
-    c = {"workload": "C4/C5: arm6 (6-link planar chain) SQP PCG-SS, N=64, dt=0.1, euler, QuadraticCost Q=I QF=100I R=0.1I, "
-                     "goals U(-0.5,0.5)^6 seeded, %s, batch %d per GPU" %
-                     ("quadratic-penalty box limits |u|<=1.0 |q|<=0.45" if args.limits else "no box limits", args.batch),
-         "batch_per_gpu": args.batch, "knots": N_KNOTS, "method": "PCG-SS", "limits": bool(args.limits),
-         "l2": "no explicit flush: the per-step working set (solver workspace, see workspace_gb) exceeds the 126 MB L2 at the default batch"}
-    if note:
-        c["note"] = note
-    return c
+def config_dict(args):
+    """Identical in both arms (the driver compares them)."""
+    return {"workload": "%s: arm6 (6-link planar chain) SQP PCG-SS, N=64, dt=0.1, euler, QuadraticCost Q=I QF=100I R=0.1I, "
+                        "goals U(-0.5,0.5)^6 seeded, %s, batch %d per GPU" %
+                        ("C5 shards (default_rng(2))" if (args.workload == "c5" or args.gpus > 1) else "C4 (default_rng(1))",
+                         "quadratic-penalty box limits |u|<=1.0 |q|<=0.45" if args.limits else "no box limits", args.batch),
+            "batch_per_gpu": args.batch, "knots": N_KNOTS, "method": "PCG-SS", "limits": bool(args.limits),
+            "l2": "no explicit flush: the per-step working set (solver workspace, see workspace_gb) exceeds the 126 MB L2 at the default batch"}
 
 
 # ------------------------------------------------------------------------------------------------ GPU arm
@@ -233,8 +348,12 @@ def run_b200_arm(args):
         if os.environ.get("NCCL_DEBUG", "").upper() in ("", "VERSION", "WARN"):      # keep stdout to the single JSON line:
             os.environ["NCCL_DEBUG"] = "NONE"                                        # VERSION / WARN print "NCCL version ..." there
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+    if args.total:          # strong scaling (BASELINE config C5 as stated: 65 536 instances over 2 / 4 / 8 GPUs)
+        if args.total % world:
+            raise SystemExit("--total must be a multiple of the number of GPUs")
+        args.batch = args.total // world
     B, N = args.batch, N_KNOTS
-    xg_np = workload_goals(world, rank, B)
+    xg_np = workload_goals(world, rank, B, c5=args.workload == "c5")
 
     plant = t.URDFPlant(options={"path_to_urdf": "arm6"})
     cost = t.QuadraticCost(np.eye(12), 100.0 * np.eye(12), 0.1 * np.eye(6), np.zeros(12))
@@ -342,7 +461,7 @@ def run_b200_arm(args):
         dom_launch = fam[dom][1] / args.steps if fam else 1
         ach = fam_flops[dom] / dom_sec / 1e12 if dom_sec > 0 else 0.0
         alg_bytes = B * (2 * 8 * (12 * N + 6 * (N - 1)) + 8 * 12 + 64)
-        traffic, traffic_src = ncu_traffic(dom, B, dom_launch, qp / B if B else 0)
+        traffic, traffic_src = ncu_traffic(dom, B, dom_launch, qp / B if B else 0, solver.pcg_kernel_name() if dom == "pcg" else None)
         roof = {"bound": "fp64_fma" if args.dtype == "f64" else "fp32_fma", "kernel": "k_" + dom, "achieved": ach, "peak": peak64, "unit": "TFLOP/s",
                 "frac": ach / peak64 if peak64 else None, "traffic": traffic, "traffic_source": traffic_src,
                 "peak_source": "measured in this run: DFMA chain micro-benchmark b2t_measure_fma_peak (MEASURED_PEAKS.json has no fp64 entry)",
@@ -359,15 +478,33 @@ def run_b200_arm(args):
         h2d = (hx0.numel() + hu0.numel() + hxg.numel()) * 8
         d2h = (hxo.numel() + huo.numel()) * 8 + hst.numel() * 4
         line = {"metric": METRIC, "value": value, "unit": "solves/s", "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3),
-                "ms_per_step": 1e3 * sec / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": args.dtype,
+                "ms_per_step": 1e3 * sec / args.steps, "higher_is_better": True, "scaling": "strong" if args.total else "weak", "vs_baseline": None, "dtype": args.dtype,
                 "data": "synthetic", "config": config_dict(args), "clocks": sampler.summary(),
                 "e2e": {"value": total_solves / sec_e2e, "unit": "solves/s", "h2d_bytes_per_step": h2d * world, "d2h_bytes_per_step": d2h * world},
                 "gpu_launches": launches, "roofline": roof,
                 "iterations": {"qp_solves_per_instance": qp / B, "pcg_iters_per_instance": pcg / B, "ls_trials_per_instance": trials / B,
                                "exit_sqp_hist": np.bincount(r.exit_sqp, minlength=4).tolist(), "exit_soft_hist": np.bincount(r.exit_soft, minlength=4).tolist()},
                 "host_wall_s": wall, "workspace_gb": solver.workspace_bytes / 1e9}
+        line["passes"] = pass_stats
         if world == 1 and not args.no_cpu_baseline:
-            line["cpu_baseline"] = cpu_baseline_port(xg_np, bool(args.limits))
+            # oracle port, 1 core, first instances of this workload (child process: thread pins before numpy loads); the same
+            # instances are then compared with the GPU results of the timed steps -> parity_check
+            import tempfile
+            tmp = os.path.join(tempfile.gettempdir(), "b2t_cpu_baseline_%d.npz" % os.getpid())
+            cb = run_cpu_worker("port-seq", args, ["--budget", "20", "--max-instances", "8", "--out", tmp])
+            line["cpu_baseline"] = cb
+            if "error" not in cb and os.path.isfile(tmp):
+                o = np.load(tmp)
+                k = len(o["J"])
+                st = np.stack([r.exit_sqp[:k], r.exit_soft[:k], r.outer_iter[:k], r.sqp_iter[:k], r.total_qp[:k], r.total_pcg[:k], r.total_trials[:k]], axis=1)
+                same = np.all(st == o["counts"], axis=1)
+                relJ = np.abs(np.asarray(r.J[:k]) - o["J"]) / np.maximum(1.0, np.abs(o["J"]))
+                dx = np.max(np.abs(np.asarray(r.x[:k]) - o["x"]).reshape(k, -1), axis=1)
+                line["parity_check"] = {"matched": int(same.sum()), "of": int(k), "what": "exit codes, outer / SQP iterations, QP solves, PCG iterations, line-search trials of "
+                                        "the first instances of the batch vs the oracle run in the cpu_baseline leg",
+                                        "max_rel_J": float(relJ[same].max()) if same.any() else None, "max_abs_x": float(dx[same].max()) if same.any() else None,
+                                        "max_rel_J_all": float(relJ.max()), "max_abs_x_all": float(dx.max())}
+                os.remove(tmp)
         print(json.dumps(line))
     if world > 1:
         dist.barrier()
@@ -384,7 +521,18 @@ def main():
     ap.add_argument("--dtype", default="f64", choices=["f64", "f32"])
     ap.add_argument("--limits", type=int, default=1)
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--workload", default="c4", choices=["c4", "c5"], help="c5: shard 0 of the C5 goal stream also at 1 GPU (scaling series)")
+    ap.add_argument("--total", type=int, default=0, help="strong scaling: this many instances in total, split over the GPUs")
+    ap.add_argument("--stock", action="store_true", help="reference arm: also time ONE solve of the stock (un-memoised) reference (~100 s)")
+    ap.add_argument("--no-ref-anchor", action="store_true")
+    ap.add_argument("--cpu-worker", default=None, choices=["port-seq", "ref-anchor"], help=argparse.SUPPRESS)
+    ap.add_argument("--budget", type=float, default=20.0, help=argparse.SUPPRESS)
+    ap.add_argument("--max-instances", type=int, default=8, help=argparse.SUPPRESS)
+    ap.add_argument("--out", default=None, help=argparse.SUPPRESS)
     args = ap.parse_args()
+    if args.cpu_worker:
+        cpu_worker(args)
+        return
     if args.impl == "reference":
         run_reference_arm(args)
     else:

@@ -43,7 +43,8 @@ typedef enum {
   B2T_ERR_INVALID = -1,      /* bad argument (the reference print()s and exit()s) */
   B2T_ERR_CUDA = -2,         /* CUDA runtime error; see b2t_last_error */
   B2T_ERR_UNSUPPORTED = -3,  /* e.g. the end-effector cost on a 1-joint robot, integrator types 2-4 */
-  B2T_ERR_NOMEM = -4
+  B2T_ERR_NOMEM = -4,
+  B2T_ERR_UNFINISHED = -5    /* the pass budget ran out with instances still active (results of the others are valid) */
 } b2t_status;
 
 typedef enum { B2T_COST_QUADRATIC = 0, B2T_COST_URDF_EE = 1 } b2t_cost_kind;
@@ -178,6 +179,11 @@ enum { B2T_K_FD = 0, B2T_K_FDGRAD, B2T_K_KKT, B2T_K_SCHUR, B2T_K_PCG, B2T_K_RECO
 /* mode 0: no events; 1: every launch bracketed by CUDA events on the solver's stream; 2 + f: only the launches of family f */
 int b2t_set_profiling(b2t_solver* s, int mode);
 int b2t_get_kernel_times(b2t_solver* s, double* seconds, long long* launches);
+/* SQP passes of the last b2t_sqp_solve (one pass = one SQP iteration of every instance still active: the batched form of the loop
+ * TrajoptMPCReference.py:573-750) and the number of instances still active after each of the first `cap` passes */
+int b2t_get_pass_trace(b2t_solver* s, int* active_counts, int cap, int* passes);
+/* name of the PCG kernel b2t_sqp_solve launches for this problem ("k_pcg3", "k_pcg2", "k_pcg"): the key of the ncu captures in profiles/ */
+const char* b2t_pcg_kernel_name(b2t_solver* s);
 
 /* host -> device, solve, device -> host in one call (pinned staging inside the handle) */
 int b2t_sqp_solve_host(b2t_solver* s, const double* x0, const double* u0, const double* xg, int method, const b2t_options* opts,

@@ -1,0 +1,61 @@
+#!/usr/bin/env python
+"""Recipe for oracle/_ref: the UNMODIFIED reference's solve path, staged for the GPU box (test / bench infrastructure only).
+
+  python oracle/build_ref.py            (run by __graft_entry__.build() whenever /root/reference is present)
+
+The reference is pure Python (nothing to compile): its "build" is a verbatim copy of the modules the SQP path imports --
+TrajoptMPCReference.py, TrajoptPlant.py, TrajoptCost.py, TrajoptConstraint.py, overloading.py, GBD-PCG-Python/, GRiD/__init__.py,
+GRiD/RBDReference/, GRiD/URDFParser/ -- from where they lie under /root/reference into oracle/_ref/ (git-ignored, NOT
+gpurun-ignored: it travels to the GPU box like a built .so, and stays out of the repository's history).  Nothing in the product
+package imports it; bench.py's `--impl reference` arm and cpu_baseline leg time it on the box's host cores for the
+reference-pinned variant of the workload (no box limits: the reference crashes on multi-coordinate limits), next
+to the oracle port that runs the full workload.  A manifest with the sha1 of every staged file is written beside it.
+"""
+import hashlib
+import json
+import os
+import shutil
+import sys
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+REF = os.environ.get("B2T_REFERENCE", "/root/reference")
+DST = os.path.join(HERE, "_ref")
+
+FILES = ["TrajoptMPCReference.py", "TrajoptPlant.py", "TrajoptCost.py", "TrajoptConstraint.py", "overloading.py", "LICENSE",
+         "GRiD/__init__.py", "GRiD/LICENSE"]
+DIRS = ["GBD-PCG-Python", "GRiD/RBDReference", "GRiD/URDFParser"]
+SKIP = ("RBDReference_generalized.py", "test.py")      # unparseable / stale files, not on the solve path
+
+
+def build(verbose=True):
+    if not os.path.isfile(os.path.join(REF, "TrajoptMPCReference.py")):
+        if verbose:
+            print("oracle/_ref: reference tree not present at %s (the GPU box uses the staged copy)" % REF)
+        return False
+    manifest = {}
+    todo = [(f, f) for f in FILES]
+    for d in DIRS:
+        for name in sorted(os.listdir(os.path.join(REF, d))):
+            if name.endswith((".py", "LICENSE")) and name not in SKIP:
+                todo.append((os.path.join(d, name), os.path.join(d, name)))
+    for src, dst in todo:
+        s, t = os.path.join(REF, src), os.path.join(DST, dst)
+        if not os.path.isfile(s):
+            continue
+        os.makedirs(os.path.dirname(t), exist_ok=True)
+        shutil.copyfile(s, t)
+        with open(s, "rb") as f:
+            manifest[dst] = hashlib.sha1(f.read()).hexdigest()
+    with open(os.path.join(DST, "MANIFEST.json"), "w") as f:
+        json.dump({"source": REF, "files": manifest}, f, indent=1)
+    if verbose:
+        print("oracle/_ref: staged %d reference files" % len(manifest))
+    return True
+
+
+def staged():
+    return os.path.isfile(os.path.join(DST, "TrajoptMPCReference.py"))
+
+
+if __name__ == "__main__":
+    sys.exit(0 if build() else 1)

@@ -229,3 +229,33 @@ def test_ragged_horizons_vs_oracle(name, N, oracle_models):
             else:
                 assert abs(ro["sqp_iter"] - r.sqp_iter[b]) <= 1
         assert same >= B - 2, (name, N, om, same)
+
+
+def test_in_place_mutators_invalidate_cached_workspace(oracle_models):
+    """The reference API mutates costs and limits in place (QuadraticCost.increase_QF / shift_QF_start, TrajoptCost.py:85-104;
+    set_*_limits on an existing TrajoptConstraint).  A cached device workspace uploads those once, so the cache is keyed on their
+    content: after a mutation the next solve must equal a FRESH solver's, not the stale one's."""
+    N = 12
+    (plant, pc, _), _ = make_pair("arm3", N, oracle_models)
+    solver = t.TrajoptMPCReference(plant, pc)
+    opts = {"expected_reduction_min_SQP_DDP": -100}
+    x0, u0 = np.zeros((6, N)), np.zeros((3, N - 1))
+    xa = solver.SQP(x0, u0, N, 0.1, t.SQPSolverMethods.PCG_SS, dict(opts))[0]
+    pc.increase_QF(4.0)
+    xb = solver.SQP(x0, u0, N, 0.1, t.SQPSolverMethods.PCG_SS, dict(opts))[0]
+    fresh_cost = t.QuadraticCost(pc.Q.copy(), pc.QF.copy(), pc.R.copy(), pc.xg.copy())
+    xf = t.TrajoptMPCReference(plant, fresh_cost).SQP(x0, u0, N, 0.1, t.SQPSolverMethods.PCG_SS, dict(opts))[0]
+    assert np.array_equal(xb, xf) and not np.array_equal(xa, xb)
+    # the per-knot cost callback follows the mutated weights too
+    xk = np.linspace(-0.3, 0.4, 6)
+    assert abs(pc.value(xk) - fresh_cost.value(xk)) < 1e-15
+    # limits added AFTER the first solve are honoured
+    cons = t.TrajoptConstraint(3, 3, 3, N)
+    solver2 = t.TrajoptMPCReference(plant, fresh_cost, cons)
+    r_free = solver2.SQP(x0, u0, N, 0.1, t.SQPSolverMethods.PCG_SS, dict(opts))
+    cons.set_torque_limits([0.2], [-0.2], "QUADRATIC_PENALTY", {})
+    r_lim = solver2.SQP(x0, u0, N, 0.1, t.SQPSolverMethods.PCG_SS, dict(opts))
+    assert np.max(np.abs(r_free[1])) > 0.25 and np.max(np.abs(r_lim[1])) < np.max(np.abs(r_free[1]))
+    cons.set_torque_limits([0.1], [-0.1], "QUADRATIC_PENALTY", {})
+    r_lim2 = solver2.SQP(x0, u0, N, 0.1, t.SQPSolverMethods.PCG_SS, dict(opts))
+    assert not np.array_equal(r_lim[1], r_lim2[1])

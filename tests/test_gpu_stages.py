@@ -178,6 +178,37 @@ def test_standalone_pcg_class(nb, N, kind):
     assert np.max(np.abs(x2[:, 0] - exact)) < 1e-8 and len(tr2) <= 3
 
 
+@pytest.mark.parametrize("nb,N,kind", [(4, 4, "SS"), (12, 8, "BJ"), (6, 5, "SS"), (4, 6, "J")])
+def test_standalone_pcg_positive_definite(nb, N, kind):
+    """GBD-PCG-Python/test.py passes a POSITIVE-definite A ('PCG expects a positive semidefinite matrix': A = M M^T, M block
+    tridiagonal-free block diagonal with symmetric blocks, utils.py:60-79); the reference inverts blocks with np.linalg.inv and so
+    accepts either sign.  Here an SPD block-tridiagonal system: the result must equal np.linalg.solve and the trace / iterates must
+    be those of the negated (negative-definite) system the solver itself produces."""
+    rng = np.random.default_rng(nb * 10 + N)
+    L = np.zeros((nb * N, nb * N))
+    for k in range(N):
+        blk = rng.uniform(0, 1, (nb, nb)); blk = 0.5 * (blk + blk.T) + 0.1 * np.eye(nb) + 2 * np.eye(nb)
+        L[k * nb:(k + 1) * nb, k * nb:(k + 1) * nb] = blk
+        if k > 0:
+            L[k * nb:(k + 1) * nb, (k - 1) * nb:k * nb] = 0.3 * rng.uniform(-1, 1, (nb, nb))
+    A = L @ L.T
+    b = rng.uniform(0, 1, nb * N)
+    pcg = t.PCG(A, b, nb, N, options={"preconditioner_type": kind})
+    pcg.update_RETURN_TRACE(True); pcg.update_DEBUG_MODE(False)
+    x, (trace, _) = pcg.solve()
+    exact = np.linalg.solve(A, b)
+    assert np.all(np.isfinite(x)) and np.max(np.abs(x[:, 0] - exact)) < 5e-3 * max(1.0, np.max(np.abs(exact)))
+    neg = t.PCG(-A, -b, nb, N, options={"preconditioner_type": kind})
+    xn, (trn, _) = neg.solve()
+    assert np.array_equal(x, xn) and trace == trn                  # negation is exact: identical iterates
+    assert np.allclose(pcg.Pinv, -neg.Pinv)
+    if kind != "J":                                              # block inverse with the reference's sign
+        assert np.allclose(pcg.Pinv[0], np.linalg.inv(A[:nb, :nb]), rtol=1e-9, atol=1e-12)
+    pcg.update_exit_tolerance(1e-12); pcg.update_max_iter(100)
+    x3, _ = pcg.solve()
+    assert np.max(np.abs(x3[:, 0] - exact)) < 1e-6 * max(1.0, np.max(np.abs(exact)))
+
+
 def test_soft_constraint_callbacks(oracle_models):
     """TrajoptConstraint.value_soft_constraints / jacobian_soft_constraints (TrajoptConstraint.py:295-340) through the constraint kernels,
     with non-trivial multipliers, against the oracle's element-wise restatement."""

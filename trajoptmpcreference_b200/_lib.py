@@ -65,6 +65,8 @@ _SIGNATURES = {
     "b2t_get_trace": (c_int, [c_void_p, c_void_p, c_int]),
     "b2t_get_multipliers": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p]),
     "b2t_get_launch_stats": (c_int, [c_void_p, POINTER(c_longlong), _DP]),
+    "b2t_get_pass_trace": (c_int, [c_void_p, POINTER(c_int), c_int, POINTER(c_int)]),
+    "b2t_pcg_kernel_name": (ctypes.c_char_p, [c_void_p]),
     "b2t_set_profiling": (c_int, [c_void_p, c_int]),
     "b2t_get_kernel_times": (c_int, [c_void_p, _DP, POINTER(c_longlong)]),
     "b2t_sqp_solve_host": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_int, POINTER(Options), c_void_p, c_void_p, c_void_p]),

@@ -10,6 +10,7 @@ Differences from the reference, all deliberate:
   * `solve_batch` solves many independent instances (different goals / initial trajectories) in one launch sequence
 """
 import ctypes
+import hashlib
 import enum
 import os
 
@@ -258,9 +259,11 @@ class UrdfCost(QuadraticCost):
         """Evaluate this cost at one knot on the GPU (1 instance, 2 knots: knot 0 = (x,u) as a running knot, knot 1 = x as terminal)."""
         n = self.n
         use_qf_running = timestep is not None and self.QF_start is not None and timestep >= self.QF_start
-        key = ("probe", use_qf_running)
+        key = ("probe", use_qf_running, _cost_digest(self))
         cache = self.__dict__.setdefault("_probe", {})
         if key not in cache:
+            for k in [k for k in cache if k[:2] == key[:2]]:
+                cache.pop(k)
             cache[key] = BatchSolver(self.plant, self, None, N=2, dt=0.1, batch=1, qf_start_override=(0 if use_qf_running else -1))
         s = cache[key]
         s.set_goals(_as_f64(self.xg).reshape(1, -1))
@@ -408,9 +411,11 @@ class TrajoptConstraint:
         if timestep is None:
             timestep = N - 1
         cache = self.__dict__.setdefault("_probe", {})
-        if "s" not in cache:
+        dig = (_constraint_digest(self), id(plant))
+        if cache.get("key") != dig:
             n = self.nq
             cache["s"] = BatchSolver(plant, QuadraticCost(np.eye(2 * n), np.eye(2 * n), np.eye(n), np.zeros(2 * n)), self, N=N, dt=0.1, batch=1)
+            cache["key"] = dig
         s = cache["s"]
         mu, lam, phi = self.pack(N)
         s.set_multipliers(mu[None], lam[None], phi[None])
@@ -464,6 +469,35 @@ def _as_f64(a, shape=None):
     if shape is not None and a.shape != tuple(shape):
         raise ValueError("expected array of shape %r, got %r" % (tuple(shape), a.shape))
     return a
+
+
+def _cost_digest(cost):
+    """Content digest of everything a BatchSolver uploads ONCE from a cost object (Q, QF, R, QF_start, kind).  The reference's
+    in-place mutators (increase_QF / increase_Q / shift_QF_start, TrajoptCost.py:85-104) change these after a solver was cached;
+    xg is re-sent on every call and is not part of the digest."""
+    h = hashlib.sha1()
+    for a in (cost.Q, cost.QF, cost.R):
+        h.update(np.ascontiguousarray(np.asarray(a, dtype=np.float64)).tobytes())
+    h.update(repr((cost._kind, cost.QF_start, getattr(cost, "hess_mode", 0))).encode())
+    return h.hexdigest()
+
+
+def _constraint_digest(cons):
+    """Content digest of the limit description a BatchSolver uploads once: per limit type the bounds, mode and the mu / phi
+    schedule options (not the multipliers: those are re-sent per call).  set_*_limits after a first solve changes it."""
+    if cons is None:
+        return "none"
+    h = hashlib.sha1()
+    h.update(repr((cons.nq, cons.nv, cons.nu, cons.num_timesteps)).encode())
+    for ty, lim, off, cs in cons._types():
+        if lim is None:
+            h.update(b"-")
+            continue
+        h.update(np.ascontiguousarray(np.asarray(lim.bounds, dtype=np.float64)).tobytes())
+        o = lim.options
+        h.update(repr((ty, lim.mode, lim.num_timesteps, o["quadratic_penalty_mu_init"], o["quadratic_penalty_mu_factor"], o["quadratic_penalty_mu_max"],
+                       o["augmentated_lagrangian_phi_init"], o["augmentated_lagrangian_phi_factor"])).encode())
+    return h.hexdigest()
 
 
 class BatchResult(dict):
@@ -679,6 +713,17 @@ class BatchSolver:
         _lib.check(self.lib, self.lib.b2t_get_launch_stats(self._h, ctypes.byref(n), ctypes.byref(s)))
         return int(n.value), float(s.value)
 
+    def pass_trace(self):
+        """(number of SQP passes of the last solve, active-instance count after each pass)."""
+        n = ctypes.c_int()
+        _lib.check(self.lib, self.lib.b2t_get_pass_trace(self._h, None, 0, ctypes.byref(n)))
+        buf = (ctypes.c_int * max(1, n.value))()
+        _lib.check(self.lib, self.lib.b2t_get_pass_trace(self._h, buf, n.value, ctypes.byref(n)))
+        return n.value, np.array(buf[:min(n.value, 2048)], dtype=np.int64)
+
+    def pcg_kernel_name(self):
+        return self.lib.b2t_pcg_kernel_name(self._h).decode()
+
     def set_profiling(self, enabled, family=None):
         """CUDA-event timing of the kernel families of the next solves: all of them, or only `family` (a name of
         _lib.KERNEL_FAMILY_NAMES; two event records per launch cost ~2 % of a step when every family is timed)."""
@@ -818,9 +863,15 @@ class TrajoptMPCReference:
         return c
 
     def batch_solver(self, N, dt, batch, dtype="f64", device=0):
-        key = (N, float(dt), batch, dtype, device, id(self.cost), id(self.other_constraints))
+        # keyed on the CONTENT the workspace uploads once (weights, QF_start, bounds, modes, penalty options), not on object identity:
+        # the reference API mutates costs and limits in place (increase_QF, shift_QF_start, set_*_limits after a first solve)
+        cons = self._constraints_or_none()
+        key = (N, float(dt), batch, dtype, device, self.plant.integrator_type, _cost_digest(self.cost), _constraint_digest(cons))
         if key not in self._solvers:
-            self._solvers[key] = BatchSolver(self.plant, self.cost, self._constraints_or_none(), N, dt, batch, dtype, device)
+            shape = key[:5]
+            for k in [k for k in self._solvers if k[:5] == shape]:      # same shape, stale content: drop it (freed when unreferenced)
+                self._solvers.pop(k)
+            self._solvers[key] = BatchSolver(self.plant, self.cost, cons, N, dt, batch, dtype, device)
         return self._solvers[key]
 
     def SQP(self, x, u, N, dt, LINEAR_SYSTEM_SOLVER_METHOD=SQPSolverMethods.N, options=None, dtype="f64", record=False):
@@ -1026,6 +1077,12 @@ class PCG:
         self.validate_precon_type(type)
         self.options["preconditioner_type"] = type
 
+    def update_DEBUG_MODE(self, mode):                  # PCG.py:45-46
+        self.options["DEBUG_MODE"] = mode
+
+    def update_RETURN_TRACE(self, mode):                # PCG.py:48-49
+        self.options["RETURN_TRACE"] = mode
+
     def _blocks(self):
         nb, N = self.block_size, self.Nblocks
         A = self.A
@@ -1056,13 +1113,20 @@ class PCG:
         if N < 2:
             raise ValueError("Nblocks >= 2 required")
         method = {"J": SQPSolverMethods.PCG_J, "BJ": SQPSolverMethods.PCG_BJ, "SS": SQPSolverMethods.PCG_SS}[self.options["preconditioner_type"]]
-        s.set_block_system(Sd.reshape(1, N, nb * nb), So.reshape(1, N, nb * nb), b.reshape(1, N, nb))
+        # The kernels factor the diagonal blocks of -S by Cholesky (the solver's Schur complement is NEGATIVE definite), while the
+        # reference inverts blocks with np.linalg.inv and works for either sign (its own test.py passes a positive-definite A).
+        # PCG on (-A, -b) produces exactly the iterates of PCG on (A, b) (negation is exact in floating point: r, Pinv and nu change
+        # sign, alpha, beta, p, x and |nu| do not), so a positive-definite system is handed to the kernel negated.
+        sign = -1.0 if float(np.einsum("kii->", Sd)) > 0.0 else 1.0
+        s.set_block_system((sign * Sd).reshape(1, N, nb * nb), (sign * So).reshape(1, N, nb * nb), (sign * b).reshape(1, N, nb))
         s.stage_precond(method)
         it = s.stage_pcg(method, self.options["exit_tolerance"], self.options["max_iter"])
         x = s.fetch("l")[0].reshape(-1)
+        if not np.all(np.isfinite(x)):
+            raise ValueError("PCG: the diagonal blocks of A must be (positive or negative) definite")
         if self.guess is not None:
             x = x + self.guess
         trace = s.fetch("nu_trace")[0, :int(it[0]) + 1].tolist()
-        self.Pinv = s.fetch("Pd")[0].reshape(N, nb, nb)
+        self.Pinv = sign * s.fetch("Pd")[0].reshape(N, nb, nb)
         self.iterations = int(it[0])
         return x.reshape(-1, 1), (trace, [])

@@ -58,10 +58,19 @@ def build_model(model: dict, tag: str, force: bool = False, verbose: bool = Fals
     return out
 
 
-def build_builtin(names=None, force=False, verbose=False):
-    outs = []
-    for name in (names or BUILTIN):
-        outs.append(build_model(extract_model(builtin_urdf(name)), name, force, verbose))
+def build_builtin(names=None, force=False, verbose=False, jobs=None):
+    """Build the libraries of the built-in robots, `jobs` nvcc processes at a time (default: one per core, at most one per robot)."""
+    from concurrent.futures import ThreadPoolExecutor
+    names = list(names or BUILTIN)
+    jobs = jobs or max(1, min(len(names), os.cpu_count() or 1))
+    models = [extract_model(builtin_urdf(name)) for name in names]
+    # longest compile first (the 6-joint robot), so that it overlaps all the others
+    order = sorted(range(len(names)), key=lambda i: -models[i]["n"])
+    outs = [None] * len(names)
+    with ThreadPoolExecutor(max_workers=jobs) as ex:
+        futs = {i: ex.submit(build_model, models[i], names[i], force, verbose) for i in order}
+        for i, f in futs.items():
+            outs[i] = f.result()
     return outs
 
 

@@ -1882,7 +1882,7 @@ __global__ void k_outer(Dev<T> d, Opts<T> o, int fused_restart) {
 
 // rebuild the active list (order-preserving, single block of 1024 threads: per-thread chunk counts + block scan)
 template <typename T>
-__global__ void __launch_bounds__(1024) k_compact(Dev<T> d, int* scratch) {
+__global__ void __launch_bounds__(1024) k_compact(Dev<T> d, int* scratch, int* pass_trace = nullptr, int pass = 0) {
   __shared__ int s_cnt[1024];
   const int n = *d.n_act;
   const int chunk = (n + blockDim.x - 1) / blockDim.x;
@@ -1906,7 +1906,7 @@ __global__ void __launch_bounds__(1024) k_compact(Dev<T> d, int* scratch) {
   __syncthreads();
   for (int s = threadIdx.x; s < total; s += blockDim.x) d.act[s] = scratch[s];
   __syncthreads();
-  if (threadIdx.x == 0) { *d.n_act = total; *d.n_restart = 0; }
+  if (threadIdx.x == 0) { *d.n_act = total; *d.n_restart = 0; if (pass_trace) pass_trace[pass] = total; }
 }
 
 // -----------------------------------------------------------------------------------------------------------------

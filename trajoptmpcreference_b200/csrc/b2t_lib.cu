@@ -49,6 +49,8 @@ struct SolverBase {
   virtual int stage_precond(int method) = 0;
   virtual int stage_merit(double alpha, double* J, double* c, double* D) = 0;
   virtual int fetch(int which, double* out) = 0;
+  virtual int get_pass_trace(int* counts, int cap, int* passes) = 0;
+  virtual const char* pcg_kernel_name() = 0;
   b2t_iteration_hook hook = nullptr;
   void* hook_user = nullptr;
   size_t ws_bytes = 0;
@@ -76,6 +78,9 @@ struct SolverT : SolverBase {
   int schur_minb = 2;
   int* d_status = nullptr; double* d_scalars = nullptr;
   int* d_scratch = nullptr;
+  enum { PASS_TRACE_CAP = 2048 };
+  int* d_pass_trace = nullptr;      // active-instance count after every pass of the last solve (written by k_compact)
+  int n_passes = 0;
   cudaEvent_t ev0 = nullptr, ev1 = nullptr;
   std::vector<cudaEvent_t> ev_pool; size_t ev_used = 0;
   std::vector<int> ev_family;
@@ -184,7 +189,7 @@ struct SolverT : SolverBase {
     B2T_ALLOC(d.nu_trace, B * NU_TRACE_LEN);
     d.trace_cap = 104;
     B2T_ALLOC(d.trace, B * d.trace_cap * TRACE_FIELDS); B2T_ALLOC(d.trace_rows, B);
-    B2T_ALLOC(d_scratch, B); B2T_ALLOC(d_status, B * 8); B2T_ALLOC(d_scalars, B * 4);
+    B2T_ALLOC(d_scratch, B); B2T_ALLOC(d_status, B * 8); B2T_ALLOC(d_scalars, B * 4); B2T_ALLOC(d_pass_trace, PASS_TRACE_CAP);
     B2T_ALLOC(stage_x, (size_t)B * NX * d.N); B2T_ALLOC(stage_u, (size_t)B * NU * (d.N - 1)); B2T_ALLOC(stage_g, (size_t)B * NX);
     stage_out_bytes = std::max<size_t>({(size_t)NM * NM * K, (size_t)NDYN * K, (size_t)2 * NM * K, B * (size_t)d.trace_cap * TRACE_FIELDS,
                                         (size_t)(2 * NX * NX + NX) * K}) * sizeof(double);
@@ -203,6 +208,10 @@ struct SolverT : SolverBase {
     B2T_CUDA(cudaFuncSetAttribute(b2t::k_pcg2<T, PCG_RPT, 1, true, 256>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
     B2T_CUDA(cudaFuncSetAttribute(b2t::k_pcg2<T, PCG_RPT, 1, true, 512>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
     B2T_CUDA(cudaFuncSetAttribute(b2t::k_pcg2<T, PCG_RPT, 1, true, 1024>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+    // the streaming variant (SM = false) keeps 3 (N+2) nx scalars of vectors in shared memory: beyond 48 KB for long horizons
+    B2T_CUDA(cudaFuncSetAttribute(b2t::k_pcg2<T, PCG_RPT, 1, false, 256>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+    B2T_CUDA(cudaFuncSetAttribute(b2t::k_pcg2<T, PCG_RPT, 1, false, 512>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+    B2T_CUDA(cudaFuncSetAttribute(b2t::k_pcg2<T, PCG_RPT, 1, false, 1024>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
     if constexpr (b2t::NX % 4 == 0) {
       B2T_CUDA(cudaFuncSetAttribute(b2t::k_pcg3<T, 256, false, 4>, cudaFuncAttributeMaxDynamicSharedMemorySize, 160 * 1024));
       B2T_CUDA(cudaFuncSetAttribute(b2t::k_pcg3<T, 512, false, 4>, cudaFuncAttributeMaxDynamicSharedMemorySize, 160 * 1024));
@@ -213,6 +222,9 @@ struct SolverT : SolverBase {
       B2T_CUDA(cudaFuncSetAttribute(b2t::k_pcg2<T, PCG_RPT, 2, true, 256>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
       B2T_CUDA(cudaFuncSetAttribute(b2t::k_pcg2<T, PCG_RPT, 2, true, 512>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
       B2T_CUDA(cudaFuncSetAttribute(b2t::k_pcg2<T, PCG_RPT, 2, true, 1024>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+      B2T_CUDA(cudaFuncSetAttribute(b2t::k_pcg2<T, PCG_RPT, 2, false, 256>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+      B2T_CUDA(cudaFuncSetAttribute(b2t::k_pcg2<T, PCG_RPT, 2, false, 512>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+      B2T_CUDA(cudaFuncSetAttribute(b2t::k_pcg2<T, PCG_RPT, 2, false, 1024>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
     }
     int r = reset_multipliers();
     if (r) return r;
@@ -539,6 +551,10 @@ struct SolverT : SolverBase {
         method != B2T_METHOD_PCG_SS)
       return fail(B2T_ERR_INVALID, "method must be N, S, PCG-J, PCG-BJ or PCG-SS");
     if (o->max_iter_SQP + 1 > d.trace_cap) return fail(B2T_ERR_UNSUPPORTED, "max_iter_SQP_DDP > 103");
+    // the backtracking loop of k_linesearch ends when alpha <= alpha_min: it needs a factor that shrinks alpha
+    if (!(o->alpha_factor > 0.0 && o->alpha_factor < 1.0)) return fail(B2T_ERR_INVALID, "alpha_factor_SQP_DDP must lie in (0, 1)");
+    if (!(o->alpha_min > 0.0)) return fail(B2T_ERR_INVALID, "alpha_min_SQP_DDP must be positive");
+    if (o->max_iter_SQP < 1 || o->max_iter_soft < 1) return fail(B2T_ERR_INVALID, "max_iter_SQP_DDP and max_iter_softConstraints must be >= 1");
     B2T_CUDA(cudaSetDevice(device));
     explicit_system = false;
     Opts<T> op = convert(o);
@@ -588,7 +604,8 @@ struct SolverT : SolverBase {
         { Scope sc(this, B2T_K_CTRL); k_outer<T><<<n, mt, osmem, stream>>>(d, op, 0); tick(B2T_K_CTRL); }
         { Scope sc(this, B2T_K_MERIT); k_outer_begin<T><<<n, mt, msmem, stream>>>(d, d.restart_list, d.n_restart, op, 0); tick(B2T_K_MERIT); }
       }
-      { Scope sc(this, B2T_K_CTRL); k_compact<T><<<1, 1024, 0, stream>>>(d, d_scratch); tick(B2T_K_CTRL); }
+      { Scope sc(this, B2T_K_CTRL); k_compact<T><<<1, 1024, 0, stream>>>(d, d_scratch, iter < PASS_TRACE_CAP ? d_pass_trace : nullptr, (int)iter); tick(B2T_K_CTRL); }
+      n_passes = (int)iter + 1;
       if (lagged) {
         // no host round trip between passes: the count of pass i is copied asynchronously and read one pass later.  The active count
         // never grows, so the count of pass i-1 is a valid grid bound for pass i+1 (every kernel checks the device-side count), and
@@ -609,6 +626,7 @@ struct SolverT : SolverBase {
       if (trace_active) fprintf(stderr, "%d ", n);
       if (hook && hook(hook_user, B2T_HOOK_STEP, (int)iter)) return fail(B2T_ERR_INVALID, "iteration hook asked to stop");
     }
+    B2T_CUDA(cudaMemcpyAsync(h_count, d.n_act, sizeof(int), cudaMemcpyDeviceToHost, stream));
     B2T_CUDA(cudaEventRecord(ev1, stream));
     B2T_CUDA(cudaEventSynchronize(ev1));
     float ms = 0;
@@ -616,7 +634,22 @@ struct SolverT : SolverBase {
     device_seconds = ms * 1e-3;
     collect_profile();
     B2T_CUDA(cudaGetLastError());
+    // the pass budget (max_iter_soft * max_iter_SQP + 8) bounds every legal run; instances still active here mean a broken invariant
+    if (h_count[0] > 0) return fail(B2T_ERR_UNFINISHED, std::to_string(h_count[0]) + " instances still active after the pass budget");
     return 0;
+  }
+  int get_pass_trace(int* counts, int cap, int* passes) override {
+    if (passes) *passes = n_passes;
+    if (counts && cap > 0) {
+      B2T_CUDA(cudaSetDevice(device));
+      const int n = std::min(std::min(cap, n_passes), (int)PASS_TRACE_CAP);
+      B2T_CUDA(cudaMemcpy(counts, d_pass_trace, (size_t)n * sizeof(int), cudaMemcpyDeviceToHost));
+    }
+    return 0;
+  }
+  const char* pcg_kernel_name() override {
+    decide_pcg_variant();
+    return (pcg_variant == 3 || pcg_variant == 4) ? "k_pcg3" : ((pcg_variant == 1 || pcg_variant == 2) ? "k_pcg2" : "k_pcg");
   }
 
   int mpc_shift(const double* x_next, double* x0_out, double* u0_out, double* xnext_out) override {
@@ -979,6 +1012,8 @@ int b2t_set_block_system(b2t_solver* s, const double* a, const double* b, const 
 int b2t_stage_precond(b2t_solver* s, int method) { B2T_FWD(stage_precond(method)); }
 int b2t_stage_merit(b2t_solver* s, double a, double* J, double* c, double* D) { B2T_FWD(stage_merit(a, J, c, D)); }
 int b2t_fetch(b2t_solver* s, int which, double* out) { B2T_FWD(fetch(which, out)); }
+int b2t_get_pass_trace(b2t_solver* s, int* counts, int cap, int* passes) { B2T_FWD(get_pass_trace(counts, cap, passes)); }
+const char* b2t_pcg_kernel_name(b2t_solver* s) { return s ? s->impl->pcg_kernel_name() : ""; }
 int b2t_measure_fma_peak(int device, int dtype, double* tflops) {
   if (!tflops) return fail(B2T_ERR_INVALID, "tflops required");
   int ndev = 0;
