@@ -436,6 +436,12 @@ def run_b200_arm(args):
     fam = {k: (v[0] * args.steps, v[1] * args.steps) for k, v in fam_all.items()}        # per-step figures of the profiled warm-up step
     fam[dom] = fam_dom[dom]                                                               # dominant family: measured inside the timed region
     r = solver.result()
+    n_pass, act = solver.pass_trace()
+    sms = torch.cuda.get_device_properties(local).multi_processor_count
+    edges = [1, 16, sms, 2 * sms, 1024, 4096, 1 << 30]
+    pass_stats = {"passes_per_step": int(n_pass), "what": "one pass = one SQP iteration of every instance still active; histogram of the active count after each pass",
+                  "active_hist": {("<%d" % edges[i + 1] if i + 1 < len(edges) - 1 else ">=%d" % edges[i]): int(((act >= edges[i]) & (act < edges[i + 1])).sum()) for i in range(len(edges) - 1)},
+                  "finished_after": int((act == 0).argmax() + 1) if (act == 0).any() else int(n_pass)}
     # end-to-end leg
     step_host()
     sec_e2e, _, _, _ = timed(step_host, args.steps)

@@ -4,7 +4,7 @@
   python oracle/build_ref.py            (run by __graft_entry__.build() whenever /root/reference is present)
 
 The reference is pure Python (nothing to compile): its "build" is a verbatim copy of the modules the SQP path imports --
-TrajoptMPCReference.py, TrajoptPlant.py, TrajoptCost.py, TrajoptConstraint.py, overloading.py, GBD-PCG-Python/, GRiD/__init__.py,
+TrajoptMPCReference.py, TrajoptPlant.py, TrajoptCost.py, TrajoptConstraint.py, overloading.py, expressions.py (imported by TrajoptCost), GBD-PCG-Python/, GRiD/__init__.py,
 GRiD/RBDReference/, GRiD/URDFParser/ -- from where they lie under /root/reference into oracle/_ref/ (git-ignored, NOT
 gpurun-ignored: it travels to the GPU box like a built .so, and stays out of the repository's history).  Nothing in the product
 package imports it; bench.py's `--impl reference` arm and cpu_baseline leg time it on the box's host cores for the
@@ -21,7 +21,7 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 REF = os.environ.get("B2T_REFERENCE", "/root/reference")
 DST = os.path.join(HERE, "_ref")
 
-FILES = ["TrajoptMPCReference.py", "TrajoptPlant.py", "TrajoptCost.py", "TrajoptConstraint.py", "overloading.py", "LICENSE",
+FILES = ["TrajoptMPCReference.py", "TrajoptPlant.py", "TrajoptCost.py", "TrajoptConstraint.py", "overloading.py", "expressions.py", "LICENSE",
          "GRiD/__init__.py", "GRiD/LICENSE"]
 DIRS = ["GBD-PCG-Python", "GRiD/RBDReference", "GRiD/URDFParser"]
 SKIP = ("RBDReference_generalized.py", "test.py")      # unparseable / stale files, not on the solve path

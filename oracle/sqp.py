@@ -79,6 +79,8 @@ def solve_qp(model, cost, cons, X, U, xs, dt, rho, method, o, integrator_type=0,
         sch = None
     else:
         sch = kkt.schur(blocks, rho, nx)
+        if o.get("_perturb_S") is not None:      # parity-floor experiments only (scripts/parity_floor.py, make_c4_fixture.py): S -> S (1 +/- ulp)
+            sch["Sd"], sch["So"] = o["_perturb_S"](sch["Sd"], sch["So"])
         if method == "S":
             l = kkt.bt_solve_dense(sch["Sd"], sch["So"], sch["gamma"])
         else:

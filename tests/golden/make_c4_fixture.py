@@ -13,6 +13,9 @@ bench.workload_goals(1, 0, 8192), i.e. exactly the instances bench.py solves at 
 Stored per instance: exit codes, outer_iter, sqp_iter, number of QP solves, sum of PCG iterations, sum of line-search trials,
 J, c, x, u, and the per-QP PCG iteration / line-search-trial sequences (padded with -1) plus J at the start of every outer
 iteration and the QP-solve / PCG-iteration / trial counts of every outer iteration, so that a mismatch can be located (first outer iteration / QP solve at which the GPU path leaves the oracle's path).
+Also stored: the oracle's OWN parity floor on each instance (`floor_*`): the solve repeated with S perturbed by 1 ulp in every QP
+solve (FLOOR_SEEDS sign patterns) -- whether the counts survive, and how far J, x, u move.  An instance whose counts do not
+survive a 1-ulp perturbation cannot be expected to reproduce them on different hardware arithmetic either.
 """
 import os
 import sys
@@ -30,13 +33,33 @@ os.environ.setdefault("MKL_NUM_THREADS", "1")
 QP_CAP = 1100          # 10 outer iterations x up to 100 SQP iterations (+ slack)
 
 
-def _solve(xg):
+EPS = 2.0 ** -52
+FLOOR_SEEDS = 2
+
+
+def _perturber(seed):
+    """S -> S (1 +/- 2^-52) with a symmetric random sign pattern: the 1-ulp perturbation of scripts/parity_floor.py."""
+    rng = np.random.default_rng(seed)
+
+    def f(Sd, So):
+        sd = rng.integers(0, 2, Sd.shape) * 2 - 1
+        sd = np.triu(sd) + np.transpose(np.triu(sd, 1), (0, 2, 1))
+        so = rng.integers(0, 2, So.shape) * 2 - 1
+        return Sd * (1.0 + EPS * sd), So * (1.0 + EPS * so)
+    return f
+
+
+def _solve(args):
+    xg, seed = args
     import bench
     from oracle import sqp
     model, c, cons = bench._oracle_problem(True)
     c.xg = np.asarray(xg)
     N = bench.N_KNOTS
-    r = sqp.sqp(model, c, cons, np.zeros((12, N)), np.zeros((6, N - 1)), N, bench.DT, "PCG-SS", dict(bench.SOLVER_OPTS))
+    opts = dict(bench.SOLVER_OPTS)
+    if seed >= 0:
+        opts["_perturb_S"] = _perturber(seed)
+    r = sqp.sqp(model, c, cons, np.zeros((12, N)), np.zeros((6, N - 1)), N, bench.DT, "PCG-SS", opts)
     outer_J = [row["J"] for row in r["trace"] if row["D"] is None]
     # QP solves per outer iteration: every QP solve appends exactly one row (accepted or failed search) after the outer-start row
     outer_qp, q = [], 0
@@ -59,8 +82,20 @@ def main():
     xg = bench.workload_goals(1, 0, 8192)[:n_inst]
     t0 = time.perf_counter()
     with mp.get_context("fork").Pool(min(os.cpu_count() or 1, n_inst)) as pool:
-        res = pool.map(_solve, list(xg), chunksize=1)
+        res_all = pool.map(_solve, [(g, s) for s in range(-1, FLOOR_SEEDS) for g in xg], chunksize=1)
     el = time.perf_counter() - t0
+    res = res_all[:n_inst]
+    # parity floor of the oracle itself on these instances: how far the result moves when S is perturbed by 1 ulp in every QP solve
+    floor_same = np.zeros(n_inst, dtype=np.int32); floor_J = np.zeros(n_inst); floor_x = np.zeros(n_inst); floor_u = np.zeros(n_inst)
+    for s in range(FLOOR_SEEDS):
+        for i in range(n_inst):
+            p, b = res_all[(s + 1) * n_inst + i], res[i]
+            same = p["exits"] == b["exits"] and p["pcg"] == b["pcg"] and p["ls"] == b["ls"]
+            floor_same[i] += int(same)
+            if same:
+                floor_J[i] = max(floor_J[i], abs(p["J"] - b["J"]) / max(1.0, abs(b["J"])))
+                floor_x[i] = max(floor_x[i], float(np.max(np.abs(p["x"] - b["x"]))))
+                floor_u[i] = max(floor_u[i], float(np.max(np.abs(p["u"] - b["u"]))))
     pcg_seq = -np.ones((n_inst, QP_CAP), dtype=np.int16)
     ls_seq = -np.ones((n_inst, QP_CAP), dtype=np.int8)
     outer_J = np.full((n_inst, 10), np.nan)
@@ -77,11 +112,17 @@ def main():
                total_trials=np.array([sum(r["ls"]) for r in res], dtype=np.int64),
                J=np.array([r["J"] for r in res]), c=np.array([r["c"] for r in res]),
                x=np.stack([r["x"] for r in res]), u=np.stack([r["u"] for r in res]),
-               pcg_seq=pcg_seq, ls_seq=ls_seq, outer_J=outer_J, outer_qp=outer_qp, outer_pcg=outer_pcg, outer_ls=outer_ls)
+               pcg_seq=pcg_seq, ls_seq=ls_seq, outer_J=outer_J, outer_qp=outer_qp, outer_pcg=outer_pcg, outer_ls=outer_ls,
+               floor_seeds=np.int32(FLOOR_SEEDS), floor_counts_identical=floor_same, floor_rel_J=floor_J, floor_abs_x=floor_x, floor_abs_u=floor_u)
     path = os.path.join(HERE, "c4_fixture.npz")
     np.savez_compressed(path, **out)
     print("wrote %s: %d instances in %.1f s; qp solves per instance mean %.1f, exit_soft hist %s" %
           (path, n_inst, el, out["qp"].mean(), np.bincount(out["exits"][:, 1], minlength=4).tolist()))
+    print("floor (1-ulp perturbation of S, %d seeds): %d of %d instances keep every count under all seeds; on those max rel J %.1e, max |dx| %.1e, max |du| %.1e" %
+          (FLOOR_SEEDS, int((floor_same == FLOOR_SEEDS).sum()), n_inst, floor_J[floor_same == FLOOR_SEEDS].max(), floor_x[floor_same == FLOOR_SEEDS].max(),
+           floor_u[floor_same == FLOOR_SEEDS].max()))
+    for i in np.nonzero(floor_same < FLOOR_SEEDS)[0]:
+        print("  instance %d (qp %d): counts change under a 1-ulp perturbation in %d of %d seeds" % (i, out["qp"][i], FLOOR_SEEDS - floor_same[i], FLOOR_SEEDS))
 
 
 if __name__ == "__main__":

@@ -18,7 +18,7 @@ LIBDIR = os.path.join(HERE, "_lib")
 BUILTIN = ["pend", "arm1", "arm2", "arm3", "arm4", "arm6", "cartpole"]
 NVCC = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")
 NVCC_FLAGS = ["-O3", "-std=c++17", "-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "--expt-relaxed-constexpr",
-              "-Xcompiler", "-fPIC", "-shared", "-Xptxas", "-v"]
+              "-Xcompiler", "-fPIC", "-Xptxas", "-v"]
 
 
 def lib_path(tag: str) -> str:
@@ -44,13 +44,28 @@ def build_model(model: dict, tag: str, force: bool = False, verbose: bool = Fals
     dig = _sources_digest(header)
     if not force and os.path.isfile(out) and os.path.isfile(stamp) and open(stamp).read().strip() == dig:
         return out
-    cmd = [NVCC] + NVCC_FLAGS + ['-DB2T_MODEL_HEADER="gen/model_%s.h"' % tag, "-I", CSRC, os.path.join(CSRC, "b2t_lib.cu"), "-o", out]
-    res = subprocess.run(cmd, capture_output=True, text=True)
-    log = res.stdout + res.stderr
+    # two translation units (double solver + C ABI, float solver) compiled in parallel, then linked into one shared library
+    from concurrent.futures import ThreadPoolExecutor
+    objdir = os.path.join(HERE, "_build")
+    os.makedirs(objdir, exist_ok=True)
+    objs = [os.path.join(objdir, "b2t_%s_part%d.o" % (tag, part)) for part in (1, 2)]
+    cmds = [[NVCC] + NVCC_FLAGS + ['-DB2T_MODEL_HEADER="gen/model_%s.h"' % tag, "-DB2T_PART=%d" % part, "-I", CSRC, "-c",
+                                   os.path.join(CSRC, "b2t_lib.cu"), "-o", obj] for part, obj in zip((1, 2), objs)]
+    with ThreadPoolExecutor(max_workers=2) as ex:
+        results = list(ex.map(lambda c: subprocess.run(c, capture_output=True, text=True), cmds))
+    log = "".join(" ".join(c) + "\n" + r.stdout + r.stderr for c, r in zip(cmds, results))
+    ok = all(r.returncode == 0 for r in results)
+    if ok:
+        link = [NVCC, "-shared", "-gencode", "arch=compute_100a,code=sm_100a", "-Xcompiler", "-fPIC"] + objs + ["-o", out]
+        res = subprocess.run(link, capture_output=True, text=True)
+        log += " ".join(link) + "\n" + res.stdout + res.stderr
+        ok = res.returncode == 0
     with open(out + ".buildlog", "w") as f:
-        f.write(" ".join(cmd) + "\n" + log)
-    if res.returncode != 0:
+        f.write(log)
+    if not ok:
         raise RuntimeError("nvcc failed for %s:\n%s" % (tag, log[-6000:]))
+    for obj in objs:
+        os.remove(obj)
     if verbose:
         print(log)
     with open(stamp, "w") as f:

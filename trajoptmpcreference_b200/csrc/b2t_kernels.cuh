@@ -1277,6 +1277,558 @@ __global__ void __launch_bounds__(MAXT, PDS ? 2 : 1) k_pcg3(Dev<T> d, const int*
 }
 
 // -----------------------------------------------------------------------------------------------------------------
+// k_pcg4: k_pcg3's algorithm (matrix-free, register-resident, four lanes per knot, identical arithmetic per product) with the
+// shared-memory pipe and the barrier waits taken off the critical path.  ncu on k_pcg3 (profiles/r01_v8_*): the LSU / shared
+// data pipe carries ~300 wavefronts per thread and iteration (2 400 cycles per SM and iteration against 1 400 cycles of FP64
+// issue and ~4 600 measured), so this variant
+//   * splits every product into the part that only needs the group's OWN block (published by the four lanes of the knot, a
+//     __syncwarp away) and the part that needs a neighbour's block, and runs the first part BEFORE the block barrier: the barrier
+//     wait overlaps AB^T z resp. the AB w products, their shuffles and loads instead of preceding them;
+//   * EUL (explicit Euler, tau = 0): AB^T z needs only the velocity half of z (3 instead of 6 128-bit loads);
+//   * loads and stores that exist only for the q / qd columns or the top rows are predicated off in the other lanes
+//     (W[:, nx:] is never read; full[] only feeds the q rows), which halves their wavefronts.
+// Same summation order inside every product as k_pcg3 => bit-identical iterates (tests/test_gpu_variants.py).
+// -----------------------------------------------------------------------------------------------------------------
+template <typename T, int MAXT, bool EUL>
+__global__ void __launch_bounds__(MAXT, 1) k_pcg4(Dev<T> d, const int* list, const int* count, int stair, T tol, int max_iter) {
+  if ((int)blockIdx.x >= *count) return;
+  constexpr int LPK = 4;
+  constexpr int RPT = (NX % LPK == 0) ? NX / LPK : 1;   // owned rows per lane; divides NJ
+  constexpr int MC = (NM + LPK - 1) / LPK;               // Ab columns per lane
+  constexpr int NMS = PCG3_NMS;
+  using T2 = typename std::conditional<sizeof(T) == 8, double2, float2>::type;
+  const int b = list[blockIdx.x];
+  const int N = d.N;
+  const size_t K = d.K;
+  const int tid = threadIdx.x, nt = blockDim.x;
+  const bool live = tid < LPK * N;
+  const int k = live ? tid / LPK : 0;
+  const int g = tid % LPK;
+  const bool has_next = live && (k < N - 1);
+  const int jo = (k + 1 == N) ? 0 : k + 1;
+  const int c0 = g * MC, i0 = g * RPT;
+  const size_t tk = (size_t)b * N + k, tj = (size_t)b * N + jo;
+  const T dte = d.integrator == 0 ? d.dt : T(0);
+  const T tau = d.integrator == 0 ? T(0) : d.dt;
+  extern __shared__ unsigned char smem_raw[];
+  T* V = reinterpret_cast<T*>(smem_raw);      // [(N+1)][NX]  p / r / O y; block N stays zero
+  T* V2 = V + (N + 1) * NX;                   // [(N+1)][NX]  y; block N stays zero
+  T* W = V2 + (N + 1) * NX;                   // [N][NMS]     w or q'   (only the first NX entries of a row are ever read)
+  T* Wq = W + N * NMS;                        // [N][NMS]     q
+  T* red = Wq + N * NMS;                      // 2 x 32 warp partial sums
+  T ab[NJ][MC], dinv[MC], hh[MC], pd[RPT][NX];
+  bool cval[MC], sval[MC];
+  T emul[MC];
+  int eidx[MC], sidx[MC];
+#pragma unroll
+  for (int i = 0; i < MC; ++i) {
+    const int c = c0 + i;
+    cval[i] = live && c < NM;
+    dinv[i] = cval[i] ? d.Gh[(size_t)c * K + tk] : T(0);
+    hh[i] = cval[i] ? d.Gh[(size_t)(NM + c) * K + tk] : T(0);
+#pragma unroll
+    for (int a = 0; a < NJ; ++a)
+      ab[a][i] = (cval[i] && has_next) ? d.dt * d.dyn[(size_t)(a * 3 * NJ + c) * K + tk] + ((c == NJ + a) ? T(1) : T(0)) : T(0);
+    emul[i] = (!has_next || !cval[i] || c >= NX) ? T(0) : (c < NJ ? T(1) : dte);
+    eidx[i] = (c < NJ) ? c : ((c < NX) ? c - NJ : 0);
+    sval[i] = cval[i] && c < NX;
+    sidx[i] = (c < NX) ? c : 0;
+  }
+  const T sS = live ? d.Gh[(size_t)(2 * NM) * K + tk] : T(0);
+  bool hnz = false;
+#pragma unroll
+  for (int i = 0; i < MC; ++i) hnz = hnz || (hh[i] != T(0));
+  const bool rank1 = d.lim.any != 0 && __any_sync(0xffffffffu, hnz);
+#pragma unroll
+  for (int r = 0; r < RPT; ++r)
+#pragma unroll
+    for (int c = 0; c < NX; ++c) pd[r][c] = live ? d.Pd[(size_t)((i0 + r) * NX + c) * K + tj] : T(0);
+  for (int idx = tid; idx < 2 * (N + 1) * NX + 2 * N * NMS + 64; idx += nt) V[idx] = T(0);
+  __syncthreads();
+  const bool top = i0 < NJ;
+  const bool odd = (i0 % NJ) != 0;
+  const int ownV = jo * NX, ownW = jo * NMS + i0, kV = k * NX, nV = (k + 1) * NX, kW = k * NMS;
+
+  auto quad = [&](T v) -> T {
+    v += __shfl_xor_sync(0xffffffffu, v, 1);
+    v += __shfl_xor_sync(0xffffffffu, v, 2);
+    return v;
+  };
+  int red_sel = 0;
+  auto bsum = [&](T v) -> T {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+    T* rb = red + 32 * red_sel;
+    red_sel ^= 1;
+    if ((tid & 31) == 0) rb[tid >> 5] = v;
+    __syncthreads();
+    constexpr int NW = MAXT / 32;
+    T t[NW];
+#pragma unroll
+    for (int i = 0; i < NW; i += 2) { const T2 p2 = *reinterpret_cast<const T2*>(rb + i); t[i] = p2.x; t[i + 1] = p2.y; }
+#pragma unroll
+    for (int st = 1; st < NW; st *= 2)
+#pragma unroll
+      for (int i = 0; i + st < NW; i += 2 * st) t[i] += t[i + st];
+    return t[0];
+  };
+  auto publish = [&](T* buf, const T* val) {
+    if (live) {
+#pragma unroll
+      for (int r = 0; r < RPT; ++r) buf[ownV + i0 + r] = val[r];
+    }
+  };
+  // tc_i = (AB_k^T z)_c for my columns, z = block k+1 of `buf` = the group's own block (or the zero block for k = N-1)
+  auto abt = [&](const T* buf, T* tc) {
+    T pi[NJ];
+#pragma unroll
+    for (int a = 0; a < NJ; a += 2) {
+      const T2 zv = *reinterpret_cast<const T2*>(buf + nV + NJ + a);
+      if constexpr (EUL) {
+        pi[a] = zv.x;
+        if (a + 1 < NJ) pi[a + 1] = zv.y;
+      } else {
+        const T2 zq = *reinterpret_cast<const T2*>(buf + nV + a);
+        pi[a] = tau * zq.x + zv.x;
+        if (a + 1 < NJ) pi[a + 1] = tau * zq.y + zv.y;
+      }
+    }
+#pragma unroll
+    for (int i = 0; i < MC; ++i) {
+      T acc0 = (emul[i] != T(0)) ? emul[i] * buf[nV + eidx[i]] : T(0), acc1 = T(0);
+#pragma unroll
+      for (int a = 0; a < NJ; a += 2) {
+        acc0 += ab[a][i] * pi[a];
+        if (a + 1 < NJ) acc1 += ab[a + 1][i] * pi[a + 1];
+      }
+      tc[i] = acc0 + acc1;
+    }
+  };
+  // first half of  out = AB_k zz + sign Wn[jo]:  val_r = (AB_k zz)_row for the owned rows; zz: my columns in zc, all columns in `full`
+  // (written by the lanes of this group: a __syncwarp away)
+  auto abmul_own = [&](const T* zc, const T* full, T* val) {
+    T pb[NJ];
+#pragma unroll
+    for (int a = 0; a < NJ; ++a) {
+      T acc = T(0);
+#pragma unroll
+      for (int i = 0; i < MC; ++i) acc += ab[a][i] * zc[i];
+      pb[a] = acc;
+    }
+    T bot[RPT];
+#pragma unroll
+    for (int r = 0; r < RPT; ++r) {
+      const T send = odd ? pb[r] : pb[RPT + r];
+      T keep = odd ? pb[RPT + r] : pb[r];
+      keep += __shfl_xor_sync(0xffffffffu, send, 1);
+      keep += __shfl_xor_sync(0xffffffffu, keep, 2);
+      bot[r] = keep;
+    }
+#pragma unroll
+    for (int r = 0; r < RPT; ++r) {
+      if (top) {
+        const T zq = full[kW + i0 + r], zd = full[kW + NJ + i0 + r];
+        val[r] = zq + dte * zd + tau * bot[r];
+      } else {
+        val[r] = bot[r];
+      }
+    }
+  };
+  // second half, after the block barrier: the neighbour's rows
+  auto abmul_nb = [&](const T* val, const T* Wn, T sign, T* out) {
+#pragma unroll
+    for (int r = 0; r < RPT; ++r) out[r] = has_next ? val[r] + sign * Wn[ownW + r] : (live ? sign * Wn[ownW + r] : T(0));
+  };
+  auto pd_mul = [&](const T* buf, T* out) {
+    T o0[RPT], o1[RPT];
+#pragma unroll
+    for (int r = 0; r < RPT; ++r) { o0[r] = T(0); o1[r] = T(0); }
+#pragma unroll
+    for (int c = 0; c < NX; c += 2) {
+      const T2 v = *reinterpret_cast<const T2*>(buf + ownV + c);
+#pragma unroll
+      for (int r = 0; r < RPT; ++r) { o0[r] += pd[r][c] * v.x; o1[r] += pd[r][c + 1] * v.y; }
+    }
+#pragma unroll
+    for (int r = 0; r < RPT; ++r) out[r] = o0[r] + o1[r];
+  };
+  T rr[RPT], xx[RPT], pp[RPT], rt[RPT], yv[RPT], tmp[RPT], val[RPT];
+  auto precond = [&]() {
+    publish(V, rr);
+    __syncwarp();
+    pd_mul(V, yv);
+    if (!stair) {
+#pragma unroll
+      for (int r = 0; r < RPT; ++r) rt[r] = yv[r];
+      return;
+    }
+    publish(V2, yv);
+    __syncwarp();
+    T u1[MC], u2[MC], h1 = T(0), h2 = T(0);
+    abt(V2, u2);                                // own block: before the barrier
+    __syncthreads();
+#pragma unroll
+    for (int i = 0; i < MC; ++i) {
+      u1[i] = sval[i] ? V2[kV + sidx[i]] : T(0);
+      h1 += hh[i] * u1[i];
+      h2 += hh[i] * u2[i];
+    }
+    if (rank1) { h1 = sS * quad(h1); h2 = sS * quad(h2); } else { h1 = T(0); h2 = T(0); }
+#pragma unroll
+    for (int i = 0; i < MC; ++i) {
+      u1[i] = dinv[i] * u1[i] - hh[i] * h1;
+      u2[i] = dinv[i] * u2[i] - hh[i] * h2;
+      if (sval[i]) { Wq[kW + c0 + i] = u1[i]; W[kW + c0 + i] = u2[i]; }
+    }
+    __syncwarp();
+    abmul_own(u1, Wq, val);                     // own knot: before the barrier
+    __syncthreads();
+    abmul_nb(val, W, T(1), tmp);
+    publish(V, tmp);
+    __syncwarp();
+    pd_mul(V, tmp);
+#pragma unroll
+    for (int r = 0; r < RPT; ++r) rt[r] = yv[r] - tmp[r];
+  };
+#pragma unroll
+  for (int r = 0; r < RPT; ++r) { rr[r] = live ? d.gam[(size_t)(i0 + r) * K + tj] : T(0); xx[r] = T(0); }
+  precond();
+  T part = T(0);
+#pragma unroll
+  for (int r = 0; r < RPT; ++r) { pp[r] = rt[r]; part += rr[r] * rt[r]; }
+  T nu = bsum(part);
+  if (tid == 0 && d.nu_trace) d.nu_trace[(size_t)b * NU_TRACE_LEN] = fabs(nu);
+  int iters = 0;
+  for (int it = 0; it < max_iter; ++it) {
+    const T inv_nu = T(1) / nu;
+    publish(V, pp);
+    __syncwarp();
+    T uc[MC], hu = T(0), ap[RPT];
+    abt(V, uc);                                 // own block: before the barrier
+    __syncthreads();
+#pragma unroll
+    for (int i = 0; i < MC; ++i) {
+      uc[i] = (sval[i] ? V[kV + sidx[i]] : T(0)) - uc[i];
+      hu += hh[i] * uc[i];
+    }
+    hu = rank1 ? sS * quad(hu) : T(0);
+#pragma unroll
+    for (int i = 0; i < MC; ++i) {
+      uc[i] = dinv[i] * uc[i] - hh[i] * hu;
+      if (sval[i]) W[kW + c0 + i] = uc[i];
+    }
+    __syncwarp();
+    abmul_own(uc, W, val);
+    __syncthreads();
+    abmul_nb(val, W, T(-1), ap);
+    part = T(0);
+#pragma unroll
+    for (int r = 0; r < RPT; ++r) part += pp[r] * ap[r];
+    const T pAp = bsum(part);
+    const T alpha = nu / pAp;
+#pragma unroll
+    for (int r = 0; r < RPT; ++r) { rr[r] -= ap[r] * alpha; xx[r] += pp[r] * alpha; }
+    precond();
+    part = T(0);
+#pragma unroll
+    for (int r = 0; r < RPT; ++r) part += rr[r] * rt[r];
+    const T nu_prime = bsum(part);
+    iters = it + 1;
+    if (tid == 0 && d.nu_trace && iters < NU_TRACE_LEN) d.nu_trace[(size_t)b * NU_TRACE_LEN + iters] = fabs(nu_prime);
+    if (fabs(nu_prime) < tol) break;
+    const T beta = nu_prime * inv_nu;
+#pragma unroll
+    for (int r = 0; r < RPT; ++r) pp[r] = rt[r] + pp[r] * beta;
+    nu = nu_prime;
+  }
+  if (live) {
+#pragma unroll
+    for (int r = 0; r < RPT; ++r) d.l[(size_t)(i0 + r) * K + tj] = xx[r];
+  }
+  if (tid == 0) {
+    d.pcg_iters[b] = iters;
+    d.tot_pcg[b] += iters;
+    d.tot_qp[b] += 1;
+  }
+}
+
+// -----------------------------------------------------------------------------------------------------------------
+// k_pcg6: the matrix-free PCG of k_pcg3 with SIX lanes per knot (robots with nj % 6 == 0: arm6).  Lane g of a knot holds the three
+// columns [3g, 3g+3) of Ab_k -- with nm = 18 columns and six lanes every lane's columns lie in ONE of the blocks q / qd / u, so the
+// E0 coupling, the self term and the "only the state part of w is ever read" predicates are lane-uniform scalars instead of
+// per-column tables -- and rows [2g, 2g+2) of the preconditioner block of the block row it owns.  Five knots per warp (30 lanes),
+// 13 warps for N = 64: the per-thread instruction stream of one PCG iteration is ~35 % shorter than with four lanes and the SM
+// runs 13 instead of 8 warps against the same shared-memory / FP64 work, which is what a latency-bound kernel needs (ncu on
+// k_pcg3: 6 cycles between issues of a warp, 2 warps per scheduler).  48 doubles of matrix data per lane => <= 152 registers.
+// Summation orders differ from k_pcg3 (6-lane reductions) -- same recurrence and exit test (PCG.py:66-111).
+// -----------------------------------------------------------------------------------------------------------------
+constexpr int PCG6_KPW = 5;                       // knots per warp
+constexpr int PCG6_THREADS = 416;                 // 13 warps: N <= 65
+constexpr int PCG6_VS = NX + 2;                   // row stride of the shared vectors: 5 knots x 16-byte accesses fall into distinct banks
+template <typename T, bool EUL>
+__global__ void __launch_bounds__(PCG6_THREADS, 1) k_pcg6(Dev<T> d, const int* list, const int* count, int stair, T tol, int max_iter) {
+  if ((int)blockIdx.x >= *count) return;
+  constexpr int LPK = 6;
+  constexpr int RPT = (NX % LPK == 0) ? NX / LPK : 1;
+  constexpr int MC = (NM % LPK == 0) ? NM / LPK : 1;
+  constexpr int VS = PCG6_VS;
+  constexpr int NW = PCG6_THREADS / 32;
+  using T2 = typename std::conditional<sizeof(T) == 8, double2, float2>::type;
+  const int b = list[blockIdx.x];
+  const int N = d.N;
+  const size_t K = d.K;
+  const int tid = threadIdx.x, nt = blockDim.x, lane = tid & 31, warp = tid >> 5;
+  const int kq = lane / LPK, g = lane - kq * LPK;
+  const bool valid = lane < PCG6_KPW * LPK;
+  const int kk = warp * PCG6_KPW + kq;
+  const bool live = valid && kk < N;
+  const int k = live ? kk : 0;
+  const bool has_next = live && (k < N - 1);
+  const int jo = (k + 1 == N) ? 0 : k + 1;
+  const int cls = g / 2;                      // 0: q columns, 1: qd columns, 2: u columns (MC = NJ / 2)
+  const bool xcol = live && cls < 2;          // my columns belong to the state part
+  const bool top = g < LPK / 2;               // my rows are q rows of [A B]
+  const int j3 = g % 3;                       // position inside the half
+  const int c0 = g * MC, i0 = g * RPT;
+  const int base = valid ? kq * LPK : lane;   // first lane of my knot group (idle lanes talk to themselves)
+  const int partner = valid ? (top ? lane + 3 : lane - 3) : lane;
+  const int src1 = valid ? base + (top ? 0 : 3) + (j3 + 2) % 3 : lane;     // the lane one position before me in my half
+  const int src2 = valid ? base + (top ? 0 : 3) + (j3 + 1) % 3 : lane;     // two positions before me
+  const size_t tk = (size_t)b * N + k, tj = (size_t)b * N + jo;
+  const T dte = d.integrator == 0 ? d.dt : T(0);
+  const T tau = d.integrator == 0 ? T(0) : d.dt;
+  extern __shared__ unsigned char smem_raw[];
+  T* V = reinterpret_cast<T*>(smem_raw);      // [(N+1)][VS]  p / r / O y; block N stays zero
+  T* V2 = V + (N + 1) * VS;                   // [(N+1)][VS]  y
+  T* W = V2 + (N + 1) * VS;                   // [N][VS]      state part of w or q'
+  T* Wq = W + N * VS;                         // [N][VS]      state part of q
+  T* red = Wq + N * VS;                       // 2 x 16 warp partial sums
+  T ab[NJ][MC], dinv[MC], hh[MC], pd[RPT][NX];
+#pragma unroll
+  for (int i = 0; i < MC; ++i) {
+    const int c = c0 + i;
+    dinv[i] = live ? d.Gh[(size_t)c * K + tk] : T(0);
+    hh[i] = live ? d.Gh[(size_t)(NM + c) * K + tk] : T(0);
+#pragma unroll
+    for (int a = 0; a < NJ; ++a)
+      ab[a][i] = has_next ? d.dt * d.dyn[(size_t)(a * 3 * NJ + c) * K + tk] + ((c == NJ + a) ? T(1) : T(0)) : T(0);
+  }
+  const T ecoef = has_next ? (cls == 0 ? T(1) : (cls == 1 ? dte : T(0))) : T(0);     // E0^T z_q: column c takes z_q[c % nj]
+  const int ec0 = (cls == 1) ? c0 - NJ : (cls == 0 ? c0 : 0);
+  const T sS = live ? d.Gh[(size_t)(2 * NM) * K + tk] : T(0);
+  bool hnz = false;
+#pragma unroll
+  for (int i = 0; i < MC; ++i) hnz = hnz || (hh[i] != T(0));
+  const bool rank1 = d.lim.any != 0 && __any_sync(0xffffffffu, hnz);
+#pragma unroll
+  for (int r = 0; r < RPT; ++r)
+#pragma unroll
+    for (int c = 0; c < NX; ++c) pd[r][c] = live ? d.Pd[(size_t)((i0 + r) * NX + c) * K + tj] : T(0);
+  for (int idx = tid; idx < 2 * (N + 1) * VS + 2 * N * VS + 32; idx += nt) V[idx] = T(0);
+  __syncthreads();
+  const int ownV = jo * VS, ownW = jo * VS + i0, kV = k * VS, nV = (k + 1) * VS, kW = k * VS;
+
+  // sum over the six lanes of the knot group, identical bits in all of them: pairs, then the three pair sums in a fixed order
+  auto gsum = [&](T v) -> T {
+    v += __shfl_xor_sync(0xffffffffu, v, 1);
+    const T p0 = __shfl_sync(0xffffffffu, v, base), p1 = __shfl_sync(0xffffffffu, v, valid ? base + 2 : lane),
+            p2 = __shfl_sync(0xffffffffu, v, valid ? base + 4 : lane);
+    return (p0 + p1) + p2;
+  };
+  // deterministic block sum: warp butterfly, one barrier, butterfly over the (<= 16) warp partials -- the same pairwise tree in every lane
+  int red_sel = 0;
+  auto bsum = [&](T v) -> T {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+    T* rb = red + 16 * red_sel;
+    red_sel ^= 1;
+    if (lane == 0) rb[warp] = v;
+    __syncthreads();
+    T t = rb[lane & 15];
+#pragma unroll
+    for (int o = 1; o < 16; o <<= 1) t += __shfl_xor_sync(0xffffffffu, t, o);
+    return t;
+  };
+  static_assert(NW <= 16, "bsum holds 16 warp partials");
+  auto publish = [&](T* buf, const T* val) {
+    if (live) {
+#pragma unroll
+      for (int r = 0; r < RPT; ++r) buf[ownV + i0 + r] = val[r];
+    }
+  };
+  // tc_i = (AB_k^T z)_c for my columns; z = block k+1 of `buf` = the group's own block (zero block for k = N-1)
+  auto abt = [&](const T* buf, T* tc) {
+    T pi[NJ];
+#pragma unroll
+    for (int a = 0; a < NJ; a += 2) {
+      const T2 zv = *reinterpret_cast<const T2*>(buf + nV + NJ + a);
+      if constexpr (EUL) {
+        pi[a] = zv.x;
+        if (a + 1 < NJ) pi[a + 1] = zv.y;
+      } else {
+        const T2 zq = *reinterpret_cast<const T2*>(buf + nV + a);
+        pi[a] = tau * zq.x + zv.x;
+        if (a + 1 < NJ) pi[a + 1] = tau * zq.y + zv.y;
+      }
+    }
+#pragma unroll
+    for (int i = 0; i < MC; ++i) {
+      T acc0 = xcol ? ecoef * buf[nV + ec0 + i] : T(0), acc1 = T(0);
+#pragma unroll
+      for (int a = 0; a < NJ; a += 2) {
+        acc0 += ab[a][i] * pi[a];
+        if (a + 1 < NJ) acc1 += ab[a + 1][i] * pi[a + 1];
+      }
+      tc[i] = acc0 + acc1;
+    }
+  };
+  // val_r = (AB_k zz)_row for my rows; zz: my columns in zc (registers), its state part in `full` (written by this group)
+  auto abmul_own = [&](const T* zc, const T* full, T* val) {
+    T pb[NJ];
+#pragma unroll
+    for (int a = 0; a < NJ; ++a) {
+      T acc = T(0);
+#pragma unroll
+      for (int i = 0; i < MC; ++i) acc += ab[a][i] * zc[i];
+      pb[a] = acc;
+    }
+    // reduce-scatter over the six lanes: rows (2 j3, 2 j3 + 1) of the half sums go to position j3 of each half (two rounds inside the
+    // half, the sender picks what its receiver needs), then the two halves are added
+#pragma unroll
+    for (int r = 0; r < RPT; ++r) {
+      // what the lane one / two positions AFTER me needs: its rows RPT * ((j3 + 1) % 3) + r, RPT * ((j3 + 2) % 3) + r
+      const T s1 = j3 == 0 ? pb[RPT + r] : (j3 == 1 ? pb[2 * RPT + r] : pb[r]);
+      const T s2 = j3 == 0 ? pb[2 * RPT + r] : (j3 == 1 ? pb[r] : pb[RPT + r]);
+      T keep = j3 == 0 ? pb[r] : (j3 == 1 ? pb[RPT + r] : pb[2 * RPT + r]);
+      keep += __shfl_sync(0xffffffffu, s1, src1);
+      keep += __shfl_sync(0xffffffffu, s2, src2);
+      keep += __shfl_sync(0xffffffffu, keep, partner);
+      if (top) {
+        const T zq = full[kW + i0 + r], zd = full[kW + NJ + i0 + r];
+        val[r] = zq + dte * zd + tau * keep;
+      } else {
+        val[r] = keep;
+      }
+    }
+  };
+  auto abmul_nb = [&](const T* val, const T* Wn, T sign, T* out) {
+#pragma unroll
+    for (int r = 0; r < RPT; ++r) out[r] = has_next ? val[r] + sign * Wn[ownW + r] : (live ? sign * Wn[ownW + r] : T(0));
+  };
+  auto pd_mul = [&](const T* buf, T* out) {
+    T o0[RPT], o1[RPT];
+#pragma unroll
+    for (int r = 0; r < RPT; ++r) { o0[r] = T(0); o1[r] = T(0); }
+#pragma unroll
+    for (int c = 0; c < NX; c += 2) {
+      const T2 v = *reinterpret_cast<const T2*>(buf + ownV + c);
+#pragma unroll
+      for (int r = 0; r < RPT; ++r) { o0[r] += pd[r][c] * v.x; o1[r] += pd[r][c + 1] * v.y; }
+    }
+#pragma unroll
+    for (int r = 0; r < RPT; ++r) out[r] = o0[r] + o1[r];
+  };
+  T rr[RPT], xx[RPT], pp[RPT], rt[RPT], yv[RPT], tmp[RPT], val[RPT];
+  auto precond = [&]() {
+    publish(V, rr);
+    __syncwarp();
+    pd_mul(V, yv);
+    if (!stair) {
+#pragma unroll
+      for (int r = 0; r < RPT; ++r) rt[r] = yv[r];
+      return;
+    }
+    publish(V2, yv);
+    __syncwarp();
+    T u1[MC], u2[MC], h1 = T(0), h2 = T(0);
+    abt(V2, u2);                                // own block: before the barrier
+    __syncthreads();
+#pragma unroll
+    for (int i = 0; i < MC; ++i) {
+      u1[i] = xcol ? V2[kV + c0 + i] : T(0);
+      h1 += hh[i] * u1[i];
+      h2 += hh[i] * u2[i];
+    }
+    if (rank1) { h1 = sS * gsum(h1); h2 = sS * gsum(h2); } else { h1 = T(0); h2 = T(0); }
+#pragma unroll
+    for (int i = 0; i < MC; ++i) {
+      u1[i] = dinv[i] * u1[i] - hh[i] * h1;
+      u2[i] = dinv[i] * u2[i] - hh[i] * h2;
+      if (xcol) { Wq[kW + c0 + i] = u1[i]; W[kW + c0 + i] = u2[i]; }
+    }
+    __syncwarp();
+    abmul_own(u1, Wq, val);                     // own knot: before the barrier
+    __syncthreads();
+    abmul_nb(val, W, T(1), tmp);
+    publish(V, tmp);
+    __syncwarp();
+    pd_mul(V, tmp);
+#pragma unroll
+    for (int r = 0; r < RPT; ++r) rt[r] = yv[r] - tmp[r];
+  };
+#pragma unroll
+  for (int r = 0; r < RPT; ++r) { rr[r] = live ? d.gam[(size_t)(i0 + r) * K + tj] : T(0); xx[r] = T(0); }
+  precond();
+  T part = T(0);
+#pragma unroll
+  for (int r = 0; r < RPT; ++r) { pp[r] = rt[r]; part += rr[r] * rt[r]; }
+  T nu = bsum(part);
+  if (tid == 0 && d.nu_trace) d.nu_trace[(size_t)b * NU_TRACE_LEN] = fabs(nu);
+  int iters = 0;
+  for (int it = 0; it < max_iter; ++it) {
+    const T inv_nu = T(1) / nu;
+    publish(V, pp);
+    __syncwarp();
+    T uc[MC], hu = T(0), ap[RPT];
+    abt(V, uc);                                 // own block: before the barrier
+    __syncthreads();
+#pragma unroll
+    for (int i = 0; i < MC; ++i) {
+      uc[i] = (xcol ? V[kV + c0 + i] : T(0)) - uc[i];
+      hu += hh[i] * uc[i];
+    }
+    hu = rank1 ? sS * gsum(hu) : T(0);
+#pragma unroll
+    for (int i = 0; i < MC; ++i) {
+      uc[i] = dinv[i] * uc[i] - hh[i] * hu;
+      if (xcol) W[kW + c0 + i] = uc[i];
+    }
+    __syncwarp();
+    abmul_own(uc, W, val);
+    __syncthreads();
+    abmul_nb(val, W, T(-1), ap);
+    part = T(0);
+#pragma unroll
+    for (int r = 0; r < RPT; ++r) part += pp[r] * ap[r];
+    const T pAp = bsum(part);
+    const T alpha = nu / pAp;
+#pragma unroll
+    for (int r = 0; r < RPT; ++r) { rr[r] -= ap[r] * alpha; xx[r] += pp[r] * alpha; }
+    precond();
+    part = T(0);
+#pragma unroll
+    for (int r = 0; r < RPT; ++r) part += rr[r] * rt[r];
+    const T nu_prime = bsum(part);
+    iters = it + 1;
+    if (tid == 0 && d.nu_trace && iters < NU_TRACE_LEN) d.nu_trace[(size_t)b * NU_TRACE_LEN + iters] = fabs(nu_prime);
+    if (fabs(nu_prime) < tol) break;
+    const T beta = nu_prime * inv_nu;
+#pragma unroll
+    for (int r = 0; r < RPT; ++r) pp[r] = rt[r] + pp[r] * beta;
+    nu = nu_prime;
+  }
+  if (live) {
+#pragma unroll
+    for (int r = 0; r < RPT; ++r) d.l[(size_t)(i0 + r) * K + tj] = xx[r];
+  }
+  if (tid == 0) {
+    d.pcg_iters[b] = iters;
+    d.tot_pcg[b] += iters;
+    d.tot_qp[b] += 1;
+  }
+}
+
+// -----------------------------------------------------------------------------------------------------------------
 // k_bt_solve: exact solve of S l = gamma (methods 'S' and 'N' of the reference: np.linalg.solve on the Schur system,
 // TrajoptMPCReference.py:430-436, resp. on the full KKT system :349-357 -- the same solution up to rounding).
 // Block Thomas algorithm on the SPD block-tridiagonal matrix T = -S, one thread per instance:

@@ -10,9 +10,19 @@
 #include "b2t_ilqr.cuh"
 #include "../../include/b2t.h"
 
+// The library is compiled as two translation units so that the double and the float instantiations of every kernel build in
+// parallel (B2T_PART = 1: double solver + the C ABI, B2T_PART = 2: float solver; undefined: everything in one unit).
+#if !defined(B2T_PART)
+#define B2T_PART 0
+#endif
+#define B2T_HIDDEN __attribute__((visibility("hidden")))
+B2T_HIDDEN std::string& b2t_err_slot();         // thread-local last-error string (defined in the unit that holds the C ABI)
+#if B2T_PART != 2
+std::string& b2t_err_slot() { thread_local std::string e; return e; }
+#endif
+
 namespace {
-thread_local std::string g_err;
-int fail(int code, const std::string& msg) { g_err = msg; return code; }
+int fail(int code, const std::string& msg) { b2t_err_slot() = msg; return code; }
 
 #define B2T_CUDA(call)                                                                              \
   do {                                                                                              \
@@ -22,6 +32,7 @@ int fail(int code, const std::string& msg) { g_err = msg; return code; }
   } while (0)
 
 inline unsigned cdiv(size_t a, size_t b) { return (unsigned)((a + b - 1) / b); }
+}  // namespace
 
 struct SolverBase {
   virtual ~SolverBase() {}
@@ -62,6 +73,12 @@ struct SolverBase {
   double fam_seconds[B2T_KERNEL_FAMILIES] = {0};
   long long fam_launches[B2T_KERNEL_FAMILIES] = {0};
 };
+B2T_HIDDEN SolverBase* b2t_make_solver_f64();
+B2T_HIDDEN SolverBase* b2t_make_solver_f32();
+B2T_HIDDEN int b2t_fma_peak_f64(int device, double* tflops);
+B2T_HIDDEN int b2t_fma_peak_f32(int device, double* tflops);
+
+namespace {
 
 template <typename T>
 struct SolverT : SolverBase {
@@ -425,7 +442,7 @@ struct SolverT : SolverBase {
       // the matrix-free PCG kernels never read the sub-diagonal blocks S_{k,k-1}: skip their stores (half of this kernel's traffic)
       decide_pcg_variant();
       const bool exact = method == B2T_METHOD_N || method == B2T_METHOD_S;
-      const int need_so = (all_outputs || exact || !(pcg_variant == 3 || pcg_variant == 4)) ? 1 : 0;
+      const int need_so = (all_outputs || exact || pcg_variant < 3) ? 1 : 0;
       { Scope sc(this, B2T_K_KKT); k_kkt_diag<T><<<cdiv(nthreads, 128), 128, 0, stream>>>(d, list, count); tick(B2T_K_KKT); }
       if (schur_v1) { Scope sc(this, B2T_K_SCHUR); k_schur_diag<T><<<cdiv(nthreads, SCHUR_THREADS), SCHUR_THREADS, (size_t)NJ * NM * SCHUR_THREADS * sizeof(T), stream>>>(d, list, count, need_so); tick(B2T_K_SCHUR); }
       else {
@@ -481,9 +498,11 @@ struct SolverT : SolverBase {
     if (pcg_variant < 0) {
       const char* e = getenv("B2T_PCG_VARIANT");
       if (e) pcg_variant = atoi(e);
-      else if (d.diag_mode && b2t::NX % 4 == 0 && 4 * d.N <= 256) pcg_variant = 3;     // measured: 21.9 ms vs 24.0 ms (variant 1) per 2048-instance step
+      else if (d.diag_mode && b2t::NX % 4 == 0 && 4 * d.N <= 256) pcg_variant = 3;     // k_pcg3 (variant 3): 21.9 ms vs 24.0 ms (variant 1) per 2048-instance step
       else if (pcg2_threads() > 1024) pcg_variant = 0;
       else pcg_variant = pcg2_smem(true) <= (size_t)220 * 1024 ? 1 : 2;
+      if (pcg_variant == 6 && !(d.diag_mode && b2t::NJ % 6 == 0 && d.N <= b2t::PCG6_KPW * (b2t::PCG6_THREADS / 32))) pcg_variant = 3;
+      if (pcg_variant == 5 && !(d.diag_mode && b2t::NX % 4 == 0 && 4 * d.N <= 256)) pcg_variant = 3;
       if (pcg_variant == 3 && !(d.diag_mode && b2t::NX % 4 == 0 && 4 * d.N <= 1024)) pcg_variant = 1;
       if (pcg_variant == 4 && !(d.diag_mode && b2t::NX % 4 == 0 && 2 * d.N <= 128)) pcg_variant = 1;
     }
@@ -492,7 +511,7 @@ struct SolverT : SolverBase {
     using namespace b2t;
     decide_pcg_variant();
     const int saved_variant = pcg_variant;
-    if (explicit_system && (pcg_variant == 3 || pcg_variant == 4))
+    if (explicit_system && pcg_variant >= 3)
       pcg_variant = pcg2_threads() > 1024 ? 0 : (pcg2_smem(true) <= (size_t)220 * 1024 ? 1 : 2);
     struct Restore { int& v; int s; ~Restore() { v = s; } } restore{pcg_variant, saved_variant};
     const int stair = method == B2T_METHOD_PCG_SS ? 1 : 0;
@@ -503,12 +522,27 @@ struct SolverT : SolverBase {
       return 0;
     }
     const int nt = pcg2_threads();
-    if (pcg_variant == 3 || pcg_variant == 4) {
+    if (pcg_variant == 6) {
+      // six lanes per knot, five knots per warp (robots with nj % 6 == 0)
+      if constexpr (b2t::NJ % 6 == 0) {
+        const int nt6 = ((d.N + PCG6_KPW - 1) / PCG6_KPW) * 32;
+        const size_t sm6 = ((size_t)2 * (d.N + 1) * PCG6_VS + (size_t)2 * d.N * PCG6_VS + 32) * sizeof(T);
+        if (d.integrator == 0) k_pcg6<T, true><<<bound, nt6, sm6, stream>>>(d, list, count, stair, tol, max_iter);
+        else k_pcg6<T, false><<<bound, nt6, sm6, stream>>>(d, list, count, stair, tol, max_iter);
+      }
+      tick(B2T_K_PCG);
+      return 0;
+    }
+    if (pcg_variant == 3 || pcg_variant == 4 || pcg_variant == 5) {
       // 3: four lanes per knot, everything in registers, one instance per SM;  4: two lanes per knot, preconditioner rows in
-      // shared memory, two instances per SM
+      // shared memory, two instances per SM;  5: k_pcg4 = 3 with the own-block halves of the products ahead of the barriers
       if constexpr (b2t::NX % 4 == 0) {
         const size_t smv = ((size_t)2 * (d.N + 1) * NX + (size_t)2 * d.N * PCG3_NMS + 64) * sizeof(T);
-        if (pcg_variant == 4) {
+        if (pcg_variant == 5) {
+          const int nt3 = ((4 * d.N + 31) / 32) * 32;
+          if (d.integrator == 0) k_pcg4<T, 256, true><<<bound, nt3, smv, stream>>>(d, list, count, stair, tol, max_iter);
+          else k_pcg4<T, 256, false><<<bound, nt3, smv, stream>>>(d, list, count, stair, tol, max_iter);
+        } else if (pcg_variant == 4) {
           const int nt4 = ((2 * d.N + 31) / 32) * 32;
           const size_t smp = smv + (size_t)(NX / 2) * NX * 128 * sizeof(T);
           k_pcg3<T, 128, true, 2><<<bound, nt4, smp, stream>>>(d, list, count, stair, tol, max_iter);
@@ -649,7 +683,7 @@ struct SolverT : SolverBase {
   }
   const char* pcg_kernel_name() override {
     decide_pcg_variant();
-    return (pcg_variant == 3 || pcg_variant == 4) ? "k_pcg3" : ((pcg_variant == 1 || pcg_variant == 2) ? "k_pcg2" : "k_pcg");
+    return pcg_variant == 6 ? "k_pcg6" : pcg_variant == 5 ? "k_pcg4" : ((pcg_variant == 3 || pcg_variant == 4) ? "k_pcg3" : ((pcg_variant == 1 || pcg_variant == 2) ? "k_pcg2" : "k_pcg"));
   }
 
   int mpc_shift(const double* x_next, double* x0_out, double* u0_out, double* xnext_out) override {
@@ -919,6 +953,16 @@ int fma_peak(int device, double* tflops) {
   return 0;
 }
 
+#if B2T_PART != 2
+SolverBase* b2t_make_solver_f64() { return new SolverT<double>(); }
+int b2t_fma_peak_f64(int device, double* tflops) { return fma_peak<double>(device, tflops); }
+#endif
+#if B2T_PART != 1
+SolverBase* b2t_make_solver_f32() { return new SolverT<float>(); }
+int b2t_fma_peak_f32(int device, double* tflops) { return fma_peak<float>(device, tflops); }
+#endif
+
+#if B2T_PART != 2
 struct b2t_solver { SolverBase* impl; };
 
 extern "C" {
@@ -931,7 +975,7 @@ int b2t_model_dims(int* nq, int* nx, int* nu) {
   if (nu) *nu = b2t::NU;
   return 0;
 }
-const char* b2t_last_error(void) { return g_err.c_str(); }
+const char* b2t_last_error(void) { return b2t_err_slot().c_str(); }
 void b2t_default_options(b2t_options* o) {
   if (!o) return;
   o->exit_tolerance_linSys = 1e-6; o->max_iter_linSys = 100;
@@ -949,8 +993,8 @@ int b2t_solver_create(const b2t_problem_desc* desc, int device, b2t_solver** out
     return fail(B2T_ERR_CUDA, "no CUDA device: this library has no CPU fallback");
   if (device < 0 || device >= ndev) return fail(B2T_ERR_INVALID, "bad device index");
   SolverBase* impl = nullptr;
-  if (desc->dtype == B2T_F64) impl = new SolverT<double>();
-  else if (desc->dtype == B2T_F32) impl = new SolverT<float>();
+  if (desc->dtype == B2T_F64) impl = b2t_make_solver_f64();
+  else if (desc->dtype == B2T_F32) impl = b2t_make_solver_f32();
   else return fail(B2T_ERR_INVALID, "dtype");
   int r = impl->init(desc, device);
   if (r) { delete impl; return r; }
@@ -1018,6 +1062,7 @@ int b2t_measure_fma_peak(int device, int dtype, double* tflops) {
   if (!tflops) return fail(B2T_ERR_INVALID, "tflops required");
   int ndev = 0;
   if (cudaGetDeviceCount(&ndev) != cudaSuccess || device < 0 || device >= ndev) return fail(B2T_ERR_CUDA, "no such CUDA device");
-  return dtype == B2T_F32 ? fma_peak<float>(device, tflops) : fma_peak<double>(device, tflops);
+  return dtype == B2T_F32 ? b2t_fma_peak_f32(device, tflops) : b2t_fma_peak_f64(device, tflops);
 }
 }
+#endif  // B2T_PART != 2
