@@ -30,15 +30,25 @@ def test_config2_arm2_urdfcost_N32_batch4096(oracle_models):
     r = solver.solve_batch(x0, u0, xg, N, 0.1, t.SQPSolverMethods.PCG_SS, dict(opts))
     assert set(np.unique(r.exit_sqp)) <= {1, 2, 3} and np.all(np.isfinite(r.x)) and np.all(np.isfinite(r.J))
     # spot checks against the oracle
+    import os
+    import sys
+    sys.path.insert(0, os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden"))
+    from make_c4_fixture import _perturber          # S -> S (1 +/- 2^-52): the oracle's own sensitivity sets the tolerance
     same = 0
     idx = [0, 1, 7, 100, 2047, 4095]
     for b in idx:
         ocb = copy.copy(oc); ocb.xg = xg[b]
         ro = sqp.sqp(m, ocb, None, np.zeros((4, N)), np.zeros((2, N - 1)), N, 0.1, "PCG-SS", dict(opts))
+        rp = sqp.sqp(m, ocb, None, np.zeros((4, N)), np.zeros((2, N - 1)), N, 0.1, "PCG-SS", dict(opts, _perturb_S=_perturber(b)))
+        stable = rp["pcg_iters"] == ro["pcg_iters"] and rp["ls_trials"] == ro["ls_trials"]
+        fJ = abs(rp["J"] - ro["J"]) / max(1.0, abs(ro["J"])); fx = float(np.max(np.abs(rp["x"] - ro["x"])))
         ok = (ro["exit_sqp"], ro["sqp_iter"], sum(ro["pcg_iters"]), sum(ro["ls_trials"])) == (r.exit_sqp[b], r.sqp_iter[b], r.total_pcg[b], r.total_trials[b])
         same += int(ok)
-        if ok:
-            assert abs(ro["J"] - r.J[b]) < 1e-6 * max(1.0, abs(ro["J"])) and np.max(np.abs(ro["x"] - r.x[b])) < 1e-4
+        eJ = abs(ro["J"] - r.J[b]) / max(1.0, abs(ro["J"])); ex = float(np.max(np.abs(ro["x"] - r.x[b])))
+        print("C3 instance %d: counts %s, rel J %.1e (1-ulp floor %.1e), |dx| %.1e (floor %.1e)%s" %
+              (b, "same" if ok else "DIFFER", eJ, fJ, ex, fx, "" if stable else "  [oracle counts unstable under 1 ulp]"))
+        if ok and stable:
+            assert eJ <= max(100 * fJ, 1e-9) and ex <= max(100 * fx, 1e-9), (b, eJ, fJ, ex, fx)
     assert same >= len(idx) - 1
     # permutation invariance at full size
     perm = rng.permutation(B)
@@ -66,9 +76,16 @@ def test_config1_cartpole_ilqr_batch1024():
     assert np.mean(np.abs(r.x[:, 1, -1] - np.pi) < 0.1) > 0.95               # the pole is swung up
     assert np.max(np.abs(r.u[:, 0, :])) < 12.3                                  # cart force inside its (soft) limit
     # returned trajectories are rollouts: x_{k+1} = integrator(x_k, u_k)
-    for b in (0, 511, 1023):
+    matched, spots = 0, (0, 255, 511, 767, 1023)
+    for b in spots:
         X = ilqr.rollout(m, r.x[b][:, 0], r.u[b].T, dt)
         assert np.max(np.abs(X.T - r.x[b])) < 1e-8
         ro = ilqr.ilqr(m, ocost.QuadraticCost(Q, QF, R, xg[b]), copy.deepcopy(ocn), np.zeros((4, N)), 0.01 * np.ones((2, N - 1)), N, dt, dict(opts))
-        if (ro["total_iters"], ro["total_trials"]) == (r.total_qp[b], r.total_trials[b]):
+        same = (ro["total_iters"], ro["total_trials"]) == (r.total_qp[b], r.total_trials[b])
+        print("cart-pole iLQR instance %d: oracle (iterations, rollouts) %s gpu %s  rel J %.1e" %
+              (b, (ro["total_iters"], ro["total_trials"]), (int(r.total_qp[b]), int(r.total_trials[b])), abs(ro["J"] - r.J[b]) / abs(ro["J"])))
+        matched += int(same)
+        if same:
             assert abs(ro["J"] - r.J[b]) < 1e-6 * abs(ro["J"])
+    # no silent skip: at least 4 of the 5 spot-checked instances must reproduce the oracle's iteration and rollout counts
+    assert matched >= len(spots) - 1, "only %d of %d spot checks reproduce the oracle's counts" % (matched, len(spots))

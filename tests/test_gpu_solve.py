@@ -10,42 +10,60 @@ from oracle import sqp
 pytestmark = pytest.mark.gpu
 
 PCG_TAGS = list(solve_meta().keys())       # PCG-J/BJ/SS and the exact methods N, S
-LONG = {"pend_N20_SS_al01", "pend_N20_SS_qp01"}     # hundreds of QP solves: chaotic amplification, compared loosely
+
+
+def _floor():
+    """Measured parity floor of the reference itself (tests/golden/floor.json, scripts/parity_floor.py): how far the UNMODIFIED
+    reference's final J, x, u move when S is perturbed by 1 ulp in every QP solve."""
+    import json
+    import os
+    from conftest import GOLDEN
+    with open(os.path.join(GOLDEN, "floor.json")) as f:
+        return json.load(f)["cases"]
+
+
+FLOOR_FACTOR = 10.0      # allowed multiple of the reference's own 1-ulp sensitivity
+NORTH_STAR = 1e-9        # BASELINE.json north_star: <= 1e-9 relative in fp64 (never asserted tighter than this)
 
 
 @pytest.mark.parametrize("tag", PCG_TAGS)
 def test_sqp_vs_reference_golden(tag, oracle_models):
-    """Same call as the reference's examples; exits / iteration counts / alpha sequence identical, J, x, u within the
-    measured parity floor (a 1-ulp change of S moves the reference's own result by 1e-9..6e-8)."""
+    """Same call as the reference's examples, against outputs of the unmodified reference (tests/golden/solve.npz): exits, every
+    iteration count, the alpha / rho sequences identical; J, x, u, multipliers within max(1e-9 relative, 10 x the reference's own
+    sensitivity to a 1-ulp perturbation of S) -- including the soft-limit cases with 165 / 255 QP solves over 10 outer iterations."""
     S = load_npz("solve.npz")
     mt = solve_meta()[tag]
+    fl = _floor()[tag]
     N = mt["N"]
     (plant, pc, pcons), _ = make_pair(mt["robot"], N, oracle_models, xg=S[tag + "/xg"], limits=mt["limits"], integrator=mt["integrator"])
     solver = t.TrajoptMPCReference(plant, pc, pcons) if pcons is not None else t.TrajoptMPCReference(plant, pc)
     n = plant.get_num_pos()
     opts = dict(mt["options"]); opts["overloading"] = False
     x, u, e1, e2, outer, it = solver.SQP(np.zeros((2 * n, N)), np.zeros((n, N - 1)), N, 0.1, getattr(t.SQPSolverMethods, mt["method"]), options=opts)
-    if tag in LONG:
-        assert [e1, e2, outer] == S[tag + "/exits"].tolist()[:3]
-        assert abs(solver.last_result.J[0] - float(S[tag + "/J"])) < 1e-3 * abs(float(S[tag + "/J"]))
-        assert np.max(np.abs(u)) < 0.2
-        return
     assert [e1, e2, outer, it] == S[tag + "/exits"].tolist()
-    rows = solver.trace[1:]
+    rows = solver.trace[1:]            # the reference keeps the rows of the LAST outer iteration (:555)
     k = len(rows)
     if mt["method"].startswith("PCG"):
         assert [r["pcg_iters"] for r in rows] == S[tag + "/pcg_iters"].tolist()[-k:]
+        # every QP solve of every outer iteration: totals over the whole solve
+        assert int(solver.last_result.total_qp[0]) == len(S[tag + "/pcg_iters"]) and int(solver.last_result.total_pcg[0]) == int(S[tag + "/pcg_iters"].sum())
     else:
         assert all(r["pcg_iters"] == 0 for r in rows)
+    assert int(solver.last_result.total_trials[0]) == int((S[tag + "/tr_ls"] + 1).sum())
     assert [r["line_search_iteration"] for r in rows] == S[tag + "/tr_ls"].tolist()[-k:]
-    assert np.allclose([r["alpha"] for r in rows], S[tag + "/tr_alpha"][-k:])
-    assert np.allclose([r["rho"] for r in rows], S[tag + "/tr_rho"][-k:], rtol=1e-12)
-    assert np.allclose([r["J"] for r in rows], S[tag + "/tr_J"][-k:], rtol=2e-7)
-    assert abs(solver.last_result.J[0] - float(S[tag + "/J"])) < 2e-7 * abs(float(S[tag + "/J"]))
-    assert np.max(np.abs(x - S[tag + "/x"])) < 2e-5
-    assert np.max(np.abs(u - S[tag + "/u"])) < 2e-5
+    assert np.array_equal([r["alpha"] for r in rows], S[tag + "/tr_alpha"][-k:])
+    assert np.allclose([r["rho"] for r in rows], S[tag + "/tr_rho"][-k:], rtol=1e-15)
+    tolJ = max(FLOOR_FACTOR * fl["rel_J"], NORTH_STAR)
+    tolx = max(FLOOR_FACTOR * fl["abs_x"], NORTH_STAR * max(1.0, float(np.max(np.abs(S[tag + "/x"])))))
+    tolu = max(FLOOR_FACTOR * fl["abs_u"], NORTH_STAR * max(1.0, float(np.max(np.abs(S[tag + "/u"])))))
+    eJ = abs(solver.last_result.J[0] - float(S[tag + "/J"])) / abs(float(S[tag + "/J"]))
+    ex = float(np.max(np.abs(x - S[tag + "/x"]))); eu = float(np.max(np.abs(u - S[tag + "/u"])))
+    print("%s: rel J %.1e (tol %.1e)  |dx| %.1e (tol %.1e)  |du| %.1e (tol %.1e)" % (tag, eJ, tolJ, ex, tolx, eu, tolu))
+    assert eJ <= tolJ and ex <= tolx and eu <= tolu
+    assert np.allclose([r["J"] for r in rows], S[tag + "/tr_J"][-k:], rtol=tolJ, atol=0)
     if pcons is not None:
-        assert np.allclose(pcons.torque_limits.quadratic_penalty_mu, S[tag + "/mu"], rtol=1e-12)
+        assert np.allclose(pcons.torque_limits.quadratic_penalty_mu, S[tag + "/mu"], rtol=1e-15)
+        assert np.max(np.abs(pcons.torque_limits.augmented_lagrangian_lambda - S[tag + "/lam"])) <= NORTH_STAR * max(1.0, float(np.max(np.abs(S[tag + "/lam"]))))
 
 
 @pytest.mark.parametrize("run", ["4", "3"])
@@ -61,9 +79,13 @@ def test_recorded_author_runs(run, oracle_models):
     assert solver.pcg_iters == D[run + "/pcg_iters"].tolist()
     rows = solver.trace[1:]
     assert [r["line_search_iteration"] for r in rows] == D[run + "/tr_ls"].tolist()
-    assert np.allclose([r["alpha"] for r in rows], D[run + "/tr_alpha"])
-    assert np.allclose([r["J"] for r in rows], D[run + "/tr_J"], rtol=1e-6)
-    assert np.max(np.abs(x - D[run + "/final_x"])) < 1e-4 and np.max(np.abs(u - D[run + "/final_u"])) < 1e-4
+    assert np.array_equal([r["alpha"] for r in rows], D[run + "/tr_alpha"])
+    # recorded on the authors' machine (another numpy / BLAS build): 10 x the measured 1-ulp floor of the same case
+    fl = _floor()["arm2_N10_SS" if run == "4" else "arm2_N10_SS_xg3"]
+    ex, eu = float(np.max(np.abs(x - D[run + "/final_x"]))), float(np.max(np.abs(u - D[run + "/final_u"])))
+    eJ = float(np.max(np.abs(np.array([r["J"] for r in rows]) / D[run + "/tr_J"] - 1.0)))
+    print("data/%s: rel J %.1e (floor %.1e)  |dx| %.1e (floor %.1e)  |du| %.1e (floor %.1e)" % (run, eJ, fl["rel_J"], ex, fl["abs_x"], eu, fl["abs_u"]))
+    assert eJ <= FLOOR_FACTOR * fl["rel_J"] and ex <= FLOOR_FACTOR * fl["abs_x"] and eu <= FLOOR_FACTOR * fl["abs_u"]
 
 
 def _batch_goals(n, B, seed):
@@ -87,18 +109,27 @@ def test_batch_vs_oracle(name, N, B, limits, oracle_models):
     solver = t.TrajoptMPCReference(plant, pc, pcons) if pcons is not None else t.TrajoptMPCReference(plant, pc)
     opts = {"expected_reduction_min_SQP_DDP": -100, "max_iter_softConstraints": 4}
     r = solver.solve_batch(np.zeros((B, 2 * n, N)), np.zeros((B, n, N - 1)), xg, N, 0.1, t.SQPSolverMethods.PCG_SS, dict(opts))
-    same_iters = 0
+    import copy
+    import sys
+    import os
+    sys.path.insert(0, os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden"))
+    from make_c4_fixture import _perturber          # S -> S (1 +/- 2^-52): the oracle's own sensitivity = the tolerance scale
+    same_iters, worst = 0, (0.0, 0.0)
     for b in range(B):
-        import copy
         oc_b = copy.copy(oc); oc_b.xg = xg[b]
-        ocn_b = copy.deepcopy(ocn)
-        ro = sqp.sqp(m, oc_b, ocn_b, np.zeros((2 * n, N)), np.zeros((n, N - 1)), N, 0.1, "PCG-SS", dict(opts))
+        ro = sqp.sqp(m, oc_b, copy.deepcopy(ocn), np.zeros((2 * n, N)), np.zeros((n, N - 1)), N, 0.1, "PCG-SS", dict(opts))
+        rp = sqp.sqp(m, oc_b, copy.deepcopy(ocn), np.zeros((2 * n, N)), np.zeros((n, N - 1)), N, 0.1, "PCG-SS", dict(opts, _perturb_S=_perturber(b)))
+        stable = rp["pcg_iters"] == ro["pcg_iters"] and rp["ls_trials"] == ro["ls_trials"]
+        fJ = abs(rp["J"] - ro["J"]) / max(1.0, abs(ro["J"])); fx = float(np.max(np.abs(rp["x"] - ro["x"])))
         same = (ro["exit_sqp"], ro["exit_soft"], ro["outer_iter"], ro["sqp_iter"]) == (r.exit_sqp[b], r.exit_soft[b], r.outer_iter[b], r.sqp_iter[b]) \
             and sum(ro["pcg_iters"]) == r.total_pcg[b] and sum(ro["ls_trials"]) == r.total_trials[b]
         same_iters += int(same)
-        if same:
-            assert abs(ro["J"] - r.J[b]) < 1e-6 * max(1.0, abs(ro["J"]))
-            assert np.max(np.abs(ro["x"] - r.x[b])) < 1e-4
+        if same and stable:        # within 100 x the oracle's own 1-ulp sensitivity on this instance (one perturbation seed), never tighter than 1e-9
+            eJ = abs(ro["J"] - r.J[b]) / max(1.0, abs(ro["J"])); ex = float(np.max(np.abs(ro["x"] - r.x[b])))
+            worst = (max(worst[0], eJ), max(worst[1], ex))
+            assert eJ <= max(100 * fJ, 1e-9), (b, eJ, fJ)
+            assert ex <= max(100 * fx, 1e-9), (b, ex, fx)
+    print("%s N=%d: %d of %d instances reproduce every oracle count; worst rel J %.1e, worst |dx| %.1e" % (name, N, same_iters, B, worst[0], worst[1]))
     assert same_iters >= int(0.9 * B), "only %d of %d instances reproduce the oracle's iteration counts" % (same_iters, B)
 
 
