@@ -788,9 +788,11 @@ struct SolverT : SolverBase {
     B2T_CUDA(cudaSetDevice(device));
     int r = all_list(); if (r) return r;
     B2T_CUDA(cudaMemsetAsync(d.dyn_ok, 0, (size_t)d.B * sizeof(int), stream));
+    for (int i = 0; i < B2T_KERNEL_FAMILIES; ++i) { fam_seconds[i] = 0; fam_launches[i] = 0; }
     launch_dynamics(d.act, d.n_act, d.B);
     B2T_CUDA(cudaGetLastError());
     B2T_CUDA(cudaStreamSynchronize(stream));
+    collect_profile();           // with profiling on: CUDA-event times of k_fd / k_fd_grad (b2t_get_kernel_times)
     return 0;
   }
   int stage_kkt(double rho, int method) override {
