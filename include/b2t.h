@@ -121,7 +121,11 @@ typedef enum {
   B2T_ARR_AB,           /* [N][nx*m] [A_k B_k] of the integrator, from the last dynamics pass (row N-1 zero) (:229-233) */
   B2T_ARR_SOFT_VALUE,   /* [N][1]   value_soft_constraints at (x_k, u_k) with the current multipliers (TrajoptConstraint.py:295-308) */
   B2T_ARR_SOFT_GRAD,    /* [N][m]   summed penalty gradient gck (jacobian_soft_constraints, :310-340; element-wise restatement) */
-  B2T_ARR_NU_TRACE      /* [128]    per instance: |r^T Pinv r| of PCG iteration 0..127 of the last b2t_stage_pcg (PCG.py:82,95) */
+  B2T_ARR_NU_TRACE,     /* [128]    per instance: |r^T Pinv r| of PCG iteration 0..127 of the last b2t_stage_pcg (PCG.py:82,95) */
+  B2T_ARR_COST_JTOT,    /* [N][nx*nx] Jacobian of the cost's state map at x_k: UrdfCost jacobian_tot_state (ne x nx row-major in the slot; identity for
+                           the joint-space cost) -- the entries of UrdfCost.saved_Jacobian_tot_state (TrajoptCost.py:439,480) */
+  B2T_ARR_PLANT_TERMS   /* [N][2n + 3n*n] per knot [c | qdd | Minv (n x n) | d rnea / d(q, qd) (n x 2n)] at (x_k, u_k): the entries of
+                           URDFPlant.saved_c / saved_qdd / saved_Minv / saved_dc_du (TrajoptPlant.py:283-323); row N-1 zero */
 } b2t_array;
 
 typedef struct b2t_solver b2t_solver;

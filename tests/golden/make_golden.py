@@ -298,6 +298,17 @@ def sec_refdata(R):
         for key in ("Ak", "Bk", "xkp1"):
             recs = ld(key + ".plk").to_dict("records")
             out["%s/%s_first" % (run, key)] = np.stack([np.array(r["value"], dtype=float).reshape(np.array(recs[0]["value"]).shape) for r in recs[:9]])
+        # cost- and plant-level lists (one entry per callback invocation; TrajoptCost.py:411-517, TrajoptPlant.py:297-322): values flattened
+        # and NaN-padded to the widest entry, plus the three counters each entry was tagged with
+        for key in ("cost", "dx", "grad", "hess", "Jacobian_tot_state", "Minv", "qdd", "dc_du", "dqdd"):
+            recs = ld(key + ".plk").to_dict("records")
+            vals = [np.asarray(r["value"], dtype=float).reshape(-1) for r in recs]
+            w = max(v.size for v in vals)
+            arr = np.full((len(vals), w), np.nan)
+            for i, v in enumerate(vals):
+                arr[i, :v.size] = v
+            out["%s/lvl_%s" % (run, key)] = arr
+            out["%s/lvl_%s_tags" % (run, key)] = np.array([[int(r["iteration"]), int(r["outer_iteration"]), int(r["line_search_iteration"])] for r in recs])
     np.savez_compressed(os.path.join(HERE, "ref_data.npz"), **out)
     print("ref_data.npz written", {k: v.shape for k, v in out.items() if k.startswith("4/")})
 

@@ -87,3 +87,43 @@ def test_record_files(tmp_path, oracle_models):
     assert outers == list(range(len(outers))) and outers[-1] in (res[0][4], res[0][4] - 1)
     results = pd.read_pickle(base / "results.plk")
     assert len(results) == 10
+
+
+@pytest.mark.parametrize("run", ["4", "3"])
+def test_cost_and_plant_level_lists_match_author_recordings(run, oracle_models):
+    """UrdfCost.saved_cost / saved_dx / saved_grad / saved_hess / saved_Jacobian_tot_state (TrajoptCost.py:411-517) and
+    URDFPlant.saved_Minv / saved_qdd / saved_dc_du / saved_dqdd (TrajoptPlant.py:297-322): one entry per callback invocation of the
+    reference, reproduced by replaying its call sequence on the recorded iterates (record.py).  Entry counts, the iteration /
+    line-search tags and the values against the authors' pickles of data/3, data/4 (first QP solve exact to rounding; later entries
+    inherit the parity floor of the iterate they are evaluated at)."""
+    D = load_npz("ref_data.npz")
+    N = 10
+    (plant, pc, _), _ = make_pair("arm2", N, oracle_models, xg=D[run + "/xg"])
+    solver = t.TrajoptMPCReference(plant, pc)
+    solver.SQP(np.zeros((4, N)), np.zeros((2, N - 1)), N, 0.1, t.SQPSolverMethods.PCG_SS,
+               options={"expected_reduction_min_SQP_DDP": -100, "overloading": False}, record=True)
+    post = 4 * (N - 1) + 2          # cost.value calls of runSolversSQP's post-processing (exampleHelpers.py:98-107), recorded after the solve
+    lists = {"cost": pc.saved_cost, "dx": pc.saved_dx, "grad": pc.saved_grad, "hess": pc.saved_hess, "Jacobian_tot_state": pc.saved_Jacobian_tot_state,
+             "Minv": plant.saved_Minv, "qdd": plant.saved_qdd, "dc_du": plant.saved_dc_du, "dqdd": plant.saved_dqdd}
+    floor_x = 10 * {"4": 1.7e-7, "3": 4.1e-6}[run]          # tests/golden/floor.json (arm2_N10_SS, arm2_N10_SS_xg3)
+    for name, got in lists.items():
+        ref, tags = D["%s/lvl_%s" % (run, name)], D["%s/lvl_%s_tags" % (run, name)]
+        n_ref = len(ref) - (post if name in ("cost", "dx") else 0)
+        assert len(got) == n_ref, (name, len(got), n_ref)
+        if name not in ("cost", "dx"):      # the authors' build did not tag cost.value calls (all zeros in cost.plk)
+            assert [[e["iteration"], e["outer_iteration"], e["line_search_iteration"]] for e in got] == tags[:n_ref].tolist(), name
+        first = {"cost": N, "dx": N, "grad": N, "hess": N, "Jacobian_tot_state": 2 * N, "Minv": 4 * (N - 1), "qdd": 4 * (N - 1), "dc_du": N - 1, "dqdd": N - 1}[name]
+        worst = 0.0
+        for i, e in enumerate(got):
+            v = np.asarray(e["value"], dtype=float).reshape(-1)
+            r = ref[i][:v.size]
+            assert not np.any(np.isnan(r)) and (ref[i].size == v.size or np.all(np.isnan(ref[i][v.size:]))), (name, i)
+            scale = max(1.0, float(np.max(np.abs(r))))
+            err = float(np.max(np.abs(v - r))) / scale
+            worst = max(worst, err)
+            assert err < (1e-12 if i < first else 1e3 * floor_x), (name, i, err)
+        print("data/%s %-20s %4d entries, worst relative error %.1e" % (run, name, len(got), worst))
+    # direct calls after the solve keep appending while recording is on, like the reference's post-processing
+    n0 = len(pc.saved_cost)
+    pc.value(np.zeros(4), np.zeros(2)); pc.value(np.zeros(4), None)
+    assert len(pc.saved_cost) == n0 + 2 and len(pc.saved_dx) == n0 + 2

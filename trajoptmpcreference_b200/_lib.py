@@ -18,7 +18,8 @@ LIMIT_NONE, LIMIT_QUADRATIC_PENALTY, LIMIT_AUGMENTED_LAGRANGIAN = 0, 1, 2
 STATUS_FIELDS, SCALAR_FIELDS, TRACE_FIELDS, KERNEL_FAMILIES = 8, 4, 12, 9
 KERNEL_FAMILY_NAMES = ["fd", "fd_grad", "kkt", "schur", "pcg", "recover", "trial_fd", "merit", "ctrl"]
 ARR = {"x": 0, "u": 1, "xkp1": 2, "dqdd": 3, "Ghat": 4, "g": 5, "Sd": 6, "So": 7, "Pd": 8, "gamma": 9, "l": 10, "dz": 11, "xn": 12, "un": 13,
-       "cost_value": 14, "cost_grad": 15, "cost_hess": 16, "cost_err": 17, "kkt_hess": 18, "AB": 19, "soft_value": 20, "soft_grad": 21, "nu_trace": 22}
+       "cost_value": 14, "cost_grad": 15, "cost_hess": 16, "cost_err": 17, "kkt_hess": 18, "AB": 19, "soft_value": 20, "soft_grad": 21, "nu_trace": 22,
+       "cost_jtot": 23, "plant_terms": 24}
 HOOK_LINSYS, HOOK_STEP = 1, 2
 ITERATION_HOOK = ctypes.CFUNCTYPE(c_int, c_void_p, c_int, c_int)
 

@@ -102,6 +102,10 @@ class URDFPlant(TrajoptPlant):
         self.rbdReference = _RbdHandle(self.model)
         self._lib = None
         self._probe = None
+        # plant-level recording lists of the reference (TrajoptPlant.py:297-299, 318-322): one entry per callback invocation, filled
+        # while `recording` is on (SQP(record=True) switches it on and replays the reference's call sequence, record.py)
+        self.recording = False
+        self.saved_c, self.saved_Minv, self.saved_qdd, self.saved_dc_du, self.saved_dqdd = [], [], [], [], []
 
     @property
     def lib(self):
@@ -140,14 +144,31 @@ class URDFPlant(TrajoptPlant):
         p.stage_dynamics()
         return p.fetch("dqdd")[0, 0].reshape(n, 3 * n), p.fetch("xkp1")[0, 0]
 
+    def _terms(self, xk, uk):
+        """(c, qdd, Minv, dc_du) at one knot from the plant kernel (B2T_ARR_PLANT_TERMS)."""
+        p = self._probe_solver()
+        n = self.model["n"]
+        x = np.zeros((1, 2 * n, 2)); u = np.zeros((1, n, 1))
+        x[0, :, 0] = np.asarray(xk, dtype=np.float64).reshape(-1); u[0, :, 0] = np.asarray(uk, dtype=np.float64).reshape(-1)
+        p.set_trajectory(x, u)
+        return split_plant_terms(p.fetch("plant_terms")[0, 0], n)
+
+    def _save(self, tag, **entries):
+        for name, value in entries.items():
+            getattr(self, "saved_" + name).append(dict(value=value, **tag))
+
     def forward_dynamics_gradient(self, x, u, iter_1=0, iter_2=0, iter_3=0):
-        return self._eval(x, u, 1.0)[0]
+        dqdd = self._eval(x, u, 1.0)[0]
+        if self.recording:
+            c, qdd, Minv, dc_du = self._terms(x, u)
+            self._save(dict(iteration=iter_1, outer_iteration=iter_2, line_search_iteration=iter_3), Minv=Minv, c=c, qdd=qdd, dc_du=dc_du, dqdd=dqdd)
+        return dqdd
 
     def forward_dynamics(self, x, u, iter_1=0, iter_2=0, iter_3=0):
-        n = self.model["n"]
-        big = 2.0 ** 40         # v+ = qd + dt*qdd for both integrators; a power-of-two dt makes the division exact
-        xn = self._eval(x, u, big)[1]
-        return (xn[n:] - np.asarray(x, dtype=np.float64).reshape(-1)[n:]) / big
+        c, qdd, Minv, _ = self._terms(x, u)
+        if self.recording:
+            self._save(dict(iteration=iter_1, outer_iteration=iter_2, line_search_iteration=iter_3), c=c, Minv=Minv, qdd=qdd)
+        return qdd
 
     def integrator(self, xk, uk, dt, return_gradient=False, iter_1=0, iter_2=0, iter_3=0):
         n = self.model["n"]
@@ -161,6 +182,11 @@ class URDFPlant(TrajoptPlant):
         Iz = np.hstack((np.eye(2 * n), np.zeros((2 * n, n))))
         AB = Iz + dt * np.vstack((top + dt * dqdd, dqdd))
         return AB[:, :2 * n], AB[:, 2 * n:]
+
+
+def split_plant_terms(t, n):
+    """[c | qdd | Minv | d rnea / d(q, qd)] of one knot (B2T_ARR_PLANT_TERMS) -> (c (n,), qdd (n,), Minv (n, n), dc_du (n, 2n))."""
+    return t[:n].copy(), t[n:2 * n].copy(), t[2 * n:2 * n + n * n].reshape(n, n).copy(), t[2 * n + n * n:].reshape(n, 2 * n).copy()
 
 
 # --------------------------------------------------------------------------------------------------- costs
@@ -254,6 +280,9 @@ class UrdfCost(QuadraticCost):
         self.plant.rbdReference.overloading = overloading
         self.overloading = overloading
         self.hess_mode = 0
+        # cost-level recording lists of the reference (TrajoptCost.py:382-386, appended at :411-412, :420-421, :457-458, :516-517)
+        self.recording = False
+        self.saved_cost, self.saved_grad, self.saved_hess, self.saved_Jacobian_tot_state, self.saved_dx = [], [], [], [], []
 
     def _knot(self, x, u, timestep):
         """Evaluate this cost at one knot on the GPU (1 instance, 2 knots: knot 0 = (x,u) as a running knot, knot 1 = x as terminal)."""
@@ -275,20 +304,36 @@ class UrdfCost(QuadraticCost):
         s.set_trajectory(X, U)
         return s, (1 if u is None else 0)
 
+    def _save(self, tag, **entries):
+        for name, value in entries.items():
+            getattr(self, "saved_" + name).append(dict(value=value, **tag))
+
+    def _jtot(self, s, k):
+        return s.fetch("cost_jtot")[0, k].reshape(2 * self.n, 2 * self.n)[:4].copy()
+
     def value(self, x, u=None, timestep=None, iter_1=0, iter_2=0, iter_3=0):
         s, k = self._knot(x, u, timestep)
-        return float(s.fetch("cost_value")[0, k, 0])
+        v = float(s.fetch("cost_value")[0, k, 0])
+        if self.recording:
+            self._save(dict(iteration=iter_1, outer_iteration=iter_2, line_search_iteration=iter_3), cost=v, dx=s.fetch("cost_err")[0, k, :4].copy())
+        return v
 
     def gradient(self, x, u=None, timestep=None, iter_1=0, iter_2=0, iter_3=0):
         s, k = self._knot(x, u, timestep)
         g = s.fetch("cost_grad")[0, k]
-        return g[:2 * self.n].copy() if u is None else g.copy()
+        g = g[:2 * self.n].copy() if u is None else g.copy()
+        if self.recording:
+            self._save(dict(iteration=iter_1, outer_iteration=iter_2, line_search_iteration=iter_3), grad=g, Jacobian_tot_state=self._jtot(s, k))
+        return g
 
     def hessian(self, x, u=None, timestep=None, iter_1=0, iter_2=0, iter_3=0):
         s, k = self._knot(x, u, timestep)
         m = 3 * self.n
         H = s.fetch("cost_hess")[0, k].reshape(m, m)
-        return H[:2 * self.n, :2 * self.n].copy() if u is None else H.copy()
+        H = H[:2 * self.n, :2 * self.n].copy() if u is None else H.copy()
+        if self.recording:
+            self._save(dict(iteration=iter_1, outer_iteration=iter_2, line_search_iteration=iter_3), hess=H, Jacobian_tot_state=self._jtot(s, k))
+        return H
 
     def delta_x(self, x):
         """End-effector state error [ee_pos; J qd] - xg (TrajoptCost.py:425-435), evaluated by the cost kernel."""
@@ -781,7 +826,8 @@ class BatchSolver:
         E = {"x": self.nx, "u": self.nu, "xkp1": self.nx, "dqdd": self.n * 3 * self.n, "Ghat": self.m * self.m, "g": self.m,
              "Sd": self.nx * self.nx, "So": self.nx * self.nx, "Pd": self.nx * self.nx, "gamma": self.nx, "l": self.nx, "dz": self.m,
              "xn": self.nx, "un": self.nu, "cost_value": 1, "cost_grad": self.m, "cost_hess": self.m * self.m, "cost_err": self.nx,
-             "kkt_hess": self.m * self.m, "AB": self.nx * self.m, "soft_value": 1, "soft_grad": self.m, "nu_trace": None}[name]
+             "kkt_hess": self.m * self.m, "AB": self.nx * self.m, "soft_value": 1, "soft_grad": self.m, "nu_trace": None,
+             "cost_jtot": self.nx * self.nx, "plant_terms": 2 * self.n + 3 * self.n * self.n}[name]
         if name == "nu_trace":
             out = np.zeros((self.batch, 128))
             _lib.check(self.lib, self.lib.b2t_fetch(self._h, _lib.ARR[name], _dptr(out)))

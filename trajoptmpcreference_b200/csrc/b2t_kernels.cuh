@@ -2514,6 +2514,14 @@ __global__ void k_cost_eval(Dev<T> d, int what, double* out) {
     for (int i = 0; i < NX; ++i) out[gt * NX + i] = i < ne ? (double)e[i] : 0.0;
     return;
   }
+  if (what == 8) {      // Jacobian of the cost's state map (UrdfCost: jacobian_tot_state, TrajoptCost.py:439), ne x nx row-major in an nx*nx slot
+    T e[NX], Jt[NX * NX]; bool hj;
+    const int ne = cost_state(d.cost, z, xg, e, Jt, &hj);
+    for (int i = 0; i < NX * NX; ++i) out[gt * NX * NX + i] = 0.0;
+    for (int i = 0; i < ne; ++i)
+      for (int j = 0; j < NX; ++j) out[gt * NX * NX + i * NX + j] = hj ? (double)Jt[i * NX + j] : (i == j ? 1.0 : 0.0);
+    return;
+  }
   if (what == 6 || what == 7) {      // soft box limits at (x_k, u_k) with the current multipliers: value, resp. summed gradient gck (NM)
     T gck[NM];
     for (int i = 0; i < NM; ++i) gck[i] = T(0);
@@ -2543,6 +2551,31 @@ __global__ void k_cost_eval(Dev<T> d, int what, double* out) {
   }
   if (what == 1) { for (int i = 0; i < NM; ++i) out[gt * NM + i] = (double)g[i]; }
   else { for (int i = 0; i < NM * NM; ++i) out[gt * NM * NM + i] = (double)H[i]; }
+}
+// plant-level terms of one knot at (x_k, u_k), what the reference's URDFPlant callbacks append to saved_c / saved_qdd / saved_Minv /
+// saved_dc_du (TrajoptPlant.py:283-323): out[knot] = [c (n) | qdd (n) | Minv (n x n) | dc/d(q, qd) (n x 2n)], row-major doubles
+constexpr int PLANT_TERMS = 2 * NJ + NJ * NJ + 2 * NJ * NJ;
+template <typename T>
+__global__ void __launch_bounds__(64) k_plant_eval(Dev<T> d, double* out) {
+  const size_t gt = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (gt >= d.K) return;
+  const int k = (int)(gt % d.N);
+  double* o = out + gt * PLANT_TERMS;
+  if (k == d.N - 1) { for (int i = 0; i < PLANT_TERMS; ++i) o[i] = 0.0; return; }
+  T z[NM];
+  load_xu(d.x, d.u, d.K, gt, false, z, z + NX);
+  T xe[NJ][NXE], c[NJ], qdd[NJ], Minv[NJ * NJ], v[NJ][6], a[NJ][6], f[NJ][6];
+  xset_all(z, xe);
+  rnea<T, false>(xe, z + NJ, nullptr, d.gravity, v, a, f, c);
+  for (int i = 0; i < NJ; ++i) o[i] = (double)c[i];
+  forward_dynamics<T, true>(z, z + NJ, z + NX, d.gravity, qdd, Minv, v, a, f);      // leaves v, a, f of rnea(q, qd, qdd)
+  for (int i = 0; i < NJ; ++i) o[NJ + i] = (double)qdd[i];
+  for (int i = 0; i < NJ * NJ; ++i) o[2 * NJ + i] = (double)Minv[i];
+  for (int col = 0; col < 2 * NJ; ++col) {
+    T dq[NJ], dc[NJ];
+    fd_grad_column(z, z + NJ, v, a, f, Minv, d.gravity, col % NJ, col >= NJ, dq, dc);
+    for (int i = 0; i < NJ; ++i) o[2 * NJ + NJ * NJ + i * 2 * NJ + col] = (double)dc[i];
+  }
 }
 // standalone PCG entry (PCG(A, b, block_size, Nblocks).solve()): upload of a block-tridiagonal system in knot-major doubles
 template <typename T>

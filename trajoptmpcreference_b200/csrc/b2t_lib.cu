@@ -893,6 +893,8 @@ struct SolverT : SolverBase {
       case B2T_ARR_AB: E = NX * NM; break;
       case B2T_ARR_SOFT_VALUE: E = 1; break;
       case B2T_ARR_SOFT_GRAD: E = NM; break;
+      case B2T_ARR_COST_JTOT: E = NX * NX; break;
+      case B2T_ARR_PLANT_TERMS: E = PLANT_TERMS; break;
       case B2T_ARR_NU_TRACE: {
         std::vector<T> h((size_t)d.B * NU_TRACE_LEN);
         B2T_CUDA(cudaStreamSynchronize(stream));
@@ -905,6 +907,8 @@ struct SolverT : SolverBase {
     const size_t n = K * E;
     if (n * sizeof(double) > stage_out_bytes) return fail(B2T_ERR_INVALID, "array too large for staging");
     if (which >= B2T_ARR_COST_VALUE && which <= B2T_ARR_SOFT_GRAD) k_cost_eval<T><<<cdiv(K, 64), 64, 0, stream>>>(d, which - B2T_ARR_COST_VALUE, stage_out);
+    else if (which == B2T_ARR_COST_JTOT) k_cost_eval<T><<<cdiv(K, 64), 64, 0, stream>>>(d, 8, stage_out);
+    else if (which == B2T_ARR_PLANT_TERMS) k_plant_eval<T><<<cdiv(K, 64), 64, 0, stream>>>(d, stage_out);
     else if (which == B2T_ARR_GHAT && d.diag_mode) k_fetch_ghat_diag<T><<<cdiv(K, 128), 128, 0, stream>>>(d, stage_out);
     else k_fetch_soa<T><<<cdiv(K, 128), 128, 0, stream>>>(src, K, E, stage_out);
     B2T_CUDA(cudaGetLastError());

@@ -9,8 +9,15 @@ b2t_set_iteration_hook) that reads the KKT blocks of every SQP iteration back an
 matrices:  z = [x_0,u_0,...,x_{N-1}],  G = blkdiag(G_k) + rho I (what solveKKTSystem_Schur stores, :369),  C rows [I], [-A_k,-B_k,I],
 c = [x_0-xs; x_{k+1}-f(x_k,u_k)],  invG,  S (block tridiagonal),  gamma,  Pinv (J / BJ: block diagonal, SS: PCG.py:113-212),  l,
 dxul = [dz; l].  Every entry is tagged {'iteration','outer_iteration','line_search_iteration'} like the reference's.
-Lists the batched solver has no per-call equivalent of (cost- and plant-level `saved_*`: one entry per Python callback invocation)
-are not produced; see INTEGRATION.md.
+The cost- and plant-level lists (`UrdfCost.saved_cost / saved_dx / saved_grad / saved_hess / saved_Jacobian_tot_state`,
+TrajoptCost.py:411-421, 457-458, 516-517; `URDFPlant.saved_c / saved_Minv / saved_qdd / saved_dc_du / saved_dqdd`, TrajoptPlant.py:297-299,
+318-322) hold one entry per Python callback invocation in the reference.  The batched solver makes no such calls, so the Recorder
+REPLAYS the reference's call sequence from the recorded iterates: per outer iteration totalCost (:296-310) and
+totalHardConstraintViolation (:273-294) of the start point; per QP solve the loop of formKKTSystemBlocks (:200-271: hessian, gradient,
+integrator with and without gradient per knot); per line-search trial totalCost, the violation and the directional-derivative loop
+(:617-648) at x - alpha dz.  Every knot of a trajectory is evaluated in one launch of the cost / plant kernels
+(B2T_ARR_COST_*, B2T_ARR_PLANT_TERMS) and the entries carry the reference's three counters as it would hold them at that call
+(`matrix_.iteration`, `.soft_constraint_iteration`, `.line_search_iteration`, incl. their stale values between loops).
 """
 import os
 import time
@@ -22,6 +29,10 @@ from . import _lib
 SQP_VARS = ["saved_Pinv", "saved_inner_traces", "saved_G", "trace", "saved_invG", "saved_c", "saved_g", "saved_C", "saved_tot_cost",
             "saved_J_tot_constraints", "saved_Ak", "saved_Bk", "saved_xkp1", "saved_dxul", "saved_x", "saved_u", "saved_S", "saved_gamma",
             "saved_l"]
+
+
+COST_VARS = ["saved_cost", "saved_grad", "saved_hess", "saved_Jacobian_tot_state", "saved_dx"]
+PLANT_VARS = ["saved_Minv", "saved_c", "saved_dc_du", "saved_qdd", "saved_dqdd"]
 
 
 class Recorder:
@@ -37,6 +48,95 @@ class Recorder:
                 setattr(owner, name, [])
         self._tag = None
         self._last_xu = None
+        # replay of the cost- / plant-level callbacks (see the module docstring)
+        self.alpha_factor = float(options.get("alpha_factor_SQP_DDP", 0.5))
+        self.max_iter_sqp = int(options.get("max_iter_SQP_DDP", 100))
+        self._cost_lists = hasattr(owner.cost, "saved_cost")
+        self._ref_it, self._ref_ls, self._outer_seen = 0, 0, -1
+        self._probe = None
+        self._pre = None                    # (X, U, dz, iteration, outer, total_trials) of the QP solve whose line search is running
+        for obj, names in ((owner.cost, ("cost", "grad", "hess", "Jacobian_tot_state", "dx")), (owner.plant, ("c", "Minv", "qdd", "dc_du", "dqdd"))):
+            for name in names:
+                if hasattr(obj, "saved_" + name):
+                    setattr(obj, "saved_" + name, [])
+            if hasattr(obj, "recording"):
+                obj.recording = True        # later direct calls (e.g. runSolversSQP's post-processing) append like the reference's do
+
+    # ---- cost / plant kernels over all knots of one trajectory
+    def _eval(self, X, U):
+        from .api import BatchSolver, split_plant_terms
+        s = self.s
+        if self._probe is None:
+            self._probe = BatchSolver(self.o.plant, self.o.cost, None, N=s.N, dt=s.dt, batch=1)
+        p = self._probe
+        p.set_goals(np.asarray(self.o.cost.xg, dtype=np.float64).reshape(1, -1))
+        p.set_trajectory(X[None], U[None])
+        n, N = s.n, s.N
+        out = dict(value=p.fetch("cost_value")[0, :, 0], dx=p.fetch("cost_err")[0], grad=p.fetch("cost_grad")[0],
+                   hess=p.fetch("cost_hess")[0].reshape(N, s.m, s.m), jtot=p.fetch("cost_jtot")[0].reshape(N, s.nx, s.nx))
+        p.stage_dynamics()
+        out["dqdd"] = p.fetch("dqdd")[0].reshape(N, n, 3 * n)
+        out["plant"] = [split_plant_terms(t, n) for t in p.fetch("plant_terms")[0]]
+        return out
+
+    def _put(self, obj, tag, **entries):
+        for name, value in entries.items():
+            lst = getattr(obj, "saved_" + name, None)
+            if lst is not None:
+                lst.append(dict(value=value, iteration=tag[0], outer_iteration=tag[1], line_search_iteration=tag[2]))
+
+    def _fd(self, e, k, tag, gradient=False):
+        c, qdd, Minv, dc_du = e["plant"][k]
+        if gradient:        # forward_dynamics_gradient (TrajoptPlant.py:318-322)
+            self._put(self.o.plant, tag, Minv=Minv, c=c, qdd=qdd, dc_du=dc_du, dqdd=e["dqdd"][k].copy())
+        else:               # forward_dynamics (:297-299)
+            self._put(self.o.plant, tag, c=c, Minv=Minv, qdd=qdd)
+
+    def _cost(self, e, k, tag, what):
+        if not self._cost_lists:
+            return
+        s, ne = self.s, 4
+        w = s.m if k < s.N - 1 else s.nx
+        jt = e["jtot"][k][:ne].copy()
+        if what == "value":
+            self._put(self.o.cost, tag, cost=float(e["value"][k]), dx=e["dx"][k][:ne].copy())
+        elif what == "grad":
+            self._put(self.o.cost, tag, grad=e["grad"][k][:w].copy(), Jacobian_tot_state=jt)
+        else:
+            self._put(self.o.cost, tag, hess=e["hess"][k][:w, :w].copy(), Jacobian_tot_state=jt)
+
+    def _total_cost_and_violation(self, e, tag):
+        N = self.s.N
+        for k in range(N):                    # totalCost (:296-310)
+            self._cost(e, k, tag, "value")
+        for k in range(N - 1):                # totalHardConstraintViolation (:273-294): integrator -> forward_dynamics
+            self._fd(e, k, tag)
+
+    def _replay_kkt(self, e, tag):
+        N = self.s.N
+        ptag = (tag[0], tag[1], 0)            # the numpy branch passes no iter_3 to plant.integrator here (:227, :230): default 0
+        for k in range(N - 1):                # formKKTSystemBlocks (:200-271)
+            self._cost(e, k, tag, "hess")
+            self._cost(e, k, tag, "grad")
+            self._fd(e, k, ptag)              # integrator(return_gradient=True): forward_dynamics, then its gradient (TrajoptPlant.py:95-101)
+            self._fd(e, k, ptag, gradient=True)
+            self._fd(e, k, ptag)              # integrator() for x_{k+1}
+        self._cost(e, N - 1, tag, "hess")
+        self._cost(e, N - 1, tag, "grad")
+
+    def _replay_line_search(self, trials):
+        X, U, dz, it, outer = self._pre
+        s = self.s
+        for j in range(trials):               # SQP :606-744: one trial per alpha = alpha_factor^j
+            a = self.alpha_factor ** j
+            Xn = X - a * dz[:, :s.nx].T
+            Un = U - a * dz[:s.N - 1, s.nx:].T
+            e = self._eval(Xn, Un)
+            tag = (it, outer, j)
+            self._total_cost_and_violation(e, tag)
+            for k in range(s.N):              # directional derivative D (:635-648)
+                self._cost(e, k, tag, "grad")
+        self._ref_ls = trials - 1
 
     # ---- dense layouts of the reference
     def _dense(self):
@@ -97,6 +197,15 @@ class Recorder:
                 self._last_xu = s.get_trajectory()
             d = self._dense()
             tag = self._tag
+            # cost- / plant-level callbacks the reference makes up to and inside this QP solve
+            it, outer = int(st[3]), int(st[2])
+            Xc, Uc = s.get_trajectory()
+            e = self._eval(Xc[0], Uc[0])
+            if outer != self._outer_seen:     # start of an outer iteration: J and c of the start point, counters still stale (:541-542)
+                self._outer_seen = outer
+                self._total_cost_and_violation(e, (self._ref_it, outer, self._ref_ls))
+            self._ref_it = it
+            self._replay_kkt(e, (it, outer, self._ref_ls))
 
             def put(name, value):
                 getattr(o, name).append(dict(value=value, **tag))
@@ -112,7 +221,14 @@ class Recorder:
                 o.saved_inner_traces.append(((nu[:n_it + 1].tolist(), []), tag["iteration"], tag["outer_iteration"]))
                 put("saved_Pinv", d["Pinv"])
             put("saved_l", d["l"]); put("saved_dxul", d["dxul"])
+            self._pre = (Xc[0].copy(), Uc[0].copy(), s.fetch("dz")[0].copy(), it, outer)
+            self._trials_before = int(st[6]) - 0
         elif event == _lib.HOOK_STEP:
+            if self._pre is not None:
+                self._replay_line_search(int(st[6]) - self._trials_before)
+                it = self._pre[3]
+                self._ref_it = it if it == self.max_iter_sqp - 1 else it + 1          # check_for_exit_or_error (:476-479)
+                self._pre = None
             x, u = s.get_trajectory()
             if self._last_xu is None or not (np.array_equal(x, self._last_xu[0]) and np.array_equal(u, self._last_xu[1])):
                 o.saved_x.append(dict(value=x[0].copy(), **self._tag))
@@ -174,6 +290,14 @@ def runSolversSQP(trajoptMPCReference, N, dt, solver_methods, options=None, n_te
         save_in_file(os.path.join(base, "results.plk"), [t2 - t1, J, Jx, Ju, error, E, exit_sqp, exit_soft, outer_iter, sqp_iter])
         for var in SQP_VARS:
             save_in_file(os.path.join(base, var + ".plk"), getattr(trajoptMPCReference, var))
+        # plant- and cost-level lists (exampleHelpers.py:140-154; the plant's saved_c is written after, and over, the solver's c.plk
+        # there -- kept apart here as plant_c.plk, with c.plk holding the solver-level list the analysis notebooks read)
+        for var in PLANT_VARS:
+            if hasattr(trajoptMPCReference.plant, var):
+                save_in_file(os.path.join(base, ("plant_c" if var == "saved_c" else var) + ".plk"), getattr(trajoptMPCReference.plant, var))
+        for var in COST_VARS:
+            if hasattr(cost, var):
+                save_in_file(os.path.join(base, var + ".plk"), getattr(cost, var))
     return results_all
 
 
