@@ -36,7 +36,7 @@
 extern "C" {
 #endif
 
-#define B2T_ABI_VERSION 1
+#define B2T_ABI_VERSION 2
 
 typedef enum {
   B2T_OK = 0,
@@ -72,6 +72,7 @@ typedef struct {
   const double* lower;    /* [nx+nu] lower bounds of z = [q; qd; u] (read where the type's mode != NONE) */
   const double* upper;    /* [nx+nu] */
   double mu_init[3], mu_factor[3], mu_max[3], phi_init[3], phi_factor[3];   /* TrajoptConstraint.py:40-44 */
+  int hess_mode;          /* UrdfCost.hess_mode (TrajoptCost.py:391-395): 0 Gauss-Newton J^T Q J, 1 exact Hessian (ABI version 2) */
 } b2t_problem_desc;
 
 typedef struct {           /* TrajoptMPCReference.set_default_options (:91-115) */

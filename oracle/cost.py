@@ -65,6 +65,8 @@ class QuadraticCost:
         else:
             QJ = np.matmul(Qs, Jt)
             H[:, :self.nx, :self.nx] = np.matmul(np.swapaxes(QJ, -1, -2), Jt)    # ((Q J)^T) J  (:493)
+            if getattr(self, "hess_mode", 0) == 1:
+                H[:, :self.nx, :self.nx] += self.second_order_term(X, Qs)
         H[:N - 1, self.nx:, self.nx:] = self.R
         return H
 
@@ -81,6 +83,26 @@ class UrdfCost(QuadraticCost):
         self.n = model.n
         self.nx = 2 * self.n
         assert self.n >= 2 and self.Q.shape == (4, 4)
+
+    hess_mode = 0       # 0: Gauss-Newton J_tot^T Q J_tot (:493); 1: exact = Gauss-Newton + sum_i (Q e)_i d2 e_i / dx2
+
+    def second_order_term(self, X, Qs):
+        """hess_mode 1 (TrajoptCost.py:494-499 computes `hess_1 + (dx^T Q dJtotdq)` but crashes: `hess_x` is unbound and
+        RBDReference has no d2Jdq2): the intent is the EXACT Hessian of 0.5 e^T Q e, i.e. the Gauss-Newton part plus
+        sum_i (Q e)_i * Hessian(e_i), e = [p(q); J(q) qd] - xg.  UNPINNED: this exact form is the specification, for every n >= 2.
+            d2 p_r / dq dq = Hs_r;   d2 (J qd)_r / dq dq = sum_j d3 p_r/dq dq dq_j qd_j;   d2 (J qd)_r / dq dqd = Hs_r."""
+        n, nx = self.n, self.nx
+        q, qd = X[..., :n], X[..., n:]
+        e = self.state_error(X)
+        w = np.matmul(Qs, e[..., None])[..., 0]                     # (N, 4)
+        _, Hs = rbd.planar_jacobians(self.model, q)                  # (N, 2, n, n)
+        T3 = rbd.planar_third_derivative_times_qd(self.model, q, qd)
+        S2 = np.zeros(X.shape[:-1] + (nx, nx))
+        for r in range(2):
+            S2[..., :n, :n] += w[..., r, None, None] * Hs[..., r, :, :] + w[..., 2 + r, None, None] * T3[..., r, :, :]
+            S2[..., :n, n:] += w[..., 2 + r, None, None] * Hs[..., r, :, :]
+            S2[..., n:, :n] += w[..., 2 + r, None, None] * Hs[..., r, :, :]
+        return S2
 
     def state_error(self, X):
         """delta_x (:425-435): [ee_pos; J qd] - xg"""

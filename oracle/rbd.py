@@ -77,6 +77,14 @@ class Model:
         return np.zeros(t.shape + (4, 4))
 
 
+    def dddH(self, j, t):
+        """third derivative of the homogeneous transform (revolute: -dH; prismatic: 0)"""
+        t = np.asarray(t, dtype=np.float64)
+        if self.jtype[j] == "revolute":
+            return -self.dH(j, t)
+        return np.zeros(t.shape + (4, 4))
+
+
 def _mv(M, v):
     """(..,a,b) @ (..,b) -> (..,a)"""
     return np.matmul(M, v[..., None])[..., 0]
@@ -339,6 +347,36 @@ def planar_jacobians(model, q, offset=EE_OFFSET):
             Hs[..., :, c, d] = v
             Hs[..., :, d, c] = v
     return J, Hs
+
+
+def planar_third_derivative_times_qd(model, q, qd, offset=EE_OFFSET):
+    """sum_j d3(x,y)/dq_a dq_b dq_j qd_j  -> (..,2,n,n): the q-q block of the second derivative of the end-effector velocity J(q) qd
+    (exact; needed by the exact Hessian of the end-effector cost, UrdfCost.hess_mode 1)."""
+    q = np.asarray(q, dtype=np.float64)
+    qd = np.asarray(qd, dtype=np.float64)
+    n = model.n
+    chain = _chain(model)
+    off = np.broadcast_to(offset, q.shape[:-1] + (4,))
+    mats = {0: model.H, 1: model.dH, 2: model.ddH, 3: model.dddH}
+
+    def prod(orders):
+        T = np.broadcast_to(np.eye(4), q.shape[:-1] + (4, 4))
+        for j in chain:
+            T = np.matmul(T, mats[orders.get(j, 0)](j, q[..., j]))
+        return _mv(T, off)[..., :2]
+
+    out = np.zeros(q.shape[:-1] + (2, n, n))
+    for ia, a in enumerate(chain):
+        for b in chain[ia:]:
+            acc = np.zeros(q.shape[:-1] + (2,))
+            for j in chain:
+                orders = {}
+                for idx in (a, b, j):
+                    orders[idx] = orders.get(idx, 0) + 1
+                acc = acc + prod(orders) * qd[..., j, None]
+            out[..., :, a, b] = acc
+            out[..., :, b, a] = acc
+    return out
 
 
 def jacobian_tot_state_general(model, q, qd, offset=EE_OFFSET):

@@ -27,9 +27,18 @@ int he_dynamics(int count, const double* x, const double* u, double dt, double g
   return 0;
 }
 // cost value / gradient / hessian and soft terms of `count` knots
+int he_cost_mode(int count, int kind, int qf_start, int hess_mode, const double* Q, const double* QF, const double* R, const double* xg,
+                 const double* x, const double* u, const int* kidx, const int* terminal, double* val, double* grad, double* hess) {
+  CostParams<double> cp{kind, qf_start, hess_mode, Q, QF, R};
+  for (int t = 0; t < count; ++t) {
+    val[t] = cost_value(cp, x + t * NX, u + t * NU, xg, kidx[t], terminal[t] != 0);
+    cost_grad_hess<double, true>(cp, x + t * NX, u + t * NU, xg, kidx[t], terminal[t] != 0, grad + t * NM, hess + t * NM * NM);
+  }
+  return 0;
+}
 int he_cost(int count, int kind, int qf_start, const double* Q, const double* QF, const double* R, const double* xg, const double* x,
             const double* u, const int* kidx, const int* terminal, double* val, double* grad, double* hess) {
-  CostParams<double> cp{kind, qf_start, Q, QF, R};
+  CostParams<double> cp{kind, qf_start, 0, Q, QF, R};
   for (int t = 0; t < count; ++t) {
     val[t] = cost_value(cp, x + t * NX, u + t * NU, xg, kidx[t], terminal[t] != 0);
     cost_grad_hess<double, true>(cp, x + t * NX, u + t * NU, xg, kidx[t], terminal[t] != 0, grad + t * NM, hess + t * NM * NM);

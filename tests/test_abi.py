@@ -17,7 +17,7 @@ def test_library_exports_every_declared_symbol(name):
     for sym in decl:
         assert hasattr(lib, sym), sym
     assert set(decl) == set(_lib._SIGNATURES), set(decl) ^ set(_lib._SIGNATURES)
-    assert lib.b2t_abi_version() == 1
+    assert lib.b2t_abi_version() == 2
     assert lib.b2t_model_name().decode() == name
     nq, nx, nu = ctypes.c_int(), ctypes.c_int(), ctypes.c_int()
     lib.b2t_model_dims(ctypes.byref(nq), ctypes.byref(nx), ctypes.byref(nu))

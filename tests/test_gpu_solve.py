@@ -290,3 +290,40 @@ def test_in_place_mutators_invalidate_cached_workspace(oracle_models):
     cons.set_torque_limits([0.1], [-0.1], "QUADRATIC_PENALTY", {})
     r_lim2 = solver2.SQP(x0, u0, N, 0.1, t.SQPSolverMethods.PCG_SS, dict(opts))
     assert not np.array_equal(r_lim[1], r_lim2[1])
+
+
+@pytest.mark.parametrize("name,N,B,iters", [("arm3", 12, 6, 10), ("arm2", 10, 4, 8)])
+def test_end_effector_cost_exact_hessian_mode(name, N, B, iters, oracle_models):
+    """UrdfCost.hess_mode = 1 (TrajoptCost.py:391-395, 494-499): the reference's branch crashes (`hess_x` unbound, no d2Jdq2), so the
+    exact Hessian  J_tot^T Q J_tot + sum_i (Q e)_i Hessian(e_i)  is the specification (oracle/cost.py second_order_term; finite-
+    difference checked in tests/test_hostemu.py).  Callback against the oracle, then complete solves with the exact linear solver."""
+    import copy
+    m = oracle_models[name]
+    n = m.n
+    rng = np.random.default_rng(5)
+    ang = rng.uniform(0.4, 2.6, B); rad = rng.uniform(0.6, 0.8 * n, B)
+    xg = np.stack([rad * np.cos(ang), rad * np.sin(ang), np.zeros(B), np.zeros(B)], axis=1)
+    (plant, pc, _), (_, oc, _) = make_pair(name, N, oracle_models, xg=xg[0], cost_kind="urdf")
+    xk = rng.uniform(-1, 1, 2 * n); uk = rng.uniform(-1, 1, n)
+    X = np.stack([xk, xk]); U = uk[None]
+    H0 = pc.hessian(xk, uk)
+    pc.hess_mode = 1; oc.hess_mode = 1
+    H1 = pc.hessian(xk, uk)
+    assert np.allclose(H1, oc.hessians(X, U)[0], rtol=1e-12, atol=1e-12)
+    assert np.max(np.abs(H1 - H0)) > 1e-3 * np.max(np.abs(H0))        # the mode switch reaches the device (cached probe re-keyed on content)
+    assert np.allclose(pc.hessian(xk), oc.hessians(X, U)[1][:2 * n, :2 * n], rtol=1e-12, atol=1e-12)
+    solver = t.TrajoptMPCReference(plant, pc)
+    opts = {"expected_reduction_min_SQP_DDP": -100, "max_iter_SQP_DDP": iters}
+    r = solver.solve_batch(np.zeros((B, 2 * n, N)), np.zeros((B, n, N - 1)), xg, N, 0.1, t.SQPSolverMethods.S, dict(opts))
+    same = 0
+    for b in range(B):
+        oc_b = copy.copy(oc); oc_b.xg = xg[b]
+        ro = sqp.sqp(m, oc_b, None, np.zeros((2 * n, N)), np.zeros((n, N - 1)), N, 0.1, "S", dict(opts))
+        ok = (ro["exit_sqp"], ro["sqp_iter"]) == (r.exit_sqp[b], r.sqp_iter[b]) and sum(ro["ls_trials"]) == r.total_trials[b]
+        same += int(ok)
+        print("%s hess_mode 1 instance %d: oracle (exit, iters, trials) %s gpu %s rel J %.1e" %
+              (name, b, (ro["exit_sqp"], ro["sqp_iter"], sum(ro["ls_trials"])), (int(r.exit_sqp[b]), int(r.sqp_iter[b]), int(r.total_trials[b])),
+               abs(ro["J"] - r.J[b]) / max(1.0, abs(ro["J"]))))
+        if ok:
+            assert abs(ro["J"] - r.J[b]) < 1e-6 * max(1.0, abs(ro["J"]))
+    assert same >= B - 1

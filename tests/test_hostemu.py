@@ -133,3 +133,49 @@ def test_spd_inverse_packed(n):
         for j in range(i + 1):
             got[i, j] = got[j, i] = packed[k]; k += 1
     assert relerr(got, inv) < 1e-11
+
+
+@pytest.mark.parametrize("name", ["arm2", "arm3", "arm6", "cartpole"])
+def test_exact_hessian_mode(name, oracle_models):
+    """UrdfCost.hess_mode 1 (TrajoptCost.py:494-499; crashes in the reference, so the exact Hessian of 0.5 e^T Q e is the spec):
+    the device code against the oracle's second_order_term, and -- for n > 2, where the gradient is exact -- against central
+    differences of the analytic gradient (the Gauss-Newton Hessian of mode 0 does not pass that check)."""
+    lib = hostemu.load(name)
+    if name in oracle_models:
+        m = oracle_models[name]
+    else:
+        from oracle import rbd
+        from trajoptmpcreference_b200 import model as pmodel
+        m = rbd.Model(pmodel.extract_model(pmodel.builtin_urdf(name)))
+    n = m.n; nx = 2 * n; nm = 3 * n
+    rng = np.random.default_rng(8)
+    A = rng.uniform(-1, 1, (4, 4)); Q = A @ A.T + np.eye(4)
+    QF = 10 * Q
+    R = 0.1 * np.eye(n)
+    xg = rng.uniform(-1, 1, 4)
+    N = 5
+    X = rng.uniform(-1.5, 1.5, (N, nx)); U = rng.uniform(-1, 1, (N - 1, n))
+    c = ocost.UrdfCost(m, Q, QF, R, xg)
+    c.hess_mode = 1
+    Upad = np.zeros((N, n)); Upad[:N - 1] = U
+    val = np.zeros(N); grad = np.zeros((N, nm)); hess = np.zeros((N, nm * nm))
+    kidx = np.arange(N, dtype=np.int32); term = np.zeros(N, dtype=np.int32); term[-1] = 1
+
+    def pad(M, size):
+        out = np.zeros(size); out[:M.size] = M.reshape(-1); return out
+    lib.he_cost_mode(N, 1, -1, 1, P(pad(Q, nx * nx)), P(pad(QF, nx * nx)), P(np.ascontiguousarray(R)), P(pad(xg, nx)), P(X), P(Upad),
+                     PI(kidx), PI(term), P(val), P(grad), P(hess))
+    H = hess.reshape(N, nm, nm)
+    Ho = c.hessians(X, U)
+    assert relerr(H, Ho) < 1e-12
+    c0 = ocost.UrdfCost(m, Q, QF, R, xg)
+    if name != "cartpole":      # (the cart-pole's offset point (0,1,0) lies on the pole's y axis: its planar position does not depend on the angle)
+        assert relerr(Ho, c0.hessians(X, U)) > 1e-3                  # the second-order term is not negligible at a random point
+    assert np.max(np.abs(H - np.swapaxes(H, 1, 2))) < 1e-12 * np.max(np.abs(H))
+    if n > 2:
+        eps = 1e-6
+        for k in (0, N - 1):
+            for i in range(nx):
+                Xp = X.copy(); Xm = X.copy(); Xp[k, i] += eps; Xm[k, i] -= eps
+                fd = (c.gradients(Xp, U)[k][:nx] - c.gradients(Xm, U)[k][:nx]) / (2 * eps)
+                assert np.max(np.abs(fd - H[k, :nx, i])) < 1e-6 * max(1.0, np.max(np.abs(H[k])))

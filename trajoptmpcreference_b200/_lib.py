@@ -28,7 +28,8 @@ class ProblemDesc(ctypes.Structure):
     _fields_ = [("batch", c_int), ("knots", c_int), ("integrator_type", c_int), ("dtype", c_int), ("dt", c_double), ("gravity", c_double),
                 ("cost_kind", c_int), ("qf_start", c_int), ("Q", POINTER(c_double)), ("QF", POINTER(c_double)), ("R", POINTER(c_double)),
                 ("limit_mode", c_int * 3), ("lower", POINTER(c_double)), ("upper", POINTER(c_double)),
-                ("mu_init", c_double * 3), ("mu_factor", c_double * 3), ("mu_max", c_double * 3), ("phi_init", c_double * 3), ("phi_factor", c_double * 3)]
+                ("mu_init", c_double * 3), ("mu_factor", c_double * 3), ("mu_max", c_double * 3), ("phi_init", c_double * 3), ("phi_factor", c_double * 3),
+                ("hess_mode", c_int)]
 
 
 class Options(ctypes.Structure):
@@ -108,7 +109,7 @@ def load_library(model: dict, tag: str):
         fn = getattr(lib, name)
         fn.restype = res
         fn.argtypes = args
-    if lib.b2t_abi_version() != 1:
+    if lib.b2t_abi_version() != 2:
         raise B2TError("ABI version mismatch in %s" % path)
     if lib.b2t_model_digest().decode() != model_digest(model):
         raise B2TError("stale library %s: model digest mismatch" % path)

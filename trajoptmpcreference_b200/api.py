@@ -569,6 +569,7 @@ class BatchSolver:
         d.cost_kind = cost._kind
         qs = cost.QF_start if qf_start_override is None else qf_start_override
         d.qf_start = -1 if qs is None else int(qs)
+        d.hess_mode = int(getattr(cost, "hess_mode", 0))
         self.ne = 4 if cost._kind == _lib.COST_URDF_EE else self.nx      # size of the cost's error vector / of Q, QF, xg
 
         def padded(M):      # the C ABI takes nx*nx doubles; an end-effector cost packs its 4 x 4 weights in the first 16

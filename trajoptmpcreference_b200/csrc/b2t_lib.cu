@@ -159,6 +159,9 @@ struct SolverT : SolverBase {
     B2T_ALLOC(d.xs, NX * B); B2T_ALLOC(d.xg, NX * B);
     // cost
     d.cost.kind = p->cost_kind; d.cost.qf_start = p->qf_start;
+    if (p->hess_mode != 0 && p->hess_mode != 1)
+      return fail(B2T_ERR_UNSUPPORTED, "hess_mode must be 0 (Gauss-Newton) or 1 (exact); modes 2 and 3 crash in the reference (TrajoptCost.py:500-503)");
+    d.cost.hess_mode = p->cost_kind == B2T_COST_URDF_EE ? p->hess_mode : 0;
     {   // structured fast path when the quadratic cost is diagonal (B2T_DENSE_KKT=1 forces the general kernels)
       bool diag = p->cost_kind == B2T_COST_QUADRATIC;
       for (int i = 0; i < NX && diag; ++i)
