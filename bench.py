@@ -34,11 +34,11 @@ import numpy as np
 ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
 
-N_KNOTS = 64
+N_KNOTS = int(os.environ.get("B2T_BENCH_KNOTS", "64"))     # BASELINE.json: N = 64; the override exists for the long-horizon probe (profiles/README.md)
 DT = 0.1
 SOLVER_OPTS = {"expected_reduction_min_SQP_DDP": -100}
 U_LIM, Q_LIM = 1.0, 0.45
-METRIC = "SQP-PCG MPC solves/sec (arm6, N=64)"
+METRIC = "SQP-PCG MPC solves/sec (arm6, N=%d)" % N_KNOTS
 
 
 def goals(total, seed):
@@ -324,9 +324,9 @@ def ncu_traffic(family, batch, launches_per_step, qp_per_instance, kernel_name=N
 
 def config_dict(args):
     """Identical in both arms (the driver compares them)."""
-    return {"workload": "%s: arm6 (6-link planar chain) SQP PCG-SS, N=64, dt=0.1, euler, QuadraticCost Q=I QF=100I R=0.1I, "
+    return {"workload": "%s: arm6 (6-link planar chain) SQP PCG-SS, N=%d, dt=0.1, euler, QuadraticCost Q=I QF=100I R=0.1I, "
                         "goals U(-0.5,0.5)^6 seeded, %s, batch %d per GPU" %
-                        ("C5 shards (default_rng(2))" if (args.workload == "c5" or args.gpus > 1) else "C4 (default_rng(1))",
+                        ("C5 shards (default_rng(2))" if (args.workload == "c5" or args.gpus > 1) else "C4 (default_rng(1))", N_KNOTS,
                          "quadratic-penalty box limits |u|<=1.0 |q|<=0.45" if args.limits else "no box limits", args.batch),
             "batch_per_gpu": args.batch, "knots": N_KNOTS, "method": "PCG-SS", "limits": bool(args.limits),
             "l2": "no explicit flush: the per-step working set (solver workspace, see workspace_gb) exceeds the 126 MB L2 at the default batch"}

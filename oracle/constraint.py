@@ -20,12 +20,14 @@ Deviations from the (crashing) reference for the unpinned multi-limit case, stat
 import numpy as np
 
 SOFT_MODES = ("QUADRATIC_PENALTY", "AUGMENTED_LAGRANGIAN")
+HARD_MODES = ("ACTIVE_SET",)        # FULL_SET adds the inactive rows too (zero Jacobian rows): singular KKT in the reference
 
 
 class BoxLimit:
     def __init__(self, offset, size, T, upper, lower, mode, options=None):
-        if mode not in SOFT_MODES:
-            raise ValueError("oracle supports soft modes only: %r" % (SOFT_MODES,))
+        if mode not in SOFT_MODES + HARD_MODES:
+            raise ValueError("oracle supports %r" % (SOFT_MODES + HARD_MODES,))
+        self.hard = mode in HARD_MODES
         o = dict(options or {})
         self.mu_init = o.get("quadratic_penalty_mu_init", 1e-2)
         self.mu_factor = o.get("quadratic_penalty_mu_factor", 10.0)
@@ -109,7 +111,34 @@ class SoftConstraints:
         self.limits["torque"] = BoxLimit(self.nq + self.nv, self.nu, self.N - 1, upper, lower, mode, options)
 
     def any(self):
-        return len(self.limits) > 0
+        """any SOFT limit (total_soft_constraints() > 0, TrajoptConstraint.py:281-293)"""
+        return any(not lim.hard for lim in self.limits.values())
+
+    def any_hard(self):
+        return any(lim.hard for lim in self.limits.values())
+
+    def hard_rows(self, X, U):
+        """ACTIVE_SET hard constraints (BoxConstraint.value / .jacobian with mode ACTIVE_SET, TrajoptConstraint.py:53-67, 92-112;
+        aggregation value_hard_constraints / jacobian_hard_constraints :210-279): per knot the violated bounds only, as
+        (rows (r, m), values (r,)) in the reference's order -- limit types joint, velocity, torque; inside a type all violated lower
+        bounds, then all violated upper bounds.  value = z - lb (lower) resp. ub - z (upper), both < 0; Jacobian row +e_i resp. -e_i."""
+        Z = self._Z(X, U)
+        N, m = Z.shape
+        out = []
+        for k in range(N):
+            rows, vals = [], []
+            for name in ("joint", "velocity", "torque"):
+                lim = self.limits.get(name)
+                if lim is None or not lim.hard or k >= lim.T:
+                    continue
+                v = lim.v(Z[k:k + 1])[0]
+                for i in range(2 * lim.size):
+                    if v[i] < 0:
+                        row = np.zeros(m)
+                        row[lim.offset + (i % lim.size)] = 1.0 if i < lim.size else -1.0
+                        rows.append(row); vals.append(v[i])
+            out.append((np.array(rows).reshape(len(vals), m), np.array(vals)))
+        return out
 
     def _Z(self, X, U):
         N = X.shape[0]
@@ -122,6 +151,8 @@ class SoftConstraints:
         Z = self._Z(X, U)
         val = np.zeros(X.shape[0])
         for name, lim in self.limits.items():
+            if lim.hard:
+                continue
             T = lim.T
             val[:T] += lim.values(Z[:T])
         return val
@@ -130,6 +161,8 @@ class SoftConstraints:
         Z = self._Z(X, U)
         g = np.zeros_like(Z)
         for name, lim in self.limits.items():
+            if lim.hard:
+                continue
             T = lim.T
             g[:T] += lim.gradients(Z[:T])
         return g
@@ -138,13 +171,16 @@ class SoftConstraints:
         Z = self._Z(X, U)
         mx = 0.0
         for lim in self.limits.values():
-            mx = max(mx, lim.max_value(Z[:lim.T]))
+            if not lim.hard:
+                mx = max(mx, lim.max_value(Z[:lim.T]))
         return mx
 
     def update(self, X, U):
         Z = self._Z(X, U)
         flag = True
         for lim in self.limits.values():
+            if lim.hard:
+                continue
             f = lim.update(Z[:lim.T])
             flag = flag and f
         return flag

@@ -17,20 +17,39 @@ def assemble_bt(Sd, So):
 
 
 def assemble_kkt(blocks, nx):
+    """Dense G, g, C, c in the reference's row order (:200-271): initial-state rows, then per knot the dynamics rows of knot k+1
+    followed by the ACTIVE hard-constraint rows of knot k (:238-248), finally the hard rows of the terminal knot (:263-270).
+    blocks["dyn_rows"] receives the indices of the nx N dynamics / initial-state rows inside C."""
     G, g, A, B, c = blocks["G"], blocks["g"], blocks["A"], blocks["B"], blocks["c"]
     N, m, _ = G.shape
     nz = m * (N - 1) + nx
+    hard = blocks.get("hard")
+    nh = sum(len(v) for _, v in hard) if hard is not None else 0
     Gd = np.zeros((nz, nz)); gd = np.zeros((nz, 1))
-    C = np.zeros((nx * N, nz)); cd = np.zeros((nx * N, 1))
+    C = np.zeros((nx * N + nh, nz)); cd = np.zeros((nx * N + nh, 1))
     C[:nx, :nx] = np.eye(nx)
     cd[:nx, 0] = c[0]
+    dyn = list(range(nx))
+    r = nx
     for k in range(N - 1):
         Gd[k * m:(k + 1) * m, k * m:(k + 1) * m] = G[k]
         gd[k * m:(k + 1) * m, 0] = g[k]
-        C[(k + 1) * nx:(k + 2) * nx, k * m:k * m + m + nx] = np.hstack((-A[k], -B[k], np.eye(nx)))
-        cd[(k + 1) * nx:(k + 2) * nx, 0] = c[k + 1]
+        C[r:r + nx, k * m:k * m + m + nx] = np.hstack((-A[k], -B[k], np.eye(nx)))
+        cd[r:r + nx, 0] = c[k + 1]
+        dyn += list(range(r, r + nx))
+        r += nx
+        if hard is not None and len(hard[k][1]):
+            rows, vals = hard[k]
+            C[r:r + len(vals), k * m:(k + 1) * m] = rows
+            cd[r:r + len(vals), 0] = vals
+            r += len(vals)
     Gd[(N - 1) * m:, (N - 1) * m:] = G[N - 1, :nx, :nx]
     gd[(N - 1) * m:, 0] = g[N - 1, :nx]
+    if hard is not None and len(hard[N - 1][1]):
+        rows, vals = hard[N - 1]
+        C[r:r + len(vals), (N - 1) * m:] = rows[:, :nx]
+        cd[r:r + len(vals), 0] = vals
+    blocks["dyn_rows"] = np.array(dyn)
     return Gd, gd, C, cd
 
 
@@ -121,4 +140,4 @@ def solve_qp_dense(blocks, rho, nx, method, tol=1e-6, max_iter=100):
     dz[:N - 1] = dxu[:m * (N - 1)].reshape(N - 1, m)
     dz[N - 1, :nx] = dxu[m * (N - 1):]
     d["l"] = l
-    return dz, l[:, 0].reshape(N, nx), trace, d
+    return dz, l[blocks["dyn_rows"], 0].reshape(N, nx), trace, d

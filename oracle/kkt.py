@@ -32,7 +32,10 @@ def form_blocks(model, cost, cons, X, U, xs, dt, integrator_type=0, gravity=-9.8
     c = np.zeros((N, nx))
     c[0] = X[0] - xs
     c[1:] = X[1:] - xkp1
-    return dict(G=G, g=g, A=A, B=B, c=c, xkp1=xkp1)
+    blocks = dict(G=G, g=g, A=A, B=B, c=c, xkp1=xkp1)
+    if cons is not None and cons.any_hard():
+        blocks["hard"] = cons.hard_rows(X, U)       # extra KKT rows (:238-248, :263-270); only the dense assembly handles them
+    return blocks
 
 
 def schur(blocks, rho, nx):

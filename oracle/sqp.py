@@ -44,13 +44,18 @@ def total_cost(cost, cons, X, U):
     return float(J)
 
 
-def total_violation(model, X, U, xs, dt, integrator_type=0, gravity=-9.81):
-    """totalHardConstraintViolation (:273-294), L1 norm of the initial-state and dynamics defects."""
+def total_violation(model, X, U, xs, dt, integrator_type=0, gravity=-9.81, cons=None):
+    """totalHardConstraintViolation (:273-294), L1 norm of the initial-state and dynamics defects, then of the ACTIVE hard-constraint
+    values knot by knot (:285-293)."""
     N = X.shape[0]
     xkp1 = _plant.integrator(model, X[:N - 1], U, dt, integrator_type, False, gravity)
     c = float(np.sum(np.abs(X[0] - xs)))
     for k in range(N - 1):
         c = c + float(np.sum(np.abs(X[k + 1] - xkp1[k])))
+    if cons is not None and cons.any_hard():
+        for _, vals in cons.hard_rows(X, U):
+            if len(vals):
+                c = c + float(np.sum(np.abs(vals)))
     return c
 
 
@@ -60,6 +65,11 @@ def solve_qp(model, cost, cons, X, U, xs, dt, rho, method, o, integrator_type=0,
     nx = X.shape[1]
     blocks = kkt.form_blocks(model, cost, cons, X, U, xs, dt, integrator_type, gravity)
     trace = None
+    if "hard" in blocks:
+        if method not in ("N", "S"):
+            raise ValueError("hard (ACTIVE_SET) limits: exact methods N / S only (the reference hands PCG a Schur complement whose size "
+                             "no longer matches block_size * Nblocks)")
+        dense = True
     if dense and method != "N":
         from . import dense as _dense
         dz, l, trace, d = _dense.solve_qp_dense(blocks, rho, nx, method, o["exit_tolerance_linSys"], o["max_iter_linSys"])
@@ -75,7 +85,7 @@ def solve_qp(model, cost, cons, X, U, xs, dt, rho, method, o, integrator_type=0,
         dz = np.zeros((N, m))
         dz[:N - 1] = sol[:m * (N - 1)].reshape(N - 1, m)
         dz[N - 1, :nx] = sol[m * (N - 1):nz]
-        l = sol[nz:].reshape(N, nx)
+        l = sol[nz:][blocks["dyn_rows"]].reshape(N, nx)
         sch = None
     else:
         sch = kkt.schur(blocks, rho, nx)
@@ -114,7 +124,7 @@ def sqp(model, cost, cons, x, u, N, dt, method="PCG-SS", options=None, integrato
         rho = o["rho_init_SQP_DDP"]
         drho = 1
         J = total_cost(cost, cons, X, U)
-        c = total_violation(model, X, U, xs, dt, integrator_type, gravity)
+        c = total_violation(model, X, U, xs, dt, integrator_type, gravity, cons)
         mu = 10
         merit = J + mu * c
         trace_all.append(dict(outer_iteration=outer, iteration=0, line_search_iteration=0, alpha=1, rho=rho, J=J, c=c,
@@ -131,7 +141,7 @@ def sqp(model, cost, cons, x, u, N, dt, method="PCG-SS", options=None, integrato
                 Xn = X - alpha * dz[:, :nx]
                 Un = U - alpha * dz[:N - 1, nx:]
                 J_new = total_cost(cost, cons, Xn, Un)
-                c_new = total_violation(model, Xn, Un, xs, dt, integrator_type, gravity)
+                c_new = total_violation(model, Xn, Un, xs, dt, integrator_type, gravity, cons)
                 grad = cost.gradients(Xn, Un)
                 D = 0.0
                 sg = cons.gradients(Xn, Un) if (cons is not None and cons.any()) else None

@@ -222,6 +222,10 @@ SOLVE_CASES = [
     ("pend_N20_SS_qp2", "pend", 20, "PCG_SS", {"expected_reduction_min_SQP_DDP": -100}, {"torque": ([2.0], [-2.0], "QUADRATIC_PENALTY")}, None),
     ("pend_N20_SS_al01", "pend", 20, "PCG_SS", {"expected_reduction_min_SQP_DDP": -100}, {"torque": ([0.1], [-0.1], "AUGMENTED_LAGRANGIAN")}, None),
     ("pend_N20_SS_qp01", "pend", 20, "PCG_SS", {"expected_reduction_min_SQP_DDP": -100}, {"torque": ([0.1], [-0.1], "QUADRATIC_PENALTY")}, None),
+    # hard (ACTIVE_SET) torque limits, exact methods ("parity target for N / S only"; known answer 4 SQP, J = 61.41085)
+    ("pend_N20_S_as01", "pend", 20, "S", {"expected_reduction_min_SQP_DDP": -100}, {"torque": ([0.1], [-0.1], "ACTIVE_SET")}, None),
+    ("pend_N20_N_as01", "pend", 20, "N", {"expected_reduction_min_SQP_DDP": -100}, {"torque": ([0.1], [-0.1], "ACTIVE_SET")}, None),
+    ("pend_N20_S_as2", "pend", 20, "S", {"expected_reduction_min_SQP_DDP": -100}, {"torque": ([2.0], [-2.0], "ACTIVE_SET")}, None),
 ]
 
 

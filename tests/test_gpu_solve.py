@@ -9,7 +9,22 @@ from oracle import sqp
 
 pytestmark = pytest.mark.gpu
 
-PCG_TAGS = list(solve_meta().keys())       # PCG-J/BJ/SS and the exact methods N, S
+HARD_TAGS = [k for k, v in solve_meta().items() if any(l[2] == "ACTIVE_SET" for l in v["limits"].values())]
+PCG_TAGS = [k for k in solve_meta().keys() if k not in HARD_TAGS]       # PCG-J/BJ/SS and the exact methods N, S
+
+
+def test_hard_constraint_modes_are_refused_loudly():
+    """ACTIVE_SET / FULL_SET (TrajoptConstraint.py:30, 65-67) change the size of the KKT system per iteration and -- measured with the
+    oracle, which reproduces the reference bit for bit on these cases (tests/test_oracle_golden.py) -- make the iteration path
+    depend on whether a control lands one ulp above or below its bound.  The GPU path does not implement
+    them and says so instead of solving something else."""
+    assert len(HARD_TAGS) >= 2
+    with pytest.raises(ValueError):
+        cons = t.TrajoptConstraint(1, 1, 1, 20)
+        cons.set_torque_limits([0.1], [-0.1], "ACTIVE_SET", {})
+    with pytest.raises(ValueError):
+        cons = t.TrajoptConstraint(1, 1, 1, 20)
+        cons.set_torque_limits([0.1], [-0.1], "FULL_SET", {})
 
 
 def _floor():
