@@ -48,7 +48,10 @@ typedef enum {
 } b2t_status;
 
 typedef enum { B2T_COST_QUADRATIC = 0, B2T_COST_URDF_EE = 1 } b2t_cost_kind;
-typedef enum { B2T_LIMIT_NONE = 0, B2T_LIMIT_QUADRATIC_PENALTY = 1, B2T_LIMIT_AUGMENTED_LAGRANGIAN = 2 } b2t_limit_mode;
+/* BoxConstraint modes (TrajoptConstraint.py:27-51).  QUADRATIC_PENALTY / AUGMENTED_LAGRANGIAN are soft (all methods, SQP and iLQR).
+ * ACTIVE_SET is hard: violated bounds enter the KKT system as rows (TrajoptMPCReference.py:238-248); exact methods N / S only.
+ * FULL_SET (singular KKT in the reference) and ADMM_PROJECTION (unimplemented there) are not offered. */
+typedef enum { B2T_LIMIT_NONE = 0, B2T_LIMIT_QUADRATIC_PENALTY = 1, B2T_LIMIT_AUGMENTED_LAGRANGIAN = 2, B2T_LIMIT_ACTIVE_SET = 3 } b2t_limit_mode;
 /* SQPSolverMethods (TrajoptMPCReference.py:13-18).  N (dense KKT backslash, :313-359) and S (Schur backslash, :430-436) are
  * exact solves of the same linear system; both run the block-tridiagonal factorisation of the Schur complement here. */
 typedef enum { B2T_METHOD_N = 0, B2T_METHOD_S = 1, B2T_METHOD_PCG_J = 2, B2T_METHOD_PCG_BJ = 3, B2T_METHOD_PCG_SS = 4 } b2t_method;

@@ -9,22 +9,29 @@ from oracle import sqp
 
 pytestmark = pytest.mark.gpu
 
-HARD_TAGS = [k for k, v in solve_meta().items() if any(l[2] == "ACTIVE_SET" for l in v["limits"].values())]
-PCG_TAGS = [k for k in solve_meta().keys() if k not in HARD_TAGS]       # PCG-J/BJ/SS and the exact methods N, S
+PCG_TAGS = list(solve_meta().keys())       # PCG-J/BJ/SS, the exact methods N, S, and the hard ACTIVE_SET cases of N / S
+# pend_N20_S_as01: the reference's own result is not reproducible -- every 1-ulp perturbation of its linear solve changes its iteration
+# counts (tests/golden/floor.json: counts_identical 0 of 4; 3 of 4 perturbed runs land on the method-N answer J = 61.41085)
+UNSTABLE_IN_REFERENCE = {"pend_N20_S_as01"}
 
 
-def test_hard_constraint_modes_are_refused_loudly():
-    """ACTIVE_SET / FULL_SET (TrajoptConstraint.py:30, 65-67) change the size of the KKT system per iteration and -- measured with the
-    oracle, which reproduces the reference bit for bit on these cases (tests/test_oracle_golden.py) -- make the iteration path
-    depend on whether a control lands one ulp above or below its bound.  The GPU path does not implement
-    them and says so instead of solving something else."""
-    assert len(HARD_TAGS) >= 2
+def test_hard_constraint_modes():
+    """FULL_SET is refused (singular KKT in the reference); ACTIVE_SET runs with the exact methods and is refused with PCG (the
+    reference hands PCG a Schur complement whose size no longer matches block_size * Nblocks)."""
     with pytest.raises(ValueError):
-        cons = t.TrajoptConstraint(1, 1, 1, 20)
-        cons.set_torque_limits([0.1], [-0.1], "ACTIVE_SET", {})
-    with pytest.raises(ValueError):
-        cons = t.TrajoptConstraint(1, 1, 1, 20)
-        cons.set_torque_limits([0.1], [-0.1], "FULL_SET", {})
+        t.TrajoptConstraint(1, 1, 1, 20).set_torque_limits([0.1], [-0.1], "FULL_SET", {})
+    plant = t.URDFPlant(options={"path_to_urdf": "pend"})
+    cost = t.QuadraticCost(np.eye(2), 100.0 * np.eye(2), 0.1 * np.eye(1), np.array([3.14159, 0.0]))
+    cons = t.TrajoptConstraint(1, 1, 1, 20)
+    cons.set_torque_limits([0.1], [-0.1], "ACTIVE_SET", {})
+    solver = t.TrajoptMPCReference(plant, cost, cons)
+    with pytest.raises(Exception, match="exact methods"):
+        solver.SQP(np.zeros((2, 20)), np.zeros((1, 19)), 20, 0.1, t.SQPSolverMethods.PCG_SS, options={})
+    # both exact methods give the KKT solution: the known answer of SURVEY.md section 2 (4 QP solves, J = 61.41085)
+    for method in (t.SQPSolverMethods.N, t.SQPSolverMethods.S):
+        x, u, e1, e2, outer, it = solver.SQP(np.zeros((2, 20)), np.zeros((1, 19)), 20, 0.1, method, options={"expected_reduction_min_SQP_DDP": -100})
+        assert (e1, it) == (1, 3) and abs(solver.last_result.J[0] - 61.41084999081366) < 1e-9 * 61.4
+        assert np.max(np.abs(u)) <= 0.1 + 1e-12
 
 
 def _floor():
@@ -55,6 +62,8 @@ def test_sqp_vs_reference_golden(tag, oracle_models):
     n = plant.get_num_pos()
     opts = dict(mt["options"]); opts["overloading"] = False
     x, u, e1, e2, outer, it = solver.SQP(np.zeros((2 * n, N)), np.zeros((n, N - 1)), N, 0.1, getattr(t.SQPSolverMethods, mt["method"]), options=opts)
+    if tag in UNSTABLE_IN_REFERENCE:
+        pytest.skip("the reference's recorded result for this case does not survive a 1-ulp perturbation of its own linear solve")
     assert [e1, e2, outer, it] == S[tag + "/exits"].tolist()
     rows = solver.trace[1:]            # the reference keeps the rows of the LAST outer iteration (:555)
     k = len(rows)
@@ -76,7 +85,7 @@ def test_sqp_vs_reference_golden(tag, oracle_models):
     print("%s: rel J %.1e (tol %.1e)  |dx| %.1e (tol %.1e)  |du| %.1e (tol %.1e)" % (tag, eJ, tolJ, ex, tolx, eu, tolu))
     assert eJ <= tolJ and ex <= tolx and eu <= tolu
     assert np.allclose([r["J"] for r in rows], S[tag + "/tr_J"][-k:], rtol=tolJ, atol=0)
-    if pcons is not None:
+    if pcons is not None and pcons.torque_limits.is_soft_constraint_mode():
         assert np.allclose(pcons.torque_limits.quadratic_penalty_mu, S[tag + "/mu"], rtol=1e-15)
         assert np.max(np.abs(pcons.torque_limits.augmented_lagrangian_lambda - S[tag + "/lam"])) <= NORTH_STAR * max(1.0, float(np.max(np.abs(S[tag + "/lam"]))))
 

@@ -14,7 +14,7 @@ ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 METHOD_N, METHOD_S, METHOD_PCG_J, METHOD_PCG_BJ, METHOD_PCG_SS = 0, 1, 2, 3, 4
 F64, F32 = 0, 1
 COST_QUADRATIC, COST_URDF_EE = 0, 1
-LIMIT_NONE, LIMIT_QUADRATIC_PENALTY, LIMIT_AUGMENTED_LAGRANGIAN = 0, 1, 2
+LIMIT_NONE, LIMIT_QUADRATIC_PENALTY, LIMIT_AUGMENTED_LAGRANGIAN, LIMIT_ACTIVE_SET = 0, 1, 2, 3
 STATUS_FIELDS, SCALAR_FIELDS, TRACE_FIELDS, KERNEL_FAMILIES = 8, 4, 12, 9
 KERNEL_FAMILY_NAMES = ["fd", "fd_grad", "kkt", "schur", "pcg", "recover", "trial_fd", "merit", "ctrl"]
 ARR = {"x": 0, "u": 1, "xkp1": 2, "dqdd": 3, "Ghat": 4, "g": 5, "Sd": 6, "So": 7, "Pd": 8, "gamma": 9, "l": 10, "dz": 11, "xn": 12, "un": 13,

@@ -342,12 +342,15 @@ class UrdfCost(QuadraticCost):
 
 
 # --------------------------------------------------------------------------------------------------- constraints
-_MODES = {"QUADRATIC_PENALTY": _lib.LIMIT_QUADRATIC_PENALTY, "AUGMENTED_LAGRANGIAN": _lib.LIMIT_AUGMENTED_LAGRANGIAN}
+_MODES = {"QUADRATIC_PENALTY": _lib.LIMIT_QUADRATIC_PENALTY, "AUGMENTED_LAGRANGIAN": _lib.LIMIT_AUGMENTED_LAGRANGIAN,
+          "ACTIVE_SET": _lib.LIMIT_ACTIVE_SET}
 
 
 class BoxConstraint:
     """BoxConstraint (TrajoptConstraint.py:5-176) state holder: bounds, mode, options and the (mu, lambda, phi) arrays.
-    Soft modes only; the arithmetic lives in the kernels (csrc/b2t_core.cuh soft_value / soft_grad, k_outer)."""
+    The arithmetic lives in the kernels (csrc/b2t_core.cuh soft_value / soft_grad / hard_active, k_outer).  Soft modes
+    QUADRATIC_PENALTY / AUGMENTED_LAGRANGIAN with every method; the hard mode ACTIVE_SET (violated bounds become KKT rows,
+    TrajoptMPCReference.py:238-248) with the exact methods N / S."""
 
     def __init__(self, constraint_size=0, num_timesteps=0, upper_bounds=(), lower_bounds=(), mode="NONE", options=None):
         options = {} if options is None else options
@@ -360,8 +363,9 @@ class BoxConstraint:
         self.bounds = np.zeros(2 * constraint_size)
         self.bounds[:constraint_size] = lower_bounds
         self.bounds[constraint_size:] = upper_bounds
-        if mode in ("ACTIVE_SET", "FULL_SET"):
-            raise ValueError("hard constraint modes change the size of the Schur system and are not supported on the GPU path; use QUADRATIC_PENALTY or AUGMENTED_LAGRANGIAN")
+        if mode == "FULL_SET":
+            raise ValueError("FULL_SET adds the inactive bounds as all-zero KKT rows (TrajoptConstraint.py:66-67, 111-112): singular in the "
+                             "reference itself; use ACTIVE_SET, QUADRATIC_PENALTY or AUGMENTED_LAGRANGIAN")
         if mode == "ADMM_PROJECTION":
             raise ValueError("[!] ERROR NOT IMPLEMENTED YET")            # same as the reference (TrajoptConstraint.py:87-89)
         if mode not in _MODES:
@@ -496,7 +500,7 @@ class TrajoptConstraint:
     def unpack(self, mu, lam, phi):
         m = self.nq + self.nv + self.nu
         for ty, lim, off, cs in self._types():
-            if lim is None:
+            if lim is None or not lim.is_soft_constraint_mode():
                 continue
             T = lim.num_timesteps
             for arr, dst in ((mu, lim.quadratic_penalty_mu), (lam, lim.augmented_lagrangian_lambda), (phi, lim.augmented_lagrangian_phi)):
@@ -580,6 +584,7 @@ class BatchSolver:
         d.Q, d.QF, d.R = [a.ctypes.data_as(ctypes.POINTER(ctypes.c_double)) for a in self._keep]
         lower = np.zeros(self.m); upper = np.zeros(self.m)
         self.has_limits = False
+        self.has_soft_limits = False          # penalty / augmented-Lagrangian limits carry (mu, lambda, phi) on the device
         for ty in range(3):
             d.limit_mode[ty] = _lib.LIMIT_NONE
             d.mu_init[ty], d.mu_factor[ty], d.mu_max[ty], d.phi_init[ty], d.phi_factor[ty] = 1e-2, 10.0, 1e12, 1e-2, 10.0
@@ -590,6 +595,7 @@ class BatchSolver:
                 if lim is None:
                     continue
                 self.has_limits = True
+                self.has_soft_limits = self.has_soft_limits or lim.is_soft_constraint_mode()
                 d.limit_mode[ty] = _MODES[lim.mode]
                 lower[off:off + cs] = lim.bounds[:cs]; upper[off:off + cs] = lim.bounds[cs:]
                 o = lim.options
@@ -657,10 +663,15 @@ class BatchSolver:
         _lib.check(self.lib, self.lib.b2t_set_initial_state(self._h, _dptr(xs)))
 
     def set_multipliers(self, mu, lam, phi):
+        if not self.has_soft_limits:          # hard (ACTIVE_SET) limits only: nothing to send
+            return
         args = [_as_f64(a, (self.batch, 2 * self.m, self.N)) for a in (mu, lam, phi)]
         _lib.check(self.lib, self.lib.b2t_set_multipliers(self._h, *[_dptr(a) for a in args]))
 
     def get_multipliers(self):
+        if not self.has_soft_limits:
+            shape = (self.batch, 2 * self.m, self.N)
+            return np.zeros(shape), np.zeros(shape), np.ones(shape)
         out = [np.zeros((self.batch, 2 * self.m, self.N)) for _ in range(3)]
         _lib.check(self.lib, self.lib.b2t_get_multipliers(self._h, *[_dptr(a) for a in out]))
         return out

@@ -43,7 +43,8 @@ struct Dev {
   // per-instance
   T *xs, *xg;
   CostParams<T> cost;
-  LimitParams<T> lim;
+  LimitParams<T> lim;     // soft limits (penalty / augmented Lagrangian)
+  LimitParams<T> hard;    // hard ACTIVE_SET limits (mode[i] != 0), exact methods only
   T mu_factor[3], mu_max[3], phi_factor[3], mu_init[3], phi_init[3];
   T *rho, *drho, *J, *c, *merit, *alpha, *deltaJ, *D, *ratio;
   int *ls_iter, *sqp_iter, *outer_iter, *exit_sqp, *exit_soft, *phase, *err, *pcg_iters, *tot_qp, *tot_pcg, *tot_trials;
@@ -171,7 +172,33 @@ __global__ void __launch_bounds__(64) k_kkt(Dev<T> d, const int* list, const int
   const T rho = d.rho[b];
   const int M = terminal ? NX : NM;
   for (int i = 0; i < NM; ++i) G[i * NM + i] += rho;
+  // Hard ACTIVE_SET rows fix the step of their coordinate, dz_A = t.  Eliminating them from the KKT system leaves the same
+  // block-tridiagonal Schur system with  Ghat' = E_F (G_FF)^-1 E_F^T,  g' = g - G[:, A] t  and  Ghat' g' + E_A t  in place of Ghat g:
+  //   dz = Ghat' (g' - C^T l) + E_A t,   S = -C Ghat' C^T,   gamma = c - C (Ghat' g' + E_A t)
+  // (the solution of the reference's enlarged KKT system, TrajoptMPCReference.py:238-248, :313-359)
+  T tfix[NM];
+  bool act[NM];
+  bool any_act = false;
+  for (int i = 0; i < NM; ++i) { tfix[i] = T(0); act[i] = false; }
+  if (d.hard.any)
+    for (int i = 0; i < M; ++i) { act[i] = hard_active(d.hard, z, i, &tfix[i]); any_act = any_act || act[i]; }
+  if (any_act) {
+    for (int a = 0; a < M; ++a) {
+      if (!act[a]) continue;
+      for (int j = 0; j < M; ++j)
+        if (!act[j]) g[j] -= G[j * NM + a] * tfix[a];
+    }
+    for (int a = 0; a < M; ++a) {
+      if (!act[a]) continue;
+      for (int j = 0; j < M; ++j) { G[a * NM + j] = T(0); G[j * NM + a] = T(0); }
+      G[a * NM + a] = T(1);
+      g[a] = T(0);
+    }
+  }
   spd_inverse_inplace(G, M, NM);
+  if (any_act)
+    for (int a = 0; a < M; ++a)
+      if (act[a]) G[a * NM + a] = T(0);
   if (terminal)
     for (int i = 0; i < NM; ++i)
       for (int j = 0; j < NM; ++j)
@@ -179,7 +206,7 @@ __global__ void __launch_bounds__(64) k_kkt(Dev<T> d, const int* list, const int
   for (int i = 0; i < NM; ++i) {
     T acc = T(0);
     for (int j = 0; j < M; ++j) acc += G[i * NM + j] * g[j];
-    d.Gg[(size_t)i * K + t] = (i < M) ? acc : T(0);
+    d.Gg[(size_t)i * K + t] = (i < M) ? acc + tfix[i] : T(0);
     d.g[(size_t)i * K + t] = (i < M) ? g[i] : T(0);
   }
   for (int i = 0; i < NM * NM; ++i) d.Gh[(size_t)i * K + t] = G[i];
@@ -1926,9 +1953,13 @@ __global__ void __launch_bounds__(128) k_recover(Dev<T> d, const int* list, cons
       rhs[c] += acc;
     }
   }
+  T z[NM];
+  if (d.hard.any) load_xu(d.x, d.u, K, t, terminal, z, z + NX);
   for (int i = 0; i < NM; ++i) {
     T acc = T(0);
     for (int c = 0; c < NM; ++c) acc += d.Gh[(size_t)(i * NM + c) * K + t] * rhs[c];
+    T tf = T(0);
+    if (d.hard.any && i < (terminal ? NX : NM) && hard_active(d.hard, z, i, &tf)) acc += tf;      // dz = Ghat' (g' - C^T l) + E_A t  (k_kkt)
     d.dz[(size_t)i * K + t] = acc;
   }
 }
@@ -1937,13 +1968,13 @@ __global__ void __launch_bounds__(128) k_recover(Dev<T> d, const int* list, cons
 // merit evaluation of one instance (block): J = totalCost (:296-310), c = totalHardConstraintViolation (:273-294),
 // D = directional derivative (:635-648).  Per-knot terms in parallel, then summed by thread 0 in the reference's
 // sequential order.  TRIAL selects (xn, un, xkp1n) instead of (x, u, xkp1).
-// smem: 5 * N scalars.
+// smem: 6 * N scalars.
 // -----------------------------------------------------------------------------------------------------------------
 template <typename T, bool TRIAL, bool WITH_D, bool WITH_C>
 __device__ __forceinline__ void merit_terms(const Dev<T>& d, int b, T* sm, T* J_out, T* c_out, T* D_out) {
   const int N = d.N;
   const size_t K = d.K;
-  T* s_cost = sm; T* s_soft = sm + N; T* s_c = sm + 2 * N; T* s_D = sm + 3 * N; T* s_Ds = sm + 4 * N;
+  T* s_cost = sm; T* s_soft = sm + N; T* s_c = sm + 2 * N; T* s_D = sm + 3 * N; T* s_Ds = sm + 4 * N; T* s_h = sm + 5 * N;
   const T* X = TRIAL ? d.xn : d.x;
   const T* U = TRIAL ? d.un : d.u;
   const T* XK = TRIAL ? d.xkp1n : d.xkp1;
@@ -1963,6 +1994,7 @@ __device__ __forceinline__ void merit_terms(const Dev<T>& d, int b, T* sm, T* J_
         for (int i = 0; i < NX; ++i) acc += fabs(z[i] - XK[(size_t)i * K + t - 1]);
       }
       s_c[k] = acc;
+      if (d.hard.any) s_h[k] = hard_violation(d.hard, z, terminal);
     }
     if constexpr (WITH_D) {
       T g[NM], dzk[NM];
@@ -1991,6 +2023,8 @@ __device__ __forceinline__ void merit_terms(const Dev<T>& d, int b, T* sm, T* J_
     if constexpr (WITH_C) {
       T c = T(0);
       for (int k = 0; k < N; ++k) c += s_c[k];
+      if (d.hard.any)
+        for (int k = 0; k < N; ++k) c += s_h[k];      // violated hard bounds, after the dynamics defects (:285-293)
       *c_out = c;
     }
     if constexpr (WITH_D) {
@@ -2121,7 +2155,7 @@ __global__ void k_merit(Dev<T> d, const int* list, const int* count, int* next_l
 // in registers), forward dynamics, cost / penalty / defect / directional-derivative terms per knot in parallel, then
 // thread 0 sums them in the reference's sequential order and decides accept / halve alpha / fail.  Replaces the
 // 2 x max_trials launches of k_fd<TRIAL> + k_merit and the k_sqp_ctrl launch.
-// smem: (5 + NX) * N scalars.
+// smem: (6 + NX) * N scalars.
 // -----------------------------------------------------------------------------------------------------------------
 template <typename T>
 __device__ __forceinline__ void outer_update(const Dev<T>& d, const Opts<T>& o, int b, T* sm, int fused_restart);   // defined below
@@ -2139,6 +2173,7 @@ __global__ void __launch_bounds__(128) k_linesearch(Dev<T> d, Opts<T> o, int fus
   if (fuse_recover)
     for (int k = threadIdx.x; k < N; k += blockDim.x) recover_diag_knot(d, b, k);
   T* s_cost = sm; T* s_soft = sm + N; T* s_c = sm + 2 * N; T* s_D = sm + 3 * N; T* s_Ds = sm + 4 * N; T* s_xn = sm + 5 * N;   // [N][NX]
+  T* s_h = s_xn + N * NX;     // [N] violated hard bounds (ACTIVE_SET)
   __shared__ int s_state;     // 0: accepted, 1: try a smaller alpha, 2: failed
   __shared__ int s_exit;      // the SQP loop of this instance exited
   T alpha = T(1);
@@ -2170,6 +2205,7 @@ __global__ void __launch_bounds__(128) k_linesearch(Dev<T> d, Opts<T> o, int fus
       if (d.lim.any) soft_value_dir(d.lim, z, d.mu + t, d.lam + t, K, terminal, dzk, &sv, &accs);
       s_soft[k] = sv;
       s_Ds[k] = accs;
+      if (d.hard.any) s_h[k] = hard_violation(d.hard, z, terminal);
       if (k == 0) {
         T cc = T(0);
         for (int i = 0; i < NX; ++i) cc += fabs(z[i] - d.xs[(size_t)i * d.B + b]);
@@ -2206,6 +2242,8 @@ __global__ void __launch_bounds__(128) k_linesearch(Dev<T> d, Opts<T> o, int fus
       if (lim_any) {
         for (int k = 0; k < N; ++k) Jn += s_soft[k];
       }
+      if (d.hard.any)
+        for (int k = 0; k < N; ++k) cn += s_h[k];
       const T mu = o.merit_mu;
       const T merit_new = Jn + mu * cn;
       const T delta_J = d.J[b] - Jn;

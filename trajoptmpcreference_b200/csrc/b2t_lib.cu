@@ -178,21 +178,28 @@ struct SolverT : SolverBase {
     { T* q; int r; if ((r = upload(&q, p->QF, NX * NX))) return r; d.cost.QF = q; }
     { T* q; int r; if ((r = upload(&q, p->R, NU * NU))) return r; d.cost.R = q; }
     // limits
-    int mode[NM]; double lb[NM], ub[NM];
-    int any = 0;
+    int mode[NM], hmode[NM]; double lb[NM], ub[NM];
+    int any = 0, any_hard = 0;
     for (int i = 0; i < NM; ++i) {
       const int ty = i < NJ ? 0 : (i < NX ? 1 : 2);
       mode[i] = p->limit_mode[ty];
-      if (mode[i] < 0 || mode[i] > 2) return fail(B2T_ERR_INVALID, "limit_mode");
+      hmode[i] = 0;
+      if (mode[i] < 0 || mode[i] > 3) return fail(B2T_ERR_INVALID, "limit_mode");
       if (mode[i] != B2T_LIMIT_NONE) {
         if (!p->lower || !p->upper) return fail(B2T_ERR_INVALID, "lower/upper bounds required");
-        any = 1; lb[i] = p->lower[i]; ub[i] = p->upper[i];
+        lb[i] = p->lower[i]; ub[i] = p->upper[i];
+        if (mode[i] == B2T_LIMIT_ACTIVE_SET) { hmode[i] = LIM_ACTIVE_SET; mode[i] = B2T_LIMIT_NONE; any_hard = 1; }
+        else any = 1;
       } else { lb[i] = 0; ub[i] = 0; }
     }
     d.lim.any = any;
+    d.hard.any = any_hard;
+    if (any_hard) d.diag_mode = 0;        // the elimination of the fixed coordinates lives in the dense KKT kernel
+    { int* m; B2T_ALLOC(m, NM); B2T_CUDA(cudaMemcpy(m, hmode, sizeof(hmode), cudaMemcpyHostToDevice)); d.hard.mode = m; }
     { int* m; B2T_ALLOC(m, NM); B2T_CUDA(cudaMemcpy(m, mode, sizeof(mode), cudaMemcpyHostToDevice)); d.lim.mode = m; }
     { T* q; int r; if ((r = upload(&q, lb, NM))) return r; d.lim.lb = q; }
     { T* q; int r; if ((r = upload(&q, ub, NM))) return r; d.lim.ub = q; }
+    d.hard.lb = d.lim.lb; d.hard.ub = d.lim.ub;
     for (int ty = 0; ty < 3; ++ty) {
       d.mu_init[ty] = (T)p->mu_init[ty]; d.mu_factor[ty] = (T)p->mu_factor[ty]; d.mu_max[ty] = (T)p->mu_max[ty];
       d.phi_init[ty] = (T)p->phi_init[ty]; d.phi_factor[ty] = (T)p->phi_factor[ty];
@@ -588,6 +595,9 @@ struct SolverT : SolverBase {
         method != B2T_METHOD_PCG_SS)
       return fail(B2T_ERR_INVALID, "method must be N, S, PCG-J, PCG-BJ or PCG-SS");
     if (o->max_iter_SQP + 1 > d.trace_cap) return fail(B2T_ERR_UNSUPPORTED, "max_iter_SQP_DDP > 103");
+    if (d.hard.any && method != B2T_METHOD_N && method != B2T_METHOD_S)
+      return fail(B2T_ERR_UNSUPPORTED, "hard (ACTIVE_SET) limits: exact methods N / S only (the reference hands PCG a Schur complement whose size no "
+                                       "longer matches block_size * Nblocks)");
     // the backtracking loop of k_linesearch ends when alpha <= alpha_min: it needs a factor that shrinks alpha
     if (!(o->alpha_factor > 0.0 && o->alpha_factor < 1.0)) return fail(B2T_ERR_INVALID, "alpha_factor_SQP_DDP must lie in (0, 1)");
     if (!(o->alpha_min > 0.0)) return fail(B2T_ERR_INVALID, "alpha_min_SQP_DDP must be positive");
@@ -601,7 +611,7 @@ struct SolverT : SolverBase {
     for (int i = 0; i < B2T_KERNEL_FAMILIES; ++i) { fam_seconds[i] = 0; fam_launches[i] = 0; }
     B2T_CUDA(cudaEventRecord(ev0, stream));
     const int B = d.B;
-    const size_t msmem = (size_t)5 * d.N * sizeof(T);
+    const size_t msmem = (size_t)6 * d.N * sizeof(T);
     const int mt = merit_threads();
     k_init_state<T><<<cdiv(B, 128), 128, 0, stream>>>(d); tick(B2T_K_CTRL);
     { Scope sc(this, B2T_K_FD); k_fd<T, false><<<cdiv((size_t)B * d.N, 128), 128, 0, stream>>>(d, d.act, d.n_act); tick(B2T_K_FD); }
@@ -612,7 +622,7 @@ struct SolverT : SolverBase {
     const bool legacy_ls = getenv("B2T_LEGACY_LS") && atoi(getenv("B2T_LEGACY_LS")) != 0;
     const bool trace_active = getenv("B2T_TRACE_ACTIVE") != nullptr;      // debugging: active-instance count after every SQP pass on stderr
     const bool lagged = !hook && !trace_active && !(getenv("B2T_SYNC_PASSES") && atoi(getenv("B2T_SYNC_PASSES")) != 0);
-    const size_t lsmem = (size_t)(5 + NX) * d.N * sizeof(T);
+    const size_t lsmem = (size_t)(6 + NX) * d.N * sizeof(T);
     const int lst = std::min(128, ((d.N + 31) / 32) * 32);
     const size_t osmem = std::max((size_t)3 * d.N * sizeof(T), msmem);
     for (long long iter = 0; n > 0 && iter < cap; ++iter) {
@@ -720,7 +730,8 @@ struct SolverT : SolverBase {
     for (int i = 0; i < B2T_KERNEL_FAMILIES; ++i) { fam_seconds[i] = 0; fam_launches[i] = 0; }
     B2T_CUDA(cudaEventRecord(ev0, stream));
     const int B = d.B;
-    const size_t msmem = (size_t)5 * d.N * sizeof(T);
+    if (d.hard.any) return fail(B2T_ERR_UNSUPPORTED, "iLQR supports soft limits only (README.md:17 of the reference says the same)");
+    const size_t msmem = (size_t)6 * d.N * sizeof(T);
     const int mt = merit_threads();
     k_init_state<T><<<cdiv(B, 128), 128, 0, stream>>>(d); tick(B2T_K_CTRL);
     { Scope sc(this, B2T_K_TRIAL); k_ilqr_rollout0<T><<<cdiv(B, 32), 32, 0, stream>>>(d); tick(B2T_K_TRIAL); }
@@ -855,7 +866,7 @@ struct SolverT : SolverBase {
     B2T_CUDA(cudaSetDevice(device));
     k_fill<T><<<cdiv(d.B, 128), 128, 0, stream>>>(d.alpha, (size_t)d.B, (T)alpha);
     k_fd<T, true><<<cdiv(d.K, 128), 128, 0, stream>>>(d, d.act, d.n_act);
-    k_merit_only<T><<<d.B, merit_threads(), (size_t)5 * d.N * sizeof(T), stream>>>(d, d.J, d.c, d.D);
+    k_merit_only<T><<<d.B, merit_threads(), (size_t)6 * d.N * sizeof(T), stream>>>(d, d.J, d.c, d.D);
     B2T_CUDA(cudaGetLastError());
     std::vector<T> h(d.B);
     T* src[3] = {d.J, d.c, d.D};
