@@ -47,13 +47,13 @@ def main():
         total_qp = int(solver.last_result.total_qp[0]); total_pcg = int(solver.last_result.total_pcg[0])
         row = {"exits_gpu": [int(e1), int(e2), int(outer), int(it)], "exits_ref": ref_exits, "exits_identical": [int(e1), int(e2), int(outer), int(it)] == ref_exits,
                "pcg_counts_last_outer_identical": bool(pcg_same), "qp_solves_gpu": total_qp, "pcg_total_gpu": total_pcg,
-               "pcg_total_ref": int(S[tag + "/pcg_iters"].sum()), "qp_solves_ref": int(len(S[tag + "/pcg_iters"])) if mt["method"].startswith("PCG") else None,
+               "pcg_total_ref": int(S[tag + "/pcg_iters"].sum()), "qp_solves_ref": int(len(S[tag + "/pcg_iters"])) if mt["method"].startswith("PCG") else int(len(S[tag + "/tr_ls"])),
                "rel_J": abs(float(solver.last_result.J[0]) - float(S[tag + "/J"])) / max(1e-300, abs(float(S[tag + "/J"]))),
                "abs_x": float(np.max(np.abs(x - S[tag + "/x"]))), "abs_u": float(np.max(np.abs(u - S[tag + "/u"]))),
                "rel_x": float(np.max(np.abs(x - S[tag + "/x"])) / max(1e-300, np.max(np.abs(S[tag + "/x"])))),
                "rel_u": float(np.max(np.abs(u - S[tag + "/u"])) / max(1e-300, np.max(np.abs(S[tag + "/u"])))),
                "floor": floor.get(tag)}
-        if pcons is not None:
+        if pcons is not None and pcons.torque_limits.is_soft_constraint_mode() and mt["method"].startswith("PCG"):
             row["abs_mu"] = float(np.max(np.abs(pcons.torque_limits.quadratic_penalty_mu - S[tag + "/mu"]) / np.maximum(1e-300, np.abs(S[tag + "/mu"]))))
             row["abs_lam"] = float(np.max(np.abs(pcons.torque_limits.augmented_lagrangian_lambda - S[tag + "/lam"])))
             # locate the first outer iteration whose cumulative QP / PCG counts differ from the reference's trace
@@ -76,7 +76,7 @@ def main():
         print("%-22s exits %s pcg %s  rel J %.1e (floor %.1e)  |dx| %.1e (floor %.1e)  |du| %.1e (floor %.1e)%s" %
               (tag, "same" if row["exits_identical"] else "DIFF %s vs %s" % (row["exits_gpu"], ref_exits), "same" if pcg_same else "DIFF",
                row["rel_J"], fl.get("rel_J", float("nan")), row["abs_x"], fl.get("abs_x", float("nan")), row["abs_u"], fl.get("abs_u", float("nan")),
-               "" if pcons is None else "  first divergent outer iteration: %s" % (row["first_divergent_outer_iteration"],)))
+               "" if "first_divergent_outer_iteration" not in row else "  first divergent outer iteration: %s" % (row["first_divergent_outer_iteration"],)))
     os.makedirs(os.path.join(ROOT, "gpurun_out"), exist_ok=True)
     with open(os.path.join(ROOT, "gpurun_out", "parity_report.json"), "w") as f:
         json.dump(rows, f, indent=1)

@@ -48,7 +48,11 @@ def test_api_argument_errors():
         t.TrajoptMPCReference(plant, object())
     c = t.TrajoptConstraint(2, 2, 2, 10)
     with pytest.raises(ValueError):
-        c.set_torque_limits([1.0], [-1.0], "ACTIVE_SET")
+        c.set_torque_limits([1.0], [-1.0], "FULL_SET")          # singular KKT in the reference itself
+    with pytest.raises(ValueError):
+        c.set_torque_limits([1.0], [-1.0], "ADMM_PROJECTION")   # "[!] ERROR NOT IMPLEMENTED YET" in the reference
+    c.set_torque_limits([1.0], [-1.0], "ACTIVE_SET")            # hard mode, exact methods N / S
+    assert c.torque_limits.is_hard_constraint_mode() and not c.torque_limits.is_soft_constraint_mode()
     with pytest.raises(ValueError):
         c.set_torque_limits([1.0, 2.0, 3.0], [-1.0], "QUADRATIC_PENALTY")
     c.set_torque_limits([1.0], [-1.0], "QUADRATIC_PENALTY")

@@ -89,9 +89,9 @@ def test_lagged_count_readback_identical(oracle_models):
 @pytest.mark.parametrize("N", [64, 23])
 def test_pcg_kernel_variants(N, oracle_models):
     """The PCG kernels of the structured path on the same problems: k_pcg3 (default, B2T_PCG_VARIANT=3), k_pcg4 (5: the own-block halves
-    of the products ahead of the barriers, same arithmetic -> bit-identical to k_pcg3) and k_pcg6 (6: six lanes per knot, different
-    summation order -> identical iteration counts on these problems, solutions equal to rounding).  Both alternatives are measured
-    dead ends (profiles/README.md); they stay selectable for A/B runs and must stay correct."""
+    of the products ahead of the barriers) and k_pcg6 (6: six lanes per knot, different summation order): identical iteration counts
+    on these problems, solutions equal to rounding.  Both alternatives are measured dead ends (profiles/README.md); they stay
+    selectable for A/B runs and must stay correct."""
     batch = 5
     res = {}
     for variant in ("3", "5", "6"):
@@ -105,6 +105,6 @@ def test_pcg_kernel_variants(N, oracle_models):
             it = s.stage_pcg(t.SQPSolverMethods.PCG_SS, 1e-6, 100)
             res[variant] = (np.array(it), s.fetch("l").copy())
             s.close()
-    assert np.array_equal(res["3"][0], res["5"][0]) and np.array_equal(res["3"][1], res["5"][1])
-    assert np.array_equal(res["3"][0], res["6"][0])
-    assert np.max(np.abs(res["3"][1] - res["6"][1])) < 1e-9 * np.max(np.abs(res["3"][1]))
+    for v in ("5", "6"):
+        assert np.array_equal(res["3"][0], res[v][0]), v
+        assert np.max(np.abs(res["3"][1] - res[v][1])) < 1e-9 * np.max(np.abs(res["3"][1])), v

@@ -1314,7 +1314,10 @@ __global__ void __launch_bounds__(MAXT, PDS ? 2 : 1) k_pcg3(Dev<T> d, const int*
 //   * EUL (explicit Euler, tau = 0): AB^T z needs only the velocity half of z (3 instead of 6 128-bit loads);
 //   * loads and stores that exist only for the q / qd columns or the top rows are predicated off in the other lanes
 //     (W[:, nx:] is never read; full[] only feeds the q rows), which halves their wavefronts.
-// Same summation order inside every product as k_pcg3 => bit-identical iterates (tests/test_gpu_variants.py).
+// Same summation order inside every product as k_pcg3 (the E0 term is contracted differently by the compiler): identical iteration
+// counts, solutions equal to rounding (tests/test_gpu_variants.py).  MEASURED: 2.5 % SLOWER than k_pcg3 (18.67 vs 18.19 ns per
+// instance-iteration, profiles/README.md) -- the barrier waits it hides are only ~10 % of the stall samples and the extra
+// predication costs as much; kept selectable (B2T_PCG_VARIANT=5) as the record of the experiment.
 // -----------------------------------------------------------------------------------------------------------------
 template <typename T, int MAXT, bool EUL>
 __global__ void __launch_bounds__(MAXT, 1) k_pcg4(Dev<T> d, const int* list, const int* count, int stair, T tol, int max_iter) {
@@ -1588,6 +1591,10 @@ __global__ void __launch_bounds__(MAXT, 1) k_pcg4(Dev<T> d, const int* list, con
 // runs 13 instead of 8 warps against the same shared-memory / FP64 work, which is what a latency-bound kernel needs (ncu on
 // k_pcg3: 6 cycles between issues of a warp, 2 warps per scheduler).  48 doubles of matrix data per lane => <= 152 registers.
 // Summation orders differ from k_pcg3 (6-lane reductions) -- same recurrence and exit test (PCG.py:66-111).
+// MEASURED: 1.8x SLOWER than k_pcg3 (32.6 vs 18.2 ns per instance-iteration; profiles/r02_v6lane_*).  13 warps put 4 warps on one
+// scheduler, whose 16 K registers then allow only 128 per thread: 27 spilled doubles (LDL/STL 5.6 % of the instructions), address and
+// constant recomputation (IMAD 12.5 %), divergent predication (BSSY/BSYNC/BRA 10 %); the FP64 instruction count per SM is unchanged,
+// so the shorter per-thread stream the design was after never materialises.  Kept selectable (B2T_PCG_VARIANT=6) as the record.
 // -----------------------------------------------------------------------------------------------------------------
 constexpr int PCG6_KPW = 5;                       // knots per warp
 constexpr int PCG6_THREADS = 416;                 // 13 warps: N <= 65

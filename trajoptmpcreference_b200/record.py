@@ -51,11 +51,13 @@ class Recorder:
         # replay of the cost- / plant-level callbacks (see the module docstring)
         self.alpha_factor = float(options.get("alpha_factor_SQP_DDP", 0.5))
         self.max_iter_sqp = int(options.get("max_iter_SQP_DDP", 100))
-        self._cost_lists = hasattr(owner.cost, "saved_cost")
+        cost, plant = getattr(owner, "cost", None), getattr(owner, "plant", None)
+        self._replay = plant is not None and hasattr(plant, "saved_c")      # a real TrajoptMPCReference (host-side layout tests use stand-ins)
+        self._cost_lists = hasattr(cost, "saved_cost")
         self._ref_it, self._ref_ls, self._outer_seen = 0, 0, -1
         self._probe = None
         self._pre = None                    # (X, U, dz, iteration, outer, total_trials) of the QP solve whose line search is running
-        for obj, names in ((owner.cost, ("cost", "grad", "hess", "Jacobian_tot_state", "dx")), (owner.plant, ("c", "Minv", "qdd", "dc_du", "dqdd"))):
+        for obj, names in ((cost, ("cost", "grad", "hess", "Jacobian_tot_state", "dx")), (plant, ("c", "Minv", "qdd", "dc_du", "dqdd"))):
             for name in names:
                 if hasattr(obj, "saved_" + name):
                     setattr(obj, "saved_" + name, [])
@@ -199,13 +201,14 @@ class Recorder:
             tag = self._tag
             # cost- / plant-level callbacks the reference makes up to and inside this QP solve
             it, outer = int(st[3]), int(st[2])
-            Xc, Uc = s.get_trajectory()
-            e = self._eval(Xc[0], Uc[0])
-            if outer != self._outer_seen:     # start of an outer iteration: J and c of the start point, counters still stale (:541-542)
-                self._outer_seen = outer
-                self._total_cost_and_violation(e, (self._ref_it, outer, self._ref_ls))
-            self._ref_it = it
-            self._replay_kkt(e, (it, outer, self._ref_ls))
+            if self._replay:
+                Xc, Uc = s.get_trajectory()
+                e = self._eval(Xc[0], Uc[0])
+                if outer != self._outer_seen:     # start of an outer iteration: J and c of the start point, counters still stale (:541-542)
+                    self._outer_seen = outer
+                    self._total_cost_and_violation(e, (self._ref_it, outer, self._ref_ls))
+                self._ref_it = it
+                self._replay_kkt(e, (it, outer, self._ref_ls))
 
             def put(name, value):
                 getattr(o, name).append(dict(value=value, **tag))
@@ -221,8 +224,9 @@ class Recorder:
                 o.saved_inner_traces.append(((nu[:n_it + 1].tolist(), []), tag["iteration"], tag["outer_iteration"]))
                 put("saved_Pinv", d["Pinv"])
             put("saved_l", d["l"]); put("saved_dxul", d["dxul"])
-            self._pre = (Xc[0].copy(), Uc[0].copy(), s.fetch("dz")[0].copy(), it, outer)
-            self._trials_before = int(st[6]) - 0
+            if self._replay:
+                self._pre = (Xc[0].copy(), Uc[0].copy(), s.fetch("dz")[0].copy(), it, outer)
+                self._trials_before = int(st[6])
         elif event == _lib.HOOK_STEP:
             if self._pre is not None:
                 self._replay_line_search(int(st[6]) - self._trials_before)
