@@ -227,12 +227,14 @@ def cpu_worker(args):
             _reference_solve((xg[k], True)); k += 1
         out["memoised"] = {"value": k / (time.perf_counter() - t0), "unit": "solves/s", "cores": 1, "kind": "reference",
                            "sample": "first %d instances, no box limits, unmodified reference (oracle/_ref) with memoised sympy lambdify" % k}
-        if args.stock:
-            t0 = time.perf_counter()
-            _reference_solve((xg[0], False))
-            out["stock"] = {"value": 1.0 / (time.perf_counter() - t0), "unit": "solves/s", "cores": 1, "kind": "reference",
-                            "sample": "instance 0, no box limits, unmodified reference (oracle/_ref), stock (sympy lambdify per joint lookup)"}
         print(json.dumps(out))
+    elif args.cpu_worker == "ref-stock":
+        # the STOCK reference (no memoisation: sympy.lambdify on every joint-transform lookup) in a process of its own --
+        # the memoisation shim patches the Joint class for the whole process
+        t0 = time.perf_counter()
+        _reference_solve((xg[0], False))
+        print(json.dumps({"stock": {"value": 1.0 / (time.perf_counter() - t0), "unit": "solves/s", "cores": 1, "kind": "reference",
+                                    "sample": "instance 0, no box limits, unmodified reference (oracle/_ref), stock (sympy lambdify per joint lookup)"}}))
 
 
 def run_cpu_worker(mode, args, extra):
@@ -278,7 +280,9 @@ def run_reference_arm(args):
             sec_r, cnt_r = pool_throughput(_reference_solve, tasks, cores, cores)
             anchor = {"memoised_pool": {"value": cnt_r / sec_r, "unit": "solves/s", "cores": cores, "kind": "reference",
                                         "sample": "%d instances (no box limits), unmodified reference from oracle/_ref, memoised lambdify, Pool(%d)" % (cnt_r, cores)}}
-            anchor.update(run_cpu_worker("ref-anchor", args, ["--budget", "12", "--max-instances", "3"] + (["--stock"] if args.stock else [])))
+            anchor.update(run_cpu_worker("ref-anchor", args, ["--budget", "12", "--max-instances", "3"]))
+            if args.stock:
+                anchor.update(run_cpu_worker("ref-stock", args, []))
             sec_p, cnt_p = pool_throughput(_oracle_solve, [(xg[i % len(xg)], False) for i in range(9 * cores)], cores, cores)
             anchor["port_pool_nolimits"] = {"value": cnt_p / sec_p, "unit": "solves/s", "cores": cores, "kind": "port",
                                             "sample": "%d instances (no box limits), numpy oracle, Pool(%d)" % (cnt_p, cores)}
@@ -531,7 +535,7 @@ def main():
     ap.add_argument("--total", type=int, default=0, help="strong scaling: this many instances in total, split over the GPUs")
     ap.add_argument("--stock", action="store_true", help="reference arm: also time ONE solve of the stock (un-memoised) reference (~100 s)")
     ap.add_argument("--no-ref-anchor", action="store_true")
-    ap.add_argument("--cpu-worker", default=None, choices=["port-seq", "ref-anchor"], help=argparse.SUPPRESS)
+    ap.add_argument("--cpu-worker", default=None, choices=["port-seq", "ref-anchor", "ref-stock"], help=argparse.SUPPRESS)
     ap.add_argument("--budget", type=float, default=20.0, help=argparse.SUPPRESS)
     ap.add_argument("--max-instances", type=int, default=8, help=argparse.SUPPRESS)
     ap.add_argument("--out", default=None, help=argparse.SUPPRESS)
