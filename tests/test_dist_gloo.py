@@ -61,3 +61,23 @@ def test_gather_world2_gloo(total):
     for p in procs:
         p.join(timeout=60)
     assert sorted(res) == [(0, True), (1, True)]
+
+
+def test_bench_workload_shards():
+    """bench.workload_goals: C4 at one GPU (default_rng(1)); C5 shards at N GPUs tile ONE default_rng(2) stream (contiguous, disjoint);
+    `c5=True` at one GPU is shard 0 of that stream (scaling series compare like with like); strong scaling (--total) partitions the same
+    stream into larger shards."""
+    import sys
+    ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    sys.path.insert(0, ROOT)
+    import bench
+    B = 64
+    c4 = bench.workload_goals(1, 0, B)
+    assert np.array_equal(c4, bench.goals(B, 1)) and np.all(c4[:, 6:] == 0) and np.all(np.abs(c4[:, :6]) <= 0.5)
+    for world in (2, 4, 8):
+        shards = [bench.workload_goals(world, r, B) for r in range(world)]
+        assert np.array_equal(np.concatenate(shards), bench.goals(B * world, 2))
+    # shard 0 of the stream is a prefix of every larger partition of it (numpy Generator.uniform fills row-major)
+    assert np.array_equal(bench.workload_goals(1, 0, B, c5=True), bench.workload_goals(8, 0, B))
+    assert np.array_equal(bench.workload_goals(2, 0, 4 * B)[:B], bench.workload_goals(8, 0, B))
+    assert not np.array_equal(c4, bench.workload_goals(1, 0, B, c5=True))

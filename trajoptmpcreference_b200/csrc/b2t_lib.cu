@@ -94,6 +94,15 @@ struct SolverT : SolverBase {
   bool schur_v1 = false;
   int schur_minb = 2;
   int* d_status = nullptr; double* d_scalars = nullptr;
+  bool gh_dense = false;           // d.Gh holds m x m blocks (dense KKT path / iLQR) instead of the structured path's 2m+1 scalars
+  int ensure_dense_gh() {
+    if (gh_dense) return 0;
+    T* q = nullptr;
+    if (int r = alloc(&q, (size_t)b2t::NM * b2t::NM * d.K)) return r;
+    d.Gh = q;                      // the small array stays in `allocs` and is freed with the handle
+    gh_dense = true;
+    return 0;
+  }
   int* d_scratch = nullptr;
   enum { PASS_TRACE_CAP = 2048 };
   int* d_pass_trace = nullptr;      // active-instance count after every pass of the last solve (written by k_compact)
@@ -154,7 +163,7 @@ struct SolverT : SolverBase {
     const size_t K = d.K, B = d.B, R = (size_t)d.N * NX;
     B2T_ALLOC(d.x, NX * K); B2T_ALLOC(d.u, NU * K); B2T_ALLOC(d.xn, NX * K); B2T_ALLOC(d.un, NU * K);
     B2T_ALLOC(d.xkp1, NX * K); B2T_ALLOC(d.xkp1n, NX * K); B2T_ALLOC(d.dyn, (size_t)NDYN * K); B2T_ALLOC(d.vaf, (size_t)NVAF * K);
-    B2T_ALLOC(d.Gh, (size_t)NM * NM * K); B2T_ALLOC(d.g, NM * K); B2T_ALLOC(d.Gg, NM * K); B2T_ALLOC(d.dz, NM * K);
+    B2T_ALLOC(d.g, NM * K); B2T_ALLOC(d.Gg, NM * K); B2T_ALLOC(d.dz, NM * K);      // d.Gh: after the structured / dense decision below
     B2T_ALLOC(d.Sd, B * R * NX); B2T_ALLOC(d.So, B * R * NX); B2T_ALLOC(d.Pd, B * R * NX); B2T_ALLOC(d.gam, B * R); B2T_ALLOC(d.l, B * R);
     B2T_ALLOC(d.xs, NX * B); B2T_ALLOC(d.xg, NX * B);
     // cost
@@ -195,6 +204,10 @@ struct SolverT : SolverBase {
     d.lim.any = any;
     d.hard.any = any_hard;
     if (any_hard) d.diag_mode = 0;        // the elimination of the fixed coordinates lives in the dense KKT kernel
+    // Ghat_k: 2m+1 scalars per knot on the structured path (dinv, h, s), a dense m x m block otherwise.  iLQR always needs the dense
+    // block and allocates it on its first call (ensure_dense_gh).
+    gh_dense = d.diag_mode == 0;
+    B2T_ALLOC(d.Gh, (size_t)(gh_dense ? NM * NM : 2 * NM + 1) * K);
     { int* m; B2T_ALLOC(m, NM); B2T_CUDA(cudaMemcpy(m, hmode, sizeof(hmode), cudaMemcpyHostToDevice)); d.hard.mode = m; }
     { int* m; B2T_ALLOC(m, NM); B2T_CUDA(cudaMemcpy(m, mode, sizeof(mode), cudaMemcpyHostToDevice)); d.lim.mode = m; }
     { T* q; int r; if ((r = upload(&q, lb, NM))) return r; d.lim.lb = q; }
@@ -734,6 +747,7 @@ struct SolverT : SolverBase {
     B2T_CUDA(cudaEventRecord(ev0, stream));
     const int B = d.B;
     if (d.hard.any) return fail(B2T_ERR_UNSUPPORTED, "iLQR supports soft limits only (README.md:17 of the reference says the same)");
+    { int r = ensure_dense_gh(); if (r) return r; }
     const size_t msmem = (size_t)6 * d.N * sizeof(T);
     const int mt = merit_threads();
     k_init_state<T><<<cdiv(B, 128), 128, 0, stream>>>(d); tick(B2T_K_CTRL);
