@@ -26,6 +26,11 @@ int he_dynamics(int count, const double* x, const double* u, double dt, double g
   }
   return 0;
 }
+// qdd by the single-right-hand-side articulated-body solve (forward_dynamics_qdd) for `count` knots
+int he_qdd_solve(int count, const double* x, const double* u, double gravity, double* qdd) {
+  for (int t = 0; t < count; ++t) forward_dynamics_qdd<double>(x + t * NX, x + t * NX + NJ, u + t * NU, gravity, qdd + t * NJ);
+  return 0;
+}
 // cost value / gradient / hessian and soft terms of `count` knots
 int he_cost_mode(int count, int kind, int qf_start, int hess_mode, const double* Q, const double* QF, const double* R, const double* xg,
                  const double* x, const double* u, const int* kidx, const int* terminal, double* val, double* grad, double* hess) {

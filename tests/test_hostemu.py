@@ -179,3 +179,24 @@ def test_exact_hessian_mode(name, oracle_models):
                 Xp = X.copy(); Xm = X.copy(); Xp[k, i] += eps; Xm[k, i] -= eps
                 fd = (c.gradients(Xp, U)[k][:nx] - c.gradients(Xm, U)[k][:nx]) / (2 * eps)
                 assert np.max(np.abs(fd - H[k, :nx, i])) < 1e-6 * max(1.0, np.max(np.abs(H[k])))
+
+
+@pytest.mark.parametrize("name", ["pend", "arm2", "arm3", "arm6", "cartpole"])
+def test_articulated_body_solve_equals_minv_times_rhs(name, oracle_models):
+    """forward_dynamics_qdd (qdd = M^-1 (u - c) by the single-right-hand-side articulated-body recursion, used at the line-search trial
+    points) against the oracle's Minv (u - c) (URDFPlant.forward_dynamics, TrajoptPlant.py:283-299)."""
+    from oracle import rbd, plant as oplant
+    lib = hostemu.load(name)
+    if name in oracle_models:
+        m = oracle_models[name]
+    else:
+        from trajoptmpcreference_b200 import model as pmodel
+        m = rbd.Model(pmodel.extract_model(pmodel.builtin_urdf(name)))
+    n = m.n
+    rng = np.random.default_rng(12)
+    cnt = 9
+    X = rng.uniform(-2, 2, (cnt, 2 * n)); U = rng.uniform(-3, 3, (cnt, n))
+    qdd = np.zeros((cnt, n))
+    lib.he_qdd_solve(cnt, P(X), P(U), ctypes.c_double(-9.81), P(qdd))
+    ref = oplant.forward_dynamics(m, X, U, -9.81)
+    assert relerr(qdd, ref) < 1e-12
