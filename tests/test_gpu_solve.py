@@ -351,3 +351,18 @@ def test_end_effector_cost_exact_hessian_mode(name, N, B, iters, oracle_models):
         if ok:
             assert abs(ro["J"] - r.J[b]) < 1e-6 * max(1.0, abs(ro["J"]))
     assert same >= B - 1
+
+
+def test_more_than_103_sqp_iterations_allowed(oracle_models):
+    """max_iter_SQP_DDP above the 104 trace rows kept per outer iteration: the solve runs (round 1 refused it), counts and results
+    follow the oracle; `trace` keeps the first 104 rows."""
+    N = 20
+    limits = {"torque": ([0.1], [-0.1], "QUADRATIC_PENALTY")}
+    (plant, pc, pcons), (m, oc, ocn) = make_pair("pend", N, oracle_models, limits=limits)
+    opts = {"expected_reduction_min_SQP_DDP": -100, "max_iter_SQP_DDP": 150, "max_iter_softConstraints": 3}
+    solver = t.TrajoptMPCReference(plant, pc, pcons)
+    x, u, e1, e2, outer, it = solver.SQP(np.zeros((2, N)), np.zeros((1, N - 1)), N, 0.1, t.SQPSolverMethods.PCG_SS, options=dict(opts))
+    ro = sqp.sqp(m, oc, ocn, np.zeros((2, N)), np.zeros((1, N - 1)), N, 0.1, "PCG-SS", dict(opts))
+    assert (e1, e2, outer, it) == (ro["exit_sqp"], ro["exit_soft"], ro["outer_iter"], ro["sqp_iter"])
+    assert int(solver.last_result.total_qp[0]) == len(ro["pcg_iters"])
+    assert np.max(np.abs(x - ro["x"])) < 1e-9 * max(1.0, np.max(np.abs(ro["x"]))) and len(solver.trace) <= 104

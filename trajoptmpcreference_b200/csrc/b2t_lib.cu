@@ -610,7 +610,7 @@ struct SolverT : SolverBase {
     if (method != B2T_METHOD_N && method != B2T_METHOD_S && method != B2T_METHOD_PCG_J && method != B2T_METHOD_PCG_BJ &&
         method != B2T_METHOD_PCG_SS)
       return fail(B2T_ERR_INVALID, "method must be N, S, PCG-J, PCG-BJ or PCG-SS");
-    if (o->max_iter_SQP + 1 > d.trace_cap) return fail(B2T_ERR_UNSUPPORTED, "max_iter_SQP_DDP > 103");
+    // trace rows beyond trace_cap (104 per outer iteration) are dropped by trace_row(); iteration counts and results do not depend on them
     if (d.hard.any && method != B2T_METHOD_N && method != B2T_METHOD_S)
       return fail(B2T_ERR_UNSUPPORTED, "hard (ACTIVE_SET) limits: exact methods N / S only (the reference hands PCG a Schur complement whose size no "
                                        "longer matches block_size * Nblocks)");
@@ -738,7 +738,6 @@ struct SolverT : SolverBase {
   int solve_ilqr(const b2t_options* o) override {
     using namespace b2t;
     if (!o) return fail(B2T_ERR_INVALID, "options required");
-    if (o->max_iter_SQP + 1 > d.trace_cap) return fail(B2T_ERR_UNSUPPORTED, "max_iter_SQP_DDP > 103");
     if (d.N > ILQR_MAX_KNOTS) return fail(B2T_ERR_UNSUPPORTED, "iLQR supports at most 512 knot points");
     B2T_CUDA(cudaSetDevice(device));
     Opts<T> op = convert(o);
