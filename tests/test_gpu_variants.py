@@ -108,3 +108,33 @@ def test_pcg_kernel_variants(N, oracle_models):
     for v in ("5", "6"):
         assert np.array_equal(res["3"][0], res[v][0]), v
         assert np.max(np.abs(res["3"][1] - res[v][1])) < 1e-9 * np.max(np.abs(res["3"][1])), v
+
+
+@pytest.mark.parametrize("name,N,kind", [("arm6", 64, "limits"), ("arm6", 17, "limits"), ("arm2", 10, "urdf"), ("pend", 20, "hard")])
+def test_parallel_line_search_bit_identical(name, N, kind, oracle_models):
+    """k_linesearch_par (all trials of a search evaluated at once, chosen for passes with few active instances; B2T_LS_PAR sets the
+    threshold) against the sequential k_linesearch on complete solves: every count, exit code, trace row and trajectory identical."""
+    out = {}
+    for tag, thr in (("seq", "0"), ("par", "1000000")):
+        with _env(B2T_LS_PAR=thr):
+            if kind == "limits":
+                plant, pc, pcons, x, u = _problem(name, N, 6, oracle_models, seed=3 + N)
+                method = t.SQPSolverMethods.PCG_SS
+            elif kind == "urdf":
+                (plant, pc, pcons), _ = make_pair(name, N, oracle_models)
+                x = np.zeros((6, 4, N)); u = np.zeros((6, 2, N - 1)); method = t.SQPSolverMethods.PCG_SS
+            else:
+                (plant, pc, pcons), _ = make_pair(name, N, oracle_models, limits={"torque": ([0.5], [-0.5], "ACTIVE_SET")})
+                x = np.zeros((6, 2, N)); u = np.zeros((6, 1, N - 1)); method = t.SQPSolverMethods.S
+            n = plant.get_num_pos()
+            rng = np.random.default_rng(9)
+            xg = np.zeros((6, pc.xg.size)); xg[:] = pc.xg; xg[:, :min(n, 2)] += 0.1 * rng.standard_normal((6, min(n, 2)))
+            solver = t.TrajoptMPCReference(plant, pc, pcons) if pcons is not None else t.TrajoptMPCReference(plant, pc)
+            r = solver.solve_batch(x, u, xg, N, 0.1, method, {"expected_reduction_min_SQP_DDP": -100, "max_iter_softConstraints": 3})
+            s = solver.batch_solver(N, 0.1, 6)
+            out[tag] = ({k: np.array(v) for k, v in r.items()}, s.get_trace().copy())
+    a, b = out["seq"], out["par"]
+    for k in a[0]:
+        assert np.array_equal(a[0][k], b[0][k]), k
+    assert np.array_equal(a[1], b[1])
+    assert a[0]["total_trials"].sum() > a[0]["total_qp"].sum()          # searches with more than one trial were exercised

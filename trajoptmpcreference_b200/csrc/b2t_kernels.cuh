@@ -2317,6 +2317,178 @@ __global__ void __launch_bounds__(128) k_linesearch(Dev<T> d, Opts<T> o, int fus
   }
 }
 
+// -----------------------------------------------------------------------------------------------------------------
+// k_linesearch_par: the same line search with ALL trial step lengths of an instance evaluated at once, one block per
+// (instance, trial) -- for passes with few active instances, where the sequential kernel costs its latency (~12 us per trial,
+// ~7 trials per search on the benchmark workload) while most SMs idle.  Trial t evaluates alpha_t = alpha_factor^t exactly like
+// iteration t of the sequential loop and stores (J, c, D); the LAST block of an instance to finish (atomic counter) walks the
+// trials in order, takes the sequential loop's decision at the first trial that accepts or fails -- later trials are discarded, so
+// counts and results are bit-identical (tests/test_gpu_variants.py) -- writes the accepted point x - alpha dz and runs the exit
+// tests / outer update.  Work grows by max_trials / (trials used); the host selects it only below a small active count.
+// smem: (6 + 2 NX) * N scalars.   scratch: trial_out [B][max_trials][3], done [B] (zero between passes).
+// -----------------------------------------------------------------------------------------------------------------
+template <typename T>
+__global__ void __launch_bounds__(128) k_linesearch_par(Dev<T> d, Opts<T> o, int fuse_outer, int fuse_recover, int max_trials, T* trial_out, int* done) {
+  const int slot = (int)blockIdx.x / max_trials, trial = (int)blockIdx.x % max_trials;
+  if (slot >= *d.n_act) return;
+  const int b = d.act[slot];
+  const int N = d.N;
+  const size_t K = d.K;
+  extern __shared__ unsigned char smem_raw[];
+  T* sm = reinterpret_cast<T*>(smem_raw);
+  if (fuse_recover)        // every trial block of the instance computes the same dz (identical values; the write is idempotent)
+    for (int k = threadIdx.x; k < N; k += blockDim.x) recover_diag_knot(d, b, k);
+  T* s_cost = sm; T* s_soft = sm + N; T* s_c = sm + 2 * N; T* s_D = sm + 3 * N; T* s_Ds = sm + 4 * N; T* s_xn = sm + 5 * N;   // [N][NX]
+  T* s_h = s_xn + N * NX;     // [N]
+  T* s_x = s_h + N;           // [N][NX] trial states
+  __shared__ int s_last, s_state, s_exit, s_ls;
+  __shared__ T s_alpha;
+  T alpha = T(1);
+  for (int i = 0; i < trial; ++i) alpha *= o.alpha_factor;        // the sequential loop's alpha after `trial` halvings, bit for bit
+  for (int k = threadIdx.x; k < N; k += blockDim.x) {
+    const size_t t = (size_t)b * N + k;
+    const bool terminal = (k == N - 1);
+    T z[NM], dzk[NM], xg[NX];
+    load_xu(d.x, d.u, K, t, terminal, z, z + NX);
+    for (int i = 0; i < NM; ++i) dzk[i] = d.dz[(size_t)i * K + t];
+    for (int i = 0; i < NX; ++i) { z[i] = z[i] - alpha * dzk[i]; s_x[k * NX + i] = z[i]; xg[i] = d.xg[(size_t)i * d.B + b]; }
+    if (!terminal)
+      for (int i = 0; i < NU; ++i) z[NX + i] = z[NX + i] - alpha * dzk[NX + i];
+    const int M = terminal ? NX : NM;
+    if (d.diag_mode) {
+      T cv, cd;
+      cost_value_dir_diag(d.cost, z, z + NX, xg, k, terminal, dzk, &cv, &cd);
+      s_cost[k] = cv; s_D[k] = cd;
+    } else {
+      s_cost[k] = cost_value(d.cost, z, z + NX, xg, k, terminal);
+      T g[NM];
+      cost_grad_hess<T, false>(d.cost, z, z + NX, xg, k, terminal, g, (T*)nullptr);
+      T acc = T(0);
+      for (int i = 0; i < M; ++i) acc += g[i] * dzk[i];
+      s_D[k] = acc;
+    }
+    T sv = T(0), accs = T(0);
+    if (d.lim.any) soft_value_dir(d.lim, z, d.mu + t, d.lam + t, K, terminal, dzk, &sv, &accs);
+    s_soft[k] = sv;
+    s_Ds[k] = accs;
+    if (d.hard.any) s_h[k] = hard_violation(d.hard, z, terminal);
+    if (k == 0) {
+      T cc = T(0);
+      for (int i = 0; i < NX; ++i) cc += fabs(z[i] - d.xs[(size_t)i * d.B + b]);
+      s_c[0] = cc;
+    }
+    if (!terminal) {
+      T qdd[NJ], Minv[NJ * NJ], v[NJ][6], a[NJ][6], f[NJ][6], xnext[NX];
+      forward_dynamics<T, false>(z, z + NJ, z + NX, d.gravity, qdd, Minv, v, a, f);
+      integrate(d.integrator, z, qdd, d.dt, xnext);
+      for (int i = 0; i < NX; ++i) s_xn[k * NX + i] = xnext[i];
+    }
+  }
+  __syncthreads();
+  for (int k = threadIdx.x; k < N; k += blockDim.x) {
+    if (k == 0) continue;
+    T cc = T(0);
+    for (int i = 0; i < NX; ++i) cc += fabs(s_x[k * NX + i] - s_xn[(k - 1) * NX + i]);
+    s_c[k] = cc;
+  }
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    T Jn = T(0), cn = T(0), D = T(0);
+    const bool lim_any = d.lim.any != 0;
+    for (int k = 0; k < N; ++k) {
+      Jn += s_cost[k];
+      cn += s_c[k];
+      D += s_D[k];
+      if (lim_any) D += s_Ds[k];
+    }
+    if (lim_any) {
+      for (int k = 0; k < N; ++k) Jn += s_soft[k];
+    }
+    if (d.hard.any)
+      for (int k = 0; k < N; ++k) cn += s_h[k];
+    T* out = trial_out + ((size_t)b * max_trials + trial) * 3;
+    out[0] = Jn; out[1] = cn; out[2] = D;
+    __threadfence();
+    const int prev = atomicAdd(done + b, 1);
+    s_last = (prev == max_trials - 1) ? 1 : 0;
+    if (s_last) { done[b] = 0; __threadfence(); }
+  }
+  __syncthreads();
+  if (!s_last) return;
+  // ---- last block of this instance: the sequential loop's decisions over the stored trials
+  if (threadIdx.x == 0) {
+    T al = T(1);
+    int ls = 0, state = 2;
+    const T mu = o.merit_mu;
+    for (int t = 0; t < max_trials; ++t) {
+      const volatile T* in = trial_out + ((size_t)b * max_trials + t) * 3;
+      const T Jn = in[0], cn = in[1], D = in[2];
+      const T merit_new = Jn + mu * cn;
+      const T delta_J = d.J[b] - Jn;
+      const T delta_merit = d.merit[b] - merit_new;
+      const T expected = al * (D - mu * cn);
+      const T ratio = delta_merit / expected;
+      d.deltaJ[b] = delta_J;
+      d.tot_trials[b] += 1;
+      if (delta_merit >= T(0) && ratio >= o.er_min && ratio <= o.er_max) {
+        state = 0;
+        d.J[b] = Jn; d.c[b] = cn; d.merit[b] = merit_new;
+        const T drho = fmin(d.drho[b] / o.rho_factor, T(1) / o.rho_factor);
+        d.drho[b] = drho; d.rho[b] = fmax(d.rho[b] * drho, o.rho_min);
+        trace_row(d, b, ls, al, D, ratio, d.pcg_iters[b], 1);
+        break;
+      } else if (al > o.alpha_min) {
+        al *= o.alpha_factor;
+        ls += 1;
+      } else {
+        state = 2;
+        trace_row(d, b, ls, al, D, ratio, d.pcg_iters[b], 0);
+        break;
+      }
+    }
+    s_state = state; s_alpha = al; s_ls = ls;
+  }
+  __syncthreads();
+  const int st = s_state;
+  const T al = s_alpha;
+  // the deciding trial's point (what the sequential kernel leaves in xn / un), and on acceptance the new iterate
+  for (int k = threadIdx.x; k < N; k += blockDim.x) {
+    const size_t t = (size_t)b * N + k;
+    const bool terminal = (k == N - 1);
+    for (int i = 0; i < NX; ++i) {
+      const T v = d.x[(size_t)i * K + t] - al * d.dz[(size_t)i * K + t];
+      d.xn[(size_t)i * K + t] = v;
+      if (st == 0) d.x[(size_t)i * K + t] = v;
+    }
+    if (!terminal)
+      for (int i = 0; i < NU; ++i) {
+        const T v = d.u[(size_t)i * K + t] - al * d.dz[(size_t)(NX + i) * K + t];
+        d.un[(size_t)i * K + t] = v;
+        if (st == 0) d.u[(size_t)i * K + t] = v;
+      }
+  }
+  if (threadIdx.x == 0) {           // check_for_exit_or_error (:463-481)
+    bool exit_flag = false;
+    if (st == 2) {
+      const T drho = fmax(d.drho[b] * o.rho_factor, o.rho_factor);
+      const T rho = fmax(d.rho[b] * drho, o.rho_min);
+      d.drho[b] = drho; d.rho[b] = rho;
+      if (rho > o.rho_max) { d.exit_sqp[b] = 2; exit_flag = true; }
+    } else if (d.deltaJ[b] < o.tol_sqp) {
+      d.exit_sqp[b] = 1; exit_flag = true;
+    }
+    if (d.sqp_iter[b] == o.max_iter_sqp - 1) { d.exit_sqp[b] = 3; exit_flag = true; }
+    else d.sqp_iter[b] += 1;
+    if (exit_flag) d.phase[b] = PH_OUTER;
+    d.ls_iter[b] = s_ls;
+    d.alpha[b] = al;
+    d.dyn_ok[b] = (st == 2) ? 1 : 0;
+    s_exit = exit_flag ? 1 : 0;
+  }
+  __syncthreads();
+  if (fuse_outer && s_exit) outer_update(d, o, b, sm, 1);
+}
+
 // stage entry point: J, c, D of the trial point for alpha (no decision)
 template <typename T>
 __global__ void k_merit_only(Dev<T> d, T* J, T* c, T* D) {

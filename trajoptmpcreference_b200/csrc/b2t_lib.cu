@@ -94,6 +94,8 @@ struct SolverT : SolverBase {
   bool schur_v1 = false;
   int schur_minb = 2;
   int* d_status = nullptr; double* d_scalars = nullptr;
+  T* d_trial_out = nullptr; int* d_trial_done = nullptr;      // k_linesearch_par: (J, c, D) per (instance, trial), arrival counters
+  int ls_par_max = 160;            // passes with at most this many active instances evaluate all trials of a search at once (B2T_LS_PAR)
   bool gh_dense = false;           // d.Gh holds m x m blocks (dense KKT path / iLQR) instead of the structured path's 2m+1 scalars
   int ensure_dense_gh() {
     if (gh_dense) return 0;
@@ -240,6 +242,9 @@ struct SolverT : SolverBase {
     // kernels that need > 48 KB of dynamic shared memory
     B2T_CUDA(cudaFuncSetAttribute(b2t::k_pcg<T>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
     B2T_CUDA(cudaFuncSetAttribute(b2t::k_linesearch<T>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+    B2T_CUDA(cudaFuncSetAttribute(b2t::k_linesearch_par<T>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+    B2T_ALLOC(d_trial_out, (size_t)B * MAX_LS_TRIALS * 3); B2T_ALLOC(d_trial_done, B);
+    { const char* e = getenv("B2T_LS_PAR"); if (e) ls_par_max = atoi(e); }
     B2T_CUDA(cudaFuncSetAttribute(b2t::k_schur_diag<T>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)((size_t)NJ * NM * SCHUR_THREADS * sizeof(T))));
     B2T_CUDA(cudaFuncSetAttribute(b2t::k_schur_rows<T, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)((size_t)SCHUR_REC * SCHUR_KB * sizeof(T))));
     B2T_CUDA(cudaFuncSetAttribute(b2t::k_schur_rows<T, 3>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)((size_t)SCHUR_REC * SCHUR_KB * sizeof(T))));
@@ -622,7 +627,8 @@ struct SolverT : SolverBase {
     explicit_system = false;
     Opts<T> op = convert(o);
     int max_trials = 1;
-    { double a = 1.0; while (a > o->alpha_min && max_trials < MAX_LS_TRIALS) { a *= o->alpha_factor; ++max_trials; } }
+    bool trials_exact = false;      // max_trials is the sequential loop's true bound (not the MAX_LS_TRIALS cap)
+    { T a = T(1); while (a > op.alpha_min && max_trials < MAX_LS_TRIALS) { a *= op.alpha_factor; ++max_trials; } trials_exact = !(a > op.alpha_min); }
     launches = 0; device_seconds = 0;
     for (int i = 0; i < B2T_KERNEL_FAMILIES; ++i) { fam_seconds[i] = 0; fam_launches[i] = 0; }
     B2T_CUDA(cudaEventRecord(ev0, stream));
@@ -639,6 +645,7 @@ struct SolverT : SolverBase {
     const bool trace_active = getenv("B2T_TRACE_ACTIVE") != nullptr;      // debugging: active-instance count after every SQP pass on stderr
     const bool lagged = !hook && !trace_active && !(getenv("B2T_SYNC_PASSES") && atoi(getenv("B2T_SYNC_PASSES")) != 0);
     const size_t lsmem = (size_t)(6 + NX) * d.N * sizeof(T);
+    const size_t lsmem_par = (size_t)(6 + 2 * NX) * d.N * sizeof(T);
     const int lst = std::min(128, ((d.N + 31) / 32) * 32);
     const size_t osmem = std::max((size_t)3 * d.N * sizeof(T), msmem);
     for (long long iter = 0; n > 0 && iter < cap; ++iter) {
@@ -654,7 +661,12 @@ struct SolverT : SolverBase {
       }
       if (!legacy_ls) {
         // k_linesearch also runs the outer (soft-constraint) update of the instances whose SQP loop exits in this pass
-        { Scope sc(this, B2T_K_TRIAL); k_linesearch<T><<<n, lst, lsmem, stream>>>(d, op, 1, fuse_recover); tick(B2T_K_TRIAL); }
+        // few active instances: all trials of a search at once (one block per instance and trial; bit-identical decisions)
+        if (n <= ls_par_max && trials_exact) {
+          Scope sc(this, B2T_K_TRIAL);
+          k_linesearch_par<T><<<n * max_trials, lst, lsmem_par, stream>>>(d, op, 1, fuse_recover, max_trials, d_trial_out, d_trial_done);
+          tick(B2T_K_TRIAL);
+        } else { Scope sc(this, B2T_K_TRIAL); k_linesearch<T><<<n, lst, lsmem, stream>>>(d, op, 1, fuse_recover); tick(B2T_K_TRIAL); }
       } else {
         { Scope sc(this, B2T_K_CTRL); k_iter_begin<T><<<cdiv(n, 128), 128, 0, stream>>>(d); tick(B2T_K_CTRL); }
         for (int t = 0; t < max_trials; ++t) {
