@@ -123,7 +123,8 @@ class ClockSampler(threading.Thread):
 # Two CPU implementations are timed on the box's host cores (never on the product path):
 #   "port"      oracle/sqp.py, the numpy restatement (block-structured, no sympy): runs the FULL workload incl. the multi-coordinate
 #               box limits, on which the reference itself crashes;
-#   "reference" the UNMODIFIED reference staged in oracle/_ref by oracle/build_ref.py, imported through tests/ref/refshim.py
+#   "reference" the UNMODIFIED reference packed into oracle/_ref/reference_solve_path.zip by oracle/build_ref.py, imported (zipimport)
+#               through tests/ref/refshim.py
 #               (stock, or with the bit-identical lambdify memoisation of SURVEY.md 0.10): runs the reference-pinned variant
 #               (same robot / horizon / cost / goals, no box limits).
 def _oracle_problem(use_limits):
@@ -162,7 +163,7 @@ def _reference_solve(args):
     xg, memoise = args
     key = bool(memoise)
     if key not in _REF_NS:
-        os.environ["B2T_REFERENCE"] = os.path.join(ROOT, "oracle", "_ref")
+        os.environ["B2T_REFERENCE"] = os.path.join(ROOT, "oracle", "_ref", "reference_solve_path.zip")
         sys.path.insert(0, os.path.join(ROOT, "tests", "ref"))
         import refshim
         _REF_NS[key] = refshim.load(memoise=key)
@@ -181,7 +182,7 @@ def _reference_solve(args):
 
 
 def reference_staged():
-    return os.path.isfile(os.path.join(ROOT, "oracle", "_ref", "TrajoptMPCReference.py"))
+    return os.path.isfile(os.path.join(ROOT, "oracle", "_ref", "reference_solve_path.zip"))
 
 
 def pool_throughput(fn, tasks, warm, cores):

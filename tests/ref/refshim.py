@@ -15,6 +15,9 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 
 
 def available() -> bool:
+    """REF is the reference tree, or the archive oracle/build_ref.py packs for the GPU box (imported through zipimport)."""
+    if REF.endswith(".zip"):
+        return os.path.isfile(REF)
     return os.path.isdir(REF) and os.path.isfile(os.path.join(REF, "TrajoptMPCReference.py"))
 
 
