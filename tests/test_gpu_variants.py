@@ -89,23 +89,24 @@ def test_lagged_count_readback_identical(oracle_models):
 @pytest.mark.parametrize("N", [64, 23])
 def test_pcg_kernel_variants(N, oracle_models):
     """The PCG kernels of the structured path on the same problems: k_pcg3 (default, B2T_PCG_VARIANT=3), k_pcg4 (5: the own-block halves
-    of the products ahead of the barriers) and k_pcg6 (6: six lanes per knot, different summation order): identical iteration counts
-    on these problems, solutions equal to rounding.  Both alternatives are measured dead ends (profiles/README.md); they stay
+    of the products ahead of the barriers), k_pcg6 (6: six lanes per knot, different summation order) and k_pcg3 with the column
+    form of the D^-1 products (7: partial sums + a reduce-scatter over the knot's lanes): identical iteration counts
+    on these problems, solutions equal to rounding.  The alternatives are measured dead ends (profiles/README.md); they stay
     selectable for A/B runs and must stay correct."""
     batch = 5
     res = {}
-    for variant in ("3", "5", "6"):
+    for variant in ("3", "5", "6", "7"):
         with _env(B2T_PCG_VARIANT=variant):
             plant, pc, pcons, x, u = _problem("arm6", N, batch, oracle_models, seed=N)
             s = t.BatchSolver(plant, pc, pcons, N=N, dt=0.1, batch=batch)
-            assert s.pcg_kernel_name() == {"3": "k_pcg3", "5": "k_pcg4", "6": "k_pcg6"}[variant]
+            assert s.pcg_kernel_name() == {"3": "k_pcg3", "5": "k_pcg4", "6": "k_pcg6", "7": "k_pcg3"}[variant]
             s.set_trajectory(x, u)
             s.stage_dynamics()
             s.stage_kkt(1e-3, t.SQPSolverMethods.PCG_SS)
             it = s.stage_pcg(t.SQPSolverMethods.PCG_SS, 1e-6, 100)
             res[variant] = (np.array(it), s.fetch("l").copy())
             s.close()
-    for v in ("5", "6"):
+    for v in ("5", "6", "7"):
         assert np.array_equal(res["3"][0], res[v][0]), v
         assert np.max(np.abs(res["3"][1] - res[v][1])) < 1e-9 * np.max(np.abs(res["3"][1])), v
 

@@ -1032,7 +1032,7 @@ __global__ void __launch_bounds__(MAXT) k_pcg2(Dev<T> d, const int* list, const 
 // (verified against the explicit form: identical iteration counts, SURVEY.md 7.2 parity floor).
 // -----------------------------------------------------------------------------------------------------------------
 constexpr int PCG3_NMS = (NM + 3) / 4 * 4;   // 18 -> 20 doubles: rows of consecutive knots start 4 double-banks apart
-template <typename T, int MAXT, bool PDS, int LPK>
+template <typename T, int MAXT, bool PDS, int LPK, bool PDC = false>
 __global__ void __launch_bounds__(MAXT, PDS ? 2 : 1) k_pcg3(Dev<T> d, const int* list, const int* count, int stair, T tol, int max_iter) {
   if ((int)blockIdx.x >= *count) return;
   // LPK lanes per knot (2 or 4).  Only launched when nx % (2 LPK) == 0; the max() keeps the definition well-formed otherwise.
@@ -1208,11 +1208,40 @@ __global__ void __launch_bounds__(MAXT, PDS ? 2 : 1) k_pcg3(Dev<T> d, const int*
 #pragma unroll
     for (int r = 0; r < RPT; ++r) out[r] = o0[r] + o1[r];
   };
+  // PDC (experiment, B2T_PCG_VARIANT=7): D^-1 is symmetric, so the lane's RPT rows are also its RPT COLUMNS: partial products from the
+  // lane's own RPT entries of the vector (registers, no publish / load), then a reduce-scatter over the four lanes (9 shuffles)
+  auto pd_mul_col = [&](const T* val, T* out) {
+    T y[NX];
+#pragma unroll
+    for (int j = 0; j < NX; ++j) {
+      T acc = T(0);
+#pragma unroll
+      for (int r = 0; r < RPT; ++r) acc += pd[r][j] * val[r];
+      y[j] = acc;
+    }
+    constexpr int H = NX / 2;
+    const bool hi = (g & 2) != 0, od = (g & 1) != 0;
+    T keep[H];
+#pragma unroll
+    for (int j = 0; j < H; ++j) {
+      const T send = hi ? y[j] : y[H + j];
+      keep[j] = (hi ? y[H + j] : y[j]) + __shfl_xor_sync(0xffffffffu, send, 2);
+    }
+#pragma unroll
+    for (int r = 0; r < RPT; ++r) {
+      const T send = od ? keep[r] : keep[RPT + r];
+      out[r] = (od ? keep[RPT + r] : keep[r]) + __shfl_xor_sync(0xffffffffu, send, 1);
+    }
+  };
   T rr[RPT], xx[RPT], pp[RPT], rt[RPT], yv[RPT], tmp[RPT];
   auto precond = [&]() {
-    publish(V, rr);
-    __syncwarp();
-    pd_mul(V, yv);
+    if constexpr (PDC && !PDS && LPK == 4) {
+      pd_mul_col(rr, yv);
+    } else {
+      publish(V, rr);
+      __syncwarp();
+      pd_mul(V, yv);
+    }
     if (!stair) {
 #pragma unroll
       for (int r = 0; r < RPT; ++r) rt[r] = yv[r];
@@ -1238,9 +1267,16 @@ __global__ void __launch_bounds__(MAXT, PDS ? 2 : 1) k_pcg3(Dev<T> d, const int*
     }
     __syncthreads();
     abmul(u1, Wq, W, T(1), tmp);
-    publish(V, tmp);
-    __syncwarp();
-    pd_mul(V, tmp);
+    if constexpr (PDC && !PDS && LPK == 4) {
+      T t2[RPT];
+      pd_mul_col(tmp, t2);
+#pragma unroll
+      for (int r = 0; r < RPT; ++r) tmp[r] = t2[r];
+    } else {
+      publish(V, tmp);
+      __syncwarp();
+      pd_mul(V, tmp);
+    }
 #pragma unroll
     for (int r = 0; r < RPT; ++r) rt[r] = yv[r] - tmp[r];
   };

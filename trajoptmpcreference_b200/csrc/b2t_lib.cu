@@ -521,11 +521,13 @@ struct SolverT : SolverBase {
   // 3: k_pcg3 matrix-free, register-resident (default for the structured path when 4 N <= 256), 4: k_pcg3 with two lanes per knot
   // and the preconditioner rows in shared memory (two instances per SM; measured 24.4 ms)
   int pcg_variant = -1;
+  bool pcg_col = false;
   bool explicit_system = false;   // set by b2t_set_block_system: only S / Pinv blocks are valid -> the explicit kernels must run
   void decide_pcg_variant() {
     if (pcg_variant < 0) {
       const char* e = getenv("B2T_PCG_VARIANT");
       if (e) pcg_variant = atoi(e);
+      if (pcg_variant == 7) { pcg_variant = 3; pcg_col = true; }      // experiment: k_pcg3 with the column form of the D^-1 products
       // k_pcg3: 21.9 ms vs 24.0 ms (variant 1) per 2048-instance step at N = 64.  Longer horizons use its 512- / 1024-thread
       // instantiations (128 / 64 registers, spilling): still 1.85x (N = 128: 76.7 vs 141.8 ns per instance-iteration) and 3.2x
       // (N = 256: 289 vs 932 ns) faster than the explicit-block kernel, which no longer fits its blocks in shared memory there
@@ -579,7 +581,8 @@ struct SolverT : SolverBase {
           k_pcg3<T, 128, true, 2><<<bound, nt4, smp, stream>>>(d, list, count, stair, tol, max_iter);
         } else {
           const int nt3 = ((4 * d.N + 31) / 32) * 32;
-          if (nt3 <= 256) k_pcg3<T, 256, false, 4><<<bound, nt3, smv, stream>>>(d, list, count, stair, tol, max_iter);
+          if (nt3 <= 256 && pcg_col) k_pcg3<T, 256, false, 4, true><<<bound, nt3, smv, stream>>>(d, list, count, stair, tol, max_iter);
+          else if (nt3 <= 256) k_pcg3<T, 256, false, 4><<<bound, nt3, smv, stream>>>(d, list, count, stair, tol, max_iter);
           else if (nt3 <= 512) k_pcg3<T, 512, false, 4><<<bound, nt3, smv, stream>>>(d, list, count, stair, tol, max_iter);
           else k_pcg3<T, 1024, false, 4><<<bound, nt3, smv, stream>>>(d, list, count, stair, tol, max_iter);
         }
