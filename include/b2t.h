@@ -18,7 +18,7 @@
  *   b2t_get_trajectory / b2t_get_status / b2t_get_trace / b2t_get_multipliers
  *                            the 6-tuple SQP returns (:760), self.trace (:555-569), mu/lambda/phi state
  *   b2t_sqp_solve_host       one call from host buffers to host buffers (what examples/exampleHelpers.py:80 does)
- *   b2t_stage_dynamics       TrajoptPlant.integrator(.., return_gradient) (TrajoptPlant.py:83-138)
+ *   b2t_stage_dynamics       TrajoptPlant.integrator(.., return_gradient) (TrajoptPlant.py:83-205)
  *   b2t_stage_kkt            formKKTSystemBlocks (:200-271) + Schur complement and preconditioner blocks
  *                            (solveKKTSystem_Schur :419-424, PCG.compute_preconditioner PCG.py:166-212)
  *   b2t_stage_pcg            PCG.solve (PCG.py:66-111, 214)
@@ -42,7 +42,7 @@ typedef enum {
   B2T_OK = 0,
   B2T_ERR_INVALID = -1,      /* bad argument (the reference print()s and exit()s) */
   B2T_ERR_CUDA = -2,         /* CUDA runtime error; see b2t_last_error */
-  B2T_ERR_UNSUPPORTED = -3,  /* e.g. the end-effector cost on a 1-joint robot, integrator types 2-4 */
+  B2T_ERR_UNSUPPORTED = -3,  /* e.g. the end-effector cost on a 1-joint robot, integrator type 4 */
   B2T_ERR_NOMEM = -4,
   B2T_ERR_UNFINISHED = -5    /* the pass budget ran out with instances still active (results of the others are valid) */
 } b2t_status;
@@ -62,7 +62,7 @@ enum { B2T_LIM_JOINT = 0, B2T_LIM_VELOCITY = 1, B2T_LIM_TORQUE = 2 };
 typedef struct {
   int batch;              /* independent MPC instances */
   int knots;              /* N */
-  int integrator_type;    /* 0 euler, 1 semi-implicit euler (TrajoptPlant.py:92-138) */
+  int integrator_type;    /* 0 euler, 1 semi-implicit euler, 2 midpoint, 3 rk3 -- 2 / 3 with the reference's own arithmetic (TrajoptPlant.py:92-205) */
   int dtype;              /* b2t_dtype: arithmetic type of the whole path */
   double dt;
   double gravity;         /* options['gravity'], default -9.81 (TrajoptPlant.py:31) */
@@ -105,7 +105,7 @@ typedef enum {
   B2T_ARR_X = 0,        /* [N][nx]   current iterate */
   B2T_ARR_U,            /* [N][nu]   (row N-1 unused) */
   B2T_ARR_XKP1,         /* [N][nx]   integrator(x_k,u_k) (row N-1 unused) */
-  B2T_ARR_DQDD,         /* [N][n*3n] forward_dynamics_gradient */
+  B2T_ARR_DQDD,         /* [N][n*3n] forward_dynamics_gradient (integrator types 0 / 1; 2 / 3 evaluate it per stage: fetch B2T_ARR_AB) */
   B2T_ARR_GHAT,         /* [N][m*m]  inv(G_k + rho I) */
   B2T_ARR_G,            /* [N][m]    gradient g_k */
   B2T_ARR_SD,           /* [N][nx*nx] diagonal blocks of S */

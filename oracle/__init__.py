@@ -11,7 +11,7 @@ vectorised over knot points; `oracle.dense` re-assembles the reference's dense f
 Parity status: PINNED.  The oracle is checked (tests/test_oracle_golden.py) against
   * golden vectors recorded by the reference's authors (`data/3`, `data/4`, re-packed into tests/golden/ref_data*.npz),
   * outputs of the unmodified reference imported in the build container (tests/golden/make_golden.py -> *.npz),
-for: rigid-body dynamics (rnea, minv, rnea_grad, EE kinematics), integrators 0/1, QuadraticCost, UrdfCost (n=2),
+for: rigid-body dynamics (rnea, minv, rnea_grad, EE kinematics), integrators 0-3 (2 / 3 literally as the reference computes them; 4 raises like it), QuadraticCost, UrdfCost (n=2),
 torque box limits (1-DoF, QUADRATIC_PENALTY / AUGMENTED_LAGRANGIAN, and the hard ACTIVE_SET mode of the exact methods N / S,
 where the literal dense form is bit-identical to the reference), KKT blocks, Schur complement, J/BJ/SS preconditioners, PCG
 traces, and complete SQP solves (iteration counts, alpha sequences, J, c, x, u) within the reference's own measured 1-ulp floor

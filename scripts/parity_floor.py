@@ -46,7 +46,7 @@ def _run(args):
     import TrajoptMPCReference as TM
     case = [c for c in mg.SOLVE_CASES if c[0] == tag][0]
     _, name, N, meth, opts, limits, xg = case
-    integ = 1 if tag.endswith("_semi") else 0
+    integ = mg.integ_of(tag)
     plant, cost, cons, solver, xg = mg.make_problem(R, name, N, limits=limits, integrator=integ, xg=xg)
     n = plant.get_num_pos()
     rng = np.random.default_rng(1000 + seed)
@@ -76,14 +76,19 @@ def main():
     import multiprocessing as mp
     import make_golden as mg
     seeds = int(sys.argv[1]) if len(sys.argv) > 1 else 4
-    tags = [c[0] for c in mg.SOLVE_CASES]
+    fpath = os.path.join(ROOT, "tests", "golden", "floor.json")
+    have = {}
+    if os.path.exists(fpath) and not os.environ.get("FORCE"):      # only the cases floor.json does not hold yet (FORCE=1: all)
+        with open(fpath) as f:
+            have = json.load(f)["cases"]
+    tags = [c[0] for c in mg.SOLVE_CASES if c[0] not in have]
     jobs = [(t, s) for t in tags for s in range(-1, seeds)]          # seed -1 = unperturbed
     with mp.get_context("fork").Pool(os.cpu_count() or 1) as pool:
         res = pool.map(_run, jobs, chunksize=1)
     by = {}
     for tag, seed, r in res:
         by.setdefault(tag, {})[seed] = r
-    out = {}
+    out = dict(have)
     for tag in tags:
         base = by[tag][-1]
         fl = dict(rel_J=0.0, abs_x=0.0, abs_u=0.0, rel_x=0.0, rel_u=0.0, counts_identical=0, seeds=seeds, qp_solves=base["qp"], exits=base["exits"])
@@ -101,7 +106,7 @@ def main():
         out[tag] = fl
         print("%-22s qp %4d  counts identical %d/%d  floor: rel J %.1e  |dx| %.1e (rel %.1e)  |du| %.1e (rel %.1e)" %
               (tag, fl["qp_solves"], fl["counts_identical"], seeds, fl["rel_J"], fl["abs_x"], fl["rel_x"], fl["abs_u"], fl["rel_u"]))
-    with open(os.path.join(ROOT, "tests", "golden", "floor.json"), "w") as f:
+    with open(fpath, "w") as f:
         json.dump({"perturbation": "S * (1 +/- 2^-52), symmetric random signs, every QP solve", "cases": out}, f, indent=1)
 
 

@@ -1,7 +1,8 @@
 """Generate the golden fixtures in this directory from the UNMODIFIED reference at /root/reference.
 
 Run in the build container only (python tests/golden/make_golden.py [section ...]); the fixtures are committed,
-the GPU box never needs the reference.  Sections: models dynamics cost kkt solve refdata
+the GPU box never needs the reference.  Sections: models dynamics integrators cost kkt solve refdata record_integrators
+(`solve` only runs the cases that solve.npz does not hold yet; FORCE=1 regenerates all.)
 """
 import json
 import os
@@ -88,6 +89,46 @@ def kat_point(n):
     qd = [0.43302, -0.421561, -0.645439, -1.86055, -0.0130938, -0.458284]
     u = [0.741788, 1.92844, -0.903882, 0.0333959, 1.17986, -1.94599]
     return np.array(q[:n]), np.array(qd[:n]), np.array(u[:n])
+
+
+def integ_of(tag):
+    """integrator type of a solve case, from its tag suffix"""
+    for suffix, it in (("_semi", 1), ("_mid", 2), ("_rk3", 3)):
+        if tag.endswith(suffix):
+            return it
+    return 0
+
+
+def sec_integrators(R):
+    """Integrator types 2 (midpoint), 3 (rk3), 4 (rk4) of the unmodified reference (TrajoptPlant.py:140-270) at the points of
+    sec_dynamics: step and (A, B) for 2 / 3; for 4 the step only -- its gradient branch raises TypeError (:259), recorded as such."""
+    out = {}
+    rng = np.random.default_rng(1234)
+    for name in ROBOTS:
+        plants = {it: ref_plant(R, name, it) for it in (2, 3, 4)}
+        n = plants[2].get_num_pos()
+        pts = [kat_point(n)] + [(rng.uniform(-2, 2, n), rng.uniform(-2, 2, n), rng.uniform(-2, 2, n)) for _ in range(5)]
+        rec = {k: [] for k in ("q", "qd", "u", "A2", "B2", "xn2", "A3", "B3", "xn3", "xn4")}
+        for q, qd, u in pts:
+            x = np.concatenate([q, qd])
+            for it in (2, 3):
+                A, B = plants[it].integrator(x, u, 0.1, return_gradient=True)
+                rec["A%d" % it].append(np.array(A)); rec["B%d" % it].append(np.array(B))
+                rec["xn%d" % it].append(np.array(plants[it].integrator(x, u, 0.1)).reshape(-1))
+            rec["xn4"].append(np.array(plants[4].integrator(x, u, 0.1)).reshape(-1))
+            try:
+                plants[4].integrator(x, u, 0.1, return_gradient=True)
+                raised = ""
+            except Exception as e:      # noqa: BLE001
+                raised = type(e).__name__
+            for k, val in (("q", q), ("qd", qd), ("u", u)):
+                rec[k].append(np.array(val, dtype=float))
+        for k, lst in rec.items():
+            out[name + "/" + k] = np.stack(lst)
+        out[name + "/rk4_gradient_raises"] = np.array(raised)
+        print(name, "rk4 gradient raises:", raised)
+    np.savez_compressed(os.path.join(HERE, "integrators.npz"), **out)
+    print("integrators.npz written")
 
 
 def sec_dynamics(R):
@@ -226,6 +267,14 @@ SOLVE_CASES = [
     ("pend_N20_S_as01", "pend", 20, "S", {"expected_reduction_min_SQP_DDP": -100}, {"torque": ([0.1], [-0.1], "ACTIVE_SET")}, None),
     ("pend_N20_N_as01", "pend", 20, "N", {"expected_reduction_min_SQP_DDP": -100}, {"torque": ([0.1], [-0.1], "ACTIVE_SET")}, None),
     ("pend_N20_S_as2", "pend", 20, "S", {"expected_reduction_min_SQP_DDP": -100}, {"torque": ([2.0], [-2.0], "ACTIVE_SET")}, None),
+    # integrator types 2 (midpoint, tag suffix _mid) and 3 (rk3, _rk3) exactly as the reference computes them
+    ("pend_N20_SS_mid", "pend", 20, "PCG_SS", {"expected_reduction_min_SQP_DDP": -100}, None, None),
+    ("pend_N20_SS_rk3", "pend", 20, "PCG_SS", {"expected_reduction_min_SQP_DDP": -100}, None, None),
+    ("pend_N20_SS_qp2_mid", "pend", 20, "PCG_SS", {"expected_reduction_min_SQP_DDP": -100}, {"torque": ([2.0], [-2.0], "QUADRATIC_PENALTY")}, None),
+    ("arm2_N10_SS_mid", "arm2", 10, "PCG_SS", {"expected_reduction_min_SQP_DDP": -100}, None, None),
+    ("arm2_N10_S_rk3", "arm2", 10, "S", {"expected_reduction_min_SQP_DDP": -100}, None, None),
+    ("arm2_N10_N_mid", "arm2", 10, "N", {"expected_reduction_min_SQP_DDP": -100}, None, None),
+    ("arm6_N16_SS_rk3", "arm6", 16, "PCG_SS", {"expected_reduction_min_SQP_DDP": -100}, None, None),
 ]
 
 
@@ -233,8 +282,14 @@ def sec_solve(R):
     """Complete SQP solves from x=0,u=0 with the unmodified reference (SURVEY.md appendix D known answers)."""
     out = {}
     meta = {}
+    if os.path.exists(os.path.join(HERE, "solve.npz")) and not os.environ.get("FORCE"):
+        out = dict(np.load(os.path.join(HERE, "solve.npz")))
+        with open(os.path.join(HERE, "solve_meta.json")) as f:
+            meta = json.load(f)
     for tag, name, N, meth, opts, limits, xg in SOLVE_CASES:
-        integ = 1 if tag.endswith("_semi") else 0
+        if tag in meta:
+            continue
+        integ = integ_of(tag)
         plant, cost, cons, solver, xg = make_problem(R, name, N, limits=limits, integrator=integ, xg=xg)
         n = plant.get_num_pos(); nx = 2 * n
         x0 = np.zeros((nx, N)); u0 = np.zeros((n, N - 1))
@@ -317,7 +372,32 @@ def sec_refdata(R):
     print("ref_data.npz written", {k: v.shape for k, v in out.items() if k.startswith("4/")})
 
 
-SECTIONS = {"models": sec_models, "dynamics": sec_dynamics, "kkt": sec_kkt, "solve": sec_solve, "refdata": sec_refdata}
+def sec_record_integrators(R):
+    """Plant-level lists (URDFPlant.saved_Minv / saved_qdd / saved_dc_du / saved_dqdd, TrajoptPlant.py:297-322) of one complete solve of
+    the unmodified reference per integrator type 1, 2, 3 (pend, N = 6, PCG-SS): entry counts, counters and values, i.e. the callback
+    sequence of the semi-implicit / midpoint / rk3 branches of TrajoptPlant.integrator."""
+    out = {}
+    for integ in (1, 2, 3):
+        N = 6
+        plant, cost, cons, solver, xg = make_problem(R, "pend", N, integrator=integ)
+        n = plant.get_num_pos()
+        import overloading      # the counters are class attributes that survive a solve (overloading.py:8-10): start each run like a fresh process
+        overloading.matrix_.iteration = overloading.matrix_.line_search_iteration = overloading.matrix_.soft_constraint_iteration = 0
+        with quiet():
+            x, u, e1, e2, outer, it = solver.SQP(np.zeros((2 * n, N)), np.zeros((n, N - 1)), N, 0.1, R.SQPSolverMethods.PCG_SS,
+                                                 options={"expected_reduction_min_SQP_DDP": -100, "overloading": False})
+        out["%d/xg" % integ] = np.asarray(xg, float); out["%d/x" % integ] = np.array(x); out["%d/u" % integ] = np.array(u)
+        out["%d/exits" % integ] = np.array([e1, e2, outer, it])
+        for key in ("Minv", "qdd", "dc_du", "dqdd"):
+            recs = getattr(plant, "saved_" + key)
+            out["%d/lvl_%s" % (integ, key)] = np.stack([np.asarray(r["value"], dtype=float).reshape(-1) for r in recs])
+            out["%d/lvl_%s_tags" % (integ, key)] = np.array([[int(r["iteration"]), int(r["outer_iteration"]), int(r["line_search_iteration"])] for r in recs])
+        print("integrator", integ, "exits", (e1, e2, outer, it), {k: len(getattr(plant, "saved_" + k)) for k in ("Minv", "qdd", "dc_du", "dqdd")})
+    np.savez_compressed(os.path.join(HERE, "record_integrators.npz"), **out)
+    print("record_integrators.npz written")
+
+
+SECTIONS = {"record_integrators": sec_record_integrators, "models": sec_models, "dynamics": sec_dynamics, "integrators": sec_integrators, "kkt": sec_kkt, "solve": sec_solve, "refdata": sec_refdata}
 
 if __name__ == "__main__":
     R = refshim.load()

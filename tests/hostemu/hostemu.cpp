@@ -26,6 +26,14 @@ int he_dynamics(int count, const double* x, const double* u, double dt, double g
   }
   return 0;
 }
+// integrator types 2 / 3 (the reference's midpoint / rk3): step and [A B] for `count` knots
+int he_integrator_multi(int count, int integrator, const double* x, const double* u, double dt, double gravity, double* xn, double* AB) {
+  for (int t = 0; t < count; ++t) {
+    integrator_multi_value<double>(integrator, x + t * NX, u + t * NU, gravity, dt, xn + t * NX);
+    integrator_multi_AB<double>(integrator, x + t * NX, u + t * NU, gravity, dt, AB + t * NX * NM);
+  }
+  return 0;
+}
 // qdd by the single-right-hand-side articulated-body solve (forward_dynamics_qdd) for `count` knots
 int he_qdd_solve(int count, const double* x, const double* u, double gravity, double* qdd) {
   for (int t = 0; t < count; ++t) forward_dynamics_qdd<double>(x + t * NX, x + t * NX + NJ, u + t * NU, gravity, qdd + t * NJ);

@@ -127,3 +127,26 @@ def test_cost_and_plant_level_lists_match_author_recordings(run, oracle_models):
     n0 = len(pc.saved_cost)
     pc.value(np.zeros(4), np.zeros(2)); pc.value(np.zeros(4), None)
     assert len(pc.saved_cost) == n0 + 2 and len(pc.saved_dx) == n0 + 2
+
+
+@pytest.mark.parametrize("integ", [1, 2, 3])
+def test_plant_level_lists_follow_the_integrator_branch(integ, oracle_models):
+    """URDFPlant.saved_Minv / saved_qdd / saved_dc_du / saved_dqdd of a complete solve with the semi-implicit (1), midpoint (2) and rk3 (3)
+    integrators against lists recorded from the unmodified reference (tests/golden/record_integrators.npz): the multi-stage branches
+    call forward_dynamics / forward_dynamics_gradient once per stage point (TrajoptPlant.py:141-156, :171-198), the semi-implicit
+    branch drops the counters on the gradient call (:131).  Counts, counters and values."""
+    D = load_npz("record_integrators.npz")
+    N = 6
+    (plant, pc, _), _ = make_pair("pend", N, oracle_models, xg=D["%d/xg" % integ], integrator=integ)
+    solver = t.TrajoptMPCReference(plant, pc)
+    x, u, e1, e2, outer, it = solver.SQP(np.zeros((2, N)), np.zeros((1, N - 1)), N, 0.1, t.SQPSolverMethods.PCG_SS,
+                                         options={"expected_reduction_min_SQP_DDP": -100, "overloading": False}, record=True)
+    assert [int(e1), int(e2), int(outer), int(it)] == D["%d/exits" % integ].tolist()
+    assert np.max(np.abs(x - D["%d/x" % integ])) < 1e-9 and np.max(np.abs(u - D["%d/u" % integ])) < 1e-9
+    for name in ("Minv", "qdd", "dc_du", "dqdd"):
+        got = getattr(plant, "saved_" + name)
+        ref, tags = D["%d/lvl_%s" % (integ, name)], D["%d/lvl_%s_tags" % (integ, name)]
+        assert len(got) == len(ref), (name, len(got), len(ref))
+        assert [[e["iteration"], e["outer_iteration"], e["line_search_iteration"]] for e in got] == tags.tolist(), name
+        worst = max(float(np.max(np.abs(np.asarray(e["value"], dtype=float).reshape(-1) - r))) / max(1.0, float(np.max(np.abs(r)))) for e, r in zip(got, ref))
+        assert worst < 1e-9, (name, worst)

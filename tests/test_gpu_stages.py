@@ -33,6 +33,53 @@ def test_dynamics_kernels_vs_reference(name, integ, oracle_models):
     assert relerr(plant.forward_dynamics(x[0, :, 0], uu[0, :, 0]), D[name + "/qdd"][0]) < 1e-12
 
 
+@pytest.mark.parametrize("name", ["pend", "arm2", "arm3", "arm6"])
+@pytest.mark.parametrize("integ", [2, 3])
+def test_multi_stage_integrator_kernels_vs_reference(name, integ, oracle_models):
+    """Integrator types 2 (midpoint) and 3 (rk3) -- k_fd's multi-stage branch and k_ab_multi -- against the step and (A, B) the
+    unmodified reference returns (tests/golden/integrators.npz; TrajoptPlant.py:140-205 as written), through the batch
+    workspace and through the plant object's reference-API callbacks."""
+    D = load_npz("integrators.npz")
+    n = oracle_models[name].n
+    q, qd, u = D[name + "/q"], D[name + "/qd"], D[name + "/u"]
+    P = q.shape[0]
+    (plant, pc, _), _ = make_pair(name, 2, oracle_models, integrator=integ, cost_kind="quadratic")
+    s = t.BatchSolver(plant, pc, None, N=2, dt=0.1, batch=P)
+    x = np.zeros((P, 2 * n, 2)); uu = np.zeros((P, n, 1))
+    x[:, :n, 0] = q; x[:, n:, 0] = qd; uu[:, :, 0] = u
+    s.set_trajectory(x, uu)
+    s.stage_dynamics()
+    AB = s.fetch("AB")[:, 0].reshape(P, 2 * n, 3 * n)
+    assert relerr(AB[:, :, :2 * n], D[name + "/A%d" % integ]) < 1e-12
+    assert relerr(AB[:, :, 2 * n:], D[name + "/B%d" % integ]) < 1e-12
+    assert relerr(s.fetch("xkp1")[:, 0], D[name + "/xn%d" % integ]) < 1e-13
+    with pytest.raises(t.B2TError):
+        s.fetch("dqdd")                     # stage-wise for these integrators: the workspace holds [A B] instead
+    for i in (0, P - 1):
+        A, B = plant.integrator(x[i, :, 0], uu[i, :, 0], 0.1, return_gradient=True)
+        assert relerr(A, D[name + "/A%d" % integ][i]) < 1e-12 and relerr(B, D[name + "/B%d" % integ][i]) < 1e-12
+        assert relerr(plant.integrator(x[i, :, 0], uu[i, :, 0], 0.1), D[name + "/xn%d" % integ][i]) < 1e-13
+    # the per-point callbacks of such a plant still answer (Euler probe): dqdd does not depend on the integrator
+    Dd = load_npz("dynamics.npz")
+    assert relerr(plant.forward_dynamics_gradient(x[0, :, 0], uu[0, :, 0]), Dd[name + "/dqdd"][0]) < 1e-12
+
+
+@pytest.mark.parametrize("name", ["pend", "arm3"])
+def test_rk4_steps_but_its_gradient_raises_like_the_reference(name, oracle_models):
+    """Integrator type 4: the reference's step works, its gradient branch raises TypeError (TrajoptPlant.py:259), so every solve does."""
+    D = load_npz("integrators.npz")
+    n = oracle_models[name].n
+    plant = t.URDFPlant(integrator_type=4, options={"path_to_urdf": name})
+    x = np.concatenate([D[name + "/q"][1], D[name + "/qd"][1]]); u = D[name + "/u"][1]
+    assert relerr(plant.integrator(x, u, 0.1), D[name + "/xn4"][1]) < 1e-13
+    assert str(D[name + "/rk4_gradient_raises"]) == "TypeError"
+    with pytest.raises(TypeError):
+        plant.integrator(x, u, 0.1, return_gradient=True)
+    cost = t.QuadraticCost(np.eye(2 * n), np.eye(2 * n), np.eye(n), np.zeros(2 * n))
+    with pytest.raises(TypeError):
+        t.TrajoptMPCReference(plant, cost).SQP(np.zeros((2 * n, 5)), np.zeros((n, 4)), 5, 0.1, t.SQPSolverMethods.PCG_SS)
+
+
 def _kkt_case(tag, oracle_models):
     K = load_npz("kkt.npz")
     robot = {"arm2_urdf": "arm2", "arm3_qc": "arm3", "arm6_qc": "arm6", "pend_al": "pend"}[tag]

@@ -44,6 +44,25 @@ def test_dynamics_math(name, integ, oracle_models):
     assert relerr(ABr[:, :, 2 * n:], D[name + "/B%d" % integ]) < 1e-13
 
 
+@pytest.mark.parametrize("name", ["pend", "arm2", "arm3", "arm6"])
+@pytest.mark.parametrize("integ", [2, 3])
+def test_multi_stage_integrator_math(name, integ, oracle_models):
+    """integrator_multi_value / integrator_multi_AB (midpoint, rk3 exactly as TrajoptPlant.py:140-205 computes them) against the
+    outputs of the unmodified reference (tests/golden/integrators.npz)."""
+    lib = hostemu.load(name)
+    D = load_npz("integrators.npz")
+    n = oracle_models[name].n
+    x = np.ascontiguousarray(np.concatenate([D[name + "/q"], D[name + "/qd"]], -1))
+    u = np.ascontiguousarray(D[name + "/u"])
+    cnt = x.shape[0]
+    xn = np.zeros((cnt, 2 * n)); AB = np.zeros((cnt, 2 * n * 3 * n))
+    lib.he_integrator_multi(cnt, integ, P(x), P(u), ctypes.c_double(0.1), ctypes.c_double(-9.81), P(xn), P(AB))
+    assert relerr(xn, D[name + "/xn%d" % integ]) < 1e-13
+    ABr = AB.reshape(cnt, 2 * n, 3 * n)
+    assert relerr(ABr[:, :, :2 * n], D[name + "/A%d" % integ]) < 1e-12
+    assert relerr(ABr[:, :, 2 * n:], D[name + "/B%d" % integ]) < 1e-12
+
+
 @pytest.mark.parametrize("name,kind", [("arm2", 1), ("arm2", 0), ("arm6", 0), ("arm3", 1), ("arm6", 1), ("cartpole", 1)])
 def test_cost_math(name, kind, oracle_models):
     """kind 1 = end-effector cost: 4 x 4 weights on (x, y, vx, vy); n = 2 is the reference's literal arithmetic, n > 2 the exact

@@ -55,8 +55,10 @@ class TrajoptPlant:
         options = {} if options is None else options
         if integrator_type not in (0, 1, 2, 3, 4, -1):
             raise ValueError("Invalid integrator options are [0 : euler, 1 : semi-implicit euler, 2 : midpoint, 3 : rk3, 4 : rk4, -1 : hard-coded as dynamics")
-        if integrator_type not in (0, 1):
-            raise ValueError("integrator types 2-4 of the reference are inconsistent or crash (SURVEY.md 0.9); only 0 and 1 are supported")
+        if integrator_type == -1:
+            raise ValueError("integrator type -1 (dynamics hard-coded in a user plant class) cannot run inside the kernels; use 0-3")
+        # 2 (midpoint) and 3 (rk3) reproduce the reference's own arithmetic, whose Jacobians do not match its step;
+        # 4 (rk4) steps, but its gradient -- hence every solve -- raises TypeError exactly like TrajoptPlant.py:259
         self.integrator_type = integrator_type
         options.setdefault("path_to_urdf", None)
         options.setdefault("gravity", -9.81)
@@ -123,24 +125,29 @@ class URDFPlant(TrajoptPlant):
         return self.model["n"]
 
     # per-knot callbacks of the reference API, evaluated on the GPU (batch 1, 2 knots)
-    def _probe_solver(self):
-        if self._probe is None:
+    def _probe_solver(self, dt=None, own_integrator=False):
+        """Batch-1, 2-knot workspace for the per-knot callbacks.  The default probe integrates with Euler (dqdd, qdd, Minv, ... do not
+        depend on the integrator); `own_integrator` selects the plant's multi-stage integrator (types 2 / 3) for x+ and (A, B)."""
+        slot = "_probe_own" if own_integrator else "_probe"
+        p = getattr(self, slot, None)
+        if p is None or (dt is not None and p.dt != dt):
             n = self.model["n"]
             cost = QuadraticCost(np.eye(2 * n), np.eye(2 * n), np.eye(n), np.zeros(2 * n))
-            self._probe = BatchSolver(self, cost, None, N=2, dt=1.0, batch=1)
-        return self._probe
+            it = self.integrator_type if (own_integrator or self.integrator_type in (0, 1)) else 0
+            p = BatchSolver(self, cost, None, N=2, dt=1.0 if dt is None else dt, batch=1, integrator_type=it)
+            setattr(self, slot, p)
+        return p
 
-    def _eval(self, xk, uk, dt):
-        p = self._probe_solver()
-        if p.dt != dt:
-            self._probe = None
-            n = self.model["n"]
-            cost = QuadraticCost(np.eye(2 * n), np.eye(2 * n), np.eye(n), np.zeros(2 * n))
-            self._probe = p = BatchSolver(self, cost, None, N=2, dt=dt, batch=1)
+    def _load_point(self, p, xk, uk):
         n = self.model["n"]
         x = np.zeros((1, 2 * n, 2)); u = np.zeros((1, n, 1))
         x[0, :, 0] = np.asarray(xk, dtype=np.float64).reshape(-1); u[0, :, 0] = np.asarray(uk, dtype=np.float64).reshape(-1)
         p.set_trajectory(x, u)
+
+    def _eval(self, xk, uk, dt):
+        p = self._probe_solver(dt)
+        n = self.model["n"]
+        self._load_point(p, xk, uk)
         p.stage_dynamics()
         return p.fetch("dqdd")[0, 0].reshape(n, 3 * n), p.fetch("xkp1")[0, 0]
 
@@ -148,9 +155,7 @@ class URDFPlant(TrajoptPlant):
         """(c, qdd, Minv, dc_du) at one knot from the plant kernel (B2T_ARR_PLANT_TERMS)."""
         p = self._probe_solver()
         n = self.model["n"]
-        x = np.zeros((1, 2 * n, 2)); u = np.zeros((1, n, 1))
-        x[0, :, 0] = np.asarray(xk, dtype=np.float64).reshape(-1); u[0, :, 0] = np.asarray(uk, dtype=np.float64).reshape(-1)
-        p.set_trajectory(x, u)
+        self._load_point(p, xk, uk)
         return split_plant_terms(p.fetch("plant_terms")[0, 0], n)
 
     def _save(self, tag, **entries):
@@ -172,6 +177,26 @@ class URDFPlant(TrajoptPlant):
 
     def integrator(self, xk, uk, dt, return_gradient=False, iter_1=0, iter_2=0, iter_3=0):
         n = self.model["n"]
+        if self.integrator_type in (2, 3):
+            # midpoint / rk3 with the reference's own arithmetic (TrajoptPlant.py:140-205): x+ from k_fd, [A B] from k_ab_multi
+            p = self._probe_solver(dt, own_integrator=True)
+            self._load_point(p, xk, uk)
+            p.stage_dynamics()
+            if not return_gradient:
+                return p.fetch("xkp1")[0, 0]
+            AB = p.fetch("AB")[0, 0].reshape(2 * n, 3 * n)
+            return AB[:, :2 * n].copy(), AB[:, 2 * n:].copy()
+        if self.integrator_type == 4:
+            if return_gradient:      # the reference's numpy branch passes an extra positional xk here (TrajoptPlant.py:259)
+                raise TypeError("URDFPlant.forward_dynamics_gradient() takes from 3 to 6 positional arguments but 7 were given "
+                                "(integrator type 4 of the reference, TrajoptPlant.py:259)")
+            xk = np.asarray(xk, dtype=np.float64).reshape(-1)
+            xdot = lambda pt: np.concatenate([xk[n:], self.forward_dynamics(pt, uk, iter_1, iter_2, iter_3)])      # noqa: E731  (:61-70: x_k's velocity)
+            xdot1 = xdot(xk)
+            xdot2 = xdot(xk + 0.5 * dt * xdot1)
+            xdot3 = xdot(xk + 0.5 * dt * xdot2)
+            xdot4 = xdot(xk + dt * xdot3)
+            return xk + (dt / 6) * (xdot1 + 2 * xdot2 + 2 * xdot3 + xdot4)
         dqdd, xn = self._eval(xk, uk, dt)
         if not return_gradient:
             return xn
@@ -556,7 +581,8 @@ class BatchResult(dict):
 class BatchSolver:
     """One device workspace for `batch` independent instances of (plant, cost, constraints, N, dt)."""
 
-    def __init__(self, plant, cost, constraints, N, dt, batch=1, dtype="f64", device=0, qf_start_override=None, dense_kkt=False):
+    def __init__(self, plant, cost, constraints, N, dt, batch=1, dtype="f64", device=0, qf_start_override=None, dense_kkt=False,
+                 integrator_type=None):
         if not isinstance(plant, URDFPlant):
             raise ValueError("Must pass in a URDFPlant: the dynamics kernels are generated from the URDF")
         if not isinstance(cost, QuadraticCost):
@@ -567,7 +593,10 @@ class BatchSolver:
         self.N, self.dt, self.batch, self.dtype, self.device = int(N), float(dt), int(batch), dtype, int(device)
         self.lib = plant.lib
         d = _lib.ProblemDesc()
-        d.batch, d.knots, d.integrator_type = self.batch, self.N, plant.integrator_type
+        self.integrator_type = plant.integrator_type if integrator_type is None else int(integrator_type)
+        if self.integrator_type == 4:
+            raise TypeError("integrator type 4 (rk4): the reference's gradient branch raises TypeError (TrajoptPlant.py:259), so no solve can run")
+        d.batch, d.knots, d.integrator_type = self.batch, self.N, self.integrator_type
         d.dtype = {"f64": _lib.F64, "f32": _lib.F32}[dtype]
         d.dt, d.gravity = self.dt, float(plant.options["gravity"])
         d.cost_kind = cost._kind

@@ -38,6 +38,7 @@ struct Dev {
   size_t K;
   // per-knot SoA
   T *x, *u, *xn, *un, *xkp1, *xkp1n, *dyn, *vaf, *Gh, *g, *Gg, *dz, *mu, *lam, *phi;
+  T *ABf;             // [nx*nm][K] full [A_k B_k] of integrator types 2 / 3 (k_ab_multi); null for types 0 / 1, whose [A B] is rebuilt from dyn
   // block-tridiagonal system, per-knot SoA: [nx*nx][K] and [nx][K]
   T *Sd, *So, *Pd, *gam, *l;
   // per-instance
@@ -59,6 +60,18 @@ struct Dev {
   int trace_cap;
 };
 
+// [A_k B_k] of knot t (NX x NM row-major): rebuilt from dqdd for the Euler integrators, loaded for the multi-stage ones
+template <typename T>
+__device__ __forceinline__ void load_AB(const Dev<T>& d, size_t t, T* AB) {
+  if (d.integrator >= 2) {
+    for (int i = 0; i < NX * NM; ++i) AB[i] = d.ABf[(size_t)i * d.K + t];
+  } else {
+    T dq[NDYN];
+    for (int i = 0; i < NDYN; ++i) dq[i] = d.dyn[(size_t)i * d.K + t];
+    build_AB(d.integrator, dq, d.dt, AB);
+  }
+}
+
 template <typename T>
 __device__ __forceinline__ void load_xu(const T* xs_, const T* us_, size_t K, size_t t, bool terminal, T* x, T* u) {
   for (int i = 0; i < NX; ++i) x[i] = xs_[(size_t)i * K + t];
@@ -70,7 +83,7 @@ __device__ __forceinline__ void load_xu(const T* xs_, const T* us_, size_t K, si
 //   TRIAL = false: reads (x,u); writes xkp1, Minv block of dyn, v/a/f of rnea(q,qd,qdd) (inputs of k_fd_grad)
 //   TRIAL = true : first forms the trial point xn = x - alpha dz_x, un = u - alpha dz_u (SQP :617-622), then xkp1n
 // -----------------------------------------------------------------------------------------------------------------
-template <typename T, bool TRIAL>
+template <typename T, bool TRIAL, bool MS = false>      // MS: multi-stage integrator (types 2 / 3), its own instantiation so that the Euler code is untouched
 __global__ void __launch_bounds__(128) k_fd(Dev<T> d, const int* list, const int* count) {
   const size_t gt = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
   const int slot = (int)(gt / d.N);
@@ -91,9 +104,14 @@ __global__ void __launch_bounds__(128) k_fd(Dev<T> d, const int* list, const int
   }
   if (terminal) return;
   T qdd[NJ], Minv[NJ * NJ], v[NJ][6], a[NJ][6], f[NJ][6], xnext[NX];
+  T* outp = TRIAL ? d.xkp1n : d.xkp1;
+  if constexpr (MS) {      // midpoint / rk3 (the reference's variants): x+ here, [A B] in k_ab_multi
+    integrator_multi_value(d.integrator, x, u, d.gravity, d.dt, xnext);
+    for (int i = 0; i < NX; ++i) outp[(size_t)i * K + t] = xnext[i];
+    return;
+  }
   forward_dynamics<T, !TRIAL>(x, x + NJ, u, d.gravity, qdd, Minv, v, a, f);
   integrate(d.integrator, x, qdd, d.dt, xnext);
-  T* outp = TRIAL ? d.xkp1n : d.xkp1;
   for (int i = 0; i < NX; ++i) outp[(size_t)i * K + t] = xnext[i];
   if constexpr (!TRIAL) {
     for (int i = 0; i < NJ; ++i)
@@ -141,6 +159,25 @@ __global__ void __launch_bounds__(128) k_fd_grad(Dev<T> d, const int* list, cons
   T out[NJ];
   fd_grad_column(q, qd, v, a, f, Minv, d.gravity, col, is_qd, out);
   for (int i = 0; i < NJ; ++i) d.dyn[(size_t)(i * 3 * NJ + colid) * K + t] = out[i];
+}
+
+// -----------------------------------------------------------------------------------------------------------------
+// k_ab_multi: [A_k B_k] of integrator types 2 / 3 (TrajoptPlant.py:140-205 as written there), one knot per thread, into ABf.
+// -----------------------------------------------------------------------------------------------------------------
+template <typename T>
+__global__ void __launch_bounds__(64) k_ab_multi(Dev<T> d, const int* list, const int* count) {
+  const size_t gt = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  const int slot = (int)(gt / d.N);
+  if (slot >= *count) return;
+  const int k = (int)(gt % d.N);
+  if (k == d.N - 1) return;
+  const int b = list[slot];
+  if (d.dyn_ok[b]) return;
+  const size_t t = (size_t)b * d.N + k;
+  T x[NX], u[NU], AB[NX * NM];
+  load_xu(d.x, d.u, d.K, t, false, x, u);
+  integrator_multi_AB(d.integrator, x, u, d.gravity, d.dt, AB);
+  for (int i = 0; i < NX * NM; ++i) d.ABf[(size_t)i * d.K + t] = AB[i];
 }
 
 // -----------------------------------------------------------------------------------------------------------------
@@ -240,9 +277,8 @@ __global__ void __launch_bounds__(64) k_schur(Dev<T> d, const int* list, const i
     for (int i = 0; i < NX; ++i) gam[i] = (d.x[(size_t)i * K + t] - d.xs[(size_t)i * d.B + b]) - d.Gg[(size_t)i * K + t];
   } else {
     const size_t tp = t - 1;
-    T dq[NDYN], AB[NX * NM];
-    for (int i = 0; i < NDYN; ++i) dq[i] = d.dyn[(size_t)i * K + tp];
-    build_AB(d.integrator, dq, d.dt, AB);
+    T AB[NX * NM];
+    load_AB(d, tp, AB);
     // W = Ghat_{j-1} AB^T  (NM x NX)
     T W[NM * NX];
     for (int r = 0; r < NM; ++r) {
@@ -1987,9 +2023,8 @@ __global__ void __launch_bounds__(128) k_recover(Dev<T> d, const int* list, cons
   const T* l = d.l + (size_t)b * d.N;
   for (int i = 0; i < NX; ++i) rhs[i] -= l[(size_t)i * K + k];
   if (!terminal) {
-    T dq[NDYN], AB[NX * NM];
-    for (int i = 0; i < NDYN; ++i) dq[i] = d.dyn[(size_t)i * K + t];
-    build_AB(d.integrator, dq, d.dt, AB);
+    T AB[NX * NM];
+    load_AB(d, t, AB);
     for (int c = 0; c < NM; ++c) {
       T acc = T(0);
       for (int i = 0; i < NX; ++i) acc += AB[i * NM + c] * l[(size_t)i * K + k + 1];
@@ -2203,7 +2238,7 @@ __global__ void k_merit(Dev<T> d, const int* list, const int* count, int* next_l
 template <typename T>
 __device__ __forceinline__ void outer_update(const Dev<T>& d, const Opts<T>& o, int b, T* sm, int fused_restart);   // defined below
 
-template <typename T>
+template <typename T, bool MS = false>
 __global__ void __launch_bounds__(128) k_linesearch(Dev<T> d, Opts<T> o, int fuse_outer, int fuse_recover) {
   if ((int)blockIdx.x >= *d.n_act) return;
   const int b = d.act[blockIdx.x];
@@ -2257,8 +2292,11 @@ __global__ void __launch_bounds__(128) k_linesearch(Dev<T> d, Opts<T> o, int fus
       // dynamics last: dz, xg and the multipliers are dead by now, which keeps the recursion's temporaries in registers
       if (!terminal) {
         T qdd[NJ], Minv[NJ * NJ], v[NJ][6], a[NJ][6], f[NJ][6], xnext[NX];
-        forward_dynamics<T, false>(z, z + NJ, z + NX, d.gravity, qdd, Minv, v, a, f);
-        integrate(d.integrator, z, qdd, d.dt, xnext);
+        if constexpr (MS) integrator_multi_value(d.integrator, z, z + NX, d.gravity, d.dt, xnext);
+        else {
+          forward_dynamics<T, false>(z, z + NJ, z + NX, d.gravity, qdd, Minv, v, a, f);
+          integrate(d.integrator, z, qdd, d.dt, xnext);
+        }
         for (int i = 0; i < NX; ++i) s_xn[k * NX + i] = xnext[i];
       }
     }
@@ -2363,7 +2401,7 @@ __global__ void __launch_bounds__(128) k_linesearch(Dev<T> d, Opts<T> o, int fus
 // tests / outer update.  Work grows by max_trials / (trials used); the host selects it only below a small active count.
 // smem: (6 + 2 NX) * N scalars.   scratch: trial_out [B][max_trials][3], done [B] (zero between passes).
 // -----------------------------------------------------------------------------------------------------------------
-template <typename T>
+template <typename T, bool MS = false>
 __global__ void __launch_bounds__(128) k_linesearch_par(Dev<T> d, Opts<T> o, int fuse_outer, int fuse_recover, int max_trials, T* trial_out, int* done) {
   const int slot = (int)blockIdx.x / max_trials, trial = (int)blockIdx.x % max_trials;
   if (slot >= *d.n_act) return;
@@ -2415,8 +2453,11 @@ __global__ void __launch_bounds__(128) k_linesearch_par(Dev<T> d, Opts<T> o, int
     }
     if (!terminal) {
       T qdd[NJ], Minv[NJ * NJ], v[NJ][6], a[NJ][6], f[NJ][6], xnext[NX];
-      forward_dynamics<T, false>(z, z + NJ, z + NX, d.gravity, qdd, Minv, v, a, f);
-      integrate(d.integrator, z, qdd, d.dt, xnext);
+      if constexpr (MS) integrator_multi_value(d.integrator, z, z + NX, d.gravity, d.dt, xnext);
+      else {
+        forward_dynamics<T, false>(z, z + NJ, z + NX, d.gravity, qdd, Minv, v, a, f);
+        integrate(d.integrator, z, qdd, d.dt, xnext);
+      }
       for (int i = 0; i < NX; ++i) s_xn[k * NX + i] = xnext[i];
     }
   }
@@ -2788,9 +2829,9 @@ __global__ void k_cost_eval(Dev<T> d, int what, double* out) {
     return;
   }
   if (what == 5) {      // [A_k B_k] of the integrator at (x_k, u_k) from the stored forward-dynamics gradient (row N-1 unused: zeros)
-    T dq[NDYN], AB[NX * NM];
-    for (int i = 0; i < NDYN; ++i) dq[i] = d.dyn[(size_t)i * d.K + gt];
-    build_AB(d.integrator, dq, d.dt, AB);
+    T AB[NX * NM];
+    if (terminal) { for (int i = 0; i < NX * NM; ++i) AB[i] = T(0); }
+    else load_AB(d, gt, AB);
     for (int i = 0; i < NX * NM; ++i) out[gt * NX * NM + i] = terminal ? 0.0 : (double)AB[i];
     return;
   }
@@ -2893,7 +2934,7 @@ namespace b2t {
 // the reference's slice `[:, shift_steps:] = init` re-initialises every column but the first).
 // One block per instance, one thread per knot.  out_x0 / out_u0 (may be null): the state before the shift and the applied control.
 // -----------------------------------------------------------------------------------------------------------------
-template <typename T>
+template <typename T, bool MS = false>
 __global__ void k_mpc_shift(Dev<T> d, const double* x_next, double* out_x0, double* out_u0, double* out_xnext) {
   const int b = blockIdx.x;
   const int N = d.N;
@@ -2910,8 +2951,11 @@ __global__ void k_mpc_shift(Dev<T> d, const double* x_next, double* out_x0, doub
       for (int i = 0; i < NX; ++i) s_xn[i] = (T)x_next[(size_t)b * NX + i];
     } else {
       T qdd[NJ], Minv[NJ * NJ], v[NJ][6], a[NJ][6], f[NJ][6], xn[NX];
-      forward_dynamics<T, false>(x, x + NJ, u, d.gravity, qdd, Minv, v, a, f);
-      integrate(d.integrator, x, qdd, d.dt, xn);
+      if constexpr (MS) integrator_multi_value(d.integrator, x, u, d.gravity, d.dt, xn);
+      else {
+        forward_dynamics<T, false>(x, x + NJ, u, d.gravity, qdd, Minv, v, a, f);
+        integrate(d.integrator, x, qdd, d.dt, xn);
+      }
       for (int i = 0; i < NX; ++i) s_xn[i] = xn[i];
     }
     if (out_xnext) for (int i = 0; i < NX; ++i) out_xnext[(size_t)b * NX + i] = (double)s_xn[i];

@@ -149,8 +149,9 @@ struct SolverT : SolverBase {
   int init(const b2t_problem_desc* p, int dev) override {
     using namespace b2t;
     if (!p || p->batch < 1 || p->knots < 2) return fail(B2T_ERR_INVALID, "batch >= 1 and knots >= 2 required");
-    if (p->integrator_type != 0 && p->integrator_type != 1)
-      return fail(B2T_ERR_UNSUPPORTED, "integrator types 0 (euler) and 1 (semi-implicit euler) only");
+    if (p->integrator_type < 0 || p->integrator_type > 3)
+      return fail(B2T_ERR_UNSUPPORTED, "integrator types 0 (euler), 1 (semi-implicit euler), 2 (midpoint) and 3 (rk3); 4 (rk4) raises in the reference "
+                                       "(TrajoptPlant.py:259) and -1 needs a user-coded plant");
     if (p->cost_kind == B2T_COST_URDF_EE && NJ < 2)
       return fail(B2T_ERR_UNSUPPORTED, "the end-effector cost needs a planar chain of at least 2 joints");
     if (p->cost_kind != B2T_COST_QUADRATIC && p->cost_kind != B2T_COST_URDF_EE) return fail(B2T_ERR_INVALID, "cost_kind");
@@ -206,6 +207,10 @@ struct SolverT : SolverBase {
     d.lim.any = any;
     d.hard.any = any_hard;
     if (any_hard) d.diag_mode = 0;        // the elimination of the fixed coordinates lives in the dense KKT kernel
+    if (d.integrator >= 2) {              // [A B] is a product of stage matrices: general kernels, [A B] stored in full
+      d.diag_mode = 0;
+      B2T_ALLOC(d.ABf, (size_t)NX * NM * K);
+    }
     // Ghat_k: 2m+1 scalars per knot on the structured path (dinv, h, s), a dense m x m block otherwise.  iLQR always needs the dense
     // block and allocates it on its first call (ensure_dense_gh).
     gh_dense = d.diag_mode == 0;
@@ -243,6 +248,8 @@ struct SolverT : SolverBase {
     B2T_CUDA(cudaFuncSetAttribute(b2t::k_pcg<T>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
     B2T_CUDA(cudaFuncSetAttribute(b2t::k_linesearch<T>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
     B2T_CUDA(cudaFuncSetAttribute(b2t::k_linesearch_par<T>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+    B2T_CUDA(cudaFuncSetAttribute(b2t::k_linesearch<T, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+    B2T_CUDA(cudaFuncSetAttribute(b2t::k_linesearch_par<T, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
     B2T_ALLOC(d_trial_out, (size_t)B * MAX_LS_TRIALS * 3); B2T_ALLOC(d_trial_done, B);
     { const char* e = getenv("B2T_LS_PAR"); if (e) ls_par_max = atoi(e); }
     B2T_CUDA(cudaFuncSetAttribute(b2t::k_schur_diag<T>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)((size_t)NJ * NM * SCHUR_THREADS * sizeof(T))));
@@ -458,8 +465,10 @@ struct SolverT : SolverBase {
   int launch_dynamics(const int* list, const int* count, int bound) {
     using namespace b2t;
     const size_t nthreads = (size_t)bound * d.N;
-    { Scope sc(this, B2T_K_FD); k_fd<T, false><<<cdiv(nthreads, 128), 128, 0, stream>>>(d, list, count); tick(B2T_K_FD); }
-    { Scope sc(this, B2T_K_FDGRAD); k_fd_grad<T><<<(unsigned)(cdiv(nthreads, 128) * 2 * NJ), 128, 0, stream>>>(d, list, count); tick(B2T_K_FDGRAD); }
+    if (d.integrator >= 2) { Scope sc(this, B2T_K_FD); k_fd<T, false, true><<<cdiv(nthreads, 128), 128, 0, stream>>>(d, list, count); tick(B2T_K_FD); }
+    else { Scope sc(this, B2T_K_FD); k_fd<T, false><<<cdiv(nthreads, 128), 128, 0, stream>>>(d, list, count); tick(B2T_K_FD); }
+    if (d.integrator >= 2) { Scope sc(this, B2T_K_FDGRAD); k_ab_multi<T><<<cdiv(nthreads, 64), 64, 0, stream>>>(d, list, count); tick(B2T_K_FDGRAD); }
+    else { Scope sc(this, B2T_K_FDGRAD); k_fd_grad<T><<<(unsigned)(cdiv(nthreads, 128) * 2 * NJ), 128, 0, stream>>>(d, list, count); tick(B2T_K_FDGRAD); }
     return 0;
   }
   int launch_kkt(const int* list, const int* count, int bound, int method, bool all_outputs = false) {
@@ -526,8 +535,10 @@ struct SolverT : SolverBase {
   void decide_pcg_variant() {
     if (pcg_variant < 0) {
       const char* e = getenv("B2T_PCG_VARIANT");
-      if (e) pcg_variant = atoi(e);
-      if (pcg_variant == 7) { pcg_variant = 3; pcg_col = true; }      // experiment: k_pcg3 with the column form of the D^-1 products
+      if (e) {
+        pcg_variant = atoi(e);
+        if (pcg_variant == 7) { pcg_variant = 3; pcg_col = true; }      // experiment: k_pcg3 with the column form of the D^-1 products
+      }
       // k_pcg3: 21.9 ms vs 24.0 ms (variant 1) per 2048-instance step at N = 64.  Longer horizons use its 512- / 1024-thread
       // instantiations (128 / 64 registers, spilling): still 1.85x (N = 128: 76.7 vs 141.8 ns per instance-iteration) and 3.2x
       // (N = 256: 289 vs 932 ns) faster than the explicit-block kernel, which no longer fits its blocks in shared memory there
@@ -639,7 +650,8 @@ struct SolverT : SolverBase {
     const size_t msmem = (size_t)6 * d.N * sizeof(T);
     const int mt = merit_threads();
     k_init_state<T><<<cdiv(B, 128), 128, 0, stream>>>(d); tick(B2T_K_CTRL);
-    { Scope sc(this, B2T_K_FD); k_fd<T, false><<<cdiv((size_t)B * d.N, 128), 128, 0, stream>>>(d, d.act, d.n_act); tick(B2T_K_FD); }
+    if (d.integrator >= 2) { Scope sc(this, B2T_K_FD); k_fd<T, false, true><<<cdiv((size_t)B * d.N, 128), 128, 0, stream>>>(d, d.act, d.n_act); tick(B2T_K_FD); }
+    else { Scope sc(this, B2T_K_FD); k_fd<T, false><<<cdiv((size_t)B * d.N, 128), 128, 0, stream>>>(d, d.act, d.n_act); tick(B2T_K_FD); }
     { Scope sc(this, B2T_K_MERIT); k_outer_begin<T><<<B, mt, msmem, stream>>>(d, d.act, d.n_act, op, 1); tick(B2T_K_MERIT); }
     B2T_CUDA(cudaGetLastError());
     int n = B;
@@ -667,15 +679,18 @@ struct SolverT : SolverBase {
         // few active instances: all trials of a search at once (one block per instance and trial; bit-identical decisions)
         if (n <= ls_par_max && trials_exact) {
           Scope sc(this, B2T_K_TRIAL);
-          k_linesearch_par<T><<<n * max_trials, lst, lsmem_par, stream>>>(d, op, 1, fuse_recover, max_trials, d_trial_out, d_trial_done);
+          if (d.integrator >= 2) k_linesearch_par<T, true><<<n * max_trials, lst, lsmem_par, stream>>>(d, op, 1, fuse_recover, max_trials, d_trial_out, d_trial_done);
+          else k_linesearch_par<T><<<n * max_trials, lst, lsmem_par, stream>>>(d, op, 1, fuse_recover, max_trials, d_trial_out, d_trial_done);
           tick(B2T_K_TRIAL);
-        } else { Scope sc(this, B2T_K_TRIAL); k_linesearch<T><<<n, lst, lsmem, stream>>>(d, op, 1, fuse_recover); tick(B2T_K_TRIAL); }
+        } else if (d.integrator >= 2) { Scope sc(this, B2T_K_TRIAL); k_linesearch<T, true><<<n, lst, lsmem, stream>>>(d, op, 1, fuse_recover); tick(B2T_K_TRIAL); }
+        else { Scope sc(this, B2T_K_TRIAL); k_linesearch<T><<<n, lst, lsmem, stream>>>(d, op, 1, fuse_recover); tick(B2T_K_TRIAL); }
       } else {
         { Scope sc(this, B2T_K_CTRL); k_iter_begin<T><<<cdiv(n, 128), 128, 0, stream>>>(d); tick(B2T_K_CTRL); }
         for (int t = 0; t < max_trials; ++t) {
           int* cur = (t % 2) ? d.ls_list1 : d.ls_list0;
           int* nxt = (t % 2) ? d.ls_list0 : d.ls_list1;
-          { Scope sc(this, B2T_K_TRIAL); k_fd<T, true><<<cdiv((size_t)n * d.N, 128), 128, 0, stream>>>(d, cur, d.n_ls + t); tick(B2T_K_TRIAL); }
+          if (d.integrator >= 2) { Scope sc(this, B2T_K_TRIAL); k_fd<T, true, true><<<cdiv((size_t)n * d.N, 128), 128, 0, stream>>>(d, cur, d.n_ls + t); tick(B2T_K_TRIAL); }
+          else { Scope sc(this, B2T_K_TRIAL); k_fd<T, true><<<cdiv((size_t)n * d.N, 128), 128, 0, stream>>>(d, cur, d.n_ls + t); tick(B2T_K_TRIAL); }
           { Scope sc(this, B2T_K_MERIT); k_merit<T><<<n, mt, msmem, stream>>>(d, cur, d.n_ls + t, nxt, d.n_ls + t + 1, op); tick(B2T_K_MERIT); }
         }
         { Scope sc(this, B2T_K_CTRL); k_sqp_ctrl<T><<<cdiv(n, 128), 128, 0, stream>>>(d, op); tick(B2T_K_CTRL); }
@@ -740,7 +755,8 @@ struct SolverT : SolverBase {
       dxn = stage_g;
     }
     double* o0 = stage_out; double* o1 = stage_out + (size_t)d.B * NX; double* o2 = o1 + (size_t)d.B * NU;
-    k_mpc_shift<T><<<d.B, std::min(256, ((d.N + 31) / 32) * 32), 0, stream>>>(d, dxn, o0, o1, o2);
+    if (d.integrator >= 2) k_mpc_shift<T, true><<<d.B, std::min(256, ((d.N + 31) / 32) * 32), 0, stream>>>(d, dxn, o0, o1, o2);
+    else k_mpc_shift<T><<<d.B, std::min(256, ((d.N + 31) / 32) * 32), 0, stream>>>(d, dxn, o0, o1, o2);
     B2T_CUDA(cudaGetLastError());
     if (x0_out) B2T_CUDA(cudaMemcpyAsync(x0_out, o0, nb, cudaMemcpyDeviceToHost, stream));
     if (u0_out) B2T_CUDA(cudaMemcpyAsync(u0_out, o1, (size_t)d.B * NU * sizeof(double), cudaMemcpyDeviceToHost, stream));
@@ -761,6 +777,7 @@ struct SolverT : SolverBase {
     B2T_CUDA(cudaEventRecord(ev0, stream));
     const int B = d.B;
     if (d.hard.any) return fail(B2T_ERR_UNSUPPORTED, "iLQR supports soft limits only (README.md:17 of the reference says the same)");
+    if (d.integrator >= 2) return fail(B2T_ERR_UNSUPPORTED, "iLQR: integrator types 0 and 1 only");
     { int r = ensure_dense_gh(); if (r) return r; }
     const size_t msmem = (size_t)6 * d.N * sizeof(T);
     const int mt = merit_threads();
@@ -896,7 +913,8 @@ struct SolverT : SolverBase {
     using namespace b2t;
     B2T_CUDA(cudaSetDevice(device));
     k_fill<T><<<cdiv(d.B, 128), 128, 0, stream>>>(d.alpha, (size_t)d.B, (T)alpha);
-    k_fd<T, true><<<cdiv(d.K, 128), 128, 0, stream>>>(d, d.act, d.n_act);
+    if (d.integrator >= 2) k_fd<T, true, true><<<cdiv(d.K, 128), 128, 0, stream>>>(d, d.act, d.n_act);
+    else k_fd<T, true><<<cdiv(d.K, 128), 128, 0, stream>>>(d, d.act, d.n_act);
     k_merit_only<T><<<d.B, merit_threads(), (size_t)6 * d.N * sizeof(T), stream>>>(d, d.J, d.c, d.D);
     B2T_CUDA(cudaGetLastError());
     std::vector<T> h(d.B);
@@ -919,7 +937,9 @@ struct SolverT : SolverBase {
       case B2T_ARR_X: src = d.x; E = NX; break;
       case B2T_ARR_U: src = d.u; E = NU; break;
       case B2T_ARR_XKP1: src = d.xkp1; E = NX; break;
-      case B2T_ARR_DQDD: src = d.dyn; E = NDYN; break;
+      case B2T_ARR_DQDD:
+        if (d.integrator >= 2) return fail(B2T_ERR_UNSUPPORTED, "integrator types 2 / 3 evaluate the dynamics gradient per stage: fetch B2T_ARR_AB instead");
+        src = d.dyn; E = NDYN; break;
       case B2T_ARR_GHAT: src = d.Gh; E = NM * NM; break;
       case B2T_ARR_G: src = d.g; E = NM; break;
       case B2T_ARR_DZ: src = d.dz; E = NM; break;

@@ -68,17 +68,26 @@ class Recorder:
     def _eval(self, X, U):
         from .api import BatchSolver, split_plant_terms
         s = self.s
-        if self._probe is None:
-            self._probe = BatchSolver(self.o.plant, self.o.cost, None, N=s.N, dt=s.dt, batch=1)
+        itype = self.o.plant.integrator_type
+        if self._probe is None:       # plant terms and dqdd at given points do not depend on the integrator: the Euler kernels serve all types
+            self._probe = BatchSolver(self.o.plant, self.o.cost, None, N=s.N, dt=s.dt, batch=1, integrator_type=itype if itype in (0, 1) else 0)
         p = self._probe
         p.set_goals(np.asarray(self.o.cost.xg, dtype=np.float64).reshape(1, -1))
         p.set_trajectory(X[None], U[None])
         n, N = s.n, s.N
         out = dict(value=p.fetch("cost_value")[0, :, 0], dx=p.fetch("cost_err")[0], grad=p.fetch("cost_grad")[0],
                    hess=p.fetch("cost_hess")[0].reshape(N, s.m, s.m), jtot=p.fetch("cost_jtot")[0].reshape(N, s.nx, s.nx))
-        p.stage_dynamics()
-        out["dqdd"] = p.fetch("dqdd")[0].reshape(N, n, 3 * n)
-        out["plant"] = [split_plant_terms(t, n) for t in p.fetch("plant_terms")[0]]
+
+        def plant_at(P):
+            p.set_trajectory(P[None], U[None])
+            p.stage_dynamics()
+            return [split_plant_terms(t, n) for t in p.fetch("plant_terms")[0]], p.fetch("dqdd")[0].reshape(N, n, 3 * n)
+        # the stage points of the plant's integrator (TrajoptPlant.py:140-175): point_s = x_k + h_s dt [qd_k ; qdd(point_{s-1}, u_k)]
+        stages = [plant_at(X)]
+        for h in {2: (0.5,), 3: (0.5, 0.75)}.get(itype, ()):
+            qdd = np.stack([t[1] for t in stages[-1][0]], axis=1)           # (n, N)
+            stages.append(plant_at(X + h * s.dt * np.vstack([X[n:], qdd])))
+        out["stages"] = stages
         return out
 
     def _put(self, obj, tag, **entries):
@@ -87,12 +96,18 @@ class Recorder:
             if lst is not None:
                 lst.append(dict(value=value, iteration=tag[0], outer_iteration=tag[1], line_search_iteration=tag[2]))
 
-    def _fd(self, e, k, tag, gradient=False):
-        c, qdd, Minv, dc_du = e["plant"][k]
-        if gradient:        # forward_dynamics_gradient (TrajoptPlant.py:318-322)
-            self._put(self.o.plant, tag, Minv=Minv, c=c, qdd=qdd, dc_du=dc_du, dqdd=e["dqdd"][k].copy())
-        else:               # forward_dynamics (:297-299)
+    def _integrator(self, e, k, tag, gradient=False):
+        """The plant callbacks of ONE plant.integrator(x_k, u_k, ...) call: forward_dynamics at every stage point (TrajoptPlant.py:95,
+        :118, :141-143, :171-175; appends :297-299), then -- with return_gradient -- forward_dynamics_gradient at every stage point
+        (:100, :131, :150-156, :185-198; appends :318-322).  The semi-implicit branch calls the gradient without the counters (:131)."""
+        for terms, _ in e["stages"]:
+            c, qdd, Minv, dc_du = terms[k]
             self._put(self.o.plant, tag, c=c, Minv=Minv, qdd=qdd)
+        if gradient:
+            gtag = (0, 0, 0) if self.o.plant.integrator_type == 1 else tag
+            for terms, dqdd in e["stages"]:
+                c, qdd, Minv, dc_du = terms[k]
+                self._put(self.o.plant, gtag, Minv=Minv, c=c, qdd=qdd, dc_du=dc_du, dqdd=dqdd[k].copy())
 
     def _cost(self, e, k, tag, what):
         if not self._cost_lists:
@@ -112,7 +127,7 @@ class Recorder:
         for k in range(N):                    # totalCost (:296-310)
             self._cost(e, k, tag, "value")
         for k in range(N - 1):                # totalHardConstraintViolation (:273-294): integrator -> forward_dynamics
-            self._fd(e, k, tag)
+            self._integrator(e, k, tag)
 
     def _replay_kkt(self, e, tag):
         N = self.s.N
@@ -120,9 +135,8 @@ class Recorder:
         for k in range(N - 1):                # formKKTSystemBlocks (:200-271)
             self._cost(e, k, tag, "hess")
             self._cost(e, k, tag, "grad")
-            self._fd(e, k, ptag)              # integrator(return_gradient=True): forward_dynamics, then its gradient (TrajoptPlant.py:95-101)
-            self._fd(e, k, ptag, gradient=True)
-            self._fd(e, k, ptag)              # integrator() for x_{k+1}
+            self._integrator(e, k, ptag, gradient=True)      # Ak, Bk (:227)
+            self._integrator(e, k, ptag)                     # x_{k+1} (:230)
         self._cost(e, N - 1, tag, "hess")
         self._cost(e, N - 1, tag, "grad")
 
