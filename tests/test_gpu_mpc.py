@@ -11,10 +11,12 @@ from oracle import mpc as ompc
 pytestmark = pytest.mark.gpu
 
 
-@pytest.mark.parametrize("name,N,limits", [("arm2", 10, None), ("pend", 12, {"torque": ([0.3], [-0.3], "AUGMENTED_LAGRANGIAN")})])
-def test_mpc_loop_vs_oracle(name, N, limits, oracle_models):
+@pytest.mark.parametrize("name,N,limits,integ", [("arm2", 10, None, 0), ("pend", 12, {"torque": ([0.3], [-0.3], "AUGMENTED_LAGRANGIAN")}, 0),
+                                                 ("arm2", 10, None, 2), ("pend", 12, {"torque": ([0.3], [-0.3], "QUADRATIC_PENALTY")}, 3)])
+def test_mpc_loop_vs_oracle(name, N, limits, integ, oracle_models):
+    """integ 2 / 3: the plant simulation between solves (k_mpc_shift) and the solves themselves use the reference's midpoint / rk3."""
     steps, B = 5, 3
-    (plant, pc, pcons), (m, oc, ocn) = make_pair(name, N, oracle_models, limits=limits, cost_kind="quadratic",
+    (plant, pc, pcons), (m, oc, ocn) = make_pair(name, N, oracle_models, limits=limits, cost_kind="quadratic", integrator=integ,
                                                  xg=np.array([0.4, -0.3, 0, 0]) if name == "arm2" else None)
     n = m.n
     rng = np.random.default_rng(2)
@@ -25,7 +27,7 @@ def test_mpc_loop_vs_oracle(name, N, limits, oracle_models):
     r = solver.mpc_batch(xs, xg, N, 0.1, steps, t.SQPSolverMethods.PCG_SS, dict(opts))
     for b in range(B):
         ocb = copy.copy(oc); ocb.xg = xg[b]
-        ro = ompc.mpc(m, ocb, copy.deepcopy(ocn), xs[b], N, 0.1, steps, "PCG-SS", dict(opts))
+        ro = ompc.mpc(m, ocb, copy.deepcopy(ocn), xs[b], N, 0.1, steps, "PCG-SS", dict(opts), integrator_type=integ)
         assert ro["sqp_iter"] == r.sqp_iter[b].tolist()
         assert np.max(np.abs(ro["x_closed"] - r.x_closed[b])) < 1e-5
         assert np.max(np.abs(ro["u_applied"] - r.u_applied[b])) < 1e-4

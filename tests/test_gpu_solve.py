@@ -119,15 +119,18 @@ def _batch_goals(n, B, seed):
     return xg
 
 
-@pytest.mark.parametrize("name,N,B,limits", [
-    ("arm6", 16, 24, None),
-    ("arm3", 12, 16, {"torque": ([0.4], [-0.4], "QUADRATIC_PENALTY"), "joint": ([0.45], [-0.45], "AUGMENTED_LAGRANGIAN")}),
-    ("arm6", 16, 12, {"torque": ([1.0], [-1.0], "QUADRATIC_PENALTY"), "joint": ([0.45], [-0.45], "QUADRATIC_PENALTY")}),
+@pytest.mark.parametrize("name,N,B,limits,integ", [
+    ("arm6", 16, 24, None, 0),
+    ("arm3", 12, 16, {"torque": ([0.4], [-0.4], "QUADRATIC_PENALTY"), "joint": ([0.45], [-0.45], "AUGMENTED_LAGRANGIAN")}, 0),
+    ("arm6", 16, 12, {"torque": ([1.0], [-1.0], "QUADRATIC_PENALTY"), "joint": ([0.45], [-0.45], "QUADRATIC_PENALTY")}, 0),
+    ("arm6", 12, 8, {"torque": ([1.0], [-1.0], "QUADRATIC_PENALTY"), "joint": ([0.45], [-0.45], "QUADRATIC_PENALTY")}, 2),      # midpoint
+    ("arm3", 12, 8, {"torque": ([0.4], [-0.4], "AUGMENTED_LAGRANGIAN")}, 3),                                                    # rk3
 ])
-def test_batch_vs_oracle(name, N, B, limits, oracle_models):
+def test_batch_vs_oracle(name, N, B, limits, integ, oracle_models):
     """Independent instances with different goals in one batch; each compared with the oracle run on its own
-    (multi-coordinate box limits are UNPINNED in the reference: the oracle's element-wise restatement is the spec)."""
-    (plant, pc, pcons), (m, oc, ocn) = make_pair(name, N, oracle_models, limits=limits)
+    (multi-coordinate box limits are UNPINNED in the reference: the oracle's element-wise restatement is the spec).
+    integ 2 / 3: the reference's midpoint / rk3 integrators (general kernels, [A B] stored in full)."""
+    (plant, pc, pcons), (m, oc, ocn) = make_pair(name, N, oracle_models, limits=limits, integrator=integ)
     n = m.n
     xg = _batch_goals(n, B, 11)
     solver = t.TrajoptMPCReference(plant, pc, pcons) if pcons is not None else t.TrajoptMPCReference(plant, pc)
@@ -141,8 +144,9 @@ def test_batch_vs_oracle(name, N, B, limits, oracle_models):
     same_iters, worst = 0, (0.0, 0.0)
     for b in range(B):
         oc_b = copy.copy(oc); oc_b.xg = xg[b]
-        ro = sqp.sqp(m, oc_b, copy.deepcopy(ocn), np.zeros((2 * n, N)), np.zeros((n, N - 1)), N, 0.1, "PCG-SS", dict(opts))
-        rp = sqp.sqp(m, oc_b, copy.deepcopy(ocn), np.zeros((2 * n, N)), np.zeros((n, N - 1)), N, 0.1, "PCG-SS", dict(opts, _perturb_S=_perturber(b)))
+        ro = sqp.sqp(m, oc_b, copy.deepcopy(ocn), np.zeros((2 * n, N)), np.zeros((n, N - 1)), N, 0.1, "PCG-SS", dict(opts), integrator_type=integ)
+        rp = sqp.sqp(m, oc_b, copy.deepcopy(ocn), np.zeros((2 * n, N)), np.zeros((n, N - 1)), N, 0.1, "PCG-SS", dict(opts, _perturb_S=_perturber(b)),
+                     integrator_type=integ)
         stable = rp["pcg_iters"] == ro["pcg_iters"] and rp["ls_trials"] == ro["ls_trials"]
         fJ = abs(rp["J"] - ro["J"]) / max(1.0, abs(ro["J"])); fx = float(np.max(np.abs(rp["x"] - ro["x"])))
         same = (ro["exit_sqp"], ro["exit_soft"], ro["outer_iter"], ro["sqp_iter"]) == (r.exit_sqp[b], r.exit_soft[b], r.outer_iter[b], r.sqp_iter[b]) \
