@@ -45,11 +45,13 @@ def test_cartpole_ilqr_vs_oracle(limits):
     assert abs(x[1, -1] - np.pi) < 0.05
 
 
-def test_ilqr_batch_arm6_vs_oracle(oracle_models):
+@pytest.mark.parametrize("integ", [0, 2, 3])
+def test_ilqr_batch_arm6_vs_oracle(integ, oracle_models):
+    """integ 2 / 3: rollouts through the reference's midpoint / rk3 step, Riccati pass on the stored full [A B] (k_ab_multi)."""
     N, B = 16, 12
     m = oracle_models["arm6"]
     Q, QF, R = np.eye(12), 100.0 * np.eye(12), 0.1 * np.eye(6)
-    plant = t.URDFPlant(options={"path_to_urdf": "arm6"})
+    plant = t.URDFPlant(integrator_type=integ, options={"path_to_urdf": "arm6"})
     pc = t.QuadraticCost(Q.copy(), QF.copy(), R.copy(), np.zeros(12))
     pcons = t.TrajoptConstraint(6, 6, 6, N); ocn = ocons.SoftConstraints(6, 6, 6, N)
     for c in (pcons, ocn):
@@ -61,7 +63,8 @@ def test_ilqr_batch_arm6_vs_oracle(oracle_models):
     r = solver.ilqr_batch(np.zeros((B, 12, N)), np.zeros((B, 6, N - 1)), xg, N, 0.1, dict(opts))
     same = 0
     for b in range(B):
-        ro = ilqr.ilqr(m, ocost.QuadraticCost(Q, QF, R, xg[b]), copy.deepcopy(ocn), np.zeros((12, N)), np.zeros((6, N - 1)), N, 0.1, dict(opts))
+        ro = ilqr.ilqr(m, ocost.QuadraticCost(Q, QF, R, xg[b]), copy.deepcopy(ocn), np.zeros((12, N)), np.zeros((6, N - 1)), N, 0.1, dict(opts),
+                       integrator_type=integ)
         ok = (ro["exit_sqp"], ro["exit_soft"], ro["outer_iter"], ro["sqp_iter"], ro["total_iters"], ro["total_trials"]) == \
              (r.exit_sqp[b], r.exit_soft[b], r.outer_iter[b], r.sqp_iter[b], r.total_qp[b], r.total_trials[b])
         same += int(ok)

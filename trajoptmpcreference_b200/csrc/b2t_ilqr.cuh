@@ -59,9 +59,8 @@ __global__ void __launch_bounds__(32) k_ilqr_backward(Dev<T> d, const int* list,
   int ok = 1;
   for (int k = N - 2; k >= 0 && ok; --k) {
     const size_t t = t0 + k;
-    T dq[NDYN], AB[NX * NM];
-    for (int i = 0; i < NDYN; ++i) dq[i] = d.dyn[(size_t)i * K + t];
-    build_AB(d.integrator, dq, d.dt, AB);                 // [A B], NX x NM
+    T AB[NX * NM];
+    load_AB(d, t, AB);                                    // [A B], NX x NM
     // VAB = Vxx [A B]  (NX x NM)
     T VAB[NX * NM];
     for (int i = 0; i < NX; ++i)
@@ -186,13 +185,15 @@ __global__ void __launch_bounds__(ILQR_BW_THREADS) k_ilqr_backward2(Dev<T> d, co
   __syncthreads();
   for (int k = N - 2; k >= 0; --k) {
     const size_t t = t0 + k;
-    for (int i = tid; i < NDYN; i += nt) sdq[i] = d.dyn[(size_t)i * K + t];
+    if (d.integrator < 2)
+      for (int i = tid; i < NDYN; i += nt) sdq[i] = d.dyn[(size_t)i * K + t];
     __syncthreads();
     // [A B] (build_AB, entry-parallel)
     for (int e = tid; e < NX * NM; e += nt) {
       const int r = e / NM, c = e % NM;
       T v;
-      if (d.integrator == 0) {
+      if (d.integrator >= 2) v = d.ABf[(size_t)e * K + t];      // midpoint / rk3: the full [A B] of k_ab_multi
+      else if (d.integrator == 0) {
         if (r < NJ) v = ((c == r) ? T(1) : T(0)) + ((c == NJ + r) ? d.dt : T(0));
         else v = d.dt * sdq[(r - NJ) * 3 * NJ + c] + ((c == r) ? T(1) : T(0));
       } else {
@@ -325,8 +326,11 @@ __global__ void __launch_bounds__(32) k_ilqr_rollout0(Dev<T> d) {
   for (int k = 0; k < N - 1; ++k) {
     T u[NU], qdd[NJ], Minv[NJ * NJ], v[NJ][6], a[NJ][6], f[NJ][6], xn[NX];
     for (int i = 0; i < NU; ++i) u[i] = d.u[(size_t)i * K + t0 + k];
-    forward_dynamics<T, false>(x, x + NJ, u, d.gravity, qdd, Minv, v, a, f);
-    integrate(d.integrator, x, qdd, d.dt, xn);
+    if (d.integrator >= 2) integrator_multi_value(d.integrator, x, u, d.gravity, d.dt, xn);
+    else {
+      forward_dynamics<T, false>(x, x + NJ, u, d.gravity, qdd, Minv, v, a, f);
+      integrate(d.integrator, x, qdd, d.dt, xn);
+    }
     for (int i = 0; i < NX; ++i) { x[i] = xn[i]; d.x[(size_t)i * K + t0 + k + 1] = xn[i]; }
   }
 }
@@ -370,8 +374,11 @@ __global__ void __launch_bounds__(32) k_ilqr_search(Dev<T> d, Opts<T> o) {
       soft[k] = d.lim.any ? soft_value(d.lim, z, d.mu + t, d.lam + t, K, terminal) : T(0);
       if (!terminal) {
         T qdd[NJ], Minv[NJ * NJ], v[NJ][6], a[NJ][6], f[NJ][6], xn[NX];
-        forward_dynamics<T, false>(z, z + NJ, z + NX, d.gravity, qdd, Minv, v, a, f);
-        integrate(d.integrator, z, qdd, d.dt, xn);
+        if (d.integrator >= 2) integrator_multi_value(d.integrator, z, z + NX, d.gravity, d.dt, xn);
+        else {
+          forward_dynamics<T, false>(z, z + NJ, z + NX, d.gravity, qdd, Minv, v, a, f);
+          integrate(d.integrator, z, qdd, d.dt, xn);
+        }
         for (int i = 0; i < NX; ++i) z[i] = xn[i];
       }
     }
@@ -471,8 +478,11 @@ __global__ void __launch_bounds__(64) k_ilqr_search2(Dev<T> d, Opts<T> o, T* scr
       if (d.lim.any) SC(NM, t) = soft_value(d.lim, z, d.mu + t, d.lam + t, K, terminal);
       if (!terminal) {
         T qdd[NJ], Minv[NJ * NJ], v[NJ][6], a[NJ][6], f[NJ][6], xn[NX];
-        forward_dynamics<T, false>(z, z + NJ, z + NX, d.gravity, qdd, Minv, v, a, f);
-        integrate(d.integrator, z, qdd, d.dt, xn);
+        if (d.integrator >= 2) integrator_multi_value(d.integrator, z, z + NX, d.gravity, d.dt, xn);
+        else {
+          forward_dynamics<T, false>(z, z + NJ, z + NX, d.gravity, qdd, Minv, v, a, f);
+          integrate(d.integrator, z, qdd, d.dt, xn);
+        }
         for (int i = 0; i < NX; ++i) z[i] = xn[i];
       }
     }

@@ -777,7 +777,6 @@ struct SolverT : SolverBase {
     B2T_CUDA(cudaEventRecord(ev0, stream));
     const int B = d.B;
     if (d.hard.any) return fail(B2T_ERR_UNSUPPORTED, "iLQR supports soft limits only (README.md:17 of the reference says the same)");
-    if (d.integrator >= 2) return fail(B2T_ERR_UNSUPPORTED, "iLQR: integrator types 0 and 1 only");
     { int r = ensure_dense_gh(); if (r) return r; }
     const size_t msmem = (size_t)6 * d.N * sizeof(T);
     const int mt = merit_threads();
