@@ -111,6 +111,31 @@ def test_pcg_kernel_variants(N, oracle_models):
         assert np.max(np.abs(res["3"][1] - res[v][1])) < 1e-9 * np.max(np.abs(res["3"][1])), v
 
 
+@pytest.mark.parametrize("name,N,batch,limits", [("arm6", 64, 5, True), ("arm6", 64, 333, True), ("arm6", 23, 40, False), ("arm4", 10, 7, True)])
+def test_pcg_tensor_memory_kernel_bit_identical(name, N, batch, limits, oracle_models):
+    """k_pcg_tm (B2T_PCG_VARIANT=8, the default for fp64 on the structured path when more instances are active than there are SMs:
+    matrices in tensor memory, two instances per SM, instances drawn from a ticket counter) against k_pcg3 on the same systems:
+    the products are streamed in k_pcg3's order of operations, so iteration counts AND solutions are bit-identical.  333 instances
+    exercise the work queue (more instances than 2 x 148 halves); B2T_PCG_TM_MIN=1 forces the kernel for small batches."""
+    res = {}
+    for variant in ("3", "8"):
+        with _env(B2T_PCG_VARIANT=variant, B2T_PCG_TM_MIN="1"):
+            plant, pc, pcons, x, u = _problem(name, N, batch, oracle_models, seed=N + batch)
+            s = t.BatchSolver(plant, pc, pcons if limits else None, N=N, dt=0.1, batch=batch)
+            assert s.pcg_kernel_name() == {"3": "k_pcg3", "8": "k_pcg_tm"}[variant]
+            s.set_trajectory(x, u)
+            s.stage_dynamics()
+            s.stage_kkt(1e-3, t.SQPSolverMethods.PCG_SS)
+            for method in (t.SQPSolverMethods.PCG_SS, t.SQPSolverMethods.PCG_BJ):
+                it = s.stage_pcg(method, 1e-6, 100)
+                res[variant, method] = (np.array(it), s.fetch("l").copy())
+            s.close()
+    for method in (t.SQPSolverMethods.PCG_SS, t.SQPSolverMethods.PCG_BJ):
+        assert np.array_equal(res["3", method][0], res["8", method][0])
+        assert res["3", method][0].min() > 0
+        assert np.array_equal(res["3", method][1], res["8", method][1])
+
+
 @pytest.mark.parametrize("name,N,kind", [("arm6", 64, "limits"), ("arm6", 17, "limits"), ("arm2", 10, "urdf"), ("pend", 20, "hard")])
 def test_parallel_line_search_bit_identical(name, N, kind, oracle_models):
     """k_linesearch_par (all trials of a search evaluated at once, chosen for passes with few active instances; B2T_LS_PAR sets the

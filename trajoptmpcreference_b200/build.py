@@ -27,7 +27,7 @@ def lib_path(tag: str) -> str:
 
 def _sources_digest(header: str) -> str:
     h = hashlib.sha1()
-    for p in (header, os.path.join(CSRC, "b2t_core.cuh"), os.path.join(CSRC, "b2t_kernels.cuh"), os.path.join(CSRC, "b2t_ilqr.cuh"), os.path.join(CSRC, "b2t_lib.cu"),
+    for p in (header, os.path.join(CSRC, "b2t_core.cuh"), os.path.join(CSRC, "b2t_kernels.cuh"), os.path.join(CSRC, "b2t_pcg_tm.cuh"), os.path.join(CSRC, "b2t_ilqr.cuh"), os.path.join(CSRC, "b2t_lib.cu"),
               os.path.join(os.path.dirname(HERE), "include", "b2t.h")):
         with open(p, "rb") as f:
             h.update(f.read())

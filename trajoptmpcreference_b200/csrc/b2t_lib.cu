@@ -7,6 +7,7 @@
 #include <algorithm>
 #include <cuda_runtime.h>
 #include "b2t_kernels.cuh"
+#include "b2t_pcg_tm.cuh"
 #include "b2t_ilqr.cuh"
 #include "../../include/b2t.h"
 
@@ -106,6 +107,9 @@ struct SolverT : SolverBase {
     return 0;
   }
   int* d_scratch = nullptr;
+  int* d_ticket = nullptr;         // k_pcg_tm: work-queue ticket (next slot of the work list), zeroed before every launch
+  int sm_count = 148;
+  int tm_min = 149;                // k_pcg_tm (two instances per SM) only pays when more instances are active than there are SMs (B2T_PCG_TM_MIN)
   enum { PASS_TRACE_CAP = 2048 };
   int* d_pass_trace = nullptr;      // active-instance count after every pass of the last solve (written by k_compact)
   int n_passes = 0;
@@ -236,7 +240,7 @@ struct SolverT : SolverBase {
     B2T_ALLOC(d.nu_trace, B * NU_TRACE_LEN);
     d.trace_cap = 104;
     B2T_ALLOC(d.trace, B * d.trace_cap * TRACE_FIELDS); B2T_ALLOC(d.trace_rows, B);
-    B2T_ALLOC(d_scratch, B); B2T_ALLOC(d_status, B * 8); B2T_ALLOC(d_scalars, B * 4); B2T_ALLOC(d_pass_trace, PASS_TRACE_CAP);
+    B2T_ALLOC(d_scratch, B); B2T_ALLOC(d_ticket, 4); B2T_ALLOC(d_status, B * 8); B2T_ALLOC(d_scalars, B * 4); B2T_ALLOC(d_pass_trace, PASS_TRACE_CAP);
     B2T_ALLOC(stage_x, (size_t)B * NX * d.N); B2T_ALLOC(stage_u, (size_t)B * NU * (d.N - 1)); B2T_ALLOC(stage_g, (size_t)B * NX);
     stage_out_bytes = std::max<size_t>({(size_t)NM * NM * K, (size_t)NDYN * K, (size_t)2 * NM * K, B * (size_t)d.trace_cap * TRACE_FIELDS,
                                         (size_t)(2 * NX * NX + NX) * K}) * sizeof(double);
@@ -269,7 +273,12 @@ struct SolverT : SolverBase {
       B2T_CUDA(cudaFuncSetAttribute(b2t::k_pcg3<T, 512, false, 4>, cudaFuncAttributeMaxDynamicSharedMemorySize, 160 * 1024));
       B2T_CUDA(cudaFuncSetAttribute(b2t::k_pcg3<T, 1024, false, 4>, cudaFuncAttributeMaxDynamicSharedMemorySize, 160 * 1024));
       B2T_CUDA(cudaFuncSetAttribute(b2t::k_pcg3<T, 128, true, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, 112 * 1024));
+      if constexpr (sizeof(T) == 8 && b2t::pcg_tm_eligible())
+        B2T_CUDA(cudaFuncSetAttribute(b2t::k_pcg_tm<T>, cudaFuncAttributeMaxDynamicSharedMemorySize, 160 * 1024));
     }
+    B2T_CUDA(cudaDeviceGetAttribute(&sm_count, cudaDevAttrMultiProcessorCount, device));
+    tm_min = sm_count + 1;
+    { const char* e = getenv("B2T_PCG_TM_MIN"); if (e) tm_min = atoi(e); }
     if constexpr (PCG_CS_MAX == 2) {
       B2T_CUDA(cudaFuncSetAttribute(b2t::k_pcg2<T, PCG_RPT, 2, true, 256>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
       B2T_CUDA(cudaFuncSetAttribute(b2t::k_pcg2<T, PCG_RPT, 2, true, 512>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
@@ -532,6 +541,8 @@ struct SolverT : SolverBase {
   int pcg_variant = -1;
   bool pcg_col = false;
   bool explicit_system = false;   // set by b2t_set_block_system: only S / Pinv blocks are valid -> the explicit kernels must run
+  // k_pcg_tm: fp64, structured path, one instance per 256 threads, D^-1 rows within the per-thread TMEM window
+  bool tm_ok() const { return sizeof(T) == 8 && b2t::pcg_tm_eligible() && d.diag_mode && 4 * d.N <= b2t::PCGTM_HT; }
   void decide_pcg_variant() {
     if (pcg_variant < 0) {
       const char* e = getenv("B2T_PCG_VARIANT");
@@ -542,9 +553,11 @@ struct SolverT : SolverBase {
       // k_pcg3: 21.9 ms vs 24.0 ms (variant 1) per 2048-instance step at N = 64.  Longer horizons use its 512- / 1024-thread
       // instantiations (128 / 64 registers, spilling): still 1.85x (N = 128: 76.7 vs 141.8 ns per instance-iteration) and 3.2x
       // (N = 256: 289 vs 932 ns) faster than the explicit-block kernel, which no longer fits its blocks in shared memory there
+      else if (tm_ok()) pcg_variant = 8;
       else if (d.diag_mode && b2t::NX % 4 == 0 && 4 * d.N <= 1024) pcg_variant = 3;
       else if (pcg2_threads() > 1024) pcg_variant = 0;
       else pcg_variant = pcg2_smem(true) <= (size_t)220 * 1024 ? 1 : 2;
+      if (pcg_variant == 8 && !tm_ok()) pcg_variant = 3;
       if (pcg_variant == 6 && !(d.diag_mode && b2t::NJ % 6 == 0 && d.N <= b2t::PCG6_KPW * (b2t::PCG6_THREADS / 32))) pcg_variant = 3;
       if (pcg_variant == 5 && !(d.diag_mode && b2t::NX % 4 == 0 && 4 * d.N <= 256)) pcg_variant = 3;
       if (pcg_variant == 3 && !(d.diag_mode && b2t::NX % 4 == 0 && 4 * d.N <= 1024)) pcg_variant = 1;
@@ -577,7 +590,17 @@ struct SolverT : SolverBase {
       tick(B2T_K_PCG);
       return 0;
     }
-    if (pcg_variant == 3 || pcg_variant == 4 || pcg_variant == 5) {
+    if (pcg_variant == 8 && bound >= tm_min) {
+      // matrices in tensor memory, two instances per SM, persistent CTAs that draw instances from a ticket counter
+      if constexpr (sizeof(T) == 8 && b2t::pcg_tm_eligible()) {
+        const size_t smh = ((size_t)2 * (d.N + 1) * NX + (size_t)2 * d.N * PCG3_NMS + 64) * sizeof(T);
+        B2T_CUDA(cudaMemsetAsync(d_ticket, 0, sizeof(int), stream));
+        k_pcg_tm<T><<<std::min(sm_count, (bound + 1) / 2), 2 * PCGTM_HT, 2 * smh, stream>>>(d, list, count, d_ticket, stair, tol, max_iter);
+      }
+      tick(B2T_K_PCG);
+      return 0;
+    }
+    if (pcg_variant == 3 || pcg_variant == 4 || pcg_variant == 5 || pcg_variant == 8) {
       // 3: four lanes per knot, everything in registers, one instance per SM;  4: two lanes per knot, preconditioner rows in
       // shared memory, two instances per SM;  5: k_pcg4 = 3 with the own-block halves of the products ahead of the barriers
       if constexpr (b2t::NX % 4 == 0) {
@@ -742,7 +765,7 @@ struct SolverT : SolverBase {
   }
   const char* pcg_kernel_name() override {
     decide_pcg_variant();
-    return pcg_variant == 6 ? "k_pcg6" : pcg_variant == 5 ? "k_pcg4" : ((pcg_variant == 3 || pcg_variant == 4) ? "k_pcg3" : ((pcg_variant == 1 || pcg_variant == 2) ? "k_pcg2" : "k_pcg"));
+    return pcg_variant == 8 ? "k_pcg_tm" : pcg_variant == 6 ? "k_pcg6" : pcg_variant == 5 ? "k_pcg4" : ((pcg_variant == 3 || pcg_variant == 4) ? "k_pcg3" : ((pcg_variant == 1 || pcg_variant == 2) ? "k_pcg2" : "k_pcg"));
   }
 
   int mpc_shift(const double* x_next, double* x0_out, double* u0_out, double* xnext_out) override {
