@@ -111,12 +111,14 @@ def test_pcg_kernel_variants(N, oracle_models):
         assert np.max(np.abs(res["3"][1] - res[v][1])) < 1e-9 * np.max(np.abs(res["3"][1])), v
 
 
-@pytest.mark.parametrize("name,N,batch,limits", [("arm6", 64, 5, True), ("arm6", 64, 333, True), ("arm6", 23, 40, False), ("arm4", 10, 7, True)])
+@pytest.mark.parametrize("name,N,batch,limits", [("arm6", 64, 5, True), ("arm6", 64, 333, True), ("arm6", 23, 40, False), ("arm4", 10, 7, True),
+                                                      ("arm6", 128, 9, True), ("arm6", 100, 150, False)])
 def test_pcg_tensor_memory_kernel_bit_identical(name, N, batch, limits, oracle_models):
     """k_pcg_tm (B2T_PCG_VARIANT=8, the default for fp64 on the structured path when more instances are active than there are SMs:
     matrices in tensor memory, two instances per SM, instances drawn from a ticket counter) against k_pcg3 on the same systems:
     the products are streamed in k_pcg3's order of operations, so iteration counts AND solutions are bit-identical.  333 instances
-    exercise the work queue (more instances than 2 x 148 halves); B2T_PCG_TM_MIN=1 forces the kernel for small batches."""
+    exercise the work queue (more instances than 2 x 148 halves); B2T_PCG_TM_MIN=1 forces the kernel for small batches.  Horizons
+    64 < N <= 128 run one instance per CTA (k_pcg_tm<512>) against k_pcg3's 512-thread instantiation."""
     res = {}
     for variant in ("3", "8"):
         with _env(B2T_PCG_VARIANT=variant, B2T_PCG_TM_MIN="1"):

@@ -274,7 +274,10 @@ struct SolverT : SolverBase {
       B2T_CUDA(cudaFuncSetAttribute(b2t::k_pcg3<T, 1024, false, 4>, cudaFuncAttributeMaxDynamicSharedMemorySize, 160 * 1024));
       B2T_CUDA(cudaFuncSetAttribute(b2t::k_pcg3<T, 128, true, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, 112 * 1024));
       if constexpr (sizeof(T) == 8 && b2t::pcg_tm_eligible())
-        B2T_CUDA(cudaFuncSetAttribute(b2t::k_pcg_tm<T>, cudaFuncAttributeMaxDynamicSharedMemorySize, 160 * 1024));
+      {
+        B2T_CUDA(cudaFuncSetAttribute(b2t::k_pcg_tm<T, 256>, cudaFuncAttributeMaxDynamicSharedMemorySize, 160 * 1024));
+        B2T_CUDA(cudaFuncSetAttribute(b2t::k_pcg_tm<T, 512>, cudaFuncAttributeMaxDynamicSharedMemorySize, 160 * 1024));
+      }
     }
     B2T_CUDA(cudaDeviceGetAttribute(&sm_count, cudaDevAttrMultiProcessorCount, device));
     tm_min = sm_count + 1;
@@ -542,7 +545,7 @@ struct SolverT : SolverBase {
   bool pcg_col = false;
   bool explicit_system = false;   // set by b2t_set_block_system: only S / Pinv blocks are valid -> the explicit kernels must run
   // k_pcg_tm: fp64, structured path, one instance per 256 threads, D^-1 rows within the per-thread TMEM window
-  bool tm_ok() const { return sizeof(T) == 8 && b2t::pcg_tm_eligible() && d.diag_mode && 4 * d.N <= b2t::PCGTM_HT; }
+  bool tm_ok() const { return sizeof(T) == 8 && b2t::pcg_tm_eligible() && d.diag_mode && 4 * d.N <= b2t::PCGTM_THREADS; }
   void decide_pcg_variant() {
     if (pcg_variant < 0) {
       const char* e = getenv("B2T_PCG_VARIANT");
@@ -590,12 +593,15 @@ struct SolverT : SolverBase {
       tick(B2T_K_PCG);
       return 0;
     }
-    if (pcg_variant == 8 && bound >= tm_min) {
-      // matrices in tensor memory, two instances per SM, persistent CTAs that draw instances from a ticket counter
+    // N <= 64: two instances per CTA, worth it when more instances are active than there are SMs (below that k_pcg3 has the lower
+    // latency).  64 < N <= 128: one instance per CTA; k_pcg3's 512-thread instantiation spills at 128 registers, this one does not.
+    if (pcg_variant == 8 && (4 * d.N > 256 || bound >= tm_min)) {
+      // matrices in tensor memory, persistent CTAs that draw instances from a ticket counter
       if constexpr (sizeof(T) == 8 && b2t::pcg_tm_eligible()) {
         const size_t smh = ((size_t)2 * (d.N + 1) * NX + (size_t)2 * d.N * PCG3_NMS + 64) * sizeof(T);
         B2T_CUDA(cudaMemsetAsync(d_ticket, 0, sizeof(int), stream));
-        k_pcg_tm<T><<<std::min(sm_count, (bound + 1) / 2), 2 * PCGTM_HT, 2 * smh, stream>>>(d, list, count, d_ticket, stair, tol, max_iter);
+        if (4 * d.N <= 256) k_pcg_tm<T, 256><<<std::min(sm_count, (bound + 1) / 2), PCGTM_THREADS, 2 * smh, stream>>>(d, list, count, d_ticket, stair, tol, max_iter);
+        else k_pcg_tm<T, 512><<<std::min(sm_count, bound), PCGTM_THREADS, smh, stream>>>(d, list, count, d_ticket, stair, tol, max_iter);
       }
       tick(B2T_K_PCG);
       return 0;

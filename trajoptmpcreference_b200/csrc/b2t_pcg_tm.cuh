@@ -105,14 +105,15 @@ __device__ __forceinline__ void tm_store_f64(uint32_t a, const double* in) {
   tm_store<2 * ND>(a, w);
 }
 
-constexpr int PCGTM_HT = 256;        // threads per half (one instance)
+constexpr int PCGTM_THREADS = 512;   // threads per CTA: HT = 256 -> two instances (N <= 64) side by side, HT = 512 -> one instance (N <= 128)
 constexpr int PCGTM_CAP = 64;        // doubles per thread in TMEM: 512 columns / (4 warps per sub-partition) / 2
 constexpr bool pcg_tm_eligible() { return NX % 4 == 0 && (NX / 4) * NX <= PCGTM_CAP; }
 
-template <typename T>
-__global__ void __launch_bounds__(2 * PCGTM_HT, 1) k_pcg_tm(Dev<T> d, const int* list, const int* count, int* ticket, int stair, T tol, int max_iter) {
+template <typename T, int HT>
+__global__ void __launch_bounds__(PCGTM_THREADS, 1) k_pcg_tm(Dev<T> d, const int* list, const int* count, int* ticket, int stair, T tol, int max_iter) {
   static_assert(sizeof(T) == 8, "k_pcg_tm: fp64 only (the fp32 solver keeps k_pcg3)");
-  constexpr int LPK = 4, HT = PCGTM_HT;
+  constexpr int LPK = 4;
+  static_assert(HT == 256 || HT == 512, "one or two instances per CTA");
   constexpr int RPT = (NX % LPK == 0) ? NX / LPK : 1;   // owned rows per lane
   constexpr int MC = (NM + LPK - 1) / LPK;               // Ab columns per lane
   constexpr int NMS = PCG3_NMS;
@@ -146,7 +147,7 @@ __global__ void __launch_bounds__(2 * PCGTM_HT, 1) k_pcg_tm(Dev<T> d, const int*
   T* W = V2 + (N + 1) * NX;                   // [N][NMS]     w or q'
   T* Wq = W + N * NMS;                        // [N][NMS]     q
   T* red = Wq + N * NMS;                      // 2 x 32: double-buffered warp partial sums
-  auto hbar = [&]() { asm volatile("bar.sync %0, %1;" :: "r"(h + 1), "n"(PCGTM_HT) : "memory"); };
+  auto hbar = [&]() { asm volatile("bar.sync %0, %1;" :: "r"(h + 1), "n"(HT) : "memory"); };
   const bool live = tid < LPK * N;
   const int k = live ? tid / LPK : 0;         // knot
   const int g = tid % LPK;                    // lane within the knot group
@@ -240,7 +241,7 @@ __global__ void __launch_bounds__(2 * PCGTM_HT, 1) k_pcg_tm(Dev<T> d, const int*
       return v;
     };
     int red_sel = 0;
-    auto bsum = [&](T v) -> T {               // same tree as k_pcg3<T, 256, ...>::bsum
+    auto bsum = [&](T v) -> T {               // same tree as k_pcg3<T, HT, ...>::bsum
 #pragma unroll
       for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
       T* rb = red + 32 * red_sel;
