@@ -296,7 +296,8 @@ def run_reference_arm(args):
 def ncu_traffic(family, batch, launches_per_step, qp_per_instance, kernel_name=None):
     """DRAM bytes per launch of the dominant kernel from the NEWEST committed `ncu --set full` capture of that kernel under
     profiles/ (files named r<round>_v<n>_ncu_full_<kernel>.csv; the line names the file, so a stale capture is visible): the capture
-    gives dram__bytes_read.sum + dram__bytes_write.sum for ONE launch over `launch__grid_size` instances; scaled to the average
+    gives dram__bytes_read.sum + dram__bytes_write.sum for ONE launch over `launch__grid_size` instances (`b2t__instances` for the
+    persistent k_pcg_tm, whose grid is the SM count); scaled to the average
     number of instances per launch of this run (per-instance traffic of the PCG kernels does not depend on the batch: every
     instance's dynamics Jacobians, Ghat factors, preconditioner blocks and gamma are read once, l is written once)."""
     if family != "pcg":
@@ -319,7 +320,8 @@ def ncu_traffic(family, batch, launches_per_step, qp_per_instance, kernel_name=N
                 parts = line.strip().split(",")       # metric,unit,value (scripts/profile_summary.py)
                 if len(parts) >= 3:
                     vals[parts[0]] = parts[2]
-        grid = float(vals["launch__grid_size"])
+        # persistent kernels (k_pcg_tm: one CTA per SM) record the instances of the captured launch separately (scripts/profile_summary.py)
+        grid = float(vals.get("b2t__instances", vals["launch__grid_size"]))
         per_inst = (float(vals["dram__bytes_read.sum"]) + float(vals["dram__bytes_write.sum"])) * 1e6 / grid
         inst_per_launch = batch * qp_per_instance / max(launches_per_step, 1)
         return per_inst * inst_per_launch, "profiles/%s: %.0f bytes per instance x %.0f instances per launch (avg)" % (name, per_inst, inst_per_launch)

@@ -1,5 +1,5 @@
 """Turn the raw gpurun_out artefacts of a round into the tracked summaries under profiles/:
-   python scripts/profile_summary.py <tag> <launches.csv> <full.ncu-rep> <kernel-regex>
+   python scripts/profile_summary.py <tag> <launches.csv> <full.ncu-rep | raw.csv> <kernel> [<sass page .csv.gz of a persistent kernel>]
 writes profiles/<tag>_ncu_launch_summary.csv and profiles/<tag>_ncu_full_<kernel>.csv (needs ncu on PATH for the .ncu-rep)."""
 import collections
 import csv
@@ -40,7 +40,20 @@ def launch_summary(tag, path):
     return out
 
 
-def full_summary(tag, rep, kernel):
+def ticket_instances(sass_page, grid, halves_per_cta=2):
+    """Persistent kernels (k_pcg_tm) launch one CTA per SM, not one per instance: the number of instances a captured launch processed
+    is the number of work-queue tickets drawn (executed count of the ATOMG of the exported SASS page) minus the one terminating
+    ticket per half."""
+    import gzip
+    op = gzip.open if sass_page.endswith('.gz') else open
+    rows = list(csv.reader(l for l in op(sass_page, 'rt') if not l.startswith('==')))
+    hdr = rows[1]
+    isrc, ie = hdr.index('Source'), hdr.index('Instructions Executed')
+    tickets = sum(float(r[ie]) for r in rows[2:] if len(r) > ie and 'ATOMG' in r[isrc])
+    return int(tickets - halves_per_cta * grid)
+
+
+def full_summary(tag, rep, kernel, sass_page=None):
     """rep: a .ncu-rep (read with ncu) or the raw page already exported on the GPU box (`ncu -i x.ncu-rep --page raw --csv > x_raw.csv`;
     the reports themselves exceed gpurun's 64 MiB return limit).  One column per captured launch."""
     if rep.endswith('.csv'):
@@ -58,10 +71,13 @@ def full_summary(tag, rep, kernel):
         for k in keys:
             if k in hdr:
                 f.write('%s,%s,%s\n' % (k, units[hdr.index(k)], ','.join(r[hdr.index(k)].replace(',', '') for r in launches)))
+        if sass_page:
+            grid = float(launches[0][hdr.index('launch__grid_size')])
+            f.write('b2t__instances,instance,%d\n' % ticket_instances(sass_page, grid))
     return out
 
 
 if __name__ == '__main__':
     tag, launches, rep, kernel = sys.argv[1:5]
     print(launch_summary(tag, launches))
-    print(full_summary(tag, rep, kernel))
+    print(full_summary(tag, rep, kernel, sys.argv[5] if len(sys.argv) > 5 else None))

@@ -105,11 +105,20 @@ __device__ __forceinline__ void tm_store_f64(uint32_t a, const double* in) {
   tm_store<2 * ND>(a, w);
 }
 
+// dinv u - hh h has two products and one subtraction: which product is fused with the subtraction decides the rounding.  Left to the
+// compiler, the choice depends on predication and scheduling (it differs between instantiations of the same source), so the two forms
+// that k_pcg3's binary uses are spelled out: form A everywhere except the W-only copy (u2) of all but the lane's last column.
+__device__ __forceinline__ double ghat_a(double dinv, double u, double hh, double h) { return __fma_rn(u, dinv, -__dmul_rn(hh, h)); }
+__device__ __forceinline__ double ghat_b(double dinv, double u, double hh, double h) { return __fma_rn(-h, hh, __dmul_rn(dinv, u)); }
+
 constexpr int PCGTM_THREADS = 512;   // threads per CTA: HT = 256 -> two instances (N <= 64) side by side, HT = 512 -> one instance (N <= 128)
 constexpr int PCGTM_CAP = 64;        // doubles per thread in TMEM: 512 columns / (4 warps per sub-partition) / 2
 constexpr bool pcg_tm_eligible() { return NX % 4 == 0 && (NX / 4) * NX <= PCGTM_CAP; }
 
-template <typename T, int HT>
+// NK: compile-time horizon (0: d.N at run time), INTEG: compile-time integrator type (-1: d.integrator at run time).  The specialised
+// instantiation (N = 64 of BASELINE.json, Euler) turns the liveness tests, strides and integrator selects that the compiler otherwise
+// re-derives every iteration (it has no registers to keep them) into immediates.
+template <typename T, int HT, int NK = 0, int INTEG = -1>
 __global__ void __launch_bounds__(PCGTM_THREADS, 1) k_pcg_tm(Dev<T> d, const int* list, const int* count, int* ticket, int stair, T tol, int max_iter) {
   static_assert(sizeof(T) == 8, "k_pcg_tm: fp64 only (the fp32 solver keeps k_pcg3)");
   constexpr int LPK = 4;
@@ -139,7 +148,7 @@ __global__ void __launch_bounds__(PCGTM_THREADS, 1) k_pcg_tm(Dev<T> d, const int
   const uint32_t tmw = tm_base + ((uint32_t)(32 * (warp & 3)) << 16) + (uint32_t)((warp >> 2) * (2 * PCGTM_CAP));
   const uint32_t tm_pd = tmw, tm_ab = tmw + 2 * PD_D;
   const int h = threadIdx.x / HT, tid = threadIdx.x % HT;
-  const int N = d.N;
+  const int N = NK > 0 ? NK : d.N;
   const size_t K = d.K;
   const size_t half_T = (size_t)2 * (N + 1) * NX + (size_t)2 * N * NMS + 64;
   T* V = reinterpret_cast<T*>(smem_raw) + (size_t)h * half_T;   // [(N+1)][NX]  p / r / O y; block N stays zero
@@ -148,14 +157,15 @@ __global__ void __launch_bounds__(PCGTM_THREADS, 1) k_pcg_tm(Dev<T> d, const int
   T* Wq = W + N * NMS;                        // [N][NMS]     q
   T* red = Wq + N * NMS;                      // 2 x 32: double-buffered warp partial sums
   auto hbar = [&]() { asm volatile("bar.sync %0, %1;" :: "r"(h + 1), "n"(HT) : "memory"); };
-  const bool live = tid < LPK * N;
+  const bool live = (NK > 0 && LPK * NK >= HT) ? true : tid < LPK * N;
   const int k = live ? tid / LPK : 0;         // knot
   const int g = tid % LPK;                    // lane within the knot group
   const bool has_next = live && (k < N - 1);
   const int jo = (k + 1 == N) ? 0 : k + 1;    // owned block row
   const int c0 = g * MC, i0 = g * RPT;
-  const T dte = d.integrator == 0 ? d.dt : T(0);
-  const T tau = d.integrator == 0 ? T(0) : d.dt;
+  const int integ = INTEG >= 0 ? INTEG : d.integrator;
+  const T dte = integ == 0 ? d.dt : T(0);
+  const T tau = integ == 0 ? T(0) : d.dt;
   const bool top = i0 < NJ;
   const bool odd = (i0 % NJ) != 0;
   const int ownV = jo * NX, ownW = jo * NMS + i0, kV = k * NX, nV = (k + 1) * NX, kW = k * NMS;
@@ -365,8 +375,8 @@ __global__ void __launch_bounds__(PCGTM_THREADS, 1) k_pcg_tm(Dev<T> d, const int
       if (rank1) { h1 = sS * quad(h1); h2 = sS * quad(h2); } else { h1 = T(0); h2 = T(0); }
 #pragma unroll
       for (int i = 0; i < MC; ++i) {
-        u1[i] = dinv[i] * u1[i] - hh[i] * h1;
-        u2[i] = dinv[i] * u2[i] - hh[i] * h2;
+        u1[i] = ghat_a(dinv[i], u1[i], hh[i], h1);
+        u2[i] = (i < MC - 1) ? ghat_b(dinv[i], u2[i], hh[i], h2) : ghat_a(dinv[i], u2[i], hh[i], h2);
         if (cvalid[i]) { Wq[kW + c0 + i] = u1[i]; W[kW + c0 + i] = u2[i]; }
       }
       hbar();
@@ -400,7 +410,7 @@ __global__ void __launch_bounds__(PCGTM_THREADS, 1) k_pcg_tm(Dev<T> d, const int
       hu = rank1 ? sS * quad(hu) : T(0);
 #pragma unroll
       for (int i = 0; i < MC; ++i) {
-        uc[i] = dinv[i] * uc[i] - hh[i] * hu;
+        uc[i] = ghat_a(dinv[i], uc[i], hh[i], hu);
         if (cvalid[i]) W[kW + c0 + i] = uc[i];
       }
       hbar();
