@@ -118,7 +118,9 @@ constexpr bool pcg_tm_eligible() { return NX % 4 == 0 && (NX / 4) * NX <= PCGTM_
 // NK: compile-time horizon (0: d.N at run time), INTEG: compile-time integrator type (-1: d.integrator at run time).  The specialised
 // instantiation (N = 64 of BASELINE.json, Euler) turns the liveness tests, strides and integrator selects that the compiler otherwise
 // re-derives every iteration (it has no registers to keep them) into immediates.
-template <typename T, int HT, int NK = 0, int INTEG = -1>
+// ABC: Ab columns fetched per TMEM load (register pressure against the number of tcgen05.ld; 1 / 2 / 3 measured 688.8 / 683.1 / 681.6 ms
+// of PCG per default step: within noise of each other, 2 kept).
+template <typename T, int HT, int NK = 0, int INTEG = -1, int ABC = 2>
 __global__ void __launch_bounds__(PCGTM_THREADS, 1) k_pcg_tm(Dev<T> d, const int* list, const int* count, int* ticket, int stair, T tol, int max_iter) {
   static_assert(sizeof(T) == 8, "k_pcg_tm: fp64 only (the fp32 solver keeps k_pcg3)");
   constexpr int LPK = 4;
@@ -197,9 +199,9 @@ __global__ void __launch_bounds__(PCGTM_THREADS, 1) k_pcg_tm(Dev<T> d, const int
       hh[i] = cvalid[i] ? d.Gh[(size_t)(NM + c) * K + tk] : T(0);
       emul[i] = (!has_next || !cvalid[i] || c >= NX) ? T(0) : (c < NJ ? T(1) : dte);
     }
-    static_for<0, (MC + 1) / 2>([&](auto qc) {
-      constexpr int I0 = 2 * decltype(qc)::value;
-      constexpr int CNT = (I0 + 2 <= MC) ? 2 : 1;
+    static_for<0, (MC + ABC - 1) / ABC>([&](auto qc) {
+      constexpr int I0 = ABC * decltype(qc)::value;
+      constexpr int CNT = (I0 + ABC <= MC) ? ABC : MC - I0;
       T m[CNT * NJ];
 #pragma unroll
       for (int ii = 0; ii < CNT; ++ii) {
@@ -279,14 +281,19 @@ __global__ void __launch_bounds__(PCGTM_THREADS, 1) k_pcg_tm(Dev<T> d, const int
       T pi[NJ];
 #pragma unroll
       for (int a = 0; a < NJ; a += 2) {
-        const T2 zq = *reinterpret_cast<const T2*>(buf + nV + a);
         const T2 zv = *reinterpret_cast<const T2*>(buf + nV + NJ + a);
-        pi[a] = tau * zq.x + zv.x;
-        if (a + 1 < NJ) pi[a + 1] = tau * zq.y + zv.y;
+        if constexpr (INTEG == 0) {           // tau = 0: fma(0, z_q, z_v) = z_v, and the z_q half of the block is not loaded at all
+          pi[a] = zv.x;
+          if (a + 1 < NJ) pi[a + 1] = zv.y;
+        } else {
+          const T2 zq = *reinterpret_cast<const T2*>(buf + nV + a);
+          pi[a] = tau * zq.x + zv.x;
+          if (a + 1 < NJ) pi[a + 1] = tau * zq.y + zv.y;
+        }
       }
-      static_for<0, (MC + 1) / 2>([&](auto qc) {
-        constexpr int I0 = 2 * decltype(qc)::value;
-        constexpr int CNT = (I0 + 2 <= MC) ? 2 : 1;
+      static_for<0, (MC + ABC - 1) / ABC>([&](auto qc) {
+        constexpr int I0 = ABC * decltype(qc)::value;
+        constexpr int CNT = (I0 + ABC <= MC) ? ABC : MC - I0;
         T m[CNT * NJ];
         ab_get(std::integral_constant<int, I0>{}, std::integral_constant<int, CNT>{}, m);
 #pragma unroll
@@ -307,9 +314,9 @@ __global__ void __launch_bounds__(PCGTM_THREADS, 1) k_pcg_tm(Dev<T> d, const int
       T pb[NJ];
 #pragma unroll
       for (int a = 0; a < NJ; ++a) pb[a] = T(0);
-      static_for<0, (MC + 1) / 2>([&](auto qc) {
-        constexpr int I0 = 2 * decltype(qc)::value;
-        constexpr int CNT = (I0 + 2 <= MC) ? 2 : 1;
+      static_for<0, (MC + ABC - 1) / ABC>([&](auto qc) {
+        constexpr int I0 = ABC * decltype(qc)::value;
+        constexpr int CNT = (I0 + ABC <= MC) ? ABC : MC - I0;
         T m[CNT * NJ];
         ab_get(std::integral_constant<int, I0>{}, std::integral_constant<int, CNT>{}, m);
 #pragma unroll
@@ -329,7 +336,7 @@ __global__ void __launch_bounds__(PCGTM_THREADS, 1) k_pcg_tm(Dev<T> d, const int
 #pragma unroll
       for (int r = 0; r < RPT; ++r) {
         const T zq = full[kW + (top ? i0 + r : 0)], zd = full[kW + NJ + (top ? i0 + r : 0)];
-        const T val = top ? (zq + dte * zd + tau * bot[r]) : bot[r];
+        const T val = top ? (INTEG == 0 ? (zq + dte * zd) : (zq + dte * zd + tau * bot[r])) : bot[r];      // INTEG == 0: tau = 0
         out[r] = has_next ? val + sign * Wn[ownW + r] : (live ? sign * Wn[ownW + r] : T(0));
       }
     };
