@@ -475,7 +475,7 @@ def run_b200_arm(args):
         ach = fam_flops[dom] / dom_sec / 1e12 if dom_sec > 0 else 0.0
         alg_bytes = B * (2 * 8 * (12 * N + 6 * (N - 1)) + 8 * 12 + 64)
         traffic, traffic_src = ncu_traffic(dom, B, dom_launch, qp / B if B else 0, solver.pcg_kernel_name() if dom == "pcg" else None)
-        roof = {"bound": "fp64_fma" if args.dtype == "f64" else "fp32_fma", "kernel": "k_" + dom, "achieved": ach, "peak": peak64, "unit": "TFLOP/s",
+        roof = {"bound": "fp64_fma" if args.dtype == "f64" else "fp32_fma", "kernel": (solver.pcg_kernel_name() + (" (bulk passes; k_pcg3 in passes with fewer active instances than SMs)" if solver.pcg_kernel_name() == "k_pcg_tm" else "")) if dom == "pcg" else "k_" + dom, "achieved": ach, "peak": peak64, "unit": "TFLOP/s",
                 "frac": ach / peak64 if peak64 else None, "traffic": traffic, "traffic_source": traffic_src,
                 "peak_source": "measured in this run: DFMA chain micro-benchmark b2t_measure_fma_peak (MEASURED_PEAKS.json has no fp64 entry)",
                 "algorithmic_flops_per_launch": fam_flops[dom] / max(dom_launch, 1), "avg_launch_ms": 1e3 * dom_sec / max(dom_launch, 1),
