@@ -110,6 +110,7 @@ struct SolverT : SolverBase {
   int* d_ticket = nullptr;         // k_pcg_tm: work-queue ticket (next slot of the work list), zeroed before every launch
   int sm_count = 148;
   bool tm_generic = false;
+  bool tm_pre = true;              // A/B switch (B2T_PCG_TM_PRE=0): no TMEM prefetch ahead of the barriers
   int tm_min = 149;                // k_pcg_tm (two instances per SM) only pays when more instances are active than there are SMs (B2T_PCG_TM_MIN)
   enum { PASS_TRACE_CAP = 2048 };
   int* d_pass_trace = nullptr;      // active-instance count after every pass of the last solve (written by k_compact)
@@ -279,11 +280,13 @@ struct SolverT : SolverBase {
         B2T_CUDA(cudaFuncSetAttribute(b2t::k_pcg_tm<T, 256>, cudaFuncAttributeMaxDynamicSharedMemorySize, 160 * 1024));
         B2T_CUDA(cudaFuncSetAttribute(b2t::k_pcg_tm<T, 512>, cudaFuncAttributeMaxDynamicSharedMemorySize, 160 * 1024));
         B2T_CUDA(cudaFuncSetAttribute(b2t::k_pcg_tm<T, 256, 64, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, 160 * 1024));
+        B2T_CUDA(cudaFuncSetAttribute(b2t::k_pcg_tm<T, 256, 64, 0, 2, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 160 * 1024));
       }
     }
     B2T_CUDA(cudaDeviceGetAttribute(&sm_count, cudaDevAttrMultiProcessorCount, device));
     tm_min = sm_count + 1;
     { const char* e = getenv("B2T_PCG_TM_MIN"); if (e) tm_min = atoi(e); }
+    { const char* e = getenv("B2T_PCG_TM_PRE"); if (e) tm_pre = atoi(e) != 0; }
     { const char* e = getenv("B2T_PCG_TM_GENERIC"); tm_generic = e && atoi(e) != 0; }     // A/B switch: run-time horizon / integrator instantiation
     if constexpr (PCG_CS_MAX == 2) {
       B2T_CUDA(cudaFuncSetAttribute(b2t::k_pcg2<T, PCG_RPT, 2, true, 256>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
@@ -603,7 +606,8 @@ struct SolverT : SolverBase {
       if constexpr (sizeof(T) == 8 && b2t::pcg_tm_eligible()) {
         const size_t smh = ((size_t)2 * (d.N + 1) * NX + (size_t)2 * d.N * PCG3_NMS + 64) * sizeof(T);
         B2T_CUDA(cudaMemsetAsync(d_ticket, 0, sizeof(int), stream));
-        if (d.N == 64 && d.integrator == 0 && !tm_generic) k_pcg_tm<T, 256, 64, 0><<<std::min(sm_count, (bound + 1) / 2), PCGTM_THREADS, 2 * smh, stream>>>(d, list, count, d_ticket, stair, tol, max_iter);
+        if (d.N == 64 && d.integrator == 0 && !tm_generic && !tm_pre) k_pcg_tm<T, 256, 64, 0, 2, false><<<std::min(sm_count, (bound + 1) / 2), PCGTM_THREADS, 2 * smh, stream>>>(d, list, count, d_ticket, stair, tol, max_iter);
+        else if (d.N == 64 && d.integrator == 0 && !tm_generic) k_pcg_tm<T, 256, 64, 0><<<std::min(sm_count, (bound + 1) / 2), PCGTM_THREADS, 2 * smh, stream>>>(d, list, count, d_ticket, stair, tol, max_iter);
         else if (4 * d.N <= 256) k_pcg_tm<T, 256><<<std::min(sm_count, (bound + 1) / 2), PCGTM_THREADS, 2 * smh, stream>>>(d, list, count, d_ticket, stair, tol, max_iter);
         else k_pcg_tm<T, 512><<<std::min(sm_count, bound), PCGTM_THREADS, smh, stream>>>(d, list, count, d_ticket, stair, tol, max_iter);
       }

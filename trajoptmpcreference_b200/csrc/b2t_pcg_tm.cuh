@@ -97,6 +97,18 @@ __device__ __forceinline__ void tm_load_f64(uint32_t a, double* out) {
 #pragma unroll
   for (int i = 0; i < ND; ++i) out[i] = __hiloint2double((int)w[2 * i + 1], (int)w[2 * i]);
 }
+// the same in two halves: issue the loads (no wait), and later wait + pin + convert -- the first chunk of a product is fetched before the
+// barrier the product waits on anyway, so its TMEM latency is hidden behind the barrier
+template <int ND>
+__device__ __forceinline__ void tm_issue_f64(uint32_t a, uint32_t* w) { tm_load<2 * ND>(a, w); }
+template <int ND>
+__device__ __forceinline__ void tm_complete_f64(uint32_t* w, double* out) {
+  tm_wait_ld();
+#pragma unroll
+  for (int i = 0; i < 2 * ND; ++i) asm volatile("" : "+r"(w[i]));
+#pragma unroll
+  for (int i = 0; i < ND; ++i) out[i] = __hiloint2double((int)w[2 * i + 1], (int)w[2 * i]);
+}
 template <int ND>
 __device__ __forceinline__ void tm_store_f64(uint32_t a, const double* in) {
   uint32_t w[2 * ND];
@@ -120,7 +132,8 @@ constexpr bool pcg_tm_eligible() { return NX % 4 == 0 && (NX / 4) * NX <= PCGTM_
 // re-derives every iteration (it has no registers to keep them) into immediates.
 // ABC: Ab columns fetched per TMEM load (register pressure against the number of tcgen05.ld; 1 / 2 / 3 measured 688.8 / 683.1 / 681.6 ms
 // of PCG per default step: within noise of each other, 2 kept).
-template <typename T, int HT, int NK = 0, int INTEG = -1, int ABC = 2>
+// PRE: fetch the first TMEM chunk of every product ahead of the barrier in front of it.
+template <typename T, int HT, int NK = 0, int INTEG = -1, int ABC = 2, bool PRE = true>
 __global__ void __launch_bounds__(PCGTM_THREADS, 1) k_pcg_tm(Dev<T> d, const int* list, const int* count, int* ticket, int stair, T tol, int max_iter) {
   static_assert(sizeof(T) == 8, "k_pcg_tm: fp64 only (the fp32 solver keeps k_pcg3)");
   constexpr int LPK = 4;
@@ -239,11 +252,16 @@ __global__ void __launch_bounds__(PCGTM_THREADS, 1) k_pcg_tm(Dev<T> d, const int
     hbar();
 
     // Ab columns [I0, I0 + CNT) of this lane -> m (column-major), from TMEM and the register tail
+    constexpr int AB0 = ((ABC < MC ? ABC : MC) * NJ) < AB_T ? ((ABC < MC ? ABC : MC) * NJ) : AB_T;      // doubles of the first Ab chunk that live in TMEM
+    uint32_t wpre[2 * (AB0 > PD_CH ? AB0 : PD_CH)];          // words of a prefetched first chunk (Ab or D^-1)
+    auto ab_prefetch = [&]() { if constexpr (PRE && AB0 > 0) tm_issue_f64<AB0>(tm_ab, wpre); };
+    auto pd_prefetch = [&]() { if constexpr (PRE) tm_issue_f64<PD_CH>(tm_pd, wpre); };
     auto ab_get = [&](auto i0c, auto cntc, T* m) {
       constexpr int I0 = decltype(i0c)::value, CNT = decltype(cntc)::value;
       constexpr int f0 = I0 * NJ, f1 = (I0 + CNT) * NJ;
       constexpr int t1 = f1 < AB_T ? f1 : AB_T;
-      if constexpr (t1 > f0) tm_load_f64<t1 - f0>(tm_ab + 2 * f0, m);
+      if constexpr (PRE && I0 == 0 && AB0 > 0) tm_complete_f64<AB0>(wpre, m);
+      else if constexpr (t1 > f0) tm_load_f64<t1 - f0>(tm_ab + 2 * f0, m);
 #pragma unroll
       for (int f = (f0 > AB_T ? f0 : AB_T); f < f1; ++f) m[f - f0] = abr[f - AB_T];
     };
@@ -337,7 +355,9 @@ __global__ void __launch_bounds__(PCGTM_THREADS, 1) k_pcg_tm(Dev<T> d, const int
       for (int r = 0; r < RPT; ++r) {
         const T zq = full[kW + (top ? i0 + r : 0)], zd = full[kW + NJ + (top ? i0 + r : 0)];
         const T val = top ? (INTEG == 0 ? (zq + dte * zd) : (zq + dte * zd + tau * bot[r])) : bot[r];      // INTEG == 0: tau = 0
-        out[r] = has_next ? val + sign * Wn[ownW + r] : (live ? sign * Wn[ownW + r] : T(0));
+        // branch-free form of  has_next ? val + sign Wn : (live ? sign Wn : 0)  (sign = +-1: the product is exact, adding +0 changes nothing)
+        const T wn = live ? Wn[ownW + r] : T(0);
+        out[r] = (has_next ? val : T(0)) + sign * wn;
       }
     };
     // out = Pd_jo * buf[jo]
@@ -348,7 +368,8 @@ __global__ void __launch_bounds__(PCGTM_THREADS, 1) k_pcg_tm(Dev<T> d, const int
       static_for<0, NX / 4>([&](auto qc) {
         constexpr int q = decltype(qc)::value;
         T m[PD_CH];
-        tm_load_f64<PD_CH>(tm_pd + 2 * q * PD_CH, m);
+        if constexpr (PRE && q == 0) tm_complete_f64<PD_CH>(wpre, m);
+        else tm_load_f64<PD_CH>(tm_pd + 2 * q * PD_CH, m);
 #pragma unroll
         for (int cc = 0; cc < 2; ++cc) {
           const T2 v = *reinterpret_cast<const T2*>(buf + ownV + 4 * q + 2 * cc);
@@ -360,7 +381,7 @@ __global__ void __launch_bounds__(PCGTM_THREADS, 1) k_pcg_tm(Dev<T> d, const int
       for (int r = 0; r < RPT; ++r) out[r] = o0[r] + o1[r];
     };
     T rr[RPT], xx[RPT], pp[RPT], rt[RPT], yv[RPT], tmp[RPT];
-    auto precond = [&]() {
+    auto precond = [&]() {      // the caller has issued pd_prefetch()
       publish(V, rr);
       __syncwarp();
       pd_mul(V, yv);
@@ -370,6 +391,7 @@ __global__ void __launch_bounds__(PCGTM_THREADS, 1) k_pcg_tm(Dev<T> d, const int
         return;
       }
       publish(V2, yv);
+      ab_prefetch();
       hbar();
       T u1[MC], u2[MC], h1 = T(0), h2 = T(0);
       abt(V2, u2);
@@ -386,9 +408,11 @@ __global__ void __launch_bounds__(PCGTM_THREADS, 1) k_pcg_tm(Dev<T> d, const int
         u2[i] = (i < MC - 1) ? ghat_b(dinv[i], u2[i], hh[i], h2) : ghat_a(dinv[i], u2[i], hh[i], h2);
         if (cvalid[i]) { Wq[kW + c0 + i] = u1[i]; W[kW + c0 + i] = u2[i]; }
       }
+      ab_prefetch();
       hbar();
       abmul(u1, Wq, W, T(1), tmp);
       publish(V, tmp);
+      pd_prefetch();
       __syncwarp();
       pd_mul(V, tmp);
 #pragma unroll
@@ -396,6 +420,7 @@ __global__ void __launch_bounds__(PCGTM_THREADS, 1) k_pcg_tm(Dev<T> d, const int
     };
 #pragma unroll
     for (int r = 0; r < RPT; ++r) { rr[r] = live ? d.gam[(size_t)(i0 + r) * K + tj] : T(0); xx[r] = T(0); }
+    pd_prefetch();
     precond();
     T part = T(0);
 #pragma unroll
@@ -406,6 +431,7 @@ __global__ void __launch_bounds__(PCGTM_THREADS, 1) k_pcg_tm(Dev<T> d, const int
     for (int it = 0; it < max_iter; ++it) {
       const T inv_nu = T(1) / nu;
       publish(V, pp);
+      ab_prefetch();
       hbar();
       T uc[MC], hu = T(0), ap[RPT];
       abt(V, uc);
@@ -420,12 +446,14 @@ __global__ void __launch_bounds__(PCGTM_THREADS, 1) k_pcg_tm(Dev<T> d, const int
         uc[i] = ghat_a(dinv[i], uc[i], hh[i], hu);
         if (cvalid[i]) W[kW + c0 + i] = uc[i];
       }
+      ab_prefetch();
       hbar();
       abmul(uc, W, W, T(-1), ap);
       part = T(0);
 #pragma unroll
       for (int r = 0; r < RPT; ++r) part += pp[r] * ap[r];
       const T pAp = bsum(part);
+      pd_prefetch();                              // behind the division
       const T alpha = nu / pAp;
 #pragma unroll
       for (int r = 0; r < RPT; ++r) { rr[r] -= ap[r] * alpha; xx[r] += pp[r] * alpha; }
