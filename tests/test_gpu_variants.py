@@ -138,6 +138,32 @@ def test_pcg_tensor_memory_kernel_bit_identical(name, N, batch, limits, oracle_m
         assert np.array_equal(res["3", method][1], res["8", method][1])
 
 
+@pytest.mark.parametrize("N,batch", [(64, 200), (40, 11), (100, 7)])
+def test_tensor_memory_solve_bit_identical(N, batch, oracle_models):
+    """Complete SQP solves with k_pcg_tm in every pass (B2T_PCG_TM_MIN=1) against the k_pcg3 pipeline (B2T_PCG_VARIANT=3), and with
+    the default hand-over between the two (k_pcg_tm in passes with more active instances than SMs, k_pcg3 below): every count, exit
+    code, trace row and trajectory identical -- a solve does not depend on which kernel ran which pass, hence not on what else is
+    in the batch.  N = 64 runs the N = 64 / Euler instantiation, 40 the run-time one, 100 one instance per CTA."""
+    out = {}
+    for tag, env in (("pcg3", dict(B2T_PCG_VARIANT="3")), ("tm", dict(B2T_PCG_VARIANT="8", B2T_PCG_TM_MIN="1")),
+                     ("tm_default", dict(B2T_PCG_VARIANT=None, B2T_PCG_TM_MIN=None))):
+        with _env(**env):
+            plant, pc, pcons, x, u = _problem("arm6", N, batch, oracle_models, seed=5 + N)
+            rng = np.random.default_rng(N)
+            xg = np.zeros((batch, 12)); xg[:, :6] = rng.uniform(-0.5, 0.5, (batch, 6))
+            solver = t.TrajoptMPCReference(plant, pc, pcons)
+            r = solver.solve_batch(x, u, xg, N, 0.1, t.SQPSolverMethods.PCG_SS, {"expected_reduction_min_SQP_DDP": -100, "max_iter_softConstraints": 2,
+                                                                               "max_iter_SQP_DDP": 12})
+            s = solver.batch_solver(N, 0.1, batch)
+            assert s.pcg_kernel_name() == ("k_pcg3" if tag == "pcg3" else "k_pcg_tm")
+            out[tag] = ({k: np.array(v) for k, v in r.items()}, s.get_trace().copy())
+    for tag in ("tm", "tm_default"):
+        for k in out["pcg3"][0]:
+            assert np.array_equal(out["pcg3"][0][k], out[tag][0][k]), (tag, k)
+        assert np.array_equal(out["pcg3"][1], out[tag][1]), tag
+    assert out["pcg3"][0]["total_qp"].min() >= 2
+
+
 @pytest.mark.parametrize("name,N,kind", [("arm6", 64, "limits"), ("arm6", 17, "limits"), ("arm2", 10, "urdf"), ("pend", 20, "hard")])
 def test_parallel_line_search_bit_identical(name, N, kind, oracle_models):
     """k_linesearch_par (all trials of a search evaluated at once, chosen for passes with few active instances; B2T_LS_PAR sets the

@@ -562,7 +562,7 @@ struct SolverT : SolverBase {
       // k_pcg3: 21.9 ms vs 24.0 ms (variant 1) per 2048-instance step at N = 64.  Longer horizons use its 512- / 1024-thread
       // instantiations (128 / 64 registers, spilling): still 1.85x (N = 128: 76.7 vs 141.8 ns per instance-iteration) and 3.2x
       // (N = 256: 289 vs 932 ns) faster than the explicit-block kernel, which no longer fits its blocks in shared memory there
-      else if (tm_ok()) pcg_variant = 8;
+      else if (tm_ok() && d.N > 32) pcg_variant = 8;      // shorter horizons: k_pcg3 launches 4 N threads and already fits 2 - 4 CTAs per SM
       else if (d.diag_mode && b2t::NX % 4 == 0 && 4 * d.N <= 1024) pcg_variant = 3;
       else if (pcg2_threads() > 1024) pcg_variant = 0;
       else pcg_variant = pcg2_smem(true) <= (size_t)220 * 1024 ? 1 : 2;

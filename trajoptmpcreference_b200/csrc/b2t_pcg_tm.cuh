@@ -132,7 +132,12 @@ constexpr bool pcg_tm_eligible() { return NX % 4 == 0 && (NX / 4) * NX <= PCGTM_
 // re-derives every iteration (it has no registers to keep them) into immediates.
 // ABC: Ab columns fetched per TMEM load (register pressure against the number of tcgen05.ld; 1 / 2 / 3 measured 688.8 / 683.1 / 681.6 ms
 // of PCG per default step: within noise of each other, 2 kept).
-// PRE: fetch the first TMEM chunk of every product ahead of the barrier in front of it.
+// PRE: fetch the first TMEM chunk of every product ahead of the barrier in front of it (PCG 666 -> 650 ms per default step).
+// Measured on top of this and NOT kept (all bit-identical): requesting chunk q + 1 right after chunk q has arrived, so that it
+// loads behind the FMAs of chunk q (654 ms); issuing the shared-memory loads of the group's own block ahead of the barrier as well (653 ms,
+// more spills); neighbour-warp mbarriers instead of the 4 exchange barriers per iteration (734 ms: an arrive + try_wait round trip and ~40
+// instructions per exchange cost more than the skew of 8 warps at a block barrier); the step recovery dz = Ghat (g - C^T l) as an epilogue
+// of this kernel instead of the prologue of k_linesearch (line search -6.5 ms, this kernel +6.5 ms and a worse register allocation of its loop).
 template <typename T, int HT, int NK = 0, int INTEG = -1, int ABC = 2, bool PRE = true>
 __global__ void __launch_bounds__(PCGTM_THREADS, 1) k_pcg_tm(Dev<T> d, const int* list, const int* count, int* ticket, int stair, T tol, int max_iter) {
   static_assert(sizeof(T) == 8, "k_pcg_tm: fp64 only (the fp32 solver keeps k_pcg3)");
