@@ -31,6 +31,11 @@ def test_traffic_comes_from_newest_capture_of_the_running_kernel():
     assert t is not None and "r02_v9_ncu_full_k_pcg3.csv" in src
     per_inst = t / (8192 * 71.3 / 472)
     assert 1.4e5 < per_inst < 1.8e5                               # ~154 KB algorithmic per instance
+    # the persistent tensor-memory kernel launches one CTA per SM: its capture carries the instance count of the launch (b2t__instances,
+    # from the executed count of the work-queue ATOMG), and the per-instance traffic must come out the same as k_pcg3's
+    t3, src3 = bench.ncu_traffic("pcg", 8192, 472, 71.3, "k_pcg_tm")
+    assert t3 is not None and "_ncu_full_k_pcg_tm.csv" in src3
+    assert 1.4e5 < t3 / (8192 * 71.3 / 472) < 1.8e5
     t2, src2 = bench.ncu_traffic("pcg", 8192, 472, 71.3, "k_pcg_no_such_kernel")
     assert t2 is None and "no ncu capture" in src2
     assert bench.ncu_traffic("trial_fd", 8192, 472, 71.3)[0] is None
@@ -53,3 +58,16 @@ def test_flop_model_matches_survey():
     assert fm["trial_fd"] == 415 * 6 + 1051 * 6 + 92 * 6 * 7 + 2 * 36
     fam = bench.flops_of(fm, qp=6, pcg=563, trials=16, B=1)        # the anchor instance of SURVEY.md 8d
     assert 1.0e8 < sum(fam.values()) < 1.3e8                       # "~115 Mflop / solve"
+
+
+def test_ticket_instances_of_a_persistent_launch(tmp_path):
+    """scripts/profile_summary.ticket_instances: instances of a captured k_pcg_tm launch = work-queue tickets drawn (executed ATOMG)
+    minus the terminating ticket of every half."""
+    sys.path.insert(0, os.path.join(ROOT, "scripts"))
+    import profile_summary
+    page = tmp_path / "sass.csv"
+    page.write_text('"Kernel Name","k_pcg_tm",\n"Address","Source","# Samples","Instructions Executed"\n'
+                    '"0x10","      S2R R8, SR_TID.X","0","2368"\n'
+                    '"0x20","@P0   ATOMG.E.ADD.STRONG.GPU PT, R3, desc[UR8][R2.64], R9","2","1411"\n'
+                    '"0x30","      DFMA R4, R4, R4, R4","9","798704"\n')
+    assert profile_summary.ticket_instances(str(page), 148) == 1411 - 2 * 148

@@ -34,13 +34,13 @@ class _env:
                 os.environ[k] = v
 
 
-def _problem(name, N, batch, oracle_models, seed):
+def _problem(name, N, batch, oracle_models, seed, integrator=0):
     m = oracle_models[name]
     n = m.n
     rng = np.random.default_rng(seed)
     xg = np.concatenate([rng.uniform(-0.5, 0.5, n), np.zeros(n)])
     limits = {"torque": ([1.0] * n, [-1.0] * n, "QUADRATIC_PENALTY"), "joint": ([0.45] * n, [-0.45] * n, "QUADRATIC_PENALTY")}
-    (plant, pc, pcons), _ = make_pair(name, N, oracle_models, xg=xg, limits=limits)
+    (plant, pc, pcons), _ = make_pair(name, N, oracle_models, xg=xg, limits=limits, integrator=integrator)
     x = 0.3 * rng.standard_normal((batch, 2 * n, N))
     u = 0.5 * rng.standard_normal((batch, n, N - 1))
     return plant, pc, pcons, x, u
@@ -112,7 +112,7 @@ def test_pcg_kernel_variants(N, oracle_models):
 
 
 @pytest.mark.parametrize("name,N,batch,limits", [("arm6", 64, 5, True), ("arm6", 64, 333, True), ("arm6", 23, 40, False), ("arm4", 10, 7, True),
-                                                      ("arm6", 128, 9, True), ("arm6", 100, 150, False), ("arm6", 33, 297, True), ("arm6", 65, 149, True)])
+                                                      ("arm6", 128, 9, True), ("arm6", 100, 150, False), ("arm6", 33, 297, True), ("arm6", 65, 149, True), ("arm6", 64, 151, True)])
 def test_pcg_tensor_memory_kernel_bit_identical(name, N, batch, limits, oracle_models):
     """k_pcg_tm (B2T_PCG_VARIANT=8, the default for fp64 on the structured path when more instances are active than there are SMs:
     matrices in tensor memory, two instances per SM, instances drawn from a ticket counter) against k_pcg3 on the same systems:
@@ -122,7 +122,8 @@ def test_pcg_tensor_memory_kernel_bit_identical(name, N, batch, limits, oracle_m
     res = {}
     for variant in ("3", "8"):
         with _env(B2T_PCG_VARIANT=variant, B2T_PCG_TM_MIN="1"):
-            plant, pc, pcons, x, u = _problem(name, N, batch, oracle_models, seed=N + batch)
+            # batch 151: the semi-implicit Euler integrator (tau = dt: the run-time instantiation also at N = 64)
+            plant, pc, pcons, x, u = _problem(name, N, batch, oracle_models, seed=N + batch, integrator=1 if batch == 151 else 0)
             s = t.BatchSolver(plant, pc, pcons if limits else None, N=N, dt=0.1, batch=batch)
             assert s.pcg_kernel_name() == {"3": "k_pcg3", "8": "k_pcg_tm"}[variant]
             s.set_trajectory(x, u)
