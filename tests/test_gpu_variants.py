@@ -112,7 +112,8 @@ def test_pcg_kernel_variants(N, oracle_models):
 
 
 @pytest.mark.parametrize("name,N,batch,limits", [("arm6", 64, 5, True), ("arm6", 64, 333, True), ("arm6", 23, 40, False), ("arm4", 10, 7, True),
-                                                      ("arm6", 128, 9, True), ("arm6", 100, 150, False), ("arm6", 33, 297, True), ("arm6", 65, 149, True), ("arm6", 64, 151, True)])
+                                                      ("arm6", 128, 9, True), ("arm6", 100, 150, False), ("arm6", 33, 297, True), ("arm6", 65, 149, True), ("arm6", 64, 151, True),
+                                                      ("arm4", 48, 150, True)])
 def test_pcg_tensor_memory_kernel_bit_identical(name, N, batch, limits, oracle_models):
     """k_pcg_tm (B2T_PCG_VARIANT=8, the default for fp64 on the structured path when more instances are active than there are SMs:
     matrices in tensor memory, two instances per SM, instances drawn from a ticket counter) against k_pcg3 on the same systems:
